@@ -1,0 +1,127 @@
+"""ctypes binding of ``lib/libden_b200.so`` — the C-ABI CUDA library.
+
+The product path has NO fallback: if the library is missing or a symbol declared
+in ``include/den_b200.h`` is absent, importing the ops raises.  PyTorch only owns
+the device memory and the stream; every hot-path kernel is launched through the
+C ABI with raw pointers.
+"""
+
+import ctypes
+import os
+import re
+
+from . import _build
+
+_c = ctypes
+_P = _c.c_void_p
+_I64 = _c.c_int64
+_I32 = _c.c_int32
+_F = _c.c_float
+_D = _c.c_double
+_SZ = _c.c_size_t
+_INT = _c.c_int
+
+DEN_MAX_LEVELS = 32
+
+
+class HashGridDesc(_c.Structure):
+    _fields_ = [
+        ("n_levels", _I32), ("n_features", _I32), ("n_agg_levels", _I32), ("reserved", _I32),
+        ("scale", _F * DEN_MAX_LEVELS),
+        ("resolution", _c.c_uint32 * DEN_MAX_LEVELS),
+        ("size", _c.c_uint32 * DEN_MAX_LEVELS),
+        ("offset", _c.c_uint32 * DEN_MAX_LEVELS),
+    ]
+
+
+class MarchParams(_c.Structure):
+    _fields_ = [
+        ("roi", _F * 6), ("res", _I32 * 3), ("contraction", _I32),
+        ("step_size", _F), ("cone_angle", _F),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/den_b200.h declaration by declaration
+_SIGNATURES = {
+    "den_version": (_INT, []),
+    "den_last_error": (_c.c_char_p, []),
+    "den_device_sm_count": (_INT, []),
+    "den_hashgrid_fwd": (_INT, [_c.POINTER(HashGridDesc), _P, _P, _P, _I64, _P]),
+    "den_hashgrid_bwd": (_INT, [_c.POINTER(HashGridDesc), _P, _P, _P, _P, _P, _I64, _P]),
+    "den_ray_aabb_intersect": (_INT, [_P, _P, _c.POINTER(_F), _P, _P, _I64, _P]),
+    "den_clamp_jitter": (_INT, [_P, _P, _P, _INT, _F, _INT, _F, _F, _I64, _P]),
+    "den_march_count": (_INT, [_c.POINTER(MarchParams), _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "den_scan_workspace_bytes": (_SZ, [_I64]),
+    "den_exclusive_scan_i32": (_INT, [_P, _P, _I64, _P, _SZ, _P]),
+    "den_march_write": (_INT, [_c.POINTER(MarchParams), _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                               _I64, _I64, _P]),
+    "den_alpha_from_sigma": (_INT, [_P, _P, _P, _P, _I64, _P]),
+    "den_visibility": (_INT, [_P, _P, _I64, _F, _F, _P, _P, _P]),
+    "den_compact_samples": (_INT, [_P] * 9 + [_I64, _P]),
+    "den_weight_from_density_fwd": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
+    "den_weight_from_density_bwd": (_INT, [_P, _P, _P, _P, _I64, _P, _P, _P]),
+    "den_weight_from_alpha_fwd": (_INT, [_P, _P, _I64, _P, _P]),
+    "den_weight_from_alpha_bwd": (_INT, [_P, _P, _I64, _P, _P, _P]),
+    "den_accumulate_fwd": (_INT, [_P, _P, _P, _I64, _I32, _P, _P]),
+    "den_accumulate_bwd": (_INT, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "den_composite_fwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P,
+                                 _P, _P]),
+}
+
+
+def header_symbols():
+    """Every function name declared in include/den_b200.h (for the ABI test)."""
+    path = os.path.join(_build.INCLUDE, "den_b200.h")
+    with open(path) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(den_[a-z0-9_]+)\s*\(", text)))
+
+
+class DenError(RuntimeError):
+    pass
+
+
+class _Library:
+    def __init__(self):
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            raise DenError(
+                f"{path} is missing: the CUDA extension has not been built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` — there is no "
+                "CPU or PyTorch fallback for the den_b200 kernels.")
+        self.path = path
+        self.cdll = _c.CDLL(path)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            try:
+                fn = getattr(self.cdll, name)
+            except AttributeError as exc:
+                raise DenError(f"{path} does not export {name}") from exc
+            fn.restype = restype
+            fn.argtypes = argtypes
+        version = self.cdll.den_version()
+        if version != 1:
+            raise DenError(f"unexpected den_b200 ABI version {version}")
+
+    def last_error(self):
+        msg = self.cdll.den_last_error()
+        return msg.decode() if msg else ""
+
+    def call(self, name, *args):
+        rc = getattr(self.cdll, name)(*args)
+        if rc != 0:
+            raise DenError(f"{name} failed ({rc}): {self.last_error()}")
+
+    def raw(self, name):
+        return getattr(self.cdll, name)
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _Library()
+    return _LIB

@@ -1,0 +1,388 @@
+"""Tensor-level wrappers over the den_b200 C ABI (``include/den_b200.h``).
+
+Each function validates its tensors (CUDA, dtype, contiguity), allocates the
+outputs with torch (plumbing only) and launches the hand-written kernels on the
+current CUDA stream through ctypes.  ``torch.autograd.Function`` subclasses glue
+the forward/backward kernel pairs into autograd.  There is no CPU path: CPU
+tensors raise ``NotImplementedError`` like the upstream packages do
+(``nerfacc/ray_marching.py``: "Only support cuda inputs.").
+"""
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HashGridDesc, MarchParams
+
+_LAUNCHES = 0           # kernels launched through the C ABI (bench.py reports it)
+
+
+def launch_count():
+    return _LAUNCHES
+
+
+def _count(n=1):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise NotImplementedError(f"{name}: only CUDA tensors are supported (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _call(name, *args, launches=1):
+    _lib.lib().call(name, *args)
+    _count(launches)
+
+
+# --------------------------------------------------------------------------- #
+# hash grid
+# --------------------------------------------------------------------------- #
+def grid_level_table(n_levels, base_resolution, per_level_scale, log2_hashmap_size):
+    """tcnn grid.h level table: (scale fp32, resolution, entries, offset) per level.
+
+    ``scale = exp2(l * log2(s)) * base - 1`` in IEEE fp32; ``res = ceil(scale) + 1``;
+    entries ``min(round_up(res^3, 8), 2^T)`` (SURVEY.md §8(a) level table).
+    """
+    log2_s = np.float32(np.log2(np.float32(per_level_scale)))
+    scales, ress, sizes, offsets = [], [], [], []
+    offset = 0
+    for level in range(n_levels):
+        scale = np.float32(np.exp2(np.float32(np.float32(level) * log2_s))
+                           * np.float32(base_resolution) - np.float32(1.0))
+        res = int(math.ceil(float(scale))) + 1
+        cap = 0xFFFFFFFF // 2
+        dense = cap if float(res) ** 3 > float(cap) else res ** 3
+        dense = ((dense + 7) // 8) * 8
+        size = min(dense, 1 << log2_hashmap_size)
+        scales.append(float(scale))
+        ress.append(res)
+        sizes.append(size)
+        offsets.append(offset)
+        offset += size
+    return scales, ress, sizes, offsets, offset
+
+
+def make_hashgrid_desc(n_levels, base_resolution, per_level_scale, log2_hashmap_size,
+                       n_features=2, agg_max_resolution=512):
+    if n_levels > _lib.DEN_MAX_LEVELS:
+        raise ValueError("too many levels")
+    scales, ress, sizes, offsets, total = grid_level_table(
+        n_levels, base_resolution, per_level_scale, log2_hashmap_size)
+    d = HashGridDesc()
+    d.n_levels = n_levels
+    d.n_features = n_features
+    d.n_agg_levels = sum(1 for r in ress if r <= agg_max_resolution)
+    for i in range(n_levels):
+        d.scale[i] = scales[i]
+        d.resolution[i] = ress[i]
+        d.size[i] = sizes[i]
+        d.offset[i] = offsets[i]
+    return d, total
+
+
+def hashgrid_fwd(desc, x, table):
+    x = _req(x, torch.float32, "x")
+    table = _req(table, torch.float32, "table")
+    n = x.shape[0]
+    out = torch.empty((n, desc.n_levels * desc.n_features), dtype=torch.float32, device=x.device)
+    _call("den_hashgrid_fwd", ctypes.byref(desc), _ptr(x), _ptr(table), _ptr(out), n, _stream())
+    return out
+
+
+def hashgrid_bwd(desc, x, dout, table, need_dx, dtable=None):
+    x = _req(x, torch.float32, "x")
+    dout = _req(dout, torch.float32, "dout")
+    n = x.shape[0]
+    if dtable is None:
+        dtable = torch.zeros_like(table)
+    dx = torch.empty_like(x) if need_dx else None
+    _call("den_hashgrid_bwd", ctypes.byref(desc), _ptr(x), _ptr(dout), _ptr(table), _ptr(dtable),
+          _ptr(dx), n, _stream())
+    return dtable, dx
+
+
+class _HashGridFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, desc):
+        ctx.desc = desc
+        ctx.save_for_backward(x, table)
+        return hashgrid_fwd(desc, x, table)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, table = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        dtable, dx = hashgrid_bwd(ctx.desc, x, dout, table, need_dx)
+        return dx, (dtable if ctx.needs_input_grad[1] else None), None
+
+
+def hashgrid(x, table, desc):
+    return _HashGridFn.apply(x, table, desc)
+
+
+# --------------------------------------------------------------------------- #
+# scan / marching / visibility
+# --------------------------------------------------------------------------- #
+def exclusive_scan_i32(counts):
+    """(n,) int32 -> (n+1,) int32 exclusive prefix, last element = total."""
+    counts = _req(counts, torch.int32, "counts")
+    n = counts.numel()
+    out = torch.empty(n + 1, dtype=torch.int32, device=counts.device)
+    ws_bytes = _lib.lib().raw("den_scan_workspace_bytes")(n)
+    ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.int32, device=counts.device)
+    _call("den_exclusive_scan_i32", _ptr(counts), _ptr(out), n, _ptr(ws), ws.numel() * 4,
+          _stream(), launches=3 if n else 0)
+    return out
+
+
+def make_march_params(roi, res, contraction, step_size, cone_angle):
+    p = MarchParams()
+    for i in range(6):
+        p.roi[i] = float(roi[i])
+    for i in range(3):
+        p.res[i] = int(res[i])
+    p.contraction = int(contraction)
+    p.step_size = float(np.float32(step_size))
+    p.cone_angle = float(np.float32(cone_angle))
+    return p
+
+
+def ray_aabb_intersect(rays_o, rays_d, aabb):
+    rays_o = _req(rays_o, torch.float32, "rays_o")
+    rays_d = _req(rays_d, torch.float32, "rays_d")
+    n = rays_o.shape[0]
+    t_min = torch.empty(n, dtype=torch.float32, device=rays_o.device)
+    t_max = torch.empty_like(t_min)
+    host = (ctypes.c_float * 6)(*[float(v) for v in aabb])
+    _call("den_ray_aabb_intersect", _ptr(rays_o), _ptr(rays_d), host, _ptr(t_min), _ptr(t_max), n,
+          _stream())
+    return t_min, t_max
+
+
+def clamp_jitter_(t_min, t_max, jitter, near_plane, far_plane, step_size):
+    n = t_min.numel()
+    _call("den_clamp_jitter", _ptr(t_min), _ptr(t_max), _ptr(jitter),
+          int(near_plane is not None), float(near_plane or 0.0),
+          int(far_plane is not None), float(far_plane or 0.0), float(np.float32(step_size)), n,
+          _stream())
+
+
+def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None):
+    """Two-pass occupancy march.  Returns (ray_indices i32, t_starts, t_ends, offsets (R+1)).
+
+    With ``capacity=None`` the total is read back (one host sync, as upstream does) and
+    the outputs are exact-size; with a capacity the arena is caller-bounded, nothing is
+    synchronised and ``offsets[-1]`` (device) holds the true total.
+    """
+    rays_o = _req(rays_o, torch.float32, "rays_o")
+    rays_d = _req(rays_d, torch.float32, "rays_d")
+    t_min = _req(t_min, torch.float32, "t_min")
+    t_max = _req(t_max, torch.float32, "t_max")
+    if binary.dtype == torch.bool:
+        binary = binary.contiguous().view(torch.uint8)
+    binary = _req(binary, torch.uint8, "binary")
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    _call("den_march_count", ctypes.byref(params), _ptr(rays_o), _ptr(rays_d), _ptr(t_min),
+          _ptr(t_max), _ptr(binary), _ptr(counts), n, _stream())
+    offsets = exclusive_scan_i32(counts)
+    if capacity is None:
+        capacity = int(offsets[-1].item())
+    ray_indices = torch.empty(capacity, dtype=torch.int32, device=dev)
+    t_starts = torch.empty(capacity, dtype=torch.float32, device=dev)
+    t_ends = torch.empty(capacity, dtype=torch.float32, device=dev)
+    _call("den_march_write", ctypes.byref(params), _ptr(rays_o), _ptr(rays_d), _ptr(t_min),
+          _ptr(t_max), _ptr(binary), _ptr(offsets), _ptr(ray_indices), _ptr(t_starts),
+          _ptr(t_ends), n, capacity, _stream())
+    return ray_indices, t_starts, t_ends, offsets
+
+
+def alpha_from_sigma(sigmas, t_starts, t_ends):
+    sigmas = _req(sigmas.reshape(-1), torch.float32, "sigmas")
+    out = torch.empty_like(sigmas)
+    _call("den_alpha_from_sigma", _ptr(sigmas), _ptr(t_starts), _ptr(t_ends), _ptr(out),
+          sigmas.numel(), _stream())
+    return out
+
+
+def visibility(alphas, offsets, early_stop_eps, alpha_thre):
+    alphas = _req(alphas.reshape(-1), torch.float32, "alphas")
+    offsets = _req(offsets, torch.int32, "offsets")
+    n_rays = offsets.numel() - 1
+    mask = torch.empty(alphas.numel(), dtype=torch.uint8, device=alphas.device)
+    counts = torch.empty(n_rays, dtype=torch.int32, device=alphas.device)
+    _call("den_visibility", _ptr(alphas), _ptr(offsets), n_rays, float(early_stop_eps),
+          float(alpha_thre), _ptr(mask), _ptr(counts), _stream())
+    return mask, counts
+
+
+def compact(mask, offsets_in, offsets_out, ray_indices, t_starts, t_ends, capacity):
+    dev = mask.device
+    n_rays = offsets_in.numel() - 1
+    ro = torch.empty(capacity, dtype=torch.int32, device=dev)
+    t0 = torch.empty(capacity, dtype=torch.float32, device=dev)
+    t1 = torch.empty(capacity, dtype=torch.float32, device=dev)
+    _call("den_compact_samples", _ptr(mask), _ptr(offsets_in), _ptr(offsets_out),
+          _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _ptr(ro), _ptr(t0), _ptr(t1), n_rays,
+          _stream())
+    return ro, t0, t1
+
+
+def offsets_from_ray_indices(ray_indices, n_rays):
+    """(R+1) int32 packing offsets of a sorted ``ray_indices`` (B1 callers pass indices)."""
+    counts = torch.bincount(ray_indices.long(), minlength=n_rays).to(torch.int32)
+    return exclusive_scan_i32(counts)
+
+
+# --------------------------------------------------------------------------- #
+# weights / accumulation / fused compositor
+# --------------------------------------------------------------------------- #
+class _WeightFromDensityFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sigmas, t_starts, t_ends, offsets):
+        sigmas = _req(sigmas.reshape(-1), torch.float32, "sigmas")
+        t_starts = _req(t_starts.reshape(-1), torch.float32, "t_starts")
+        t_ends = _req(t_ends.reshape(-1), torch.float32, "t_ends")
+        n_rays = offsets.numel() - 1
+        w = torch.empty_like(sigmas)
+        _call("den_weight_from_density_fwd", _ptr(sigmas), _ptr(t_starts), _ptr(t_ends),
+              _ptr(offsets), n_rays, _ptr(w), _stream())
+        ctx.save_for_backward(sigmas, t_starts, t_ends, offsets)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        sigmas, t_starts, t_ends, offsets = ctx.saved_tensors
+        dw = _req(dw.reshape(-1), torch.float32, "dweights")
+        ds = torch.empty_like(sigmas)
+        _call("den_weight_from_density_bwd", _ptr(sigmas), _ptr(t_starts), _ptr(t_ends),
+              _ptr(offsets), offsets.numel() - 1, _ptr(dw), _ptr(ds), _stream())
+        return ds, None, None, None
+
+
+class _WeightFromAlphaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alphas, offsets):
+        alphas = _req(alphas.reshape(-1), torch.float32, "alphas")
+        w = torch.empty_like(alphas)
+        _call("den_weight_from_alpha_fwd", _ptr(alphas), _ptr(offsets), offsets.numel() - 1,
+              _ptr(w), _stream())
+        ctx.save_for_backward(alphas, offsets)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        alphas, offsets = ctx.saved_tensors
+        dw = _req(dw.reshape(-1), torch.float32, "dweights")
+        da = torch.empty_like(alphas)
+        _call("den_weight_from_alpha_bwd", _ptr(alphas), _ptr(offsets), offsets.numel() - 1,
+              _ptr(dw), _ptr(da), _stream())
+        return da, None
+
+
+class _AccumulateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, values, ray_indices, offsets):
+        weights = _req(weights.reshape(-1), torch.float32, "weights")
+        dim = 1
+        if values is not None:
+            values = _req(values, torch.float32, "values")
+            dim = values.shape[-1]
+        n_rays = offsets.numel() - 1
+        out = torch.empty((n_rays, dim), dtype=torch.float32, device=weights.device)
+        _call("den_accumulate_fwd", _ptr(weights), _ptr(values), _ptr(offsets), n_rays, dim,
+              _ptr(out), _stream())
+        ctx.dim = dim
+        ctx.has_values = values is not None
+        ctx.save_for_backward(weights, values if values is not None else weights, ray_indices)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        weights, values, ray_indices = ctx.saved_tensors
+        if not ctx.has_values:
+            values = None
+        dout = _req(dout, torch.float32, "dout")
+        n = weights.numel()
+        dw = torch.empty_like(weights) if ctx.needs_input_grad[0] else None
+        dv = (torch.empty_like(values)
+              if (values is not None and ctx.needs_input_grad[1]) else None)
+        _call("den_accumulate_bwd", _ptr(weights), _ptr(values), _ptr(ray_indices), _ptr(dout), n,
+              ctx.dim, _ptr(dw), _ptr(dv), _stream())
+        return dw, dv, None, None
+
+
+class _CompositeFn(torch.autograd.Function):
+    """Fused weights + colour/opacity/depth accumulation + background blend."""
+
+    @staticmethod
+    def forward(ctx, sigmas, rgbs, t_starts, t_ends, offsets, bkgd):
+        sigmas = _req(sigmas.reshape(-1), torch.float32, "sigmas")
+        rgbs = _req(rgbs, torch.float32, "rgbs")
+        channels = rgbs.shape[-1]
+        n_rays = offsets.numel() - 1
+        dev = sigmas.device
+        colour = torch.empty((n_rays, channels), dtype=torch.float32, device=dev)
+        opacity = torch.empty(n_rays, dtype=torch.float32, device=dev)
+        depth = torch.empty(n_rays, dtype=torch.float32, device=dev)
+        bk = None if bkgd is None else _req(bkgd.detach(), torch.float32, "bkgd")
+        _call("den_composite_fwd", _ptr(sigmas), _ptr(rgbs), _ptr(t_starts), _ptr(t_ends),
+              _ptr(offsets), n_rays, channels, _ptr(bk), _ptr(colour), _ptr(opacity), _ptr(depth),
+              _stream())
+        ctx.channels = channels
+        ctx.has_bkgd = bk is not None
+        ctx.save_for_backward(sigmas, rgbs, t_starts, t_ends, offsets,
+                              bk if bk is not None else opacity, opacity)
+        return colour, opacity, depth
+
+    @staticmethod
+    def backward(ctx, d_colour, d_opacity, d_depth):
+        sigmas, rgbs, t_starts, t_ends, offsets, bk, opacity = ctx.saved_tensors
+        if not ctx.has_bkgd:
+            bk = None
+        n_rays = offsets.numel() - 1
+        d_colour = _req(d_colour, torch.float32, "d_colour")
+        d_opacity = _req(d_opacity, torch.float32, "d_opacity")
+        d_depth = _req(d_depth, torch.float32, "d_depth")
+        d_sigmas = torch.empty_like(sigmas)
+        d_rgbs = torch.empty_like(rgbs)
+        d_bk = torch.zeros_like(bk) if (bk is not None and ctx.needs_input_grad[5]) else None
+        _call("den_composite_bwd", _ptr(sigmas), _ptr(rgbs), _ptr(t_starts), _ptr(t_ends),
+              _ptr(offsets), n_rays, ctx.channels, _ptr(bk), _ptr(opacity), _ptr(d_colour),
+              _ptr(d_opacity), _ptr(d_depth), _ptr(d_sigmas), _ptr(d_rgbs), _ptr(d_bk), _stream())
+        return d_sigmas, d_rgbs, None, None, None, d_bk
+
+
+def weight_from_density(sigmas, t_starts, t_ends, offsets):
+    return _WeightFromDensityFn.apply(sigmas, t_starts, t_ends, offsets)
+
+
+def weight_from_alpha(alphas, offsets):
+    return _WeightFromAlphaFn.apply(alphas, offsets)
+
+
+def accumulate(weights, values, ray_indices, offsets):
+    return _AccumulateFn.apply(weights, values, ray_indices, offsets)
+
+
+def composite(sigmas, rgbs, t_starts, t_ends, offsets, bkgd=None):
+    return _CompositeFn.apply(sigmas, rgbs, t_starts, t_ends, offsets, bkgd)

@@ -1,0 +1,169 @@
+/*
+ * den_b200.h — C ABI of the B200-native Deblur e-NeRF renderer kernels.
+ *
+ * This is the drop-in boundary under the reference's Python operator API
+ * ("C ABI under B1/B2").  Every entry point is `extern "C"`,
+ * takes plain device pointers + sizes + a `cudaStream_t` (passed as `void*`),
+ * never allocates, never synchronises, never touches the default stream unless
+ * it is the stream handed in, and returns 0 or a negative `den_status`; the
+ * message of the last failure on the calling thread is `den_last_error()`.
+ * Buffers (outputs, workspaces, the sample arena) are owned by the caller — the
+ * torch wrapper in `deblur-e-nerf_b200/` (loaded with ctypes, no torch types in
+ * any signature).
+ *
+ * Each declaration cites the reference interface it replaces.  The reference
+ * (wengflow/deblur-e-nerf) has no native code; its kernels live in two
+ * un-vendored third-party packages (nerfacc==0.3.1, tiny-cuda-nn) reached
+ * through the Python call sites cited below (paths relative to the reference
+ * root, `deblur_e_nerf/` prefix omitted).
+ *
+ * Conventions: all floating-point data is fp32 unless the name says f64;
+ * "samples" are ray-major, front-to-back; `offsets` is an (R+1) int32 exclusive
+ * prefix of per-ray sample counts (samples of ray r are
+ * [offsets[r], offsets[r+1])); matrices are row-major.
+ */
+#ifndef DEN_B200_H_
+#define DEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEN_ABI_VERSION 1
+#define DEN_MAX_LEVELS 32
+
+typedef enum den_status {
+    DEN_OK = 0,
+    DEN_ERR_INVALID_ARGUMENT = -1,
+    DEN_ERR_CUDA = -2,
+    DEN_ERR_UNSUPPORTED = -3,
+    DEN_ERR_WORKSPACE = -4
+} den_status;
+
+/* nerfacc.ContractionType (models/deblur_e_nerf.py:271-275) */
+typedef enum den_contraction {
+    DEN_CONTRACT_AABB = 0,
+    DEN_CONTRACT_TANH = 1,
+    DEN_CONTRACT_SPHERE = 2
+} den_contraction;
+
+/* Library identity / error reporting. */
+int den_version(void);
+const char* den_last_error(void);
+/* sm count of the current device (grid sizing), or a negative den_status */
+int den_device_sm_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * Multiresolution hash grid — replaces tinycudann.Encoding(HashGrid, Linear,
+ * fp32) constructed at external/ngp.py:166-170 and called at ngp.py:240.
+ * Level table per tcnn grid.h (grid_scale / grid_resolution / offset table),
+ * evaluated once on the host (oracle/tcnn_ref.py: grid_level_table).
+ * F (features per level) is 2.
+ * ------------------------------------------------------------------------- */
+typedef struct den_hashgrid_desc {
+    int32_t n_levels;
+    int32_t n_features;                 /* must be 2 */
+    int32_t n_agg_levels;               /* bwd: levels [0, n_agg) use warp-aggregated atomics */
+    int32_t reserved;
+    float scale[DEN_MAX_LEVELS];        /* exp2(l*log2 s)*base - 1, fp32 */
+    uint32_t resolution[DEN_MAX_LEVELS];/* ceil(scale) + 1 */
+    uint32_t size[DEN_MAX_LEVELS];      /* entries in the level's table */
+    uint32_t offset[DEN_MAX_LEVELS];    /* entry offset of the level */
+} den_hashgrid_desc;
+
+/* x (M,3) in unit-cube coordinates -> out (M, L*2).  tcnn kernel_grid. */
+int den_hashgrid_fwd(const den_hashgrid_desc* desc, const float* x, const float* table,
+                     float* out, int64_t n_samples, void* stream);
+/* dtable (n_entries*2, pre-zeroed or accumulating) += scatter of dout (M, L*2).
+ * tcnn kernel_grid_backward.  If dx != NULL also writes dL/dx (M,3)
+ * (kernel_grid_backward_input; needs `table`). */
+int den_hashgrid_bwd(const den_hashgrid_desc* desc, const float* x, const float* dout,
+                     const float* table, float* dtable, float* dx, int64_t n_samples,
+                     void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Ray marching — replaces nerfacc.ray_marching (external/utils.py:106-119)
+ * and nerfacc.ray_aabb_intersect reached through it (models/nerf.py:248-251).
+ * ------------------------------------------------------------------------- */
+typedef struct den_march_params {
+    float roi[6];                       /* grid.roi_aabb */
+    int32_t res[3];                     /* grid.binary.shape */
+    int32_t contraction;                /* den_contraction */
+    float step_size;                    /* render_step_size */
+    float cone_angle;
+} den_march_params;
+
+int den_ray_aabb_intersect(const float* rays_o, const float* rays_d, const float* aabb6_host,
+                           float* t_min, float* t_max, int64_t n_rays, void* stream);
+/* t_min = max(t_min, near); t_max = min(t_max, far); t_min += jitter*step (jitter may be NULL) */
+int den_clamp_jitter(float* t_min, float* t_max, const float* jitter, int has_near, float near_plane,
+                     int has_far, float far_plane, float step_size, int64_t n_rays, void* stream);
+/* pass 1: num_steps[r] = samples ray r emits */
+int den_march_count(const den_march_params* p, const float* rays_o, const float* rays_d,
+                    const float* t_min, const float* t_max, const uint8_t* binary,
+                    int32_t* num_steps, int64_t n_rays, void* stream);
+/* out[0..n) = exclusive prefix of in, out[n] = total.  workspace >= den_scan_workspace_bytes(n) */
+size_t den_scan_workspace_bytes(int64_t n);
+int den_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* pass 2: writes ray_indices/t_starts/t_ends at offsets[r].. (clamped to capacity) */
+int den_march_write(const den_march_params* p, const float* rays_o, const float* rays_d,
+                    const float* t_min, const float* t_max, const uint8_t* binary,
+                    const int32_t* offsets, int32_t* ray_indices, float* t_starts, float* t_ends,
+                    int64_t n_rays, int64_t capacity, void* stream);
+
+/* Visibility filter + compaction — replaces nerfacc.render_visibility and the
+ * three boolean-mask compactions inside nerfacc.ray_marching. */
+/* alpha = 1 - exp(-sigma * (t1 - t0)) */
+int den_alpha_from_sigma(const float* sigmas, const float* t_starts, const float* t_ends,
+                         float* alphas, int64_t n_samples, void* stream);
+/* mask[i] = (T_i >= eps) && (alpha_thre <= 0 || alpha_i >= alpha_thre), T sequential fp32 per ray;
+ * vis_count[r] = number of visible samples of ray r */
+int den_visibility(const float* alphas, const int32_t* offsets, int64_t n_rays, float early_stop_eps,
+                   float alpha_thre, uint8_t* mask, int32_t* vis_count, void* stream);
+int den_compact_samples(const uint8_t* mask, const int32_t* offsets_in, const int32_t* offsets_out,
+                        const int32_t* ray_indices_in, const float* t_starts_in, const float* t_ends_in,
+                        int32_t* ray_indices_out, float* t_starts_out, float* t_ends_out,
+                        int64_t n_rays, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Transmittance / weights / accumulation — replaces
+ * nerfacc.render_weight_from_density, render_weight_from_alpha and
+ * accumulate_along_rays (external/vol_rendering.py:89-122).
+ * ------------------------------------------------------------------------- */
+int den_weight_from_density_fwd(const float* sigmas, const float* t_starts, const float* t_ends,
+                                const int32_t* offsets, int64_t n_rays, float* weights, void* stream);
+int den_weight_from_density_bwd(const float* sigmas, const float* t_starts, const float* t_ends,
+                                const int32_t* offsets, int64_t n_rays, const float* dweights,
+                                float* dsigmas, void* stream);
+int den_weight_from_alpha_fwd(const float* alphas, const int32_t* offsets, int64_t n_rays,
+                              float* weights, void* stream);
+int den_weight_from_alpha_bwd(const float* alphas, const int32_t* offsets, int64_t n_rays,
+                              const float* dweights, float* dalphas, void* stream);
+/* out (R,D) = per-ray sum of w * v (v NULL -> D = 1, v = 1); deterministic (no atomics) */
+int den_accumulate_fwd(const float* weights, const float* values, const int32_t* offsets,
+                       int64_t n_rays, int32_t dim, float* out, void* stream);
+int den_accumulate_bwd(const float* weights, const float* values, const int32_t* ray_indices,
+                       const float* dout, int64_t n_samples, int32_t dim, float* dweights,
+                       float* dvalues, void* stream);
+
+/* Fused front-to-back compositing — replaces external/vol_rendering.py:16-128
+ * (`rendering`: weights + three accumulations + background blend) in one pass.
+ * colour (R,C) = sum w c + bkgd (1 - opacity); opacity (R); depth (R) = sum w (t0+t1)/2. */
+int den_composite_fwd(const float* sigmas, const float* rgbs, const float* t_starts,
+                      const float* t_ends, const int32_t* offsets, int64_t n_rays, int32_t channels,
+                      const float* bkgd, float* colour, float* opacity, float* depth, void* stream);
+/* d_bkgd (C) is accumulated with atomics (pre-zeroed by the caller); may be NULL */
+int den_composite_bwd(const float* sigmas, const float* rgbs, const float* t_starts,
+                      const float* t_ends, const int32_t* offsets, int64_t n_rays, int32_t channels,
+                      const float* bkgd, const float* opacity, const float* d_colour,
+                      const float* d_opacity, const float* d_depth, float* d_sigmas, float* d_rgbs,
+                      float* d_bkgd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEN_B200_H_ */
