@@ -373,16 +373,21 @@ class _CompositeFn(torch.autograd.Function):
 
 
 def weight_from_density(sigmas, t_starts, t_ends, offsets):
-    return _WeightFromDensityFn.apply(sigmas, t_starts, t_ends, offsets)
+    """(M,) weights; inputs of any (M,)/(M,1) shape."""
+    return _WeightFromDensityFn.apply(sigmas.reshape(-1), t_starts.reshape(-1),
+                                      t_ends.reshape(-1), offsets)
 
 
 def weight_from_alpha(alphas, offsets):
-    return _WeightFromAlphaFn.apply(alphas, offsets)
+    return _WeightFromAlphaFn.apply(alphas.reshape(-1), offsets)
 
 
 def accumulate(weights, values, ray_indices, offsets):
-    return _AccumulateFn.apply(weights, values, ray_indices, offsets)
+    return _AccumulateFn.apply(weights.reshape(-1), values, ray_indices, offsets)
 
 
 def composite(sigmas, rgbs, t_starts, t_ends, offsets, bkgd=None):
-    return _CompositeFn.apply(sigmas, rgbs, t_starts, t_ends, offsets, bkgd)
+    """Fused `rendering()`: (colour (R,C), opacity (R,), depth (R,))."""
+    t_starts = _req(t_starts.detach().reshape(-1), torch.float32, "t_starts")
+    t_ends = _req(t_ends.detach().reshape(-1), torch.float32, "t_ends")
+    return _CompositeFn.apply(sigmas.reshape(-1), rgbs, t_starts, t_ends, offsets, bkgd)
