@@ -30,6 +30,10 @@ import enum
 import torch
 
 
+# tests/golden/make_golden.py sets this to a list to record the stratified draws
+JITTER_LOG = None
+
+
 class ContractionType(enum.Enum):
     AABB = 0
     UN_BOUNDED_TANH = 1
@@ -387,7 +391,10 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
     if far_plane is not None:
         t_max = torch.clamp(t_max, max=far_plane)
     if stratified:
-        t_min = t_min + torch.rand_like(t_min) * render_step_size
+        jitter = torch.rand_like(t_min)
+        if JITTER_LOG is not None:
+            JITTER_LOG.append(jitter.clone())
+        t_min = t_min + jitter * render_step_size
 
     if grid is not None:
         roi, binary, ctype = grid.roi_aabb, grid.binary, grid.contraction_type

@@ -79,3 +79,81 @@ def uninstall():
             del sys.modules[key]
     for key in ("easydict", "roma", "nerfacc", "tinycudann"):
         sys.modules.pop(key, None)
+
+
+# --------------------------------------------------------------------------- #
+# the reference's LightningModule, without Lightning
+# --------------------------------------------------------------------------- #
+def load_lightning_module():
+    """Return the reference's ``DeblurENeRF`` class (models/deblur_e_nerf.py) with
+    ``pytorch_lightning`` / ``pypose`` stubbed: only ``training_step`` and the
+    render helpers it calls (lines 396-586, 1129-1308) are exercised."""
+    import torch
+
+    install()
+    if "pytorch_lightning" not in sys.modules:
+        pl = types.ModuleType("pytorch_lightning")
+
+        class LightningModule(torch.nn.Module):
+            pass
+
+        pl.LightningModule = LightningModule
+        sys.modules["pytorch_lightning"] = pl
+    if "pypose" not in sys.modules:
+        sys.modules["pypose"] = types.ModuleType("pypose")
+    for name in ("utils.autograd", "utils.modules", "utils.tensor_ops", "data.datasets",
+                 "external.mlp", "external.sh_encoder", "external.ngp",
+                 "external.vol_rendering", "external.utils", "external.optimizer",
+                 "loss_metric.loss", "models.event_generation_params", "models.nerf",
+                 "models.pixel_bandwidth", "models.trajectories"):
+        try:
+            load(name)
+        except Exception:
+            if name != "external.optimizer":
+                raise
+    if "deblur_e_nerf.models.offset_gamma_correction" not in sys.modules:
+        stub = types.ModuleType("deblur_e_nerf.models.offset_gamma_correction")
+        sys.modules["deblur_e_nerf.models.offset_gamma_correction"] = stub
+        sys.modules["deblur_e_nerf.models"].offset_gamma_correction = stub
+    return load("models.deblur_e_nerf").DeblurENeRF
+
+
+def make_reference_module(hparams, components, train_ray_sample_batch_size=131072):
+    """Instantiate the reference's LightningModule WITHOUT running its constructor
+    (which needs a dataset on disk and Lightning): attributes used by ``training_step``
+    are attached directly.  ``components`` maps attribute name -> reference module."""
+    import torch
+
+    cls = load_lightning_module()
+    easydict = sys.modules["easydict"]
+    inst = cls.__new__(cls)
+    torch.nn.Module.__init__(inst)
+    object.__setattr__(inst, "_hparams_shim", easydict.EasyDict(hparams))
+    cls.hparams = property(lambda self: self._hparams_shim)
+    for key, value in components.items():
+        setattr(inst, key, value)
+    inst.has_bayer_filter = False
+    inst.render_bkgd = components.get("render_bkgd_mode")
+    inst.train_ray_sample_batch_size = train_ray_sample_batch_size
+    logged = {}
+
+    class _Dataset:
+        batch_size = None
+
+    class _Sampler:
+        datasets = []
+
+    class _DataModule:
+        train_dataset = _Dataset()
+        train_normalized_sampler = _Sampler()
+
+    class _Trainer:
+        accumulate_grad_batches = 1
+        datamodule = _DataModule()
+
+    object.__setattr__(inst, "trainer", _Trainer())
+    cls.global_step = 0
+    inst.log = lambda name, value, **kw: logged.__setitem__(name, value)
+    inst.all_gather = lambda t: t[None]
+    inst.logged = logged
+    return inst

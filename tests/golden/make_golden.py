@@ -1,0 +1,101 @@
+"""Generate the golden fixtures from the REFERENCE'S OWN files (run unmodified under
+oracle/ref_shim, CPU fp32).  Build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/{training_step_pb_on,training_step_pb_off,field_small}.npz.  Each
+file carries the parameters, the inputs (events, normalised samples, the stratified
+jitter the reference drew, the occupancy grid after its step-0 update) and the
+reference's outputs (loss, loss terms, mean samples per ray, every parameter gradient),
+so the GPU box can check the CUDA path and the oracle against the reference without it.
+"""
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import nerfacc_ref, ref_shim  # noqa: E402
+
+import _scene  # noqa: E402
+
+N_EVENTS = 96
+IT_SAMPLE_SIZE = 8
+SKIP_BUFFERS = ("grid_coords", "grid_indices")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def training_step_golden(pb_on, path):
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    ref, poses = _scene.build_reference_renderer(cfg, IT_SAMPLE_SIZE, pixel_bandwidth=pb_on)
+    event, normalized = _scene.make_batch(cfg, poses, N_EVENTS, IT_SAMPLE_SIZE, seed=7,
+                                          pixel_bandwidth=pb_on)
+    ref.train()
+    nerfacc_ref.JITTER_LOG = []
+    torch.manual_seed(11)
+    loss = ref.training_step(_scene.reference_batch(event, normalized), 0)
+    jitters = nerfacc_ref.JITTER_LOG
+    nerfacc_ref.JITTER_LOG = None
+    ref.zero_grad()
+    loss.backward()
+
+    out = {"loss": _np(loss)}
+    for key, value in ref.logged.items():
+        if key.startswith("train/log_intensity") or key == "train/mean_num_samples_per_ray":
+            out["logged/" + key] = np.asarray(float(value))
+    names = ["nerf", "contrast_threshold", "refractory_period"] + (
+        ["pixel_bandwidth"] if pb_on else [])
+    for name in names:
+        for key, value in getattr(ref, name).state_dict().items():
+            if key.rsplit(".", 1)[-1] in SKIP_BUFFERS:
+                continue
+            out[f"state/{name}/{key}"] = _np(value)
+    for key, value in _scene.flat_named_grads(ref).items():
+        out["grad/" + key] = _np(value)
+    for key, value in event.items():
+        out["event/" + key] = _np(value)
+    for key, value in normalized.items():
+        out["normalized/" + key] = _np(value)
+    for i, jit in enumerate(jitters):
+        out[f"jitter/{i}"] = _np(jit)
+    np.savez_compressed(path, **out)
+    print(path, f"loss={float(loss):.6f}", f"{os.path.getsize(path) / 1e6:.2f} MB",
+          f"{len(jitters)} render calls")
+
+
+def field_golden(path):
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    ref, _ = _scene.build_reference_renderer(cfg, IT_SAMPLE_SIZE, pixel_bandwidth=False)
+    field = ref.nerf.radiance_field
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2000, 3, generator=g) * 3.4 - 1.7
+    d = torch.randn(2000, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    rgb, sigma = field(x, d)
+    w_rgb = torch.randn(rgb.shape, generator=g)
+    w_sig = torch.randn(sigma.shape, generator=g) * 0.01
+    field.zero_grad()
+    ((rgb * w_rgb).sum() + (sigma * w_sig).sum()).backward()
+    out = {"x": _np(x), "d": _np(d), "rgb": _np(rgb), "sigma": _np(sigma), "w_rgb": _np(w_rgb),
+           "w_sigma": _np(w_sig)}
+    for key, value in field.state_dict().items():
+        out["state/" + key] = _np(value)
+    for key, p in field.named_parameters():
+        out["grad/" + key] = _np(p.grad)
+    np.savez_compressed(path, **out)
+    print(path, f"{os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    assert ref_shim.available(), "needs /root/reference"
+    training_step_golden(True, os.path.join(HERE, "training_step_pb_on.npz"))
+    training_step_golden(False, os.path.join(HERE, "training_step_pb_off.npz"))
+    field_golden(os.path.join(HERE, "field_small.npz"))

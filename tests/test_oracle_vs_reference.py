@@ -1,0 +1,181 @@
+"""Pin ``oracle/path_ref.py`` against the reference's OWN files (run unmodified under
+``oracle/ref_shim``) on identical parameters and seeded inputs.  Needs
+``/root/reference`` — build container only; skipped elsewhere (the committed
+``tests/golden`` fixtures carry the same pin to the GPU box)."""
+
+import pytest
+import torch
+
+from oracle import path_ref, ref_shim
+
+import _scene
+
+pytestmark = [
+    pytest.mark.reference,
+    pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present"),
+]
+
+
+def _close(a, b, tol=1e-6):
+    a, b = a.detach().double(), b.detach().double()
+    denom = b.abs().max().clamp(min=1e-30)
+    assert ((a - b).abs().max() / denom).item() <= tol, ((a - b).abs().max(), denom)
+
+
+@pytest.fixture(scope="module")
+def pair():
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    ref, poses = _scene.build_reference_renderer(cfg, it_sample_size=8)
+    ora, _ = _scene.build_oracle_renderer(cfg, it_sample_size=8)
+    for name in ("nerf", "contrast_threshold", "refractory_period", "pixel_bandwidth"):
+        _scene.copy_params(getattr(ref, name), getattr(ora, name))
+    return cfg, ref, ora, poses
+
+
+def test_state_dict_keys_match(pair):
+    _, ref, ora, _ = pair
+    for name in ("nerf", "contrast_threshold", "refractory_period", "pixel_bandwidth"):
+        ref_keys = set(getattr(ref, name).state_dict().keys())
+        ora_keys = set(getattr(ora, name).state_dict().keys())
+        assert ref_keys == ora_keys, (name, ref_keys ^ ora_keys)
+
+
+def test_field_forward_backward(pair):
+    _, ref, ora, _ = pair
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(500, 3, generator=g) * 3.4 - 1.7)
+    d = torch.randn(500, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    rgb_r, sig_r = ref.nerf.radiance_field(x, d)
+    rgb_o, sig_o = ora.nerf.radiance_field(x, d)
+    _close(rgb_o, rgb_r)
+    _close(sig_o, sig_r)
+    ref.nerf.zero_grad()
+    ora.nerf.zero_grad()
+    (rgb_r.sum() + sig_r.sum()).backward()
+    (rgb_o.sum() + sig_o.sum()).backward()
+    gr, go = _scene.flat_named_grads(ref.nerf), _scene.flat_named_grads(ora.nerf)
+    assert gr.keys() == go.keys()
+    for k in gr:
+        _close(go[k], gr[k], 1e-5)
+
+
+def test_trajectory_and_rays(pair):
+    cfg, ref, ora, poses = pair
+    g = torch.Generator().manual_seed(1)
+    ts = (torch.rand(3, 40, generator=g, dtype=torch.float64) * float(poses[2][-1]))
+    ts[0, 0] = float(poses[2][0])            # corner case of :52-54
+    ts[0, 1] = float(poses[2][-1])
+    pr, rr = ref.trajectory(ts)
+    po, ro = ora.trajectory(ts)
+    _close(po, pr)
+    _close(ro, rr)
+    px = torch.rand(40, 2, generator=g) * 200
+    o_r, d_r = ref.nerf.pixel_params_to_ray(ref.train_intrinsics_inv, px, pr, rr)
+    o_o, d_o = path_ref.NeRF.pixel_params_to_ray(ora.train_intrinsics_inv, px, po, ro)
+    _close(d_o, d_r)
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_nerf_render(pair, training):
+    cfg, ref, ora, poses = pair
+    ref.nerf.train()
+    ora.nerf.train()
+    torch.manual_seed(3)
+    ref.nerf.update_occ_grid(0, ref.trajectory.T_wc_position)
+    torch.manual_seed(3)
+    ora.nerf.update_occ_grid(0, ora.trajectory.T_wc_position)
+    assert torch.equal(ref.nerf.occupancy_grid.binary, ora.nerf.occupancy_grid.binary)
+    ref.nerf.train(training)
+    ora.nerf.train(training)
+    g = torch.Generator().manual_seed(2)
+    ts = torch.rand(300, generator=g, dtype=torch.float64) * float(poses[2][-1])
+    px = torch.rand(300, 2, generator=g) * 250
+    pos, rot = ora.trajectory(ts)
+    o, d = path_ref.NeRF.pixel_params_to_ray(ora.train_intrinsics_inv, px, pos, rot)
+    torch.manual_seed(4)
+    out_r = ref.nerf(o, d)
+    torch.manual_seed(4)
+    out_o = ora.nerf(o, d)
+    for a, b in zip(out_o[:3], out_r[:3]):
+        _close(a, b, 1e-5)
+    assert out_o[3] == out_r[3]              # mean samples per ray: identical sample sets
+    ref.nerf.zero_grad()
+    ora.nerf.zero_grad()
+    out_r[0].log().sum().backward()
+    out_o[0].log().sum().backward()
+    gr, go = _scene.flat_named_grads(ref.nerf), _scene.flat_named_grads(ora.nerf)
+    assert gr.keys() == go.keys()
+    for k in gr:
+        _close(go[k], gr[k], 1e-4)
+
+
+@pytest.mark.parametrize("reset", [True, False])
+def test_pixel_bandwidth(pair, reset):
+    cfg, ref, ora, poses = pair
+    g = torch.Generator().manual_seed(5)
+    n, S = 50, 8
+    out_ts = (30e6 + torch.rand(n, generator=g, dtype=torch.float64) * 100e6)
+    gen = torch.full((S - 1, n), 0.5, dtype=torch.float64)
+    base = torch.rand(S, n, generator=g) * 0.8 + 0.01
+
+    def make_fn(leaf):
+        def fn(ts):
+            return leaf * (1 + 0.1 * torch.sin(ts.float() * 1e-7)), torch.tensor(1.0), 1.0, \
+                torch.ones_like(ts, dtype=torch.bool)
+        return fn
+
+    leaf_r = base.clone().requires_grad_(True)
+    leaf_o = base.clone().requires_grad_(True)
+    if not reset:      # a reset call must precede (state of :419-423)
+        ref.pixel_bandwidth(gen, out_ts - 5e6, make_fn(leaf_r.detach()), True)
+        ora.pixel_bandwidth(gen, out_ts - 5e6, make_fn(leaf_o.detach()), True)
+    y_r, _ = ref.pixel_bandwidth(gen, out_ts, make_fn(leaf_r), reset)
+    y_o, _ = ora.pixel_bandwidth(gen, out_ts, make_fn(leaf_o), reset)
+    _close(y_o, y_r, 2e-5)
+    for m in (ref.pixel_bandwidth, ora.pixel_bandwidth):
+        m.zero_grad()
+    y_r.sum().backward()
+    y_o.sum().backward()
+    _close(leaf_o.grad, leaf_r.grad, 2e-3)   # fp32 expm/solve: the reference's own noise floor
+    gr = _scene.flat_named_grads(ref.pixel_bandwidth)
+    go = _scene.flat_named_grads(ora.pixel_bandwidth)
+    assert gr.keys() == go.keys() and len(gr) == 6
+
+
+@pytest.mark.parametrize("pb_on", [True, False])
+def test_training_step(pb_on):
+    """The whole hot path: the reference's training_step (models/deblur_e_nerf.py:396-586)
+    vs oracle EventRenderer.training_step — loss, loss terms and every parameter gradient."""
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    S = 8
+    ref, poses = _scene.build_reference_renderer(cfg, S, pixel_bandwidth=pb_on)
+    ora, _ = _scene.build_oracle_renderer(cfg, S, pixel_bandwidth=pb_on)
+    names = ["nerf", "contrast_threshold", "refractory_period"] + (
+        ["pixel_bandwidth"] if pb_on else [])
+    for name in names:
+        _scene.copy_params(getattr(ref, name), getattr(ora, name))
+    event, normalized = _scene.make_batch(cfg, poses, 96, S, seed=7, pixel_bandwidth=pb_on)
+
+    ref.train()
+    ora.train()
+    torch.manual_seed(11)
+    loss_r = ref.training_step(_scene.reference_batch(event, normalized), 0)
+    torch.manual_seed(11)
+    ora.nerf.update_occ_grid(0, ora.trajectory.T_wc_position)
+    loss_o, terms_o, mean_samples = ora.training_step(event, normalized)
+    assert torch.equal(ref.nerf.occupancy_grid.binary, ora.nerf.occupancy_grid.binary)
+    _close(loss_o, loss_r, 1e-5)
+    for key, val in terms_o.items():
+        _close(val, ref.logged[f"train/{key}"], 1e-5)
+    _close(torch.tensor(mean_samples), torch.as_tensor(ref.logged["train/mean_num_samples_per_ray"]),
+           1e-6)
+    ref.zero_grad()
+    ora.zero_grad()
+    loss_r.backward()
+    loss_o.backward()
+    gr, go = _scene.flat_named_grads(ref), _scene.flat_named_grads(ora)
+    assert set(gr.keys()) == set(go.keys()), set(gr.keys()) ^ set(go.keys())
+    for k in gr:
+        tol = 5e-3 if "pixel_bandwidth" in k or "refractory" in k else 2e-4
+        _close(go[k], gr[k], tol)
