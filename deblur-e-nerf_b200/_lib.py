@@ -41,6 +41,20 @@ class MarchParams(_c.Structure):
     ]
 
 
+class FieldDesc(_c.Structure):
+    _fields_ = [
+        ("grid", HashGridDesc), ("aabb", _F * 6), ("contraction", _I32), ("channels", _I32),
+        ("hidden_act", _I32), ("density_act", _I32), ("radiance_act", _I32), ("width", _I32),
+        ("geo_feat_dim", _I32), ("sh_degree", _I32), ("n_hidden_base", _I32),
+        ("n_hidden_head", _I32),
+    ]
+
+
+class FieldParams(_c.Structure):
+    _fields_ = [(name, _P) for name in (
+        "table", "wb1", "bb1", "wb2", "bb2", "w1", "b1", "w2", "b2", "w3", "b3")]
+
+
 # name -> (restype, argtypes); mirrors include/den_b200.h declaration by declaration
 _SIGNATURES = {
     "den_version": (_INT, []),
@@ -65,6 +79,10 @@ _SIGNATURES = {
     "den_accumulate_fwd": (_INT, [_P, _P, _P, _I64, _I32, _P, _P]),
     "den_accumulate_bwd": (_INT, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
     "den_composite_fwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "den_field_fwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _P, _P, _P, _P, _P,
+                             _I64, _P, _P, _P, _P]),
+    "den_field_density_at": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _P, _I64, _P,
+                                    _P]),
     "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
 }

@@ -1,0 +1,191 @@
+// Device helpers shared by the fused field kernels (forward, backward, tensor-core).
+#pragma once
+#include "den_common.cuh"
+#include "den_hashgrid.cuh"
+
+namespace den {
+
+// The architecture every shipped config uses (configs/train/*.yaml:81-103):
+constexpr int kEncDim = 32;    // L*F, zero-padded when L < 16
+constexpr int kWidth = 64;     // n_neurons
+constexpr int kBaseOut = 16;   // 1 density + 15 geo features
+constexpr int kGeo = 15;
+constexpr int kShDim = 16;     // SH degree 4
+constexpr int kHeadIn = 32;    // 16 SH + 15 geo + 1 zero pad
+constexpr int kOutPad = 4;     // radiance channels padded to 4
+
+// activation ids (den_b200.h)
+constexpr int kActRelu = 0, kActSoftplus100 = 1;
+constexpr int kDensTruncExp = 0, kDensSoftplus = 1, kDensShiftedSoftplus = 2;
+constexpr int kRadSoftplus = 0, kRadSigmoid = 1;
+
+struct FieldSmem {
+    float *wb1, *bb1, *wb2, *bb2, *w1, *b1, *w2, *b2, *w3, *b3;
+};
+
+__host__ __device__ constexpr int field_smem_floats() {
+    return kEncDim * kWidth + kWidth + kWidth * kBaseOut + kBaseOut + kHeadIn * kWidth + kWidth +
+           kWidth * kWidth + kWidth + kWidth * kOutPad + kOutPad;
+}
+inline size_t field_smem_bytes() { return (size_t)field_smem_floats() * sizeof(float); }
+
+__device__ __forceinline__ FieldSmem carve_field_smem(float* base) {
+    FieldSmem s;
+    s.wb1 = base;                      base += kEncDim * kWidth;
+    s.bb1 = base;                      base += kWidth;
+    s.wb2 = base;                      base += kWidth * kBaseOut;
+    s.bb2 = base;                      base += kBaseOut;
+    s.w1 = base;                       base += kHeadIn * kWidth;
+    s.b1 = base;                       base += kWidth;
+    s.w2 = base;                       base += kWidth * kWidth;
+    s.b2 = base;                       base += kWidth;
+    s.w3 = base;                       base += kWidth * kOutPad;
+    s.b3 = base;
+    return s;
+}
+
+// (out, in) row-major global -> [in_pad][out_pad] shared, zero padded
+__device__ __forceinline__ void load_transposed(float* dst, const float* __restrict__ src, int n_out,
+                                                int n_in, int out_pad, int in_pad) {
+    for (int i = threadIdx.x; i < in_pad * out_pad; i += blockDim.x) {
+        const int k = i / out_pad, j = i - k * out_pad;
+        dst[i] = (k < n_in && j < n_out) ? __ldg(src + j * n_in + k) : 0.f;
+    }
+}
+__device__ __forceinline__ void load_padded(float* dst, const float* __restrict__ src, int n, int pad) {
+    for (int i = threadIdx.x; i < pad; i += blockDim.x) dst[i] = i < n ? __ldg(src + i) : 0.f;
+}
+
+__device__ __forceinline__ void load_field_weights(const FieldSmem& s, const den_field_desc& f,
+                                                   const den_field_params& p, bool full) {
+    const int enc = f.grid.n_levels * 2;
+    load_transposed(s.wb1, p.wb1, kWidth, enc, kWidth, kEncDim);
+    load_padded(s.bb1, p.bb1, kWidth, kWidth);
+    load_transposed(s.wb2, p.wb2, kBaseOut, kWidth, kBaseOut, kWidth);
+    load_padded(s.bb2, p.bb2, kBaseOut, kBaseOut);
+    if (full) {
+        load_transposed(s.w1, p.w1, kWidth, kShDim + kGeo, kWidth, kHeadIn);
+        load_padded(s.b1, p.b1, kWidth, kWidth);
+        load_transposed(s.w2, p.w2, kWidth, kWidth, kWidth, kWidth);
+        load_padded(s.b2, p.b2, kWidth, kWidth);
+        load_transposed(s.w3, p.w3, f.channels, kWidth, kOutPad, kWidth);
+        load_padded(s.b3, p.b3, f.channels, kOutPad);
+    }
+}
+
+// Field-side contraction (external/ngp.py:68-106,230-238).  Returns the selector
+// all(0 < u < 1) that gates the density (ngp.py:238,247-250).
+__device__ __forceinline__ bool contract_position(const den_field_desc& f, const float pos[3],
+                                                  float u[3]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) u[d] = __fdiv_rn(pos[d] - f.aabb[d], f.aabb[d + 3] - f.aabb[d]);
+    if (f.contraction == DEN_CONTRACT_SPHERE) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] = u[d] * 2.f - 1.f;
+        const float mag = sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (mag > 1.f) {
+            const float k = (2.f - 1.f / mag) / mag;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) u[d] *= k;
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] = u[d] * 0.25f + 0.5f;
+    } else if (f.contraction == DEN_CONTRACT_TANH) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] = (tanhf(u[d] - 0.5f) + 1.f) * 0.5f;
+    }
+    return u[0] > 0.f && u[0] < 1.f && u[1] > 0.f && u[1] < 1.f && u[2] > 0.f && u[2] < 1.f;
+}
+
+// all levels of one sample into registers (enc[2l], enc[2l+1]); unused tail zeroed
+__device__ __forceinline__ void encode_sample(const den_hashgrid_desc& g,
+                                              const float2* __restrict__ table, const float u[3],
+                                              float (&enc)[kEncDim]) {
+#pragma unroll
+    for (int level = 0; level < kEncDim / 2; ++level) {
+        if (level < g.n_levels) {
+            const LevelInfo li = make_level(g, level);
+            const float2* __restrict__ base = table + g.offset[level];
+            const CellFrac cf = locate(li.scale, u[0], u[1], u[2]);
+            float2 v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = __ldg(base + corner_index(li, cf, c));
+            float ax = 0.f, ay = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float w = corner_weight(cf, c);
+                ax = fmaf(w, v[c].x, ax);
+                ay = fmaf(w, v[c].y, ay);
+            }
+            enc[2 * level] = ax;
+            enc[2 * level + 1] = ay;
+        } else {
+            enc[2 * level] = 0.f;
+            enc[2 * level + 1] = 0.f;
+        }
+    }
+}
+
+// Real spherical harmonics, degree 4 (external/sh_encoder.py:42-77)
+__device__ __forceinline__ void sh_degree4(const float d[3], float* out) {
+    const float x = d[0], y = d[1], z = d[2];
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    out[0] = 0.28209479177387814f;
+    out[1] = -0.48860251190291987f * y;
+    out[2] = 0.48860251190291987f * z;
+    out[3] = -0.48860251190291987f * x;
+    out[4] = 1.0925484305920792f * xy;
+    out[5] = -1.0925484305920792f * yz;
+    out[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    out[7] = -1.0925484305920792f * xz;
+    out[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    out[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    out[10] = 2.8906114426405538f * xy * z;
+    out[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    out[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    out[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    out[14] = 1.4453057213202769f * z * (x2 - y2);
+    out[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+// ---- activations (models/nerf.py:17-29, external/ngp.py:45-65) -----------------
+__device__ __forceinline__ float softplus100(float z) {
+    // log1p(exp(100 z))/100 with torch's threshold 20 (z > 0.2 -> identity)
+    const float bz = 100.f * z;
+    if (bz > 20.f) return z;
+    return fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(bz))) * 0.01f;
+}
+__device__ __forceinline__ float hidden_act(int id, float z) {
+    return id == kActSoftplus100 ? softplus100(z) : fmaxf(z, 0.f);
+}
+// derivative expressed from the post-activation value h (softplus: 1 - exp(-100 h))
+__device__ __forceinline__ float hidden_act_grad_from_out(int id, float h) {
+    if (id == kActSoftplus100) return h > 0.2f ? 1.f : 1.f - __expf(-100.f * h);
+    return h > 0.f ? 1.f : 0.f;
+}
+__device__ __forceinline__ float softplus1(float z) {
+    return z > 20.f ? z : fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
+}
+__device__ __forceinline__ float density_act(int id, float raw) {
+    if (id == kDensTruncExp) return expf(raw - 1.f);
+    if (id == kDensSoftplus) return softplus1(raw);
+    return softplus1(raw - 1.f);
+}
+// d density / d raw  (trunc_exp backward clamps the exponent at 15, ngp.py:55-58)
+__device__ __forceinline__ float density_act_grad(int id, float raw) {
+    if (id == kDensTruncExp) return expf(fminf(raw - 1.f, 15.f));
+    const float z = id == kDensSoftplus ? raw : raw - 1.f;
+    return z > 20.f ? 1.f : 1.f / (1.f + expf(-z));
+}
+__device__ __forceinline__ float radiance_act(int id, float z) {
+    return id == kRadSigmoid ? 1.f / (1.f + expf(-z)) : softplus1(z);
+}
+__device__ __forceinline__ float radiance_act_grad(int id, float z) {
+    const float s = 1.f / (1.f + expf(-z));
+    if (id == kRadSigmoid) return s * (1.f - s);
+    return z > 20.f ? 1.f : s;
+}
+
+int check_field(const den_field_desc* f, const den_field_params* p, bool full);
+
+}  // namespace den

@@ -19,60 +19,12 @@
 //     cell with a segmented warp scan before issuing `red.global.add.v2.f32`
 //     (one vector atomic per run and corner instead of one per sample and corner).
 #include "den_common.cuh"
+#include "den_hashgrid.cuh"
 
 namespace den {
 
-constexpr uint32_t kPrime1 = 2654435761u;
-constexpr uint32_t kPrime2 = 805459861u;
 constexpr int kTile = 32;            // samples per tile (one per lane)
 constexpr int kHashThreads = 256;    // 8 warps
-
-struct LevelInfo {
-    float scale;
-    uint32_t size;      // entries in this level
-    uint32_t st0, st1, st2;  // dense strides (0 when the upstream loop has stopped)
-    uint32_t mask;      // size - 1 when size is a power of two, else 0
-    bool hashed;
-};
-
-__device__ __forceinline__ LevelInfo make_level(const den_hashgrid_desc& g, int level) {
-    LevelInfo li;
-    li.scale = g.scale[level];
-    li.size = g.size[level];
-    const uint32_t res = g.resolution[level];
-    uint32_t stride = 1;
-    li.st0 = li.st1 = li.st2 = 0;
-    if (stride <= li.size) { li.st0 = stride; stride *= res; }
-    if (stride <= li.size) { li.st1 = stride; stride *= res; } else { li.st1 = 0; }
-    if (li.st1 != 0 && stride <= li.size) { li.st2 = stride; stride *= res; }
-    li.hashed = li.size < stride;
-    li.mask = (li.size & (li.size - 1)) == 0 ? li.size - 1 : 0;
-    return li;
-}
-
-__device__ __forceinline__ uint32_t entry_index(const LevelInfo& li, uint32_t cx, uint32_t cy, uint32_t cz) {
-    uint32_t idx = li.hashed ? (cx ^ (cy * kPrime1) ^ (cz * kPrime2))
-                             : (cx * li.st0 + cy * li.st1 + cz * li.st2);
-    return li.mask ? (idx & li.mask) : (idx % li.size);
-}
-
-struct CellFrac {
-    uint32_t c[3];
-    float f[3];
-};
-
-__device__ __forceinline__ CellFrac locate(float scale, float x, float y, float z) {
-    CellFrac cf;
-    const float p[3] = {x, y, z};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        float pos = fmaf(scale, p[d], 0.5f);
-        float fl = floorf(pos);
-        cf.c[d] = (uint32_t)(int)fl;
-        cf.f[d] = pos - fl;
-    }
-    return cf;
-}
 
 // ------------------------------------------------------------------ forward --
 __global__ void __launch_bounds__(kHashThreads)
@@ -136,9 +88,6 @@ hashgrid_fwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
 }
 
 // ----------------------------------------------------------------- backward --
-__device__ __forceinline__ void red_add_v2(float2* addr, float a, float b) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
 
 template <bool kInputGrad>
 __global__ void __launch_bounds__(kHashThreads)

@@ -1,0 +1,200 @@
+"""B2 host mirror of the reference's ``NeRF`` (models/nerf.py:16-286) fused with its render
+loop (external/utils.py:38-140 ``render_image``) and volume renderer
+(external/vol_rendering.py:16-128 ``rendering``).
+
+Same constructor arguments, same methods (``update_occ_grid``, ``pixel_params_to_ray``,
+``forward``), same state-dict keys; ``forward(o, d)`` returns the reference's 4-tuple
+``(radiance, opacity, depth, mean_num_samples_per_ray)``.
+
+One render call is: ray/AABB slab test -> near/far clamp + stratified jitter -> two-pass
+occupancy march into an arena -> fused density pre-pass -> sequential-T visibility ->
+ballot compaction -> field evaluation -> fused compositor.  Every stage is a den_b200
+kernel; torch only allocates, draws the RNG numbers in upstream order, and (for now)
+carries the MLP gradient pass through autograd.
+"""
+
+import torch
+
+from . import nerfacc, ops
+from .field import NGPradianceField
+from .nerfacc import ContractionType
+
+
+class Softplus(torch.nn.Module):
+    """utils/modules.py:58-75 — softplus parametrization with its right inverse."""
+
+    def __init__(self, beta=1, threshold=20):
+        super().__init__()
+        self.beta, self.threshold = beta, threshold
+
+    def forward(self, x):
+        return torch.nn.functional.softplus(x, self.beta, self.threshold)
+
+    def right_inverse(self, y):
+        inv = torch.log(torch.exp(self.beta * y) - 1) / self.beta
+        return torch.where(y * self.beta > self.threshold, y, inv)
+
+
+def _get(cfg, key):
+    return cfg[key] if isinstance(cfg, dict) else getattr(cfg, key)
+
+
+class NeRF(torch.nn.Module):
+    def __init__(self, aabb, contraction_type, occ_grid_config, near_plane, far_plane,
+                 render_step_size, render_bkgd, cone_angle, early_stop_eps, alpha_thre,
+                 test_chunk_size, arch, arch_config, num_dim, radiance_dim, opacity_eps=1e-10):
+        super().__init__()
+        assert all(r > 0 for r in ([_get(occ_grid_config, "resolution")]
+                                   if isinstance(_get(occ_grid_config, "resolution"), int)
+                                   else _get(occ_grid_config, "resolution")))
+        assert 0 <= _get(occ_grid_config, "occ_thre") <= 1
+        assert 0 <= _get(occ_grid_config, "ema_decay") <= 1
+        assert _get(occ_grid_config, "warmup_steps") > 0 and _get(occ_grid_config, "n") > 0
+        if near_plane is not None and far_plane is not None:
+            assert 0 <= near_plane <= far_plane
+        assert render_step_size > 0
+        assert render_bkgd is None or render_bkgd == "parameter" \
+            or isinstance(render_bkgd, torch.Tensor)
+        assert cone_angle >= 0 and 0 <= early_stop_eps <= 1 and 0 <= alpha_thre <= 1
+        assert test_chunk_size > 0 and num_dim == 3 and radiance_dim > 0 and opacity_eps > 0
+        if arch != "ngp":
+            raise NotImplementedError("only `arch: ngp` is on the hot path (no shipped config "
+                                      "selects `mlp`, configs/train/synthetic.yaml:75)")
+
+        self.register_buffer("aabb", torch.tensor(aabb), persistent=False)
+        self._aabb_host = [float(v) for v in aabb]
+        self.contraction_type = contraction_type
+        self.occ_grid_config = occ_grid_config
+        self.near_plane, self.far_plane = near_plane, far_plane
+        self.register_buffer("render_step_size", torch.tensor(render_step_size),
+                             persistent=False)
+        self._step_host = float(render_step_size)
+        if render_bkgd is None:
+            self.render_bkgd = None
+        elif isinstance(render_bkgd, str):
+            self.render_bkgd = torch.nn.parameter.Parameter(torch.ones(radiance_dim))
+            torch.nn.utils.parametrize.register_parametrization(self, "render_bkgd", Softplus())
+        else:
+            self.register_buffer("render_bkgd", render_bkgd, persistent=False)
+        self.cone_angle = cone_angle
+        self.early_stop_eps = early_stop_eps
+        self.alpha_thre = alpha_thre
+        self.test_chunk_size = test_chunk_size
+        self.opacity_eps = opacity_eps
+
+        self.occupancy_grid = nerfacc.OccupancyGrid(
+            roi_aabb=aabb, resolution=_get(occ_grid_config, "resolution"),
+            contraction_type=contraction_type)
+        base = dict(_get(arch_config, "mlp_base"))
+        head = dict(_get(arch_config, "mlp_head"))
+        head["output_dim"] = radiance_dim
+        self.radiance_field = NGPradianceField(
+            aabb=aabb, num_dim=num_dim, use_viewdirs=True, contraction_type=contraction_type,
+            pos_encoding_config=dict(_get(arch_config, "pos_encoding")),
+            dir_encoding_config=dict(_get(arch_config, "dir_encoding")),
+            mlp_base_config=base, mlp_head_config=head)
+        self.last_num_samples = None        # device int32 scalar of the latest render call
+
+    # ---------------------------------------------------------------- occupancy ------
+    def update_occ_grid(self, step, T_wc_position=None):
+        """models/nerf.py:170-204: density * step size per cell through the fused density
+        kernel; EMA-max + threshold as upstream."""
+        def occ_eval_fn(x):
+            if self.cone_angle > 0.0:
+                camera_ids = torch.randint(0, len(T_wc_position), (x.shape[0],),
+                                           device=T_wc_position.device)
+                t = (T_wc_position[camera_ids, :] - x).norm(dim=-1, keepdim=True)
+                step_size = torch.clamp(t * self.cone_angle, min=self.render_step_size)
+                if self.near_plane is not None and self.far_plane is not None:
+                    step_size = torch.where((t > self.near_plane) & (t < self.far_plane),
+                                            step_size, torch.zeros_like(step_size))
+            else:
+                step_size = self.render_step_size
+            return self.radiance_field.density_at(x) * step_size
+
+        self.occupancy_grid.every_n_step(
+            step, occ_eval_fn, _get(self.occ_grid_config, "occ_thre"),
+            _get(self.occ_grid_config, "ema_decay"), _get(self.occ_grid_config, "warmup_steps"),
+            _get(self.occ_grid_config, "n"))
+
+    # --------------------------------------------------------------------- rays ------
+    @staticmethod
+    def pixel_params_to_ray(intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation):
+        """models/nerf.py:206-228 (small elementwise prologue; the fused trajectory->ray
+        kernel `den_rays_from_trajectory` replaces it on the training path)."""
+        homog = torch.cat((pixel_position, torch.ones_like(pixel_position[..., :1])), dim=-1)
+        d = (T_wc_orientation @ (intrinsics_inverse @ homog.unsqueeze(-1))).squeeze(-1)
+        d = d / torch.linalg.vector_norm(d, dim=-1, keepdim=True)
+        return T_wc_position, d
+
+    # ------------------------------------------------------------------- render ------
+    def _march(self, o, d, jitter):
+        grid = self.occupancy_grid
+        if self.contraction_type == ContractionType.AABB:
+            t_min, t_max = ops.ray_aabb_intersect(o, d, self._aabb_host)
+        else:
+            t_min = torch.zeros_like(o[:, 0])
+            t_max = torch.full_like(o[:, 0], 1e10)
+        stratified = self.radiance_field.training
+        if stratified and jitter is None:
+            jitter = torch.rand_like(t_min)
+        if not stratified:
+            jitter = None
+        ops.clamp_jitter_(t_min, t_max, jitter, self.near_plane, self.far_plane, self._step_host)
+        params = ops.make_march_params(grid._roi_host, grid._res_host,
+                                       self.contraction_type.to_cpp_version(), self._step_host,
+                                       self.cone_angle)
+        return ops.march(params, o, d, t_min, t_max, grid.binary)
+
+    def render_chunk(self, o, d, jitter=None):
+        """One chunk of rays (R,3),(R,3) -> colour (R,C), opacity (R,), depth (R,), M."""
+        field = self.radiance_field
+        n_rays = o.shape[0]
+        ray_idx, t0, t1, offsets = self._march(o, d, jitter)
+
+        if (self.alpha_thre > 0.0 or self.early_stop_eps > 0.0) and ray_idx.numel() > 0:
+            alpha_thre = self.alpha_thre
+            if alpha_thre > 0.0:
+                alpha_thre = min(alpha_thre, self.occupancy_grid.occs.mean().item())
+            sigma, _ = field.eval_samples(o, d, ray_idx, t0, t1, full=False)
+            alphas = ops.alpha_from_sigma(sigma, t0, t1)
+            mask, counts = ops.visibility(alphas, offsets, self.early_stop_eps, alpha_thre)
+            offsets_out = ops.exclusive_scan_i32(counts)
+            total = int(offsets_out[-1].item())
+            ray_idx, t0, t1 = ops.compact(mask, offsets, offsets_out, ray_idx, t0, t1, total)
+            offsets = offsets_out
+
+        needs_grad = torch.is_grad_enabled() and any(
+            p.requires_grad for p in field.parameters())
+        if needs_grad:
+            ril = ray_idx.long()
+            dirs = d[ril]
+            pos = o[ril] + dirs * (t0 + t1)[:, None] / 2.0
+            rgb, sigma = field(pos, dirs)
+            sigma = sigma.reshape(-1)
+        else:
+            sigma, rgb = field.eval_samples(o, d, ray_idx, t0, t1, full=True)
+        bkgd = self.render_bkgd
+        colour, opacity, depth = ops.composite(sigma, rgb, t0, t1, offsets, bkgd)
+        return colour, opacity, depth, ray_idx.numel()
+
+    def forward(self, ray_origin, ray_direction, jitter=None):
+        shape = ray_origin.shape
+        o = ray_origin.reshape(-1, 3).float().contiguous()
+        d = ray_direction.reshape(-1, 3).float().contiguous()
+        n_rays = o.shape[0]
+        chunk = n_rays if self.radiance_field.training else self.test_chunk_size
+        cols, opas, deps, total = [], [], [], 0
+        for i in range(0, max(n_rays, 1), max(chunk, 1)):
+            jit = None if jitter is None else jitter.reshape(-1)[i:i + chunk].contiguous()
+            col, opa, dep, m = self.render_chunk(o[i:i + chunk], d[i:i + chunk], jit)
+            cols.append(col)
+            opas.append(opa)
+            deps.append(dep)
+            total += m
+        colour = torch.cat(cols).view(*shape[:-1], -1)
+        opacity = torch.cat(opas).view(*shape[:-1])
+        depth = torch.cat(deps).view(*shape[:-1])
+        radiance = colour.squeeze(dim=-1)
+        depth = depth / (opacity + self.opacity_eps)
+        return radiance, opacity, depth, total / max(n_rays, 1)

@@ -391,3 +391,32 @@ def composite(sigmas, rgbs, t_starts, t_ends, offsets, bkgd=None):
     t_starts = _req(t_starts.detach().reshape(-1), torch.float32, "t_starts")
     t_ends = _req(t_ends.detach().reshape(-1), torch.float32, "t_ends")
     return _CompositeFn.apply(sigmas.reshape(-1), rgbs, t_starts, t_ends, offsets, bkgd)
+
+
+# --------------------------------------------------------------------------- #
+# fused field
+# --------------------------------------------------------------------------- #
+def field_density_at(desc, params, positions):
+    positions = _req(positions, torch.float32, "positions")
+    n = positions.shape[0]
+    sig = torch.empty(n, dtype=torch.float32, device=positions.device)
+    _call("den_field_density_at", ctypes.byref(desc), ctypes.byref(params), _ptr(positions), n,
+          _ptr(sig), _stream())
+    return sig
+
+
+def field_fwd(desc, params, rays_o, rays_d, ray_indices, t_starts, t_ends, channels, n_dev=None):
+    """channels == 0 -> density only."""
+    rays_o = _req(rays_o, torch.float32, "rays_o")
+    rays_d = _req(rays_d, torch.float32, "rays_d")
+    ray_indices = _req(ray_indices, torch.int32, "ray_indices")
+    t_starts = _req(t_starts.reshape(-1), torch.float32, "t_starts")
+    t_ends = _req(t_ends.reshape(-1), torch.float32, "t_ends")
+    n = ray_indices.numel()
+    dev = rays_o.device
+    sig = torch.empty(n, dtype=torch.float32, device=dev)
+    rgb = torch.empty((n, channels), dtype=torch.float32, device=dev) if channels else None
+    _call("den_field_fwd", ctypes.byref(desc), ctypes.byref(params), _ptr(rays_o), _ptr(rays_d),
+          _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(n_dev), _ptr(sig), _ptr(rgb),
+          _stream())
+    return sig, rgb

@@ -1,0 +1,159 @@
+"""B2 host of the hot path: the event-supervised training step of the reference's
+LightningModule (models/deblur_e_nerf.py:396-586) and its render helpers
+(``render_log_intensity`` :1129-1160, ``render_train_pixels`` :1162-1183,
+``render_pixels`` :1185-1221, ``update_train_batch_size`` :1252-1308), without Lightning.
+
+``EventRenderer.training_step(batch)`` takes the reference's batch dict
+(``{"event": {position, start_ts, end_ts, num_pos, num_neg}, "normalized": {ts_diff,
+diff_start_ts, ts_subdiff, subdiff_start_ts[, interval_gen]}}``, with or without the
+DataLoader's leading dim of 1) and returns the scalar loss; ``self.logged`` holds what the
+reference passes to ``self.log``.  Mono sensors only (``channel_idx is None``: every shipped
+config, SURVEY.md conventions table C = 1).
+"""
+
+import functools
+
+import torch
+
+
+def _get(cfg, key):
+    return cfg[key] if isinstance(cfg, dict) else getattr(cfg, key)
+
+
+class EventRenderer(torch.nn.Module):
+    def __init__(self, nerf, trajectory, contrast_threshold, refractory_period, pixel_bandwidth,
+                 loss, train_intrinsics_inv, min_modeled_intensity=0.001,
+                 train_ray_sample_batch_size=131072, accumulate_grad_batches=1,
+                 world_size=1):
+        super().__init__()
+        self.nerf = nerf
+        self.trajectory = trajectory
+        self.contrast_threshold = contrast_threshold
+        self.refractory_period = refractory_period
+        self.pixel_bandwidth = pixel_bandwidth          # None <=> pixel_bandwidth.enable: false
+        self.loss = loss
+        self.register_buffer("train_intrinsics_inv", train_intrinsics_inv, persistent=False)
+        self.min_modeled_intensity = min_modeled_intensity
+        # models/deblur_e_nerf.py:72-75 — the sample budget is split evenly over the GPUs
+        self.train_ray_sample_batch_size = train_ray_sample_batch_size // world_size
+        self.accumulate_grad_batches = accumulate_grad_batches
+        self.render_bkgd = "parameter" if nerf.render_bkgd is not None else None
+        self.logged = {}
+        self.next_train_batch_size = None
+        self._jitters = None
+        self.mean_samples_reduce_fn = None              # set by ddp.attach(): all-reduce mean
+
+    # ------------------------------------------------------------- render helpers ----
+    def render_pixels(self, intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation):
+        o, d = self.nerf.pixel_params_to_ray(intrinsics_inverse, pixel_position, T_wc_position,
+                                             T_wc_orientation)
+        jitter = self._jitters.pop(0) if self._jitters else None
+        intensity, opacity, depth, mean_samples = self.nerf(o, d, jitter=jitter)
+        intensity = intensity + self.min_modeled_intensity
+        if self.render_bkgd is None:
+            is_valid = opacity > 0
+        else:
+            is_valid = torch.ones_like(opacity, dtype=torch.bool)
+        depth = depth * torch.sum(d * T_wc_orientation[..., 2], dim=-1)
+        return intensity, opacity, depth, mean_samples, is_valid
+
+    def render_train_pixels(self, timestamp, pixel_position, pixel_channel_idx=None):
+        pos, rot = self.trajectory(timestamp)
+        intensity, opacity, _, mean_samples, is_valid = self.render_pixels(
+            self.train_intrinsics_inv, pixel_position, pos, rot)
+        occ_rate = torch.mean(opacity > 0, dtype=torch.get_default_dtype())
+        return intensity, occ_rate, mean_samples, is_valid
+
+    def render_log_intensity(self, timestamp, pixel_position, pixel_channel_idx=None,
+                             normalized_interval_gen=None, reset_diff=False):
+        if self.pixel_bandwidth is not None:
+            fn = functools.partial(self.render_train_pixels, pixel_position=pixel_position,
+                                   pixel_channel_idx=pixel_channel_idx)
+            log_it, aux = self.pixel_bandwidth(normalized_interval_gen, timestamp, fn, reset_diff)
+            occ_rate, mean_samples, is_valid = aux
+            return log_it, occ_rate, mean_samples, is_valid.any(dim=0)
+        intensity, occ_rate, mean_samples, is_valid = self.render_train_pixels(
+            timestamp, pixel_position, pixel_channel_idx)
+        return intensity.log(), occ_rate, mean_samples, is_valid
+
+    # ------------------------------------------------------------------ the step -----
+    @staticmethod
+    def supervision_timestamps(event, normalized, use_diff, use_tv):
+        """models/deblur_e_nerf.py:419-455 (float64 ns)."""
+        diff = subdiff = None
+        tv_s, tv_e = event["start_ts"], event["end_ts"]
+        if use_diff:
+            ts_diff = (event["end_ts"] - event["start_ts"]) * normalized["ts_diff"]
+            start = torch.lerp(event["start_ts"],
+                               torch.max(event["end_ts"] - ts_diff, event["start_ts"]),
+                               normalized["diff_start_ts"])
+            end = torch.min(start + ts_diff, event["end_ts"])
+            diff = {"ts_diff": ts_diff, "start_ts": start, "end_ts": end}
+            tv_s, tv_e = start, end
+        if use_tv:
+            ts_sub = (tv_e - tv_s) * normalized["ts_subdiff"]
+            start = torch.lerp(tv_s, torch.max(tv_e - ts_sub, tv_s), normalized["subdiff_start_ts"])
+            end = torch.min(start + ts_sub, tv_e)
+            subdiff = {"ts_diff": ts_sub, "start_ts": start, "end_ts": end}
+        return diff, subdiff
+
+    def training_step(self, batch, batch_index=0, global_step=0, jitters=None):
+        self._jitters = list(jitters) if jitters is not None else None
+        event = {k: (v.squeeze(0) if v.dim() > 1 and v.shape[0] == 1 and k != "position"
+                     else v) for k, v in batch["event"].items()}
+        if event["position"].dim() == 3:
+            event["position"] = event["position"].squeeze(0)
+        normalized = {k: (v.squeeze(0) if v.shape[0] == 1 and v.dim() > 1 else v)
+                      for k, v in batch["normalized"].items()}
+        size = event["start_ts"].numel()
+        for value in normalized.values():
+            assert value.shape[-1] == size
+
+        event = self.contrast_threshold(event)
+        event = self.refractory_period(event)
+        weight = self.loss.loss_weight
+        use_diff = _get(weight, "log_intensity_diff") > 0
+        use_tv = _get(weight, "log_intensity_tv") > 0
+        diff, subdiff = self.supervision_timestamps(event, normalized, use_diff, use_tv)
+        gen = normalized.get("interval_gen")
+
+        if batch_index % self.accumulate_grad_batches == 0:
+            self.nerf.update_occ_grid(step=global_step,
+                                      T_wc_position=self.trajectory.T_wc_position)
+
+        mean_samples, occ_rates, valid_rates = [], [], []
+        for seg, is_diff in ((diff, True), (subdiff, False)):
+            if seg is None:
+                continue
+            a, occ_a, ms_a, va = self.render_log_intensity(
+                seg["start_ts"], event["position"], None, gen, reset_diff=is_diff)
+            b, occ_b, ms_b, vb = self.render_log_intensity(
+                seg["end_ts"], event["position"], None, gen)
+            seg["log_intensity_diff"] = b - a
+            seg["is_valid"] = va | vb
+            mean_samples += [ms_a, ms_b]
+            occ_rates += [occ_a, occ_b]
+            valid_rates += [va, vb]
+
+        mean_samples = self.update_train_batch_size(mean_samples, batch_index)
+        terms = self.loss.compute(event, diff, subdiff,
+                                  self.contrast_threshold.mean_contrast_threshold)
+        loss = sum(v * _get(weight, k) for k, v in terms.items())
+
+        self.logged = {"train/loss": loss.detach(), "train/batch_size": size,
+                       "train/mean_num_samples_per_ray": mean_samples}
+        for key, value in terms.items():
+            self.logged[f"train/{key}"] = value.detach()
+        self.logged["train/mean_ray_occ_rate"] = sum(occ_rates) / len(occ_rates)
+        return loss
+
+    def update_train_batch_size(self, mean_samples_per_call, batch_index):
+        """models/deblur_e_nerf.py:1252-1308: N_next = int(budget / mean samples per ray)."""
+        mean = sum(mean_samples_per_call) / len(mean_samples_per_call)
+        if self.mean_samples_reduce_fn is not None:
+            mean = self.mean_samples_reduce_fn(mean)
+        acc = self.accumulate_grad_batches
+        if acc > 1 and (batch_index % acc) != (acc - 2):
+            return mean
+        self.next_train_batch_size = int(self.train_ray_sample_batch_size / max(mean, 1e-9))
+        return mean

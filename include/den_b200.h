@@ -163,6 +163,54 @@ int den_composite_bwd(const float* sigmas, const float* rgbs, const float* t_sta
                       const float* d_opacity, const float* d_depth, float* d_sigmas, float* d_rgbs,
                       float* d_bkgd, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Fused radiance field — replaces NGPradianceField.query_density / forward
+ * (external/ngp.py:230-280) together with the tcnn.Encoding call (ngp.py:240),
+ * MLP.forward (external/mlp.py:99-113), SHEncoder.forward
+ * (external/sh_encoder.py:28-77) and the position computation of the
+ * sigma_fn / rgb_sigma_fn closures (external/utils.py:68-96).
+ * Architecture: the one every shipped config uses (base 32->64->1+15, SH degree
+ * 4, head 31->64->64->C); anything else returns DEN_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------- */
+typedef struct den_field_desc {
+    den_hashgrid_desc grid;
+    float aabb[6];                      /* radiance_field.aabb */
+    int32_t contraction;                /* den_contraction */
+    int32_t channels;                   /* radiance_dim: 1 (mono) or 3 (Bayer) */
+    int32_t hidden_act;                 /* 0 relu, 1 softplus(beta=100)  (models/nerf.py:17-20) */
+    int32_t density_act;                /* 0 shifted_trunc_exp, 1 softplus, 2 shifted_softplus */
+    int32_t radiance_act;               /* 0 softplus, 1 sigmoid */
+    int32_t width;                      /* n_neurons (64) */
+    int32_t geo_feat_dim;               /* 15 */
+    int32_t sh_degree;                  /* 4 */
+    int32_t n_hidden_base;              /* 1 */
+    int32_t n_hidden_head;              /* 2 */
+} den_field_desc;
+
+/* device pointers; weights in nn.Linear layout (out, in) row-major — the reference's
+ * state-dict tensors are passed as they are (SURVEY.md §5 checkpoint keys) */
+typedef struct den_field_params {
+    const float* table;                 /* mlp_base.0.params */
+    const float* wb1; const float* bb1; /* mlp_base.1.hidden_layers.0 : (64, L*2), (64) */
+    const float* wb2; const float* bb2; /* mlp_base.1.output_layer    : (16, 64), (16) */
+    const float* w1;  const float* b1;  /* mlp_head.hidden_layers.0   : (64, 31), (64) */
+    const float* w2;  const float* b2;  /* mlp_head.hidden_layers.1   : (64, 64), (64) */
+    const float* w3;  const float* b3;  /* mlp_head.output_layer      : (C, 64), (C) */
+} den_field_params;
+
+/* Samples are given by the march output: pos = o[ray] + d[ray] * (t0 + t1) / 2, dir = d[ray].
+ * sigmas (M); rgbs (M,C) or NULL for a density-only evaluation (the visibility pre-pass).
+ * If n_samples_dev != NULL the kernel reads the sample count from device memory
+ * (min(*n_samples_dev, n_samples)) so the host never has to synchronise on the march. */
+int den_field_fwd(const den_field_desc* f, const den_field_params* p, const float* rays_o,
+                  const float* rays_d, const int32_t* ray_indices, const float* t_starts,
+                  const float* t_ends, int64_t n_samples, const int32_t* n_samples_dev,
+                  float* sigmas, float* rgbs, void* stream);
+/* density at explicit world positions (n,3): the occupancy-grid update
+ * (models/nerf.py:171-198 occ_eval_fn) */
+int den_field_density_at(const den_field_desc* f, const den_field_params* p, const float* positions,
+                         int64_t n, float* sigmas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

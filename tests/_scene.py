@@ -192,3 +192,44 @@ def load_golden_state(module, golden, name, device=None):
     grid = getattr(module, "occupancy_grid", None)
     if grid is not None and "occupancy_grid._binary" in sd:
         grid._binary = sd["occupancy_grid._binary"].to(grid.occs.device).bool()
+
+
+# --------------------------------------------------------------------------- #
+# the CUDA product
+# --------------------------------------------------------------------------- #
+def build_product_nerf(cfg, device, seed=0):
+    from deblur_e_nerf_b200 import nerf as nerf_mod
+    from deblur_e_nerf_b200.nerfacc import ContractionType
+    torch.manual_seed(seed)
+    model = nerf_mod.NeRF(cfg["aabb"], ContractionType[CONTRACTIONS[cfg["contraction"]]],
+                          cfg["occ_grid"], cfg["near_plane"], cfg["far_plane"], cfg["step"],
+                          cfg["render_bkgd"], cfg["cone_angle"], cfg["early_stop_eps"],
+                          cfg["alpha_thre"], cfg["test_chunk_size"], "ngp", cfg["arch"], 3, 1)
+    return model.to(device)
+
+
+def build_product_renderer(cfg, device, it_sample_size=8, pixel_bandwidth=True, seed=0,
+                           n_poses=200):
+    from deblur_e_nerf_b200 import event_generation_params as egp
+    from deblur_e_nerf_b200 import loss as loss_mod
+    from deblur_e_nerf_b200 import renderer, trajectories
+    nerf = build_product_nerf(cfg, device, seed)
+    poses = synthetic.camera_poses(cfg, n_poses=n_poses)
+    calib = synthetic.calibration()
+    traj = trajectories.LinearTrajectory(poses)
+    ct = egp.ContrastThreshold(calib, True)
+    rp = egp.RefractoryPeriod(calib, synthetic.MAX_REFRACTORY_PERIOD_NS)
+    pb = None
+    if pixel_bandwidth:
+        from deblur_e_nerf_b200 import pixel_bandwidth as pb_mod
+        pb = pb_mod.PixelBandwidth(calib, poses[2].min(), 21, dict(max_sample_lifetime=0.95))
+    loss_cfg = {k: dict(v) for k, v in LOSS_CFG.items()}
+    loss_cfg["weight"]["log_intensity_tv"] = cfg["tv_weight"]
+    loss = loss_mod.Loss(loss_cfg["weight"], loss_cfg["error_fn"], loss_cfg["normalize"])
+    kinv = torch.linalg.inv(torch.from_numpy(synthetic.intrinsics(cfg)))
+    model = renderer.EventRenderer(nerf, traj, ct, rp, pb, loss, kinv)
+    return model.to(device), poses
+
+
+def to_device(tree, device):
+    return {k: v.to(device) for k, v in tree.items()}
