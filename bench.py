@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the Deblur e-NeRF training hot path (event-supervised volumetric renderer).
+
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+
+A "step" is one full training step of the hot path on one synthetic event batch: event
+correction -> supervision timestamps -> 4 render calls (march, field, compositing[, pixel-
+bandwidth filter]) -> event loss -> backward -> (N>1: flat NCCL gradient all-reduce) -> Adam.
+`value` is whole-job rays/s with the batch already resident in HBM; `e2e` is the same metric
+through the public `EventRenderer.training_step` call with HOST (pinned) batches, the H2D
+copies and the loss read-back inside the timed region.
+
+Workloads (BASELINE.json `configs`):
+  synthetic_pb_off   configs[1]: synthetic.yaml shape, pixel-bandwidth model off, 2^17 rays per
+                     render call (the literal "2^17 ray batch" reading)
+  synthetic_pb_on    configs[2]: synthetic.yaml hard setting, it_sample_size 30, 2^17 rays per
+                     render call (N = 2^17/30 events)
+  synthetic_budget   reading (R): N = budget(2^17 samples)/mean samples per ray, PB on
+  eds                configs[3] shape (sphere contraction, cone 0.004, res 256, no background)
+  plumbing           configs[0]: 4096 events x 8 samples, small hash grid (CPU-runnable)
+`--impl reference` times the reference's path on the host cores instead: the CPU oracle
+(oracle/path_ref.py = the reference's own files restated and pinned against them; nerfacc /
+tiny-cuda-nn are CUDA-only, so their pure-PyTorch equivalents are used and labelled).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "synthetic_pb_off": dict(config="synthetic", pb=False, S=1, rays_per_call=1 << 17, small=False,
+                             occ_res=128),
+    "synthetic_pb_on": dict(config="synthetic", pb=True, S=30, rays_per_call=1 << 17, small=False,
+                            occ_res=128),
+    "synthetic_budget": dict(config="synthetic", pb=True, S=30, rays_per_call=None, small=False,
+                             occ_res=128),
+    "eds": dict(config="eds", pb=True, S=30, rays_per_call=1 << 17, small=False, occ_res=256),
+    "plumbing": dict(config="synthetic", pb=True, S=8, rays_per_call=4096 * 8, small=True,
+                     occ_res=32),
+}
+
+# algorithmic bytes per sample (SURVEY.md §8(d) / BASELINE.md §3), 16 levels x 8 corners x 8 B
+HASH_GATHER_BYTES = 1024
+KERNEL_BYTES_PER_SAMPLE = {
+    "den_hashgrid_fwd": 1164,        # gather + 12 B position + 128 B encoding written
+    "den_hashgrid_bwd": 1164,        # scatter (counted once) + 128 B dL/denc + 12 B position
+    "den_field_fwd": 1036,           # fused: gather + 12 B sample in, no encoding write
+    "den_field_bwd": 1036 + 1024,    # fused recompute gather + scatter
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="synthetic_pb_off", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-events", type=int, default=384,
+                    help="events per step of the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------- clocks ----
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, sm_max, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                sm_max = float(row[1])
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, row[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": sm_max,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- CPU / reference ----
+def _oracle_scene(workload, n_events, seed=0):
+    """The same workload on the CPU oracle (bounded number of events)."""
+    import torch
+    from deblur_e_nerf_b200 import synthetic
+    from oracle import nerfacc_ref, path_ref
+
+    w = WORKLOADS[workload]
+    cfg = dict(synthetic.CONFIGS[w["config"]])
+    torch.manual_seed(seed)
+    ctype = {"aabb": nerfacc_ref.ContractionType.AABB,
+             "sphere": nerfacc_ref.ContractionType.UN_BOUNDED_SPHERE}[cfg["contraction"]]
+    occ = dict(resolution=w["occ_res"], occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16)
+    nerf = path_ref.NeRF(cfg["aabb"], ctype, occ, cfg["near_plane"], cfg["far_plane"],
+                         synthetic.render_step_size(cfg["aabb"]), cfg["render_bkgd"],
+                         cfg["cone_angle"], cfg["early_stop_eps"], cfg["alpha_thre"],
+                         cfg["test_chunk_size"], synthetic.arch_config(small=w["small"]), 1)
+    nerf.occupancy_grid._binary = synthetic.solid_sphere_occupancy(w["occ_res"])
+    poses = synthetic.camera_poses(cfg)
+    calib = synthetic.calibration()
+    pb = path_ref.PixelBandwidth(calib, poses[2].min(), 21, 0.95) if w["pb"] else None
+    weight = dict(log_intensity_diff=1.0, log_intensity_tv=cfg["tv_weight"])
+    loss = path_ref.EventLoss(weight, dict(log_intensity_diff="huber", log_intensity_tv="l1"),
+                              dict(log_intensity_diff=True, log_intensity_tv=True))
+    model = path_ref.EventRenderer(
+        nerf, path_ref.LinearTrajectory(*poses),
+        path_ref.ContrastThreshold(calib["pos_contrast_threshold"],
+                                   calib["neg_contrast_threshold"]),
+        path_ref.RefractoryPeriod(calib["refractory_period"], synthetic.MAX_REFRACTORY_PERIOD_NS),
+        pb, loss, torch.linalg.inv(torch.from_numpy(synthetic.intrinsics(cfg))))
+    for m in (model.contrast_threshold, model.refractory_period, model.pixel_bandwidth):
+        if m is not None:
+            m.requires_grad_(False)
+    model.train()
+    g = torch.Generator().manual_seed(1000 + seed)
+    event = synthetic.event_batch(n_events, cfg, poses[2], g)
+    normalized = synthetic.normalized_batch(n_events, w["S"], g, w["pb"])
+    return model, event, normalized, w
+
+
+def cpu_reference_rate(workload, n_events, steps=1, warmup=0):
+    """rays/s of the reference's path (CPU oracle) on a bounded sample of the workload."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, event, normalized, w = _oracle_scene(workload, n_events)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=0.01)
+    rays_per_step = 4 * w["S"] * n_events
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _, _ = model.training_step(event, normalized)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean_t = sum(times) / len(times)
+    return {
+        "value": rays_per_step / mean_t, "unit": "rays/s", "cores": torch.get_num_threads(),
+        "kind": "port",
+        "sample": (f"{n_events} events x {w['S']} pixel-bandwidth samples x 4 render calls "
+                   f"({rays_per_step} rays/step), fwd+bwd+Adam, {len(times)} timed step(s); "
+                   "reference's own files restated in oracle/path_ref.py (pinned against them), "
+                   "nerfacc/tiny-cuda-nn replaced by their pure-PyTorch equivalents "
+                   "(reference is CUDA-only there)"),
+        "ms_per_step": mean_t * 1e3,
+    }, rays_per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, rays_per_step = cpu_reference_rate(args.workload, args.cpu_events, steps=args.steps,
+                                             warmup=min(args.warmup, 1))
+    w = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "train rays/s (fwd+bwd)", "value": base["value"],
+        "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, w, args.cpu_events, bounded=True),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "rays/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, w, n_events, bounded=False):
+    return {
+        "workload": name, "yaml": f"configs/train/{'synthetic' if w['config'] == 'synthetic' else '08_peanuts_running'}.yaml",
+        "pixel_bandwidth": w["pb"], "it_sample_size": w["S"], "events_per_step": n_events,
+        "rays_per_render_call": w["S"] * n_events, "render_calls_per_step": 4,
+        "hash_grid": "L4 T14" if w["small"] else "L16 F2 T19", "occ_resolution": w["occ_res"],
+        "occupancy": "controlled solid sphere r=0.75 (SURVEY §8(d)(ii)); grid update not in the "
+                     "timed steps (runs every 16th step; timed separately as occ_update_ms)",
+        "field": "random init", "bounded_sample": bounded,
+        "l2_policy": "inputs larger than L2: per-step sample arena + 48 MiB table + gradients "
+                     "exceed 126 MB; a fresh batch every step",
+    }
+
+
+# ------------------------------------------------------------------------- ours ------
+def run_ours(args):
+    import torch
+    import __graft_entry__ as entry
+    from deblur_e_nerf_b200 import ddp, factory, ops, synthetic
+
+    rank, local_rank, world = ddp.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if rank == 0:
+        entry.build()
+    ddp.barrier()
+
+    w = WORKLOADS[args.workload]
+    model, cfg, poses = factory.build_renderer(
+        w["config"], dev, pixel_bandwidth=w["pb"], small=w["small"], occ_resolution=w["occ_res"],
+        world_size=1, seed=0)
+    factory.freeze_like_synthetic_yaml(model)
+    model.train()
+    sphere = synthetic.solid_sphere_occupancy(w["occ_res"]).to(dev)
+    model.nerf.occupancy_grid._binary = sphere
+    model.nerf.occupancy_grid.occs.copy_(sphere.reshape(-1).float())
+    ddp.broadcast_parameters(model)
+    ddp.attach(model)
+    reducer = ddp.FlatGradAllReduce(model.parameters())
+    opt = factory.configure_optimizer(model)
+    update_occ = model.nerf.update_occ_grid
+    model.nerf.update_occ_grid = lambda *a, **k: None
+
+    # events per step (per GPU: weak scaling, fixed per-GPU work)
+    if w["rays_per_call"] is not None:
+        n_events = w["rays_per_call"] // w["S"]
+    else:
+        n_events = 256          # the controller's start (synthetic.yaml:18); adapts below
+    rays_per_step = lambda n: 4 * w["S"] * n        # noqa: E731
+
+    def host_batch(i, n):
+        g = torch.Generator().manual_seed(10_000 * (rank + 1) + i)
+        ev = synthetic.event_batch(n, cfg, poses[2], g)
+        nm = synthetic.normalized_batch(n, w["S"], g, w["pb"])
+        pin = lambda t: t.pin_memory()          # noqa: E731
+        return {"event": {k: pin(v) for k, v in ev.items()},
+                "normalized": {k: pin(v) for k, v in nm.items()}}
+
+    def to_dev(batch):
+        return {k: {kk: vv.to(dev, non_blocking=True) for kk, vv in v.items()}
+                for k, v in batch.items()}
+
+    def nbytes(batch):
+        return sum(t.numel() * t.element_size() for v in batch.values() for t in v.values())
+
+    def one_step(batch, step_index):
+        opt.zero_grad(set_to_none=True)
+        loss = model.training_step(batch, 0, step_index)
+        loss.backward()
+        reducer()
+        opt.step()
+        return loss
+
+    total = args.warmup + args.steps
+    if w["rays_per_call"] is None:
+        # reading (R): let the batch controller settle during extra warm-up steps
+        for i in range(6):
+            one_step(to_dev(host_batch(100 + i, n_events)), 1)
+            n_events = max(model.next_train_batch_size or n_events, 1)
+    host_batches = [host_batch(i, n_events) for i in range(total)]
+    dev_batches = [to_dev(b) for b in host_batches]
+    torch.cuda.synchronize()
+
+    timed_kernels = ["den_hashgrid_fwd", "den_hashgrid_bwd", "den_field_fwd", "den_field_bwd",
+                     "den_composite_fwd", "den_composite_bwd", "den_march_count",
+                     "den_march_write", "den_lpf_fwd", "den_lpf_bwd"]
+
+    # ---- device-resident loop (value) ------------------------------------------------
+    samples_seen = 0.0
+    for i in range(args.warmup):
+        one_step(dev_batches[i], 1 + i)
+    ddp.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ops.launch_count()
+    ops.enable_kernel_timing(timed_kernels)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        one_step(dev_batches[args.warmup + i], 1 + args.warmup + i)
+        samples_seen += model.logged["train/mean_num_samples_per_ray"] * rays_per_step(n_events)
+    end.record()
+    ddp.barrier()
+    torch.cuda.synchronize()
+    ms_total = start.elapsed_time(end)
+    ms_step = ddp.max_over_ranks(ms_total / args.steps, dev)
+    timings = ops.kernel_timings()
+    ops.disable_kernel_timing()
+    launches = (ops.launch_count() - launches0)
+    clock_info = clocks.stop() if rank == 0 else None
+    global_rays = ddp.sum_over_ranks(rays_per_step(n_events), dev)
+    global_samples = ddp.sum_over_ranks(samples_seen / args.steps, dev)
+    value = global_rays / (ms_step * 1e-3)
+
+    # ---- end-to-end loop through the public API with host batches ---------------------
+    e2e = None
+    if not args.no_e2e:
+        for i in range(min(args.warmup, 2)):
+            one_step(to_dev(host_batches[i]), 1 + i).item()
+        ddp.barrier()
+        torch.cuda.synchronize()
+        start.record()
+        d2h = 0
+        for i in range(args.steps):
+            loss = one_step(to_dev(host_batches[args.warmup + i]), 1 + args.warmup + i)
+            loss_host = loss.detach().to("cpu", non_blocking=False)
+            d2h = loss_host.numel() * loss_host.element_size()
+        end.record()
+        ddp.barrier()
+        torch.cuda.synchronize()
+        ms_e2e = ddp.max_over_ranks(start.elapsed_time(end) / args.steps, dev)
+        e2e = {"value": global_rays / (ms_e2e * 1e-3), "unit": "rays/s",
+               "h2d_bytes_per_step": nbytes(host_batches[0]), "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e2e}
+
+    # ---- occupancy update, timed on its own --------------------------------------------
+    occ_ms = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        start.record()
+        update_occ(0, model.trajectory.T_wc_position)
+        end.record()
+        torch.cuda.synchronize()
+        occ_ms = start.elapsed_time(end)
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------
+    peaks = {}
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback"
+    per_step_samples = samples_seen / args.steps
+    candidates = {k: v for k, v in timings.items()
+                  if v[0] > 0 and k in KERNEL_BYTES_PER_SAMPLE}
+    kernel_table = {k: {"launches": v[0], "ms_total": round(v[1], 3),
+                        "share_of_step": round(v[1] / ms_total, 4)} for k, v in timings.items()
+                    if v[0] > 0}
+    roofline = None
+    if candidates:
+        name = max(candidates, key=lambda k: candidates[k][1])
+        n_launch, ms_k = candidates[name]
+        # every timed launch of these kernels processes the surviving samples of one render call
+        samples_per_launch = per_step_samples / 4
+        bytes_per_launch = KERNEL_BYTES_PER_SAMPLE[name] * samples_per_launch
+        achieved = bytes_per_launch / (ms_k / n_launch * 1e-3) / 1e9
+        roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "peak_source": peak_src,
+                    "note": "algorithmic bytes/sample x samples per launch / mean launch time "
+                            "(CUDA events on the launching stream); the 48 MiB table is "
+                            "L2-resident, fraction is of measured HBM copy bandwidth",
+                    "avg_launch_ms": ms_k / n_launch, "samples_per_launch": samples_per_launch}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu, _ = cpu_reference_rate(args.workload, args.cpu_events, steps=1, warmup=0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": "train rays/s (fwd+bwd)", "value": value, "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.workload, w, n_events),
+        "samples_per_s": global_samples / (ms_step * 1e-3),
+        "events_per_s": world * n_events / (ms_step * 1e-3),
+        "mean_samples_per_ray": model.logged["train/mean_num_samples_per_ray"],
+        "hash_gather_gbs": HASH_GATHER_BYTES * global_samples / (ms_step * 1e-3) / 1e9,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
+        "kernels": kernel_table, "occ_update_ms": occ_ms, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

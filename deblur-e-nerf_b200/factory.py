@@ -1,0 +1,87 @@
+"""Build the hot-path modules from the reference's YAML shapes (synthetic.yaml /
+08_peanuts_running.yaml) with synthetic calibration and poses, and the optimizer with the
+reference's parameter groups (models/deblur_e_nerf.py:1055-1112)."""
+
+import torch
+
+from . import event_generation_params as egp
+from . import loss as loss_mod
+from . import nerf as nerf_mod
+from . import renderer as renderer_mod
+from . import synthetic, trajectories
+from .nerfacc import ContractionType
+
+CONTRACTIONS = {"aabb": ContractionType.AABB, "sphere": ContractionType.UN_BOUNDED_SPHERE,
+                "tanh": ContractionType.UN_BOUNDED_TANH}
+
+LOSS = dict(
+    error_fn=dict(log_intensity_diff="huber", log_intensity_tv="l1"),
+    normalize=dict(log_intensity_diff=True, log_intensity_tv=True),
+)
+
+
+def build_renderer(config="synthetic", device="cuda", pixel_bandwidth=True, small=False,
+                   occ_resolution=None, n_poses=1000, world_size=1, sample_budget=131072,
+                   accumulate_grad_batches=1, seed=0):
+    cfg = dict(synthetic.CONFIGS[config])
+    if occ_resolution is not None:
+        cfg["occ_resolution"] = occ_resolution
+    torch.manual_seed(seed)
+    arch = synthetic.arch_config(small=small)
+    occ = dict(resolution=cfg["occ_resolution"], occ_thre=1e-2, ema_decay=0.95,
+               warmup_steps=256, n=16)
+    nerf = nerf_mod.NeRF(cfg["aabb"], CONTRACTIONS[cfg["contraction"]], occ, cfg["near_plane"],
+                         cfg["far_plane"], synthetic.render_step_size(cfg["aabb"]),
+                         cfg["render_bkgd"], cfg["cone_angle"], cfg["early_stop_eps"],
+                         cfg["alpha_thre"], cfg["test_chunk_size"], "ngp", arch, 3, 1)
+    poses = synthetic.camera_poses(cfg, n_poses=n_poses)
+    calib = synthetic.calibration()
+    pb = None
+    if pixel_bandwidth:
+        from . import pixel_bandwidth as pb_mod
+        pb = pb_mod.PixelBandwidth(calib, poses[2].min(), 21, dict(max_sample_lifetime=0.95))
+    weight = dict(log_intensity_diff=1.0, log_intensity_tv=cfg["tv_weight"],
+                  nerf_mlp_weight_decay=1e-6)
+    model = renderer_mod.EventRenderer(
+        nerf, trajectories.LinearTrajectory(poses), egp.ContrastThreshold(calib, True),
+        egp.RefractoryPeriod(calib, synthetic.MAX_REFRACTORY_PERIOD_NS), pb,
+        loss_mod.Loss(weight, LOSS["error_fn"], LOSS["normalize"]),
+        torch.linalg.inv(torch.from_numpy(synthetic.intrinsics(cfg))),
+        train_ray_sample_batch_size=sample_budget,
+        accumulate_grad_batches=accumulate_grad_batches, world_size=world_size)
+    return model.to(device), cfg, poses
+
+
+def freeze_like_synthetic_yaml(model):
+    """configs/train/synthetic.yaml:31-55 — C_p, tau and the pixel-bandwidth parameters are
+    frozen; only the NeRF trains."""
+    for module in (model.contrast_threshold, model.refractory_period, model.pixel_bandwidth):
+        if module is not None:
+            module.requires_grad_(False)
+    return model
+
+
+def configure_optimizer(model, lr=0.01, weight_decay=1e-6, refractory_relative_lr=50.0,
+                        component_lr=None, fused=None):
+    """Adam with the reference's groups: tau at lr = tau_max * 50; every parameter whose name
+    starts with `nerf.radiance_field.mlp` (this includes the hash table) gets weight decay
+    1e-6; C_p / Omega `.original` parameters get their own lr; the rest default."""
+    component_lr = component_lr or {"contrast_threshold": 0.1, "pixel_bandwidth": 0.01}
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    groups, taken = [], set()
+
+    def take(pred, **opts):
+        params = [p for n, p in named if pred(n) and id(p) not in taken]
+        taken.update(id(p) for p in params)
+        if params:
+            groups.append(dict(params=params, **opts))
+
+    tau_lr = float(model.refractory_period.max_refractory_period) * refractory_relative_lr
+    take(lambda n: n.startswith("refractory_period."), lr=tau_lr)
+    take(lambda n: n.startswith("nerf.radiance_field.mlp"), weight_decay=weight_decay)
+    for comp, comp_lr in component_lr.items():
+        take(lambda n, c=comp: n.startswith(c + "."), lr=comp_lr)
+    take(lambda n: True)
+    if fused is None:
+        fused = all(p.is_cuda for _, p in named)
+    return torch.optim.Adam(groups, lr=lr, fused=fused)

@@ -47,8 +47,39 @@ def _req(t, dtype, name):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_TIMED = None           # {kernel name: [(start_event, end_event), ...]} while timing is on
+
+
+def enable_kernel_timing(names):
+    """Bracket every launch of the named C-ABI entry points with CUDA events recorded on the
+    launching (current) stream; bench.py derives the roofline from them."""
+    global _TIMED
+    _TIMED = {n: [] for n in names}
+
+
+def kernel_timings():
+    """{name: (launches, total_ms)} — call after a device synchronise."""
+    out = {}
+    for name, pairs in (_TIMED or {}).items():
+        out[name] = (len(pairs), sum(a.elapsed_time(b) for a, b in pairs))
+    return out
+
+
+def disable_kernel_timing():
+    global _TIMED
+    _TIMED = None
+
+
 def _call(name, *args, launches=1):
-    _lib.lib().call(name, *args)
+    if _TIMED is not None and name in _TIMED:
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record()
+        _lib.lib().call(name, *args)
+        end.record()
+        _TIMED[name].append((start, end))
+    else:
+        _lib.lib().call(name, *args)
     _count(launches)
 
 
