@@ -83,6 +83,9 @@ _SIGNATURES = {
                              _I64, _P, _P, _P, _P]),
     "den_field_density_at": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _P, _I64, _P,
                                     _P]),
+    "den_contract_samples": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "den_mlp_fwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _P, _P, _P, _P, _P, _P,
+                           _I64, _P, _P, _P]),
     "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
 }

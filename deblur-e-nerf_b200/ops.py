@@ -451,3 +451,26 @@ def field_fwd(desc, params, rays_o, rays_d, ray_indices, t_starts, t_ends, chann
           _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(n_dev), _ptr(sig), _ptr(rgb),
           _stream())
     return sig, rgb
+
+
+# --------------------------------------------------------------------------- #
+# tensor-core MLP on pre-encoded samples
+# --------------------------------------------------------------------------- #
+def contract_samples(desc, rays_o, rays_d, ray_indices, t_starts, t_ends):
+    n = ray_indices.numel()
+    out = torch.empty((n, 3), dtype=torch.float32, device=rays_o.device)
+    _call("den_contract_samples", ctypes.byref(desc), _ptr(rays_o), _ptr(rays_d),
+          _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(out), _stream())
+    return out
+
+
+def mlp_fwd(desc, params, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, channels):
+    enc = _req(enc, torch.float32, "enc")
+    n = ray_indices.numel()
+    dev = enc.device
+    sig = torch.empty(n, dtype=torch.float32, device=dev)
+    rgb = torch.empty((n, channels), dtype=torch.float32, device=dev) if channels else None
+    _call("den_mlp_fwd", ctypes.byref(desc), ctypes.byref(params), _ptr(enc), _ptr(rays_o),
+          _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(sig), _ptr(rgb),
+          _stream())
+    return sig, rgb

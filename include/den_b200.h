@@ -211,6 +211,24 @@ int den_field_fwd(const den_field_desc* f, const den_field_params* p, const floa
 int den_field_density_at(const den_field_desc* f, const den_field_params* p, const float* positions,
                          int64_t n, float* sigmas, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Tensor-core MLP (tcgen05.mma, TMEM accumulators) on pre-encoded samples — replaces
+ * MLP.forward (external/mlp.py:99-113) for mlp_base[1] / mlp_head, SHEncoder.forward and the
+ * activations, as reached from NGPradianceField.query_density/_query_rgb
+ * (external/ngp.py:239-267).  `enc` (M, L*2) is the output of den_hashgrid_fwd on the
+ * positions written by den_contract_samples.
+ * ------------------------------------------------------------------------- */
+/* unit-cube positions (M,3) of marched samples: contraction of o + d (t0+t1)/2
+ * (external/utils.py:68-96 + external/ngp.py:231-237) */
+int den_contract_samples(const den_field_desc* f, const float* rays_o, const float* rays_d,
+                         const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                         int64_t n_samples, float* unit_pos, void* stream);
+/* sigmas (M); rgbs (M,C) or NULL (density only) */
+int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float* enc,
+                const float* rays_o, const float* rays_d, const int32_t* ray_indices,
+                const float* t_starts, const float* t_ends, int64_t n_samples, float* sigmas,
+                float* rgbs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
