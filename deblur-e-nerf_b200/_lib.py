@@ -55,6 +55,11 @@ class FieldParams(_c.Structure):
         "table", "wb1", "bb1", "wb2", "bb2", "w1", "b1", "w2", "b2", "w3", "b3")]
 
 
+class FieldGrads(_c.Structure):
+    _fields_ = [(name, _P) for name in (
+        "wb1", "bb1", "wb2", "bb2", "w1", "b1", "w2", "b2", "w3", "b3")]
+
+
 # name -> (restype, argtypes); mirrors include/den_b200.h declaration by declaration
 _SIGNATURES = {
     "den_version": (_INT, []),
@@ -86,6 +91,9 @@ _SIGNATURES = {
     "den_contract_samples": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _I64, _P, _P]),
     "den_mlp_fwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _P, _P, _P, _P, _P, _P,
                            _I64, _P, _P, _P]),
+    "den_tc_probe_gemm": (_INT, [_INT, _P, _P, _P, _INT, _INT, _P]),
+    "den_mlp_bwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _c.POINTER(FieldGrads),
+                           _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
 }

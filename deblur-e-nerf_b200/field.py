@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from . import ops
 from . import tinycudann as tcnn
-from ._lib import FieldDesc, FieldParams
+from ._lib import FieldDesc, FieldGrads, FieldParams
 from .nerfacc import ContractionType
 
 HIDDEN_ACT_IDS = {"relu": 0, "softplus": 1}
@@ -100,6 +100,33 @@ def sh_degree4(d):
         0.45704579946446572 * y * (1.0 - 5.0 * z2), 0.3731763325901154 * z * (5.0 * z2 - 3.0),
         0.45704579946446572 * x * (1.0 - 5.0 * z2), 1.4453057213202769 * z * (x2 - y2),
         0.59004358992664352 * x * (-x2 + 3.0 * y2)], dim=-1)
+
+
+class _MlpTcFn(torch.autograd.Function):
+    """sigma, rgb = MLP(enc, dirs) on the tensor cores (den_mlp_fwd); backward recomputes the
+    forward per tile and returns dL/denc plus every weight / bias gradient (den_mlp_bwd)."""
+
+    @staticmethod
+    def forward(ctx, field, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, *weights):
+        sig, rgb = ops.mlp_fwd(field.field_desc(), field.field_params(), enc, rays_o, rays_d,
+                               ray_indices, t_starts, t_ends, field.radiance_dim)
+        ctx.field = field
+        ctx.save_for_backward(enc, rays_o, rays_d, ray_indices, t_starts, t_ends)
+        ctx.mark_non_differentiable()
+        return sig, rgb
+
+    @staticmethod
+    def backward(ctx, d_sig, d_rgb):
+        field = ctx.field
+        enc, rays_o, rays_d, ray_indices, t_starts, t_ends = ctx.saved_tensors
+        weights = field.param_tensors()[1:]
+        grads = [torch.zeros_like(w) for w in weights]
+        gs = FieldGrads()
+        for name, t in zip(("wb1", "bb1", "wb2", "bb2", "w1", "b1", "w2", "b2", "w3", "b3"), grads):
+            setattr(gs, name, t.data_ptr())
+        d_enc = ops.mlp_bwd(field.field_desc(), field.field_params(), gs, enc, rays_o, rays_d,
+                            ray_indices, t_starts, t_ends, d_sig.contiguous(), d_rgb.contiguous())
+        return (None, d_enc, None, None, None, None, None, *grads)
 
 
 class NGPradianceField(torch.nn.Module):
@@ -191,6 +218,30 @@ class NGPradianceField(torch.nn.Module):
         """(sigma (M,), rgb (M,C) | None) for marched samples: den_field_fwd."""
         return ops.field_fwd(self.field_desc(), self.field_params(), rays_o, rays_d, ray_indices,
                              t_starts, t_ends, self.radiance_dim if full else 0, n_dev)
+
+    # ---------------------------------------------- tensor-core path (with autograd) --
+    def encode_samples(self, rays_o, rays_d, ray_indices, t_starts, t_ends, enc=None):
+        """Hash-grid encoding (M, L*2) of marched samples as an autograd node on the table;
+        `enc` re-uses an encoding already computed on the same samples."""
+        u = ops.contract_samples(self.field_desc(), rays_o, rays_d, ray_indices, t_starts, t_ends)
+        if enc is not None:
+            return ops.hashgrid_reuse(u, self.encoding.params, self.encoding.desc, enc)
+        return ops.hashgrid(u, self.encoding.params, self.encoding.desc)
+
+    def mlp_samples(self, enc, rays_o, rays_d, ray_indices, t_starts, t_ends):
+        """(sigma (M,), rgb (M,C)) from encodings on the tensor cores, differentiable in the
+        encodings and in every MLP parameter."""
+        return _MlpTcFn.apply(self, enc, rays_o, rays_d, ray_indices, t_starts, t_ends,
+                              *self.param_tensors()[1:])
+
+    @torch.no_grad()
+    def density_samples_tc(self, rays_o, rays_d, ray_indices, t_starts, t_ends):
+        """Visibility pre-pass: (sigma (M,), enc (M, L*2)) — gather + density-only MLP."""
+        u = ops.contract_samples(self.field_desc(), rays_o, rays_d, ray_indices, t_starts, t_ends)
+        enc = ops.hashgrid_fwd(self.encoding.desc, u, self.encoding.params)
+        sig, _ = ops.mlp_fwd(self.field_desc(), self.field_params(), enc, rays_o, rays_d,
+                             ray_indices, t_starts, t_ends, 0)
+        return sig, enc
 
     # --------------------------------------------------- reference-signature methods --
     def _contract(self, x):

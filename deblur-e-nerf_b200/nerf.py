@@ -152,28 +152,33 @@ class NeRF(torch.nn.Module):
         n_rays = o.shape[0]
         ray_idx, t0, t1, offsets = self._march(o, d, jitter)
 
+        enc_pre = None
         if (self.alpha_thre > 0.0 or self.early_stop_eps > 0.0) and ray_idx.numel() > 0:
             alpha_thre = self.alpha_thre
             if alpha_thre > 0.0:
                 alpha_thre = min(alpha_thre, self.occupancy_grid.occs.mean().item())
-            sigma, _ = field.eval_samples(o, d, ray_idx, t0, t1, full=False)
+            sigma, enc_pre = field.density_samples_tc(o, d, ray_idx, t0, t1)
             alphas = ops.alpha_from_sigma(sigma, t0, t1)
             mask, counts = ops.visibility(alphas, offsets, self.early_stop_eps, alpha_thre)
             offsets_out = ops.exclusive_scan_i32(counts)
             total = int(offsets_out[-1].item())
-            ray_idx, t0, t1 = ops.compact(mask, offsets, offsets_out, ray_idx, t0, t1, total)
-            offsets = offsets_out
+            if total < ray_idx.numel():
+                ray_idx, t0, t1 = ops.compact(mask, offsets, offsets_out, ray_idx, t0, t1, total)
+                offsets = offsets_out
+                enc_pre = None          # positions changed: the encoding is recomputed below
 
         needs_grad = torch.is_grad_enabled() and any(
             p.requires_grad for p in field.parameters())
         if needs_grad:
-            ril = ray_idx.long()
-            dirs = d[ril]
-            pos = o[ril] + dirs * (t0 + t1)[:, None] / 2.0
-            rgb, sigma = field(pos, dirs)
-            sigma = sigma.reshape(-1)
+            enc = field.encode_samples(o, d, ray_idx, t0, t1, enc=enc_pre)
+            sigma, rgb = field.mlp_samples(enc, o, d, ray_idx, t0, t1)
         else:
-            sigma, rgb = field.eval_samples(o, d, ray_idx, t0, t1, full=True)
+            if enc_pre is None:
+                _, enc_pre = field.density_samples_tc(o, d, ray_idx, t0, t1) \
+                    if ray_idx.numel() else (None, torch.empty(0, field.encoding.n_output_dims,
+                                                               device=o.device))
+            sigma, rgb = ops.mlp_fwd(field.field_desc(), field.field_params(), enc_pre, o, d,
+                                     ray_idx, t0, t1, field.radiance_dim)
         bkgd = self.render_bkgd
         colour, opacity, depth = ops.composite(sigma, rgb, t0, t1, offsets, bkgd)
         return colour, opacity, depth, ray_idx.numel()

@@ -47,14 +47,16 @@ def _req(t, dtype, name):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_TIME_ALL = False
 _TIMED = None           # {kernel name: [(start_event, end_event), ...]} while timing is on
 
 
 def enable_kernel_timing(names):
     """Bracket every launch of the named C-ABI entry points with CUDA events recorded on the
     launching (current) stream; bench.py derives the roofline from them."""
-    global _TIMED
-    _TIMED = {n: [] for n in names}
+    global _TIMED, _TIME_ALL
+    _TIME_ALL = names is None
+    _TIMED = {n: [] for n in (names or [])}
 
 
 def kernel_timings():
@@ -71,7 +73,8 @@ def disable_kernel_timing():
 
 
 def _call(name, *args, launches=1):
-    if _TIMED is not None and name in _TIMED:
+    if _TIMED is not None and (_TIME_ALL or name in _TIMED):
+        _TIMED.setdefault(name, [])
         start = torch.cuda.Event(enable_timing=True)
         end = torch.cuda.Event(enable_timing=True)
         start.record()
@@ -167,6 +170,27 @@ class _HashGridFn(torch.autograd.Function):
 
 def hashgrid(x, table, desc):
     return _HashGridFn.apply(x, table, desc)
+
+
+class _HashGridReuseFn(torch.autograd.Function):
+    """Autograd node for an encoding that was ALREADY computed (the visibility pre-pass ran the
+    gather on the same positions): forward hands it back, backward is the usual scatter."""
+
+    @staticmethod
+    def forward(ctx, x, table, desc, enc):
+        ctx.desc = desc
+        ctx.save_for_backward(x, table)
+        return enc.view_as(enc)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, table = ctx.saved_tensors
+        dtable, dx = hashgrid_bwd(ctx.desc, x, dout, table, ctx.needs_input_grad[0])
+        return dx, (dtable if ctx.needs_input_grad[1] else None), None, None
+
+
+def hashgrid_reuse(x, table, desc, enc):
+    return _HashGridReuseFn.apply(x, table, desc, enc)
 
 
 # --------------------------------------------------------------------------- #
@@ -474,3 +498,16 @@ def mlp_fwd(desc, params, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, ch
           _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(sig), _ptr(rgb),
           _stream())
     return sig, rgb
+
+
+def mlp_bwd(desc, params, grads_struct, enc, rays_o, rays_d, ray_indices, t_starts, t_ends,
+            d_sigmas, d_rgbs):
+    """dL/denc (M, L*2); weight gradients are accumulated into the buffers of `grads_struct`."""
+    n = ray_indices.numel()
+    d_enc = torch.empty_like(enc)
+    d_sigmas = _req(d_sigmas.reshape(-1), torch.float32, "d_sigmas")
+    d_rgbs = _req(d_rgbs, torch.float32, "d_rgbs")
+    _call("den_mlp_bwd", ctypes.byref(desc), ctypes.byref(params), ctypes.byref(grads_struct),
+          _ptr(enc), _ptr(rays_o), _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends),
+          _ptr(d_sigmas), _ptr(d_rgbs), n, _ptr(d_enc), _stream())
+    return d_enc

@@ -229,6 +229,26 @@ int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float*
                 const float* t_starts, const float* t_ends, int64_t n_samples, float* sigmas,
                 float* rgbs, void* stream);
 
+/* fp32 gradient accumulators of the MLP parameters (same shapes as den_field_params; the
+ * kernel ADDS into them with atomics, so the caller zeroes them or passes .grad buffers) */
+typedef struct den_field_grads {
+    float* wb1; float* bb1; float* wb2; float* bb2;
+    float* w1;  float* b1;  float* w2;  float* b2;  float* w3;  float* b3;
+} den_field_grads;
+
+/* Backward of den_mlp_fwd with forward recompute: d_enc (M, L*2) is written, the weight /
+ * bias gradients are accumulated into `g`.  d_sigmas (M), d_rgbs (M,C). */
+int den_mlp_bwd(const den_field_desc* f, const den_field_params* p, const den_field_grads* g,
+                const float* enc, const float* rays_o, const float* rays_d,
+                const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                const float* d_sigmas, const float* d_rgbs, int64_t n_samples, float* d_enc,
+                void* stream);
+
+/* Diagnostic: one tcgen05 GEMM in each operand-major flavour the MLP kernels use (see
+ * csrc/den_tc_probe.cu); pinned by tests/test_gpu_mlp_tc.py. */
+int den_tc_probe_gemm(int mode, const float* x, const float* w, float* d, int n, int k,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
