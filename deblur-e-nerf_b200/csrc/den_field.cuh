@@ -149,19 +149,52 @@ __device__ __forceinline__ void sh_degree4(const float d[3], float* out) {
 }
 
 // ---- activations (models/nerf.py:17-29, external/ngp.py:45-65) -----------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus(beta=100): max(z,0) + log1p(exp(-100|z|))/100.  torch's threshold branch (z > 0.2 ->
+// identity) only guards exp overflow; here exp(-100|z|) <= 1 and the correction is < 2.1e-11
+// beyond the threshold, i.e. below fp32 resolution of z, so the branch-free form is exact to
+// rounding.  6 instructions: FMUL, EX2, FADD, LG2, FMNMX, FFMA.
 __device__ __forceinline__ float softplus100(float z) {
-    // log1p(exp(100 z))/100 with torch's threshold 20 (z > 0.2 -> identity)
-    const float bz = 100.f * z;
-    if (bz > 20.f) return z;
-    return fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(bz))) * 0.01f;
+    const float e = ex2_approx(-144.26950408889634f * fabsf(z));          // exp(-100 |z|)
+    return fmaf(lg2_approx(1.f + e), 0.0069314718055994531f, fmaxf(z, 0.f));   // ln2 / 100
 }
 __device__ __forceinline__ float hidden_act(int id, float z) {
     return id == kActSoftplus100 ? softplus100(z) : fmaxf(z, 0.f);
 }
-// derivative expressed from the post-activation value h (softplus: 1 - exp(-100 h))
+// derivative expressed from the post-activation value h: sigmoid(100 z) = 1 - exp(-100 h)
 __device__ __forceinline__ float hidden_act_grad_from_out(int id, float h) {
-    if (id == kActSoftplus100) return h > 0.2f ? 1.f : 1.f - __expf(-100.f * h);
+    if (id == kActSoftplus100) return 1.f - ex2_approx(-144.26950408889634f * h);
     return h > 0.f ? 1.f : 0.f;
+}
+// vector forms with the activation switch hoisted out of the element loop
+template <int N>
+__device__ __forceinline__ void bias_hidden_act(int id, float (&h)[N], const float* __restrict__ bias) {
+    if (id == kActSoftplus100) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) h[j] = softplus100(h[j] + bias[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) h[j] = fmaxf(h[j] + bias[j], 0.f);
+    }
+}
+template <int N>
+__device__ __forceinline__ void mul_hidden_act_grad(int id, float (&d)[N], const float (&h)[N]) {
+    if (id == kActSoftplus100) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) d[j] *= 1.f - ex2_approx(-144.26950408889634f * h[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) d[j] = h[j] > 0.f ? d[j] : 0.f;
+    }
 }
 __device__ __forceinline__ float softplus1(float z) {
     return z > 20.f ? z : fmaxf(z, 0.f) + log1pf(expf(-fabsf(z)));
