@@ -511,3 +511,37 @@ def mlp_bwd(desc, params, grads_struct, enc, rays_o, rays_d, ray_indices, t_star
           _ptr(enc), _ptr(rays_o), _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends),
           _ptr(d_sigmas), _ptr(d_rgbs), n, _ptr(d_enc), _stream())
     return d_enc
+
+
+# --------------------------------------------------------------------------- #
+# pixel-bandwidth low-pass filter
+# --------------------------------------------------------------------------- #
+class _LpfFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, intensity, sample_dt, coef, n_channels):
+        intensity = _req(intensity, torch.float32, "intensity")
+        sample_dt = _req(sample_dt, torch.float32, "sample_dt")
+        coef = _req(coef, torch.float64, "coef")
+        S, N = intensity.shape[0], intensity[0].numel()
+        out = torch.empty((N, n_channels), dtype=torch.float32, device=intensity.device)
+        _call("den_lpf_fwd", _ptr(intensity), _ptr(sample_dt), _ptr(coef), S, N, n_channels,
+              _ptr(out), _stream())
+        ctx.n_channels = n_channels
+        ctx.save_for_backward(intensity, sample_dt, coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        intensity, sample_dt, coef = ctx.saved_tensors
+        d_out = _req(d_out, torch.float32, "d_out")
+        S, N = intensity.shape[0], intensity[0].numel()
+        d_int = torch.empty_like(intensity)
+        d_coef = torch.zeros_like(coef) if ctx.needs_input_grad[2] else None
+        _call("den_lpf_bwd", _ptr(intensity), _ptr(sample_dt), _ptr(coef), S, N, ctx.n_channels,
+              _ptr(d_out), _ptr(d_int), _ptr(d_coef), _stream())
+        return d_int, None, d_coef, None
+
+
+def lpf(intensity, sample_dt, coef, n_channels):
+    """(S,N) intensities, (S-1,N) sample spacings [ns], 5 fp64 coefficients -> (N, n_channels)."""
+    return _LpfFn.apply(intensity, sample_dt, coef, n_channels)

@@ -244,6 +244,23 @@ int den_mlp_bwd(const den_field_desc* f, const den_field_params* p, const den_fi
                 const float* d_sigmas, const float* d_rgbs, int64_t n_samples, float* d_enc,
                 void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Pixel-bandwidth low-pass filter — replaces PixelBandwidth.intensity_sample_to_weight,
+ * linearize_sys, discretized_sys_to_weight and the normalised weighted sum of
+ * weighted_it_sample_to_output_log_it (models/pixel_bandwidth.py:181-228,260-296,369-415)
+ * with control.foh_cont2discrete (utils/control.py:29-123).
+ * intensity (S,N) fp32; sample_dt_ns (S-1,N) fp32 [ns]; coef: 5 fp64 on the DEVICE
+ * (alpha0, alpha1, beta, omega_sf, omega_diff: a = alpha0 + alpha1 I, b = beta I);
+ * out (N, n_channels) fp32: n_channels == 2 -> (source-follower output, diff-amp output) for
+ * the reset call, 1 -> diff-amp output.  fp64 internally.
+ * ------------------------------------------------------------------------- */
+int den_lpf_fwd(const float* intensity, const float* sample_dt_ns, const double* coef, int32_t S,
+                int64_t N, int32_t n_channels, float* out, void* stream);
+/* d_intensity (S,N) written; d_coef (5, fp64, device) accumulated with atomics (may be NULL) */
+int den_lpf_bwd(const float* intensity, const float* sample_dt_ns, const double* coef, int32_t S,
+                int64_t N, int32_t n_channels, const float* d_out, float* d_intensity,
+                double* d_coef, void* stream);
+
 /* Diagnostic: one tcgen05 GEMM in each operand-major flavour the MLP kernels use (see
  * csrc/den_tc_probe.cu); pinned by tests/test_gpu_mlp_tc.py. */
 int den_tc_probe_gemm(int mode, const float* x, const float* w, float* d, int n, int k,

@@ -154,3 +154,54 @@ def _run_training_step_golden(cuda, pb_on):
 
 def test_training_step_pb_off_matches_reference_golden(den_lib, cuda):
     _run_training_step_golden(cuda, pb_on=False)
+
+
+@pytest.mark.parametrize("S", [8, 30])
+def test_pixel_bandwidth_filter_matches_oracle(den_lib, cuda, S):
+    """den_lpf_{fwd,bwd} (fp64 inside) vs the oracle PixelBandwidth evaluated in fp64 (truth) and
+    in fp32 (what the reference computes): outputs, dL/dI and the six parameter gradients, for
+    the reset call (two outputs) and a following non-reset call (reset state with gradient)."""
+    from deblur_e_nerf_b200 import pixel_bandwidth as pb_mod
+    from deblur_e_nerf_b200 import synthetic
+    from oracle import path_ref
+    calib = synthetic.calibration()
+    g = torch.Generator().manual_seed(S)
+    n = 300
+    out_ts = 40e6 + torch.rand(n, generator=g, dtype=torch.float64) * 100e6
+    gen = torch.full((S - 1, n), 0.5, dtype=torch.float64)
+    base = torch.exp(torch.randn(S, n, generator=g) * 1.5 - 2.0).clamp(1e-3, 5.0)   # 0.001 .. 5
+    wts = torch.randn(2, n, generator=g)
+
+    def run(module, dev, dtype):
+        leaf = base.to(dev, dtype).detach().clone().requires_grad_(True)
+
+        def fn(ts):
+            return (leaf, torch.tensor(1.0), 1.0, torch.ones_like(ts, dtype=torch.bool))
+        module.zero_grad()
+        y0, _ = module(gen.to(dev), (out_ts - 4e6).to(dev), fn, True)
+        y1, _ = module(gen.to(dev), out_ts.to(dev), fn, False)
+        loss = (y0 * wts[0].to(dev, y0.dtype)).sum() + (y1 * wts[1].to(dev, y1.dtype)).sum()
+        loss.backward()
+        grads = {k: v.grad.detach().cpu().double() for k, v in module.named_parameters()}
+        return y0.detach().cpu().double(), y1.detach().cpu().double(), leaf.grad.cpu().double(), grads
+
+    ora64 = path_ref.PixelBandwidth(calib, 0, 21, 0.95).double()
+    ora32 = path_ref.PixelBandwidth(calib, 0, 21, 0.95)
+    prod = pb_mod.PixelBandwidth(calib, 0, 21, dict(max_sample_lifetime=0.95)).to(cuda)
+    for k, v in ora32.state_dict().items():
+        assert torch.allclose(prod.state_dict()[k].cpu(), v), k
+    ora64.load_state_dict({k: v.double() for k, v in ora32.state_dict().items()})
+    t0, t1, tg, tp = run(ora64, "cpu", torch.float64)
+    r0, r1, rg, rp = run(ora32, "cpu", torch.float32)
+    p0, p1, pg, pp = run(prod, cuda, torch.float32)
+    assert _rel(p0, t0) < 1e-5 and _rel(p1, t1) < 1e-5
+    assert _rel(pg, tg) < 1e-4
+    for k in tp:
+        assert _rel(pp[k], tp[k]) < 1e-3, (k, pp[k], tp[k])
+    # and no further from the truth than the reference's own fp32 evaluation is
+    assert _rel(p0, t0) <= max(_rel(r0, t0), 1e-6) * 1.5
+    assert _rel(pg, tg) <= max(_rel(rg, tg), 1e-5) * 1.5
+
+
+def test_training_step_pb_on_matches_reference_golden(den_lib, cuda):
+    _run_training_step_golden(cuda, pb_on=True)
