@@ -452,7 +452,8 @@ class PixelBandwidth(torch.nn.Module):
         self.omega_c_dominant_min = 2 * math.pi * f_c_dominant_min
         self.register_buffer("min_ts", torch.as_tensor(min_ts).detach().clone(),
                              persistent=False)
-        self.cumprob = float(target_cumprob_max_lifetime)
+        # the reference keeps this as a float32 buffer (models/pixel_bandwidth.py:81-83)
+        self.cumprob = float(torch.tensor(target_cumprob_max_lifetime, dtype=torch.float32))
         self.register_buffer("tau_in_it_eff_prod", c["input_time_const_eff_it_prod"],
                              persistent=False)
         init = {

@@ -1,0 +1,85 @@
+"""The N>1 path on CPU: world_size-2 `gloo` processes exercising the data-parallel plumbing
+(flat gradient all-reduce = mean over ranks, parameter broadcast, the batch controller's
+cross-rank mean, max/sum-over-ranks timing helpers) exactly as bench.py / the trainer use it."""
+
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from deblur_e_nerf_b200 import ddp
+    r, lr, w = ddp.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world) and ddp.world_size() == world
+
+    torch.manual_seed(100 + rank)                       # ranks start different ...
+    model = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3)).double()
+    model.add_module("f32", torch.nn.Linear(3, 2))       # mixed dtypes -> one flat buffer each
+    ddp.broadcast_parameters(model)                      # ... and end up identical to rank 0
+    torch.manual_seed(7 + rank)                          # each rank its own shard of the batch
+    x = torch.randn(11, 5, dtype=torch.float64)
+    y = model[1](model[0](x))
+    loss = y.pow(2).mean() + model.f32(y.float()).pow(2).mean()
+    loss.backward()
+    local = [p.grad.clone() for p in model.parameters()]
+    reducer = ddp.FlatGradAllReduce(model.parameters())
+    nbytes = reducer()
+    assert nbytes == sum(p.numel() * p.element_size() for p in model.parameters())
+
+    class _R(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+            self.mean_samples_reduce_fn = None
+    ren = ddp.attach(_R())
+    mean = ren.mean_samples_reduce_fn(10.0 * (rank + 1))          # (10 + 20) / 2
+    tmax = ddp.max_over_ranks(3.0 + rank, torch.device("cpu"))
+    tsum = ddp.sum_over_ranks(3.0 + rank, torch.device("cpu"))
+    ddp.barrier()
+    torch.save({"params": [p.detach().clone() for p in model.parameters()],
+                "local": local, "reduced": [p.grad.clone() for p in model.parameters()],
+                "mean": mean, "max": tmax, "sum": tsum}, os.path.join(out_dir, f"rank{rank}.pt"))
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_world_size_2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    for a, b in zip(res[0]["params"], res[1]["params"]):
+        assert torch.equal(a, b)                                   # broadcast replicated rank 0
+    for k in range(len(res[0]["local"])):
+        mean = (res[0]["local"][k] + res[1]["local"][k]) / 2
+        assert torch.allclose(res[0]["reduced"][k], mean, rtol=1e-12, atol=0)
+        assert torch.equal(res[0]["reduced"][k], res[1]["reduced"][k])
+    assert res[0]["mean"] == res[1]["mean"] == 15.0
+    assert res[0]["max"] == res[1]["max"] == 4.0
+    assert res[0]["sum"] == res[1]["sum"] == 7.0
+
+
+def test_single_process_is_a_noop():
+    sys.path.insert(0, ROOT)
+    from deblur_e_nerf_b200 import ddp
+    assert ddp.world_size() == 1
+    lin = torch.nn.Linear(2, 2)
+    lin(torch.ones(1, 2)).sum().backward()
+    g = lin.weight.grad.clone()
+    assert ddp.FlatGradAllReduce(lin.parameters())() == 0
+    assert torch.equal(lin.weight.grad, g)
+    assert ddp.max_over_ranks(2.5, torch.device("cpu")) == 2.5

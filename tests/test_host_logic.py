@@ -1,0 +1,117 @@
+"""CPU tests of the product's host-side mirrors (no kernels involved) against the oracle:
+trajectory / SLERP, event-generation parameters, supervision timestamps, loss, the
+pixel-bandwidth sample schedule and the affine linearisation coefficients."""
+
+import pytest
+import torch
+
+from deblur_e_nerf_b200 import event_generation_params as egp
+from deblur_e_nerf_b200 import loss as loss_mod
+from deblur_e_nerf_b200 import pixel_bandwidth as pb_mod
+from deblur_e_nerf_b200 import renderer, synthetic, trajectories
+from oracle import path_ref
+
+import _scene
+
+
+def _close(a, b, tol=1e-6):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    assert ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item() <= tol
+
+
+@pytest.mark.parametrize("scene", ["synthetic", "eds"])
+def test_trajectory_matches_oracle(scene):
+    cfg = synthetic.CONFIGS[scene]
+    poses = synthetic.camera_poses(cfg, n_poses=60)
+    prod = trajectories.LinearTrajectory(poses)
+    ora = path_ref.LinearTrajectory(*poses)
+    g = torch.Generator().manual_seed(0)
+    ts = torch.rand(4, 50, generator=g, dtype=torch.float64) * float(poses[2][-1])
+    ts[0, 0], ts[0, 1] = float(poses[2][0]), float(poses[2][-1])
+    pp, rp = prod(ts)
+    po, ro = ora(ts)
+    _close(pp, po)
+    _close(rp, ro)
+    assert torch.allclose(rp @ rp.transpose(-1, -2), torch.eye(3).expand_as(rp), atol=1e-5)
+
+
+def test_event_params_match_oracle_and_keys():
+    calib = synthetic.calibration()
+    ct = egp.ContrastThreshold(calib, True)
+    rp = egp.RefractoryPeriod(calib, synthetic.MAX_REFRACTORY_PERIOD_NS)
+    oct_ = path_ref.ContrastThreshold(calib["pos_contrast_threshold"], calib["neg_contrast_threshold"])
+    orp = path_ref.RefractoryPeriod(calib["refractory_period"], synthetic.MAX_REFRACTORY_PERIOD_NS)
+    assert set(ct.state_dict()) == set(oct_.state_dict())
+    assert set(rp.state_dict()) == set(orp.state_dict())
+    ev = {"num_pos": torch.tensor([1, 0, 1]), "num_neg": torch.tensor([0, 1, 0]),
+          "start_ts": torch.tensor([1e6, 2e6, 3e6], dtype=torch.float64)}
+    out = rp(ct(ev))
+    _close(out["log_intensity_diff"], oct_(ev["num_pos"], ev["num_neg"]))
+    _close(out["start_ts"], orp(ev["start_ts"]), 1e-12)
+    _close(ct.mean_contrast_threshold, 0.259375, 1e-5)
+    assert out["start_ts"].dtype == torch.float64
+    # tau parametrisation keeps the gradient alive at the clamp (:204-224)
+    rp.refractory_period.backward()
+    assert rp.parametrizations._refractory_period.original.grad.abs() > 0
+
+
+def test_supervision_timestamps_and_loss_match_oracle():
+    cfg = _scene.scene_config("synthetic")
+    poses = synthetic.camera_poses(cfg, n_poses=100)
+    event, normalized = _scene.make_batch(cfg, poses, 200, 8, seed=3)
+    ev = {"start_ts": event["start_ts"].double() + 40560.0, "end_ts": event["end_ts"]}
+    d_p, s_p = renderer.EventRenderer.supervision_timestamps(ev, normalized, True, True)
+    d_o, s_o = path_ref.supervision_timestamps(ev["start_ts"], ev["end_ts"], normalized, True, True)
+    for a, b in ((d_p, d_o), (s_p, s_o)):
+        for key in ("ts_diff", "start_ts", "end_ts"):
+            _close(a[key], b[key], 1e-14)
+    assert torch.all(s_p["start_ts"] >= d_p["start_ts"]) and torch.all(s_p["end_ts"] <= d_p["end_ts"])
+
+    g = torch.Generator().manual_seed(1)
+    n = 200
+    weight = dict(log_intensity_diff=1.0, log_intensity_tv=1e-3)
+    err = dict(log_intensity_diff="huber", log_intensity_tv="l1")
+    norm = dict(log_intensity_diff=True, log_intensity_tv=True)
+    lp = loss_mod.Loss(weight, err, norm)
+    lo = path_ref.EventLoss(weight, err, norm)
+    pred_d = torch.randn(n, generator=g)
+    pred_s = torch.randn(n, generator=g) * 0.1
+    valid_d = torch.rand(n, generator=g) > 0.3
+    valid_s = torch.rand(n, generator=g) > 0.3
+    log_diff = torch.where(torch.rand(n, generator=g) > 0.5, 0.26875, -0.25)
+    mean_ct = torch.tensor(0.259375)
+    be = {"log_intensity_diff": log_diff, "start_ts": ev["start_ts"], "end_ts": ev["end_ts"].double()}
+    out_p = lp.compute(dict(be), {"log_intensity_diff": pred_d, "ts_diff": d_p["ts_diff"], "is_valid": valid_d},
+                       {"log_intensity_diff": pred_s, "is_valid": valid_s}, mean_ct)
+    out_o = lo.compute(log_diff, be["start_ts"], be["end_ts"],
+                       {"log_intensity_diff": pred_d, "ts_diff": d_o["ts_diff"], "is_valid": valid_d},
+                       {"log_intensity_diff": pred_s, "is_valid": valid_s}, mean_ct)
+    for key in out_o:
+        _close(out_p[key], out_o[key], 1e-6)
+
+
+@pytest.mark.parametrize("S", [8, 30])
+def test_pixel_bandwidth_schedule_and_coefficients(S):
+    calib = synthetic.calibration()
+    prod = pb_mod.PixelBandwidth(calib, 0, 21, dict(max_sample_lifetime=0.95))
+    ora = path_ref.PixelBandwidth(calib, 0, 21, 0.95)
+    assert set(prod.state_dict()) == set(ora.state_dict())
+    for k, v in ora.state_dict().items():
+        _close(prod.state_dict()[k], v, 1e-7)
+    gen = torch.full((S - 1, 5), 0.5, dtype=torch.float64)
+    _close(prod.sample_lifetimes(gen), ora.sample_lifetimes(gen), 1e-14)
+    life = prod.sample_lifetimes(gen)
+    assert life[-1].abs().max() == 0 and torch.all(life[:-1] > life[1:])      # oldest first
+    # a = alpha0 + alpha1 I and b = beta I reproduce linearized_sys_params (:181-194)
+    it = torch.tensor([1e-3, 0.05, 0.7, 3.0], dtype=torch.float64)
+    c = prod.coefficients()
+    tau_in = ora.tau_in_it_eff_prod.double() / it
+    tau_mil = ora.param("tau_mil_it_eff_prod").double() / it
+    tau_out = ora.param("tau_out").double()
+    prod_ = (tau_in + tau_mil) * tau_out
+    two_zeta_wn = (tau_in + tau_out + (1 / ora.param("A_amp_inv").double() + 1) * tau_mil) / prod_
+    wn_sq = (1 / ora.param("A_loop_inv").double() + 1) / prod_
+    _close(c[0] + c[1] * it, two_zeta_wn, 1e-6)
+    _close(c[2] * it, wn_sq, 1e-6)
+    _close(c[3], 1 / ora.param("tau_sf").double(), 1e-6)
+    _close(c[4], 1 / ora.param("tau_diff").double(), 1e-6)
