@@ -79,16 +79,16 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         // ===================== MMA warp: one issue per round =====================
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             __syncthreads();
-            if (lane == 0) { tc::tc_fence_after_sync(); mma_fwd<kWidth, kEncDim>(tmem_base, T32, Wb1); tc::mma_commit(bar); }
+            { tc::tc_fence_after_sync(); mma_fwd<kWidth, kEncDim>(tmem_base, T32, Wb1); tc::mma_commit(bar); }
             __syncthreads();
-            if (lane == 0) { tc::tc_fence_after_sync(); mma_fwd<kBaseOut, kWidth>(tmem_base, T64, Wb2); tc::mma_commit(bar); }
+            { tc::tc_fence_after_sync(); mma_fwd<kBaseOut, kWidth>(tmem_base, T64, Wb2); tc::mma_commit(bar); }
             if (kFull) {
                 __syncthreads();
-                if (lane == 0) { tc::tc_fence_after_sync(); mma_fwd<kWidth, kHeadIn>(tmem_base, T32, W1); tc::mma_commit(bar); }
+                { tc::tc_fence_after_sync(); mma_fwd<kWidth, kHeadIn>(tmem_base, T32, W1); tc::mma_commit(bar); }
                 __syncthreads();
-                if (lane == 0) { tc::tc_fence_after_sync(); mma_fwd<kWidth, kWidth>(tmem_base, T64, W2); tc::mma_commit(bar); }
+                { tc::tc_fence_after_sync(); mma_fwd<kWidth, kWidth>(tmem_base, T64, W2); tc::mma_commit(bar); }
                 __syncthreads();
-                if (lane == 0) { tc::tc_fence_after_sync(); mma_fwd<kOutN, kWidth>(tmem_base, T64, W3); tc::mma_commit(bar); }
+                { tc::tc_fence_after_sync(); mma_fwd<kOutN, kWidth>(tmem_base, T64, W3); tc::mma_commit(bar); }
             }
             __syncwarp();
         }

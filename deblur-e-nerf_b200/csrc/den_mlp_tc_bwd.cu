@@ -119,7 +119,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #define DEN_ISSUE(...)                                                        \
     __syncthreads();                                                          \
-    if (lane == 0) { tc::tc_fence_after_sync(); __VA_ARGS__; tc::mma_commit(bar); }
+    { tc::tc_fence_after_sync(); __VA_ARGS__; tc::mma_commit(bar); }
             DEN_ISSUE(mma_fwd<kWidth, kEncDim>(D, Tenc, Wb1))
             DEN_ISSUE(mma_fwd<kBaseOut, kWidth>(D, Thb, Wb2))
             DEN_ISSUE(mma_fwd<kWidth, kHeadIn>(D, Tin1, W1))

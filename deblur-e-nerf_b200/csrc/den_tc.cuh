@@ -84,23 +84,30 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int m, int n, bool a_mn_m
            ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+// D[tmem] (+)= A[smem] * B[smem].  Called by ALL lanes of the (converged) MMA warp: the
+// descriptor arithmetic stays warp-uniform (uniform datapath, no R2UR per operand) and one
+// elected lane issues the instruction.
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          bool accumulate) {
     const uint32_t acc = accumulate ? 1u : 0u;
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, leader;\n\t"
+        "elect.sync _|leader, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "@leader tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         :
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
-// make the mbarrier track completion of all MMAs issued so far by this thread
+// make the mbarrier track completion of all MMAs issued so far (same elected lane)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                     smem_u32(bar))
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred leader;\n\t"
+        "elect.sync _|leader, 0xffffffff;\n\t"
+        "@leader tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        :
+        : "r"(smem_u32(bar))
+        : "memory");
 }
 
 // ---- TMEM -> registers (warp-collective; thread i of the warp gets lane base+i) -------

@@ -52,7 +52,7 @@ tc_probe_kernel(int mode, const float* __restrict__ x, const float* __restrict__
     tc::tc_fence_after_sync();
     const uint32_t tmem = *slot;
 
-    if (tid == 0) {
+    if (warp == 0) {
         if (mode == 0) {
             const uint32_t idesc = tc::instr_desc_bf16(128, n, false, false);
             const uint32_t sbo = (k / 8) * 128;
