@@ -93,7 +93,9 @@ _SIGNATURES = {
                            _I64, _P, _P, _P]),
     "den_tc_probe_gemm": (_INT, [_INT, _P, _P, _P, _INT, _INT, _P]),
     "den_mlp_bwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _c.POINTER(FieldGrads),
-                           _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
+                           _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
+    "den_contract_samples_bwd": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _I64, _P,
+                                        _P, _P]),
     "den_lpf_fwd": (_INT, [_P, _P, _P, _I32, _I64, _I32, _P, _P]),
     "den_lpf_bwd": (_INT, [_P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
     "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P,

@@ -176,7 +176,7 @@ accumulate_fwd_kernel(const float* __restrict__ weights, const float* __restrict
         for (int k = 0; k < dim; ++k) {
             float acc = 0.f;
             for (int i = beg + lane; i < end; i += 32)
-                acc += weights[i] * (values ? values[(int64_t)i * dim + k] : 1.f);
+                acc += (weights ? weights[i] : 1.f) * (values ? values[(int64_t)i * dim + k] : 1.f);
             acc = warp_sum(acc);
             if (lane == 0) out[r * dim + k] = acc;
         }

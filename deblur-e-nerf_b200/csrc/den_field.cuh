@@ -148,6 +148,59 @@ __device__ __forceinline__ void sh_degree4(const float d[3], float* out) {
     out[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
 
+// dL/d(dir) = J_SH(dir)^T dsh  (reverse mode of sh_degree4; the tau-gradient path)
+__device__ __forceinline__ void sh_degree4_grad(const float d[3], const float* g, float out[3]) {
+    const float x = d[0], y = d[1], z = d[2];
+    const float x2 = x * x, y2 = y * y, z2 = z * z;
+    const float c1 = 0.48860251190291987f, c2 = 1.0925484305920792f, c3 = 0.94617469575755997f,
+                c5 = 0.54627421529603959f, c6 = 0.59004358992664352f, c7 = 2.8906114426405538f,
+                c8 = 0.45704579946446572f, c9 = 0.3731763325901154f, c10 = 1.4453057213202769f;
+    out[0] = -c1 * g[3] + c2 * y * g[4] - c2 * z * g[7] + 2.f * c5 * x * g[8] - 6.f * c6 * x * y * g[9] +
+             c7 * y * z * g[10] + c8 * (1.f - 5.f * z2) * g[13] + 2.f * c10 * x * z * g[14] +
+             c6 * (3.f * y2 - 3.f * x2) * g[15];
+    out[1] = -c1 * g[1] + c2 * x * g[4] - c2 * z * g[5] - 2.f * c5 * y * g[8] +
+             c6 * (3.f * y2 - 3.f * x2) * g[9] + c7 * x * z * g[10] + c8 * (1.f - 5.f * z2) * g[11] -
+             2.f * c10 * y * z * g[14] + 6.f * c6 * x * y * g[15];
+    out[2] = c1 * g[2] - c2 * y * g[5] + 2.f * c3 * z * g[6] - c2 * x * g[7] + c7 * x * y * g[10] -
+             10.f * c8 * y * z * g[11] + c9 * (15.f * z2 - 3.f) * g[12] - 10.f * c8 * x * z * g[13] +
+             c10 * (x2 - y2) * g[14];
+}
+
+// dL/dpos = J_contract(pos)^T du  (reverse mode of contract_position)
+__device__ __forceinline__ void contract_position_grad(const den_field_desc& f, const float pos[3],
+                                                       const float du[3], float dpos[3]) {
+    float inv_ext[3], u[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        inv_ext[d] = 1.f / (f.aabb[d + 3] - f.aabb[d]);
+        u[d] = (pos[d] - f.aabb[d]) * inv_ext[d];
+    }
+    if (f.contraction == DEN_CONTRACT_SPHERE) {
+        float v[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[d] = u[d] * 2.f - 1.f;
+        const float n = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        float g[3] = {du[0] * 0.25f, du[1] * 0.25f, du[2] * 0.25f};
+        if (n > 1.f) {
+            const float s = 2.f / n - 1.f / (n * n);
+            const float k = (-2.f / (n * n * n) + 2.f / (n * n * n * n)) * (v[0] * g[0] + v[1] * g[1] + v[2] * g[2]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) g[d] = s * g[d] + k * v[d];
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dpos[d] = g[d] * 2.f * inv_ext[d];
+    } else if (f.contraction == DEN_CONTRACT_TANH) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float t = tanhf(u[d] - 0.5f);
+            dpos[d] = du[d] * 0.5f * (1.f - t * t) * inv_ext[d];
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dpos[d] = du[d] * inv_ext[d];
+    }
+}
+
 // ---- activations (models/nerf.py:17-29, external/ngp.py:45-65) -----------------
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

@@ -212,9 +212,53 @@ __global__ void contract_samples_kernel(const __grid_constant__ den_field_desc f
     }
 }
 
+// reverse mode of contract_samples_kernel w.r.t. the ray: per sample dL/dpos and dL/dpos * tm/2
+// (pos = o + d * tm / 2); the per-ray sums are taken by den_accumulate_fwd
+__global__ void contract_samples_bwd_kernel(const __grid_constant__ den_field_desc f,
+                                            const float* __restrict__ rays_o,
+                                            const float* __restrict__ rays_d,
+                                            const int32_t* __restrict__ ray_indices,
+                                            const float* __restrict__ t_starts,
+                                            const float* __restrict__ t_ends,
+                                            const float* __restrict__ d_unit, int64_t n,
+                                            float* __restrict__ d_pos, float* __restrict__ d_pos_t) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = ray_indices[i];
+        const float tm = t_starts[i] + t_ends[i];
+        float pos[3], g[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            pos[d] = __ldg(rays_o + 3 * r + d) + (__ldg(rays_d + 3 * r + d) * tm) * 0.5f;
+        const float du[3] = {d_unit[3 * i], d_unit[3 * i + 1], d_unit[3 * i + 2]};
+        contract_position_grad(f, pos, du, g);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            d_pos[3 * i + d] = g[d];
+            d_pos_t[3 * i + d] = g[d] * tm * 0.5f;
+        }
+    }
+}
+
 }  // namespace den
 
 extern "C" {
+
+int den_contract_samples_bwd(const den_field_desc* f, const float* rays_o, const float* rays_d,
+                             const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                             const float* d_unit, int64_t n, float* d_pos, float* d_pos_t,
+                             void* stream) {
+    using namespace den;
+    DEN_CHECK_ARG(f != nullptr, "null descriptor");
+    DEN_CHECK_ARG(n >= 0, "negative sample count");
+    if (n == 0) return DEN_OK;
+    DEN_CHECK_ARG(rays_o && rays_d && ray_indices && t_starts && t_ends && d_unit && d_pos && d_pos_t,
+                  "null pointer");
+    contract_samples_bwd_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
+        *f, rays_o, rays_d, ray_indices, t_starts, t_ends, d_unit, n, d_pos, d_pos_t);
+    DEN_CHECK_LAUNCH();
+    return DEN_OK;
+}
 
 int den_contract_samples(const den_field_desc* f, const float* rays_o, const float* rays_d,
                          const int32_t* ray_indices, const float* t_starts, const float* t_ends,

@@ -62,7 +62,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                   const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                   const int32_t* __restrict__ ray_indices, const float* __restrict__ t_starts,
                   const float* __restrict__ t_ends, const float* __restrict__ d_sigmas,
-                  const float* __restrict__ d_rgbs, int64_t n, float* __restrict__ d_enc) {
+                  const float* __restrict__ d_rgbs, int64_t n, float* __restrict__ d_enc,
+                  float* __restrict__ d_dirs) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BwdSmem::bar);
@@ -273,6 +274,12 @@ mul_hidden_act_grad<kBwdCols>(f.hidden_act, dl, h);
                     const float s = warp_sum(d16[j]);
                     if (lane == 0) atomicAdd(&s_small[j], s);
                 }
+            } else if (cg == 1 && d_dirs != nullptr) {
+                // dL/d(view direction) through the SH encoding (only the tau path needs it)
+                float dsh[16], dd[3];
+                tmem_ld_cols<16>(tmem_lane + kColScratch, dsh);
+                sh_degree4_grad(dir, dsh, dd);
+                if (valid) { d_dirs[3 * i] = dd[0]; d_dirs[3 * i + 1] = dd[1]; d_dirs[3 * i + 2] = dd[2]; }
             }
             publish();
 
@@ -350,7 +357,7 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
                            const den_field_grads* g, const float* enc, const float* rays_o,
                            const float* rays_d, const int32_t* ray_indices, const float* t_starts,
                            const float* t_ends, const float* d_sigmas, const float* d_rgbs,
-                           int64_t n, float* d_enc, void* stream) {
+                           int64_t n, float* d_enc, float* d_dirs, void* stream) {
     using namespace den;
     int rc = check_field(f, p, true);
     if (rc) return rc;
@@ -367,7 +374,7 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
     cudaFuncSetAttribute(mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)BwdSmem::total);
     mlp_bwd_tc_kernel<<<grid, kBwdThreads, BwdSmem::total, as_stream(stream)>>>(
-        *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, d_enc);
+        *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, d_enc, d_dirs);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }

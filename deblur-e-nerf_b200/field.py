@@ -107,26 +107,33 @@ class _MlpTcFn(torch.autograd.Function):
     forward per tile and returns dL/denc plus every weight / bias gradient (den_mlp_bwd)."""
 
     @staticmethod
-    def forward(ctx, field, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, *weights):
-        sig, rgb = ops.mlp_fwd(field.field_desc(), field.field_params(), enc, rays_o, rays_d,
-                               ray_indices, t_starts, t_ends, field.radiance_dim)
+    def forward(ctx, field, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets,
+                precomputed, *weights):
+        if precomputed is not None:
+            # the visibility pre-pass already evaluated these very samples with these weights
+            sig, rgb = (t.view_as(t) for t in precomputed)
+        else:
+            sig, rgb = ops.mlp_fwd(field.field_desc(), field.field_params(), enc, rays_o, rays_d,
+                                   ray_indices, t_starts, t_ends, field.radiance_dim)
         ctx.field = field
-        ctx.save_for_backward(enc, rays_o, rays_d, ray_indices, t_starts, t_ends)
-        ctx.mark_non_differentiable()
+        ctx.save_for_backward(enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets)
         return sig, rgb
 
     @staticmethod
     def backward(ctx, d_sig, d_rgb):
         field = ctx.field
-        enc, rays_o, rays_d, ray_indices, t_starts, t_ends = ctx.saved_tensors
+        enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets = ctx.saved_tensors
+        need_d_dirs = ctx.needs_input_grad[3]          # only when the rays carry a gradient (tau)
         weights = field.param_tensors()[1:]
         grads = [torch.zeros_like(w) for w in weights]
         gs = FieldGrads()
         for name, t in zip(("wb1", "bb1", "wb2", "bb2", "w1", "b1", "w2", "b2", "w3", "b3"), grads):
             setattr(gs, name, t.data_ptr())
-        d_enc = ops.mlp_bwd(field.field_desc(), field.field_params(), gs, enc, rays_o, rays_d,
-                            ray_indices, t_starts, t_ends, d_sig.contiguous(), d_rgb.contiguous())
-        return (None, d_enc, None, None, None, None, None, *grads)
+        d_enc, d_dirs = ops.mlp_bwd(field.field_desc(), field.field_params(), gs, enc, rays_o,
+                                    rays_d, ray_indices, t_starts, t_ends, d_sig.contiguous(),
+                                    d_rgb.contiguous(), need_d_dirs)
+        d_rays_d = ops.segment_sum(d_dirs, offsets) if need_d_dirs else None
+        return (None, d_enc, None, d_rays_d, None, None, None, None, None, *grads)
 
 
 class NGPradianceField(torch.nn.Module):
@@ -220,28 +227,38 @@ class NGPradianceField(torch.nn.Module):
                              t_starts, t_ends, self.radiance_dim if full else 0, n_dev)
 
     # ---------------------------------------------- tensor-core path (with autograd) --
-    def encode_samples(self, rays_o, rays_d, ray_indices, t_starts, t_ends, enc=None):
-        """Hash-grid encoding (M, L*2) of marched samples as an autograd node on the table;
-        `enc` re-uses an encoding already computed on the same samples."""
-        u = ops.contract_samples(self.field_desc(), rays_o, rays_d, ray_indices, t_starts, t_ends)
+    def encode_samples(self, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets, enc=None):
+        """Hash-grid encoding (M, L*2) of marched samples as an autograd node on the table (and on
+        the rays when they require grad); `enc` re-uses an encoding already computed on the same
+        samples."""
+        if rays_o.requires_grad or rays_d.requires_grad:
+            u = ops.contract_samples_autograd(self.field_desc(), rays_o, rays_d, ray_indices,
+                                              t_starts, t_ends, offsets)
+        else:
+            u = ops.contract_samples(self.field_desc(), rays_o, rays_d, ray_indices, t_starts,
+                                     t_ends)
         if enc is not None:
             return ops.hashgrid_reuse(u, self.encoding.params, self.encoding.desc, enc)
         return ops.hashgrid(u, self.encoding.params, self.encoding.desc)
 
-    def mlp_samples(self, enc, rays_o, rays_d, ray_indices, t_starts, t_ends):
+    def mlp_samples(self, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets,
+                    precomputed=None):
         """(sigma (M,), rgb (M,C)) from encodings on the tensor cores, differentiable in the
-        encodings and in every MLP parameter."""
-        return _MlpTcFn.apply(self, enc, rays_o, rays_d, ray_indices, t_starts, t_ends,
-                              *self.param_tensors()[1:])
+        encodings and in every MLP parameter.  `precomputed=(sigma, rgb)` skips the forward
+        launch when the pre-pass has already produced them (the backward recomputes anyway)."""
+        return _MlpTcFn.apply(self, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets,
+                              precomputed, *self.param_tensors()[1:])
 
     @torch.no_grad()
-    def density_samples_tc(self, rays_o, rays_d, ray_indices, t_starts, t_ends):
-        """Visibility pre-pass: (sigma (M,), enc (M, L*2)) — gather + density-only MLP."""
+    def eval_samples_tc(self, rays_o, rays_d, ray_indices, t_starts, t_ends, full=True):
+        """Gather + tensor-core MLP without autograd: (sigma (M,), rgb (M,C) | None, enc (M, L*2)).
+        This is the reference's no-grad density pre-pass (external/utils.py:68-81); evaluating
+        the colour head in the same launch lets the grad pass re-use every output."""
         u = ops.contract_samples(self.field_desc(), rays_o, rays_d, ray_indices, t_starts, t_ends)
         enc = ops.hashgrid_fwd(self.encoding.desc, u, self.encoding.params)
-        sig, _ = ops.mlp_fwd(self.field_desc(), self.field_params(), enc, rays_o, rays_d,
-                             ray_indices, t_starts, t_ends, 0)
-        return sig, enc
+        sig, rgb = ops.mlp_fwd(self.field_desc(), self.field_params(), enc, rays_o, rays_d,
+                               ray_indices, t_starts, t_ends, self.radiance_dim if full else 0)
+        return sig, rgb, enc
 
     # --------------------------------------------------- reference-signature methods --
     def _contract(self, x):

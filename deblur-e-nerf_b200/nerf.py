@@ -152,33 +152,33 @@ class NeRF(torch.nn.Module):
         n_rays = o.shape[0]
         ray_idx, t0, t1, offsets = self._march(o, d, jitter)
 
-        enc_pre = None
+        needs_grad = torch.is_grad_enabled() and any(
+            p.requires_grad for p in field.parameters())
+        pre = None                      # (sigma, rgb, enc) of the current sample set, if known
         if (self.alpha_thre > 0.0 or self.early_stop_eps > 0.0) and ray_idx.numel() > 0:
             alpha_thre = self.alpha_thre
             if alpha_thre > 0.0:
                 alpha_thre = min(alpha_thre, self.occupancy_grid.occs.mean().item())
-            sigma, enc_pre = field.density_samples_tc(o, d, ray_idx, t0, t1)
-            alphas = ops.alpha_from_sigma(sigma, t0, t1)
+            pre = field.eval_samples_tc(o, d, ray_idx, t0, t1, full=True)
+            alphas = ops.alpha_from_sigma(pre[0], t0, t1)
             mask, counts = ops.visibility(alphas, offsets, self.early_stop_eps, alpha_thre)
             offsets_out = ops.exclusive_scan_i32(counts)
             total = int(offsets_out[-1].item())
             if total < ray_idx.numel():
                 ray_idx, t0, t1 = ops.compact(mask, offsets, offsets_out, ray_idx, t0, t1, total)
                 offsets = offsets_out
-                enc_pre = None          # positions changed: the encoding is recomputed below
-
-        needs_grad = torch.is_grad_enabled() and any(
-            p.requires_grad for p in field.parameters())
+                keep = mask.bool()      # survivors keep their positions: outputs stay valid
+                pre = tuple(t[keep] for t in pre)
+        if pre is None:
+            pre = field.eval_samples_tc(o, d, ray_idx, t0, t1, full=True) if ray_idx.numel() \
+                else (torch.empty(0, device=o.device),
+                      torch.empty(0, field.radiance_dim, device=o.device),
+                      torch.empty(0, field.encoding.n_output_dims, device=o.device))
+        sigma, rgb, enc = pre
         if needs_grad:
-            enc = field.encode_samples(o, d, ray_idx, t0, t1, enc=enc_pre)
-            sigma, rgb = field.mlp_samples(enc, o, d, ray_idx, t0, t1)
-        else:
-            if enc_pre is None:
-                _, enc_pre = field.density_samples_tc(o, d, ray_idx, t0, t1) \
-                    if ray_idx.numel() else (None, torch.empty(0, field.encoding.n_output_dims,
-                                                               device=o.device))
-            sigma, rgb = ops.mlp_fwd(field.field_desc(), field.field_params(), enc_pre, o, d,
-                                     ray_idx, t0, t1, field.radiance_dim)
+            enc = field.encode_samples(o, d, ray_idx, t0, t1, offsets, enc=enc)
+            sigma, rgb = field.mlp_samples(enc, o, d, ray_idx, t0, t1, offsets,
+                                           precomputed=(sigma, rgb))
         bkgd = self.render_bkgd
         colour, opacity, depth = ops.composite(sigma, rgb, t0, t1, offsets, bkgd)
         return colour, opacity, depth, ray_idx.numel()

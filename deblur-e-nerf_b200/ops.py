@@ -501,16 +501,55 @@ def mlp_fwd(desc, params, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, ch
 
 
 def mlp_bwd(desc, params, grads_struct, enc, rays_o, rays_d, ray_indices, t_starts, t_ends,
-            d_sigmas, d_rgbs):
-    """dL/denc (M, L*2); weight gradients are accumulated into the buffers of `grads_struct`."""
+            d_sigmas, d_rgbs, need_d_dirs=False):
+    """dL/denc (M, L*2) [and dL/d(view dir) (M,3)]; weight gradients are accumulated into the
+    buffers of `grads_struct`."""
     n = ray_indices.numel()
     d_enc = torch.empty_like(enc)
+    d_dirs = torch.zeros((n, 3), dtype=torch.float32, device=enc.device) if need_d_dirs else None
     d_sigmas = _req(d_sigmas.reshape(-1), torch.float32, "d_sigmas")
     d_rgbs = _req(d_rgbs, torch.float32, "d_rgbs")
     _call("den_mlp_bwd", ctypes.byref(desc), ctypes.byref(params), ctypes.byref(grads_struct),
           _ptr(enc), _ptr(rays_o), _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends),
-          _ptr(d_sigmas), _ptr(d_rgbs), n, _ptr(d_enc), _stream())
-    return d_enc
+          _ptr(d_sigmas), _ptr(d_rgbs), n, _ptr(d_enc), _ptr(d_dirs), _stream())
+    return d_enc, d_dirs
+
+
+def segment_sum(values, offsets):
+    """(M,D) per-sample vectors -> (R,D) per-ray sums (den_accumulate_fwd with unit weights)."""
+    values = _req(values, torch.float32, "values")
+    n_rays = offsets.numel() - 1
+    out = torch.empty((n_rays, values.shape[-1]), dtype=torch.float32, device=values.device)
+    _call("den_accumulate_fwd", None, _ptr(values), _ptr(offsets), n_rays, values.shape[-1],
+          _ptr(out), _stream())
+    return out
+
+
+class _ContractSamplesFn(torch.autograd.Function):
+    """Unit-cube sample positions as a function of the rays (differentiable in rays_o / rays_d:
+    the refractory-period gradient path)."""
+
+    @staticmethod
+    def forward(ctx, desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets):
+        ctx.desc = desc
+        ctx.save_for_backward(rays_o, rays_d, ray_indices, t_starts, t_ends, offsets)
+        return contract_samples(desc, rays_o, rays_d, ray_indices, t_starts, t_ends)
+
+    @staticmethod
+    def backward(ctx, d_unit):
+        rays_o, rays_d, ray_indices, t_starts, t_ends, offsets = ctx.saved_tensors
+        n = ray_indices.numel()
+        d_unit = _req(d_unit, torch.float32, "d_unit")
+        d_pos = torch.empty_like(d_unit)
+        d_pos_t = torch.empty_like(d_unit)
+        _call("den_contract_samples_bwd", ctypes.byref(ctx.desc), _ptr(rays_o), _ptr(rays_d),
+              _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _ptr(d_unit), n, _ptr(d_pos),
+              _ptr(d_pos_t), _stream())
+        return None, segment_sum(d_pos, offsets), segment_sum(d_pos_t, offsets), None, None, None, None
+
+
+def contract_samples_autograd(desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets):
+    return _ContractSamplesFn.apply(desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets)
 
 
 # --------------------------------------------------------------------------- #

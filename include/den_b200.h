@@ -143,7 +143,7 @@ int den_weight_from_alpha_fwd(const float* alphas, const int32_t* offsets, int64
                               float* weights, void* stream);
 int den_weight_from_alpha_bwd(const float* alphas, const int32_t* offsets, int64_t n_rays,
                               const float* dweights, float* dalphas, void* stream);
-/* out (R,D) = per-ray sum of w * v (v NULL -> D = 1, v = 1); deterministic (no atomics) */
+/* out (R,D) = per-ray sum of w * v (v NULL -> D = 1, v = 1; w NULL -> 1); deterministic */
 int den_accumulate_fwd(const float* weights, const float* values, const int32_t* offsets,
                        int64_t n_rays, int32_t dim, float* out, void* stream);
 int den_accumulate_bwd(const float* weights, const float* values, const int32_t* ray_indices,
@@ -237,12 +237,21 @@ typedef struct den_field_grads {
 } den_field_grads;
 
 /* Backward of den_mlp_fwd with forward recompute: d_enc (M, L*2) is written, the weight /
- * bias gradients are accumulated into `g`.  d_sigmas (M), d_rgbs (M,C). */
+ * bias gradients are accumulated into `g`.  d_sigmas (M), d_rgbs (M,C).  d_dirs (M,3) or NULL:
+ * dL/d(view direction) through the SH encoding. */
 int den_mlp_bwd(const den_field_desc* f, const den_field_params* p, const den_field_grads* g,
                 const float* enc, const float* rays_o, const float* rays_d,
                 const int32_t* ray_indices, const float* t_starts, const float* t_ends,
                 const float* d_sigmas, const float* d_rgbs, int64_t n_samples, float* d_enc,
-                void* stream);
+                float* d_dirs, void* stream);
+/* Reverse mode of den_contract_samples w.r.t. the rays (the refractory-period gradient path,
+ * models/trajectories.py -> models/nerf.py:206-228 -> external/utils.py:83-96): per sample
+ * d_pos = J^T d_unit and d_pos_t = d_pos * (t0+t1)/2; den_accumulate_fwd sums them per ray
+ * into dL/d rays_o and dL/d rays_d. */
+int den_contract_samples_bwd(const den_field_desc* f, const float* rays_o, const float* rays_d,
+                             const int32_t* ray_indices, const float* t_starts, const float* t_ends,
+                             const float* d_unit, int64_t n_samples, float* d_pos, float* d_pos_t,
+                             void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Pixel-bandwidth low-pass filter — replaces PixelBandwidth.intensity_sample_to_weight,

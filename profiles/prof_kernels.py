@@ -31,9 +31,9 @@ def main():
     field = nerf.radiance_field
     for rep in range(2):
         ray_idx, t0, t1, offsets = nerf._march(o, d, None)
-        sig, enc = field.density_samples_tc(o, d, ray_idx, t0, t1)
-        enc_g = field.encode_samples(o, d, ray_idx, t0, t1, enc=enc)
-        sigma, rgb = field.mlp_samples(enc_g, o, d, ray_idx, t0, t1)
+        sig, rgb0, enc = field.eval_samples_tc(o, d, ray_idx, t0, t1)
+        enc_g = field.encode_samples(o, d, ray_idx, t0, t1, offsets, enc=enc)
+        sigma, rgb = field.mlp_samples(enc_g, o, d, ray_idx, t0, t1, offsets, precomputed=(sig, rgb0))
         col, opa, dep = ops.composite(sigma, rgb, t0, t1, offsets, nerf.render_bkgd)
         (col.sum() + 0.1 * opa.sum()).backward()
         torch.cuda.synchronize()

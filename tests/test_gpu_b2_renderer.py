@@ -141,11 +141,6 @@ def _run_training_step_golden(cuda, pb_on):
     assert set(ref) <= set(grads), set(ref) - set(grads)
     worst = {}
     for key in ref:
-        if key.startswith("refractory_period."):
-            # dL/dtau flows through the ray geometry (hash-grid INPUT gradient, SH derivative,
-            # pose interpolation): only config 4 (EDS, tau unfrozen) needs it and the fused
-            # sample path does not carry it yet (DESIGN.md "open rows": A7 tau path)
-            continue
         worst[key] = _rel(grads[key], ref[key])
     bad = {k: v for k, v in worst.items()
            if v > (5e-3 if ("pixel_bandwidth" in k or "refractory" in k) else TOL)}

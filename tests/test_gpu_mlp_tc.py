@@ -107,7 +107,8 @@ def test_mlp_bwd_tc_matches_fp32_autograd(den_lib, cuda, small, n):
 
     field.zero_grad()
     enc_tc = enc.clone().requires_grad_(True)
-    sig, rgb = field.mlp_samples(enc_tc, x, d, ray_idx, t0, t0)
+    offsets = torch.arange(n + 1, dtype=torch.int32, device=cuda)
+    sig, rgb = field.mlp_samples(enc_tc, x, d, ray_idx, t0, t0, offsets)
     assert _rel(sig, sig_ref) < 5e-5 and _rel(rgb, rgb_ref) < 5e-5
     ((sig * w_sig).sum() + (rgb * w_rgb).sum()).backward()
     torch.cuda.synchronize()
