@@ -57,6 +57,10 @@ KERNEL_BYTES_PER_SAMPLE = {
 }
 # tensor-pipe kernels: algorithmic FLOP per sample
 KERNEL_FLOP_PER_SAMPLE = {"den_mlp_fwd": 18432, "den_mlp_bwd": 55296}
+# dram__bytes_read.sum + dram__bytes_write.sum per sample from the ncu --set full capture of
+# profiles/r01_ncu_full_top_kernels.md (1.284 M samples per launch)
+NCU_DRAM_BYTES_PER_SAMPLE = {"den_mlp_bwd": (190.64e6 + 122.26e6) / 1284068,
+                             "den_hashgrid_bwd": (225.43e6 + 5.47e6) / 1284068}
 
 
 def parse_args():
@@ -374,28 +378,41 @@ def run_ours(args):
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             peaks = json.load(fh)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback"
+    tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     per_step_samples = samples_seen / args.steps
-    candidates = {k: v for k, v in timings.items()
-                  if v[0] > 0 and k in KERNEL_BYTES_PER_SAMPLE}
+    samples_per_launch = per_step_samples / 4        # one launch per render call per kernel
     kernel_table = {k: {"launches": v[0], "ms_total": round(v[1], 3),
                         "share_of_step": round(v[1] / ms_total, 4)} for k, v in timings.items()
                     if v[0] > 0}
-    roofline = None
-    if candidates:
-        name = max(candidates, key=lambda k: candidates[k][1])
-        n_launch, ms_k = candidates[name]
-        # every timed launch of these kernels processes the surviving samples of one render call
-        samples_per_launch = per_step_samples / 4
-        bytes_per_launch = KERNEL_BYTES_PER_SAMPLE[name] * samples_per_launch
-        achieved = bytes_per_launch / (ms_k / n_launch * 1e-3) / 1e9
-        roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                    "peak_source": peak_src,
-                    "note": "algorithmic bytes/sample x samples per launch / mean launch time "
-                            "(CUDA events on the launching stream); the 48 MiB table is "
-                            "L2-resident, fraction is of measured HBM copy bandwidth",
-                    "avg_launch_ms": ms_k / n_launch, "samples_per_launch": samples_per_launch}
+
+    def roof(name):
+        n_launch, ms_k = timings[name]
+        avg_s = ms_k / n_launch * 1e-3
+        if name in KERNEL_FLOP_PER_SAMPLE:
+            achieved = KERNEL_FLOP_PER_SAMPLE[name] * samples_per_launch / avg_s / 1e12
+            return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
+                    "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                    "traffic": NCU_DRAM_BYTES_PER_SAMPLE.get(name, 0) * samples_per_launch or None,
+                    "peak_source": peak_src + " bf16 burst", "avg_launch_ms": avg_s * 1e3,
+                    "samples_per_launch": samples_per_launch,
+                    "note": "algorithmic FLOP/sample (fp32-equivalent, the 3-pass bf16 split is "
+                            "counted once) x samples per launch / mean launch time (CUDA events "
+                            "on the launching stream)"}
+        achieved = KERNEL_BYTES_PER_SAMPLE[name] * samples_per_launch / avg_s / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": NCU_DRAM_BYTES_PER_SAMPLE.get(name, 0) * samples_per_launch or None,
+                "peak_source": peak_src + " HBM copy", "avg_launch_ms": avg_s * 1e3,
+                "samples_per_launch": samples_per_launch,
+                "note": "algorithmic bytes/sample x samples per launch / mean launch time (CUDA "
+                        "events on the launching stream); the 48 MiB table is L2-resident, the "
+                        "fraction is of measured HBM copy bandwidth"}
+
+    rated = [k for k, v in timings.items() if v[0] > 0 and
+             (k in KERNEL_BYTES_PER_SAMPLE or k in KERNEL_FLOP_PER_SAMPLE)]
+    roofline = roof(max(rated, key=lambda k: timings[k][1])) if rated else None
+    other_rooflines = [roof(k) for k in sorted(rated, key=lambda k: -timings[k][1])[1:4]]
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -412,7 +429,7 @@ def run_ours(args):
         "mean_samples_per_ray": model.logged["train/mean_num_samples_per_ray"],
         "hash_gather_gbs": HASH_GATHER_BYTES * global_samples / (ms_step * 1e-3) / 1e9,
         "e2e": e2e, "gpu_launches": launches, "clocks": clock_info, "roofline": roofline,
-        "kernels": kernel_table, "occ_update_ms": occ_ms, "cpu_baseline": cpu,
+        "other_rooflines": other_rooflines, "kernels": kernel_table, "occ_update_ms": occ_ms, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
 

@@ -45,7 +45,13 @@ def broadcast_parameters(module, src=0):
     if world_size() == 1:
         return
     for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src)
+        data = t.data
+        if data.is_contiguous():
+            dist.broadcast(data, src)
+        else:           # e.g. a transposed rotation buffer: broadcast a packed copy
+            packed = data.contiguous()
+            dist.broadcast(packed, src)
+            data.copy_(packed)
 
 
 class FlatGradAllReduce:
