@@ -1,62 +1,209 @@
 // Backward of the tensor-core MLP: forward recompute + input gradient + weight gradients,
-// fused per 128-sample tile (tcgen05.mma, TMEM accumulators; sm_100a).
+// fused per 128-sample tile (tcgen05.mma, TMEM accumulators; sm_100a), TWO tiles in flight.
 //
 // Replaces the autograd of MLP.forward / SHEncoder / activations under
 // NGPradianceField.forward (external/ngp.py:269-280) — in the reference ~30 cuBLAS and
 // elementwise launches that read and write every (M,64) activation twice.  Here nothing but
-// enc (128 B/sample in), the two upstream gradients and dL/denc (128 B/sample out) touches
-// HBM: the forward activations are recomputed into shared-memory operand tiles, which are
-// then consumed three ways without being rewritten —
+// enc (128 B/sample in, read twice), the two upstream gradients and dL/denc (128 B/sample out)
+// touches HBM: the forward activations are recomputed into shared-memory operand tiles, which
+// are then consumed three ways without being rewritten —
 //   K-major  A operand        : next layer forward,  dX = dY * W
 //   MN-major A/B operand      : dW += dY^T * X   (K = the 128 samples of the tile)
 // Weight-gradient accumulators (64 x N, fp32) stay in TMEM across all tiles of a CTA and are
-// flushed once with atomics; bias gradients of the 64-wide layers come from one extra MMA
-// against a tile of ones.
+// flushed once with atomics.  Bias gradients ride along: every activation tile carries a
+// column of ones (its own 8-column chunk, or the zero-padded 32nd input of the head), so
+// dW += dY^T [X | 1] yields db in the extra accumulator column for free.
 //
-// Thread layout: see den_mlp_tc.cuh (S = 4: 16 epilogue warps + 1 MMA warp, 1 CTA per SM —
-// the five activation tiles + gradient tiles + weights fill 213 KB of shared memory).
+// Pipeline (v3).  v2 ran ONE tile through ten strictly serial rounds (epilogue -> bar.sync ->
+// MMA issue -> commit -> mbarrier wait): ncu showed 43 % of all warp samples spinning on the
+// MMA mbarrier, 20 % issue utilisation and 11 % tensor-pipe activity
+// (profiles/r01_ncu_full_top_kernels.md).  v3 keeps two tiles ("slots") resident per CTA:
+//   * 2 x 8 epilogue warps, one group per slot (warp quadrant q = warp % 4 serves TMEM lanes
+//     32q..32q+31 = tile rows; half hf = (warp / 4) % 2 owns columns [32 hf, 32 hf + 32) of
+//     every 64-wide layer, processed 16 at a time to bound registers);
+//   * 1 MMA warp that polls the two slots' "operands ready" mbarriers and issues whichever
+//     round is ready, so one slot's tensor work overlaps the other slot's SIMT epilogue;
+//   * the (C <= 3)-row output layer runs on the SIMT side (no 64 x 16 GEMM, no h2 operand tile).
+// Shared memory per slot: E (128 x 40: enc | ones, later [SH | geo | 1], later dy, later enc
+// again), H (128 x 72: hb | ones, later h1, later hb again) and D (128 x 64: the current
+// dL/dz tile) = 88 KB; 2 slots + 36 KB of weight tiles = 223 KB.  The price of fitting two
+// slots: hb is re-derived from its pre-activation (parked in TMEM) and enc is re-read from
+// L2/HBM for the last round (+12 % epilogue instructions, no extra MMA round).
 #include "den_mlp_tc.cuh"
 
 namespace den {
 
 using namespace mlp;
 
-constexpr int kBwdS = 4;
-constexpr int kBwdCols = kWidth / kBwdS;                  // 16 accumulator columns per thread
-constexpr int kBwdEpiThreads = 128 * kBwdS;
-constexpr int kBwdThreads = kBwdEpiThreads + 32;
-constexpr uint32_t kBwdTmemCols = 256;
+namespace bwd {
+
+constexpr int kSlots = 2;
+constexpr int kGroupThreads = 256;                         // 8 epilogue warps per slot
+constexpr int kEpiThreads = kSlots * kGroupThreads;
+constexpr int kThreads = kEpiThreads + 32;                 // + the MMA warp
+constexpr int kMmaWarp = kEpiThreads / 32;
+constexpr uint32_t kTmemCols = 512;
 
 // TMEM column plan
-constexpr uint32_t kColScratch = 0;      // 64: forward / dX results (M = 128)
-constexpr uint32_t kColDW1 = 64;         // 32: dW1    (out 64 x in 32)
-constexpr uint32_t kColDW2 = 96;         // 64: dW2    (64 x 64)
-constexpr uint32_t kColDWb1 = 160;       // 32: dWb1   (64 x 32)
-constexpr uint32_t kColDWb2T = 192;      // 16: dWb2^T (in 64 x out 16)
-constexpr uint32_t kColDW3T = 208;       // 16: dW3^T  (in 64 x out 16)
-constexpr uint32_t kColDB1 = 224;        // 8
-constexpr uint32_t kColDB2 = 232;        // 8
-constexpr uint32_t kColDBb1 = 240;       // 8
+constexpr uint32_t kColZ = 0;            // + 128 * slot : 64 scratch columns (forward / dX results)
+constexpr uint32_t kColP = 64;           // + 128 * slot : 64 columns, base-layer pre-activation (kept)
+constexpr uint32_t kColDW2 = 256;        // 72: dW2 (out 64 x in 64) | db2 x 8
+constexpr uint32_t kColDW1 = 336;        // 32: dW1 (64 x 31) | db1 in column 31
+constexpr uint32_t kColDWb1 = 368;       // 40: dWb1 (64 x 32) | dbb1 x 8
+constexpr uint32_t kColDWb2T = 408;      // 16: dWb2^T (in 64 x out 16)
 
-struct BwdSmem {
-    static constexpr int w3f = Weights::end;                               // fp32 W3 rows (4 x 64)
-    static constexpr int small_acc = w3f + 4 * kWidth * 4;                 // dbb2[16] | db3[4] | pad
-    static constexpr int ones = (small_acc + 32 * 4 + 127) / 128 * 128;    // (8, 128) bf16 ones
-    static constexpr int t_enc = ones + 8 * kTile * 2;
-    static constexpr int t_hb = t_enc + Tile<kTile, kEncDim>::bytes;
-    static constexpr int t_in1 = t_hb + Tile<kTile, kWidth>::bytes;
-    static constexpr int t_h1 = t_in1 + Tile<kTile, kHeadIn>::bytes;
-    static constexpr int t_h2 = t_h1 + Tile<kTile, kWidth>::bytes;
-    static constexpr int t_d64 = t_h2 + Tile<kTile, kWidth>::bytes;
-    static constexpr int t_d16 = t_d64 + Tile<kTile, kWidth>::bytes;
-    static constexpr int bar = t_d16 + Tile<kTile, kBaseOut>::bytes;
-    static constexpr int tmem_ptr = bar + 8;
-    static constexpr int total = tmem_ptr + 8;
+// operand tile with CH 16-byte chunks (8 bf16 columns each) per row: hi half then lo half
+template <int ROWS, int CH>
+struct OpTile {
+    static constexpr uint32_t rg = CH * 128;               // bytes between groups of 8 rows
+    static constexpr uint32_t half = ROWS * CH * 16;       // bytes of the hi (or lo) half
+    static constexpr uint32_t bytes = 2 * half;
+    static __device__ __forceinline__ uint32_t off(int r, int chunk) {
+        return (uint32_t)((r >> 3) * (int)rg + chunk * 128 + (r & 7) * 16);
+    }
 };
-static_assert(BwdSmem::t_enc % 128 == 0, "tile alignment");
-static_assert(BwdSmem::total <= 227 * 1024, "shared-memory plan exceeds 227 KB");
+using TE = OpTile<kTile, 5>;     // enc | ones     /  [SH | geo | 1]  /  dy
+using TH = OpTile<kTile, 9>;     // hb | ones      /  h1
+using TD = OpTile<kTile, 8>;     // dL/dz of the current 64-wide layer
+using TWb1 = OpTile<kWidth, 4>;  // (64, 32)
+using TWb2 = OpTile<kBaseOut, 8>;// (16, 64)
+using TW1 = OpTile<kWidth, 4>;   // (64, 32)
+using TW2 = OpTile<kWidth, 8>;   // (64, 64)
 
-__global__ void __launch_bounds__(kBwdThreads, 1)
+struct Smem {
+    static constexpr int wb1 = 0;
+    static constexpr int wb2 = wb1 + TWb1::bytes;
+    static constexpr int w1 = wb2 + TWb2::bytes;
+    static constexpr int w2 = w1 + TW1::bytes;
+    static constexpr int bias = w2 + TW2::bytes;          // fp32: bb1 64 | bb2 16 | b1 64 | b2 64 | b3 16
+    static constexpr int w3f = bias + (3 * kWidth + kBaseOut + 16) * 4;   // fp32 W3 rows (3 x 64)
+    static constexpr int acc = w3f + 3 * kWidth * 4;      // fp32: dW3 (3 x 64) | dbb2 16 | db3 4 | pad
+    static constexpr int zx = acc + (3 * kWidth + 32) * 4;               // per slot (128, 2, 4) fp32
+    static constexpr int bars = zx + kSlots * kTile * 2 * 4 * 4;         // ready[2], done[2]
+    static constexpr int tmem_ptr = bars + 4 * 8;
+    static constexpr int slot0 = (tmem_ptr + 8 + 127) / 128 * 128;
+    static constexpr int e = 0;                            // offsets inside a slot
+    static constexpr int h = e + TE::bytes;
+    static constexpr int d = h + TH::bytes;
+    static constexpr int slot_bytes = d + TD::bytes;
+    static constexpr int total = slot0 + kSlots * slot_bytes;
+};
+static_assert(Smem::slot_bytes % 128 == 0 && Smem::slot0 % 128 == 0, "tile alignment");
+static_assert(Smem::total <= 227 * 1024, "shared-memory plan exceeds 227 KB");
+
+// ---- descriptors / GEMM issue (all lanes of the MMA warp, one elected lane issues) ------------
+struct OpDesc {                     // hi and lo descriptors of one operand view
+    Desc hi, lo;
+    uint32_t kstep;                 // byte advance per K step of 16 elements
+};
+template <class T>
+__device__ __forceinline__ OpDesc kmajor(const uint8_t* base) {         // K along the tile's columns
+    return {make_desc(base, 128, T::rg), make_desc(base + T::half, 128, T::rg), 256u};
+}
+template <class T>
+__device__ __forceinline__ OpDesc mnmajor(const uint8_t* base) {        // K along the tile's rows
+    return {make_desc(base, T::rg, 128), make_desc(base + T::half, T::rg, 128), 2u * T::rg};
+}
+// D (+)= A * B with the 3-product bf16 split, KSTEPS steps of 16 along K
+template <int KSTEPS>
+__device__ __forceinline__ void gemm3(uint32_t tmem_d, const OpDesc& a, const OpDesc& b, uint32_t idesc,
+                                      bool accumulate) {
+    // short K: fully unrolled; K = 128 (the dW GEMMs): rolled, one running offset per operand, so the
+    // issuing warp does not keep 48 descriptors live (it spilled them)
+    constexpr int kUnroll = KSTEPS <= 4 ? KSTEPS : 2;
+    uint32_t ao = 0, bo = 0;
+#pragma unroll kUnroll
+    for (int ks = 0; ks < KSTEPS; ++ks, ao += a.kstep, bo += b.kstep)
+        tc::mma_bf16(tmem_d, a.hi.at(ao), b.hi.at(bo), idesc, accumulate || ks > 0);
+    ao = 0, bo = 0;
+#pragma unroll kUnroll
+    for (int ks = 0; ks < KSTEPS; ++ks, ao += a.kstep, bo += b.kstep)
+        tc::mma_bf16(tmem_d, a.lo.at(ao), b.hi.at(bo), idesc, true);
+    ao = 0, bo = 0;
+#pragma unroll kUnroll
+    for (int ks = 0; ks < KSTEPS; ++ks, ao += a.kstep, bo += b.kstep)
+        tc::mma_bf16(tmem_d, a.hi.at(ao), b.lo.at(bo), idesc, true);
+}
+
+// ---- mbarrier helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(tc::smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void group_sync(int slot) {       // the 8 epilogue warps of one slot
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(kGroupThreads) : "memory");
+}
+
+// ---- epilogue helpers ----------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void store16(uint8_t* tile, int r, int chunk0, const float (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint4 hi, lo;
+        split8(&v[8 * c], hi, lo);
+        const uint32_t o = T::off(r, chunk0 + c);
+        *reinterpret_cast<uint4*>(tile + o) = hi;
+        *reinterpret_cast<uint4*>(tile + T::half + o) = lo;
+    }
+}
+template <class T>
+__device__ __forceinline__ void load16(const uint8_t* tile, int r, int chunk0, float (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t o = T::off(r, chunk0 + c);
+        const uint4 h = *reinterpret_cast<const uint4*>(tile + o);
+        const uint4 l = *reinterpret_cast<const uint4*>(tile + T::half + o);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[8 * c + 2 * q] = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+            v[8 * c + 2 * q + 1] = __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+        }
+    }
+}
+// operands written by this thread are handed to the MMA warp
+__device__ __forceinline__ void publish(uint64_t* ready) {
+    tc::fence_smem_to_async_proxy();
+    tc::tc_fence_before_sync();
+    mbar_arrive(ready);
+}
+__device__ __forceinline__ void await_mma(uint64_t* done, uint32_t& phase) {
+    tc::mbar_wait(done, phase);
+    phase ^= 1;
+    tc::tc_fence_after_sync();
+}
+// butterfly "reduce-scatter": on return lane l holds, in v[0], the sum over the warp of v[l]
+template <int N>
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane) {
+    static_assert(N == 32 || N == 16, "N must be 16 or 32");
+#pragma unroll
+    for (int off = N / 2; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; ++k) {
+            const float send = up ? v[k] : v[k + off];
+            const float keep = up ? v[k + off] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+}  // namespace bwd
+
+using namespace bwd;
+
+__global__ void __launch_bounds__(kThreads, 1)
 mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constant__ den_field_params p,
                   const __grid_constant__ den_field_grads g, const float* __restrict__ enc,
                   const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -66,238 +213,380 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                   float* __restrict__ d_dirs) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + BwdSmem::bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BwdSmem::tmem_ptr);
-    const float* s_bb1 = reinterpret_cast<const float*>(smem + Weights::bias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);       // ready[0..1], done[0..1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::tmem_ptr);
+    const float* s_bb1 = reinterpret_cast<const float*>(smem + Smem::bias);
     const float* s_bb2 = s_bb1 + kWidth;
     const float* s_b1 = s_bb2 + kBaseOut;
     const float* s_b2 = s_b1 + kWidth;
     const float* s_b3 = s_b2 + kWidth;
-    float* s_w3f = reinterpret_cast<float*>(smem + BwdSmem::w3f);
-    float* s_small = reinterpret_cast<float*>(smem + BwdSmem::small_acc);   // [0,16) dbb2, [16,20) db3
-
-    const Tile<kWidth, kEncDim> Wb1(smem + Weights::wb1);
-    const Tile<kBaseOut, kWidth> Wb2(smem + Weights::wb2);
-    const Tile<kWidth, kHeadIn> W1(smem + Weights::w1);
-    const Tile<kWidth, kWidth> W2(smem + Weights::w2);
-    const Tile<kOutN, kWidth> W3(smem + Weights::w3);
-    const Tile<kTile, kEncDim> Tenc(smem + BwdSmem::t_enc);
-    const Tile<kTile, kWidth> Thb(smem + BwdSmem::t_hb);
-    const Tile<kTile, kHeadIn> Tin1(smem + BwdSmem::t_in1);
-    const Tile<kTile, kWidth> Th1(smem + BwdSmem::t_h1);
-    const Tile<kTile, kWidth> Th2(smem + BwdSmem::t_h2);
-    const Tile<kTile, kWidth> Td64(smem + BwdSmem::t_d64);
-    const Tile<kTile, kBaseOut> Td16(smem + BwdSmem::t_d16);
-    uint8_t* ones = smem + BwdSmem::ones;
+    float* s_w3f = reinterpret_cast<float*>(smem + Smem::w3f);
+    float* s_dw3 = reinterpret_cast<float*>(smem + Smem::acc);             // (3, 64)
+    float* s_dbb2 = s_dw3 + 3 * kWidth;                                    // 16
+    float* s_db3 = s_dbb2 + kBaseOut;                                      // 4
 
     const int enc_dim = f.grid.n_levels * 2;
     const int C = f.channels;
 
-    // ---- setup ---------------------------------------------------------------------------
-    load_all_weights(smem, f, p, true);
-    for (int i = tid; i < 4 * kWidth; i += blockDim.x)
+    // ---- setup ---------------------------------------------------------------------------------
+    tc::load_weight_split(smem + Smem::wb1, smem + Smem::wb1 + TWb1::half, p.wb1, kWidth, enc_dim, kWidth, kEncDim);
+    tc::load_weight_split(smem + Smem::wb2, smem + Smem::wb2 + TWb2::half, p.wb2, kBaseOut, kWidth, kBaseOut, kWidth);
+    tc::load_weight_split(smem + Smem::w1, smem + Smem::w1 + TW1::half, p.w1, kWidth, kShDim + kGeo, kWidth, kHeadIn);
+    tc::load_weight_split(smem + Smem::w2, smem + Smem::w2 + TW2::half, p.w2, kWidth, kWidth, kWidth, kWidth);
+    {
+        float* b = reinterpret_cast<float*>(smem + Smem::bias);
+        load_padded(b, p.bb1, kWidth, kWidth);
+        load_padded(b + kWidth, p.bb2, kBaseOut, kBaseOut);
+        load_padded(b + kWidth + kBaseOut, p.b1, kWidth, kWidth);
+        load_padded(b + 2 * kWidth + kBaseOut, p.b2, kWidth, kWidth);
+        load_padded(b + 3 * kWidth + kBaseOut, p.b3, C, 16);
+    }
+    for (int i = tid; i < 3 * kWidth; i += kThreads) {
         s_w3f[i] = (i / kWidth) < C ? __ldg(p.w3 + i) : 0.f;
-    if (tid < 32) s_small[tid] = 0.f;
-    for (int i = tid; i < 8 * kTile; i += blockDim.x)
-        reinterpret_cast<__nv_bfloat16*>(ones)[i] = __float2bfloat16_rn(1.0f);
+        s_dw3[i] = 0.f;
+    }
+    if (tid < 32) s_dbb2[tid] = 0.f;                       // dbb2 | db3 | pad
+    // the "ones" chunks (bf16 1.0 in the hi half, 0 in the lo half): E chunk 4, H chunk 8
+    for (int i = tid; i < kSlots * kTile; i += kThreads) {
+        const int s = i / kTile, r = i - s * kTile;
+        uint8_t* slot = smem + Smem::slot0 + s * Smem::slot_bytes;
+        const uint4 one = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(slot + Smem::e + TE::off(r, 4)) = one;
+        *reinterpret_cast<uint4*>(slot + Smem::e + TE::half + TE::off(r, 4)) = zero;
+        *reinterpret_cast<uint4*>(slot + Smem::h + TH::off(r, 8)) = one;
+        *reinterpret_cast<uint4*>(slot + Smem::h + TH::half + TH::off(r, 8)) = zero;
+    }
     if (tid == 0) {
-        tc::mbar_init(bar, 1);
+        tc::mbar_init(&bars[0], kGroupThreads);
+        tc::mbar_init(&bars[1], kGroupThreads);
+        tc::mbar_init(&bars[2], 1);
+        tc::mbar_init(&bars[3], 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, kBwdTmemCols);
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
     tc::fence_smem_to_async_proxy();
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t D = tmem_base + kColScratch;
     const int64_t n_tiles = (n + kTile - 1) / kTile;
-    const bool have_tiles = (int64_t)blockIdx.x < n_tiles;
+    // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0 .. my_tiles-1; slot s takes k = s, s+2, ...
+    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
-    if (warp == kBwdEpiThreads / 32) {
-        // ===================== MMA warp: ten issue rounds per tile =====================
-        bool acc = false;       // weight-gradient accumulators already hold earlier tiles
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-#define DEN_ISSUE(...)                                                        \
-    __syncthreads();                                                          \
-    { tc::tc_fence_after_sync(); __VA_ARGS__; tc::mma_commit(bar); }
-            DEN_ISSUE(mma_fwd<kWidth, kEncDim>(D, Tenc, Wb1))
-            DEN_ISSUE(mma_fwd<kBaseOut, kWidth>(D, Thb, Wb2))
-            DEN_ISSUE(mma_fwd<kWidth, kHeadIn>(D, Tin1, W1))
-            DEN_ISSUE(mma_fwd<kWidth, kWidth>(D, Th1, W2))
-            DEN_ISSUE(mma_fwd<kOutN, kWidth>(D, Th2, W3))
-            DEN_ISSUE(mma_dw<kBaseOut>(tmem_base + kColDW3T, Th2, Td16, acc);      // dW3^T += h2^T d3
-                      mma_dw<kWidth>(tmem_base + kColDW2, Td64, Th1, acc);         // dW2  += d2^T h1
-                      mma_colsum(tmem_base + kColDB2, Td64, ones, acc);            // db2
-                      mma_dx<kWidth, kWidth>(D, Td64, W2))                         // dh1 = d2 W2
-            DEN_ISSUE(mma_dw<kHeadIn>(tmem_base + kColDW1, Td64, Tin1, acc);       // dW1 += d1^T in1
-                      mma_colsum(tmem_base + kColDB1, Td64, ones, acc);            // db1
-                      mma_dx<kHeadIn, kWidth>(D, Td64, W1))                        // din1 = d1 W1
-            DEN_ISSUE(mma_dw<kBaseOut>(tmem_base + kColDWb2T, Thb, Td16, acc);     // dWb2^T += hb^T dy
-                      mma_dx<kWidth, kBaseOut>(D, Td16, Wb2))                      // dhb = dy Wb2
-            DEN_ISSUE(mma_dw<kEncDim>(tmem_base + kColDWb1, Td64, Tenc, acc);      // dWb1 += db1^T enc
-                      mma_colsum(tmem_base + kColDBb1, Td64, ones, acc);           // dbb1
-                      mma_dx<kEncDim, kWidth>(D, Td64, Wb1))                       // denc = db1 Wb1
-#undef DEN_ISSUE
-            acc = true;
-            __syncwarp();
+    if (warp == kMmaWarp) {
+        // ===================== MMA warp: issue whichever slot has operands ready =====================
+        const uint8_t* wb1 = smem + Smem::wb1;
+        const uint8_t* wb2 = smem + Smem::wb2;
+        const uint8_t* w1 = smem + Smem::w1;
+        const uint8_t* w2 = smem + Smem::w2;
+        int64_t rounds_left[kSlots];
+        int round[kSlots] = {0, 0};
+        uint32_t phase[kSlots] = {0, 0};
+        for (int s = 0; s < kSlots; ++s) rounds_left[s] = 8 * ((my_tiles + 1 - s) / 2);
+        bool acc2 = false, acc1 = false, accb1 = false, accb2 = false;
+        uint32_t idle = 0;
+        while (rounds_left[0] > 0 || rounds_left[1] > 0) {
+            bool progressed = false;
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (rounds_left[s] <= 0) continue;
+                if (!mbar_try(&bars[s], phase[s])) continue;
+                phase[s] ^= 1;
+                progressed = true;
+                tc::tc_fence_after_sync();
+                uint8_t* slot = smem + Smem::slot0 + s * Smem::slot_bytes;
+                const uint32_t Z = tmem_base + kColZ + 128u * s, P = tmem_base + kColP + 128u * s;
+                const uint8_t* E = slot + Smem::e;
+                const uint8_t* H = slot + Smem::h;
+                const uint8_t* D = slot + Smem::d;
+                switch (round[s]) {
+                case 0:     // z_b1 = enc Wb1^T                                    (kept in P)
+                    gemm3<kEncDim / 16>(P, kmajor<TE>(E), kmajor<TWb1>(wb1),
+                                        tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    break;
+                case 1:     // y = hb Wb2^T
+                    gemm3<kWidth / 16>(Z, kmajor<TH>(H), kmajor<TWb2>(wb2),
+                                       tc::instr_desc_bf16(128, kBaseOut, false, false), false);
+                    break;
+                case 2:     // z1 = [SH | geo | 1] W1^T
+                    gemm3<kHeadIn / 16>(Z, kmajor<TE>(E), kmajor<TW1>(w1),
+                                        tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    break;
+                case 3:     // z2 = h1 W2^T
+                    gemm3<kWidth / 16>(Z, kmajor<TH>(H), kmajor<TW2>(w2),
+                                       tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    break;
+                case 4:     // dW2 | db2 += d2^T [h1 | 1];  dh1 = d2 W2
+                    gemm3<kTile / 16>(tmem_base + kColDW2, mnmajor<TD>(D), mnmajor<TH>(H),
+                                      tc::instr_desc_bf16(64, 72, true, true), acc2);
+                    acc2 = true;
+                    gemm3<kWidth / 16>(Z, kmajor<TD>(D), mnmajor<TW2>(w2),
+                                       tc::instr_desc_bf16(128, kWidth, false, true), false);
+                    break;
+                case 5:     // dW1 | db1 += d1^T [SH | geo | 1];  din1 = d1 W1
+                    gemm3<kTile / 16>(tmem_base + kColDW1, mnmajor<TD>(D), mnmajor<TE>(E),
+                                      tc::instr_desc_bf16(64, kHeadIn, true, true), acc1);
+                    acc1 = true;
+                    gemm3<kWidth / 16>(Z, kmajor<TD>(D), mnmajor<TW1>(w1),
+                                       tc::instr_desc_bf16(128, kHeadIn, false, true), false);
+                    break;
+                case 6:     // dWb2^T += hb^T dy;  dhb = dy Wb2
+                    gemm3<kTile / 16>(tmem_base + kColDWb2T, mnmajor<TH>(H), mnmajor<TE>(E),
+                                      tc::instr_desc_bf16(64, kBaseOut, true, true), accb2);
+                    accb2 = true;
+                    gemm3<kBaseOut / 16>(Z, kmajor<TE>(E), mnmajor<TWb2>(wb2),
+                                         tc::instr_desc_bf16(128, kWidth, false, true), false);
+                    break;
+                default:    // dWb1 | dbb1 += db1^T [enc | 1];  denc = db1 Wb1
+                    gemm3<kTile / 16>(tmem_base + kColDWb1, mnmajor<TD>(D), mnmajor<TE>(E),
+                                      tc::instr_desc_bf16(64, 40, true, true), accb1);
+                    accb1 = true;
+                    gemm3<kWidth / 16>(Z, kmajor<TD>(D), mnmajor<TWb1>(wb1),
+                                       tc::instr_desc_bf16(128, kEncDim, false, true), false);
+                    break;
+                }
+                tc::mma_commit(&bars[2 + s]);
+                round[s] = (round[s] + 1) & 7;
+                --rounds_left[s];
+            }
+            if (progressed) {
+                idle = 0;
+            } else if (++idle > (1u << 26)) {
+                if (lane == 0) printf("den_b200: mlp_bwd MMA warp starved (block %d)\n", blockIdx.x);
+                __trap();
+            }
         }
     } else {
-        // ===================== epilogue warps =====================
-        const int q = warp & 3, cg = warp >> 2;
+        // ===================== epilogue warps: one group of 8 per slot =====================
+        const int slot_id = warp >> 3;
+        const int q = warp & 3, hf = (warp >> 2) & 1;
         const int row = q * 32 + lane;
-        const int col0 = kBwdCols * cg;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint8_t* slot = smem + Smem::slot0 + slot_id * Smem::slot_bytes;
+        uint8_t* E = slot + Smem::e;
+        uint8_t* H = slot + Smem::h;
+        uint8_t* D = slot + Smem::d;
+        uint64_t* ready = &bars[slot_id];
+        uint64_t* done = &bars[2 + slot_id];
+        float* zx = reinterpret_cast<float*>(smem + Smem::zx) + slot_id * (kTile * 2 * 4);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t Z = lane_base + kColZ + 128u * slot_id, P = lane_base + kColP + 128u * slot_id;
+        const int hact = f.hidden_act;
         uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+
+        // load this thread's 16 encoding features of row i into E chunks (2 hf, 2 hf + 1)
+        auto stage_enc = [&](int64_t i, bool valid) {
+            float x[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = 0.f;
+            if (valid) {
+                const float4* src = reinterpret_cast<const float4*>(enc + i * enc_dim + 16 * hf);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4)
+                    if (16 * hf + 4 * v4 < enc_dim) {
+                        const float4 v = __ldg(src + v4);
+                        x[4 * v4] = v.x; x[4 * v4 + 1] = v.y; x[4 * v4 + 2] = v.z; x[4 * v4 + 3] = v.w;
+                    }
+            }
+            store16<TE>(E, row, 2 * hf, x);
+        };
+        // hb = act(P + bb1) for this thread's 32 columns -> H
+        auto stage_hb = [&]() {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float h[16];
+                tmem_ld_cols<16>(P + 32 * hf + 16 * c, h);
+                bias_hidden_act<16>(hact, h, s_bb1 + 32 * hf + 16 * c);
+                store16<TH>(H, row, 4 * hf + 2 * c, h);
+            }
+        };
+
+        for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
+            const int64_t tile = blockIdx.x + k * gridDim.x;
             const int64_t i = tile * kTile + row;
             const bool valid = i < n;
 
-            // ---- forward recompute -----------------------------------------------------------
-            float x8[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x8[k] = 0.f;
+            // ---- operands of round 0: enc -------------------------------------------------------
             float dir[3] = {0.f, 0.f, 1.f};
             bool inside = false;
-            float g_sigma = 0.f, g_rgb[3] = {0.f, 0.f, 0.f};
             if (valid) {
-                if (8 * cg < enc_dim) {
-                    const float4* src = reinterpret_cast<const float4*>(enc + i * enc_dim + 8 * cg);
-                    const float4 a = __ldg(src), b = __ldg(src + 1);
-                    x8[0] = a.x; x8[1] = a.y; x8[2] = a.z; x8[3] = a.w;
-                    x8[4] = b.x; x8[5] = b.y; x8[6] = b.z; x8[7] = b.w;
-                }
-                if (cg <= 1) {
-                    const int64_t r = ray_indices[i];
-                    const float tm = t_starts[i] + t_ends[i];
-                    float pos[3], u[3];
+                const int64_t r = ray_indices[i];
+                const float tm = t_starts[i] + t_ends[i];
+                float pos[3], u[3];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        dir[d] = __ldg(rays_d + 3 * r + d);
-                        pos[d] = __ldg(rays_o + 3 * r + d) + (dir[d] * tm) * 0.5f;
-                    }
-                    if (cg == 0) {
-                        inside = contract_position(f, pos, u);
-                        g_sigma = d_sigmas[i];
-                    }
+                for (int d = 0; d < 3; ++d) {
+                    dir[d] = __ldg(rays_d + 3 * r + d);
+                    pos[d] = __ldg(rays_o + 3 * r + d) + (dir[d] * tm) * 0.5f;
                 }
-                for (int c = 0; c < C; ++c) g_rgb[c] = d_rgbs[i * C + c];
+                if (hf == 0) inside = contract_position(f, pos, u);
             }
-            store_cols<8, kEncDim>(Tenc, row, 8 * cg, x8);
-            publish();
+            stage_enc(i, valid);
+            publish(ready);
 
-            float h[kBwdCols];
-            await(bar, phase);                                              // hb
-            tmem_ld_cols<kBwdCols>(tmem_lane + kColScratch + col0, h);
-bias_hidden_act<kBwdCols>(f.hidden_act, h, s_bb1 + col0);
-            store_cols<kBwdCols, kWidth>(Thb, row, col0, h);
-            publish();
+            // ---- round 0 done: hb ----------------------------------------------------------------
+            await_mma(done, phase);
+            stage_hb();
+            publish(ready);
 
+            // ---- round 1 done: y -> raw density, [SH | geo | 1] -> E -------------------------------
             float raw = 0.f;
-            await(bar, phase);                                              // y -> [SH | geo | 0]
-            if (cg == 0) {
-                float y[kBaseOut];
-                tmem_ld_cols<kBaseOut>(tmem_lane + kColScratch, y);
-#pragma unroll
-                for (int j = 0; j < kBaseOut; ++j) y[j] += s_bb2[j];
-                raw = y[0];
-#pragma unroll
-                for (int j = 0; j < kGeo; ++j) h[j] = y[1 + j];
-                h[15] = 0.f;
-                store_cols<16, kHeadIn>(Tin1, row, 16, h);
-            } else if (cg == 1) {
-                sh_degree4(dir, h);
-                store_cols<16, kHeadIn>(Tin1, row, 0, h);
-            }
-            publish();
-
-            await(bar, phase);                                              // h1
-            tmem_ld_cols<kBwdCols>(tmem_lane + kColScratch + col0, h);
-bias_hidden_act<kBwdCols>(f.hidden_act, h, s_b1 + col0);
-            store_cols<kBwdCols, kWidth>(Th1, row, col0, h);
-            publish();
-
-            await(bar, phase);                                              // h2 (kept in registers)
-            tmem_ld_cols<kBwdCols>(tmem_lane + kColScratch + col0, h);
-bias_hidden_act<kBwdCols>(f.hidden_act, h, s_b2 + col0);
-            store_cols<kBwdCols, kWidth>(Th2, row, col0, h);
-            publish();
-
-            // ---- output layer backward (SIMT: C <= 3 rows) -----------------------------------
-            await(bar, phase);
-            float d16[kBaseOut];
+            await_mma(done, phase);
             {
-                float z3[kOutN];
-                tmem_ld_cols<kOutN>(tmem_lane + kColScratch, z3);
+                float x[16];
+                if (hf == 0) {
+                    float y[16];
+                    tmem_ld_cols<16>(Z, y);
 #pragma unroll
-                for (int j = 0; j < kBaseOut; ++j) d16[j] = 0.f;
+                    for (int j = 0; j < kBaseOut; ++j) y[j] += s_bb2[j];
+                    raw = y[0];
+#pragma unroll
+                    for (int j = 0; j < kGeo; ++j) x[j] = y[1 + j];
+                    x[15] = 1.f;                          // the ones column of the head input
+                    store16<TE>(E, row, 2, x);
+                } else {
+                    sh_degree4(dir, x);
+                    store16<TE>(E, row, 0, x);
+                }
+            }
+            publish(ready);
+
+            // ---- round 2 done: h1 -> H -------------------------------------------------------------
+            await_mma(done, phase);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float h[16];
+                tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
+                bias_hidden_act<16>(hact, h, s_b1 + 32 * hf + 16 * c);
+                store16<TH>(H, row, 4 * hf + 2 * c, h);
+            }
+            publish(ready);
+
+            // ---- round 3 done: h2 (registers), output layer forward + backward on the SIMT side ---
+            float g_rgb[3] = {0.f, 0.f, 0.f};
+            float g_sigma = 0.f;
+            if (valid) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    if (c < C) d16[c] = g_rgb[c] * radiance_act_grad(f.radiance_act, z3[c] + s_b3[c]);
+                    if (c < C) g_rgb[c] = d_rgbs[i * C + c];
+                if (hf == 0) g_sigma = d_sigmas[i];
             }
-            float dl[kBwdCols];
-#pragma unroll
-            for (int j = 0; j < kBwdCols; ++j) {
-                float a = 0.f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) a = fmaf(d16[c], s_w3f[c * kWidth + col0 + j], a);
-                dl[j] = a * hidden_act_grad_from_out(f.hidden_act, h[j]);
-            }
-            store_cols<kBwdCols, kWidth>(Td64, row, col0, dl);
-            if (cg == 0) {
-                store_cols<kBaseOut, kBaseOut>(Td16, row, 0, d16);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float s = warp_sum(d16[c]);
-                    if (lane == 0 && c < C) atomicAdd(&s_small[16 + c], s);
-                }
-            }
-            publish();
-
-            await(bar, phase);                                              // dh1 -> d1
-            tmem_ld_cols<kBwdCols>(tmem_lane + kColScratch + col0, dl);
-            load_cols<kBwdCols, kWidth>(Th1, row, col0, h);
-mul_hidden_act_grad<kBwdCols>(f.hidden_act, dl, h);
-            store_cols<kBwdCols, kWidth>(Td64, row, col0, dl);
-            publish();
-
-            await(bar, phase);                                              // din1 -> dy
-            if (cg == 0) {
-                float dgeo[16];
-                tmem_ld_cols<16>(tmem_lane + kColScratch + kShDim, dgeo);
-                d16[0] = inside ? g_sigma * density_act_grad(f.density_act, raw) : 0.f;
-#pragma unroll
-                for (int j = 0; j < kGeo; ++j) d16[1 + j] = dgeo[j];
-                store_cols<kBaseOut, kBaseOut>(Td16, row, 0, d16);
-#pragma unroll
-                for (int j = 0; j < kBaseOut; ++j) {
-                    const float s = warp_sum(d16[j]);
-                    if (lane == 0) atomicAdd(&s_small[j], s);
-                }
-            } else if (cg == 1 && d_dirs != nullptr) {
-                // dL/d(view direction) through the SH encoding (only the tau path needs it)
-                float dsh[16], dd[3];
-                tmem_ld_cols<16>(tmem_lane + kColScratch, dsh);
-                sh_degree4_grad(dir, dsh, dd);
-                if (valid) { d_dirs[3 * i] = dd[0]; d_dirs[3 * i + 1] = dd[1]; d_dirs[3 * i + 2] = dd[2]; }
-            }
-            publish();
-
-            await(bar, phase);                                              // dhb -> db1
-            tmem_ld_cols<kBwdCols>(tmem_lane + kColScratch + col0, dl);
-            load_cols<kBwdCols, kWidth>(Thb, row, col0, h);
-mul_hidden_act_grad<kBwdCols>(f.hidden_act, dl, h);
-            store_cols<kBwdCols, kWidth>(Td64, row, col0, dl);
-            publish();
-
-            await(bar, phase);                                              // denc -> HBM
+            await_mma(done, phase);
             {
-                float de[8];
-                tmem_ld_cols<8>(tmem_lane + kColScratch + 8 * cg, de);
-                if (valid && 8 * cg < enc_dim) {
-                    float4* out = reinterpret_cast<float4*>(d_enc + i * enc_dim + 8 * cg);
-                    out[0] = make_float4(de[0], de[1], de[2], de[3]);
-                    out[1] = make_float4(de[4], de[5], de[6], de[7]);
+                float h2[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float h[16];
+                    tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
+                    bias_hidden_act<16>(hact, h, s_b2 + 32 * hf + 16 * c);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) h2[16 * c + j] = h[j];
+                }
+                float z3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (c < C) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) z3[c] = fmaf(h2[j], s_w3f[c * kWidth + 32 * hf + j], z3[c]);
+                    }
+                *reinterpret_cast<float4*>(zx + (row * 2 + hf) * 4) = make_float4(z3[0], z3[1], z3[2], 0.f);
+                group_sync(slot_id);
+                const float4 other = *reinterpret_cast<const float4*>(zx + (row * 2 + (hf ^ 1)) * 4);
+                float d3[3];
+                d3[0] = z3[0] + other.x; d3[1] = z3[1] + other.y; d3[2] = z3[2] + other.z;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    d3[c] = c < C ? g_rgb[c] * radiance_act_grad(f.radiance_act, d3[c] + s_b3[c]) : 0.f;
+                // d2 = (d3 W3) * act'(h2) -> D
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    float dl[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) a = fmaf(d3[c], s_w3f[c * kWidth + 32 * hf + 16 * c2 + j], a);
+                        dl[j] = a * hidden_act_grad_from_out(hact, h2[16 * c2 + j]);
+                    }
+                    store16<TD>(D, row, 4 * hf + 2 * c2, dl);
+                }
+                publish(ready);
+                // dW3 += d3^T h2, db3 += sum d3  (off the critical path: the MMA round is running)
+                for (int c = 0; c < C; ++c) {
+                    float t[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t[j] = d3[c] * h2[j];
+                    const float s = warp_transpose_sum<32>(t, lane);
+                    atomicAdd(&s_dw3[c * kWidth + 32 * hf + lane], s);
+                    if (hf == 0) {
+                        const float sb = warp_sum(d3[c]);
+                        if (lane == 0) atomicAdd(&s_db3[c], sb);
+                    }
+                }
+            }
+
+            // ---- round 4 done: dh1 -> d1 = dh1 * act'(h1) -> D ------------------------------------
+            await_mma(done, phase);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float dl[16], h[16];
+                tmem_ld_cols<16>(Z + 32 * hf + 16 * c, dl);
+                load16<TH>(H, row, 4 * hf + 2 * c, h);
+                mul_hidden_act_grad<16>(hact, dl, h);
+                store16<TD>(D, row, 4 * hf + 2 * c, dl);
+            }
+            publish(ready);
+
+            // ---- round 5 done: din1 -> dy (E), hb again (H) -----------------------------------------
+            await_mma(done, phase);
+            if (hf == 0) {
+                float dgeo[16], dy[16];
+                tmem_ld_cols<16>(Z + kShDim, dgeo);
+                dy[0] = inside ? g_sigma * density_act_grad(f.density_act, raw) : 0.f;
+#pragma unroll
+                for (int j = 0; j < kGeo; ++j) dy[1 + j] = dgeo[j];
+                store16<TE>(E, row, 0, dy);
+                stage_hb();
+                publish(ready);
+                const float s = warp_transpose_sum<16>(dy, lane & 15);
+                // lanes l and l + 16 hold the two half-warp sums of column l
+                const float tot = s + __shfl_xor_sync(0xffffffffu, s, 16);
+                if (lane < 16) atomicAdd(&s_dbb2[lane], tot);
+            } else {
+                if (d_dirs != nullptr) {
+                    // dL/d(view direction) through the SH encoding (only the tau path needs it)
+                    float dsh[16], dd[3];
+                    tmem_ld_cols<16>(Z, dsh);
+                    sh_degree4_grad(dir, dsh, dd);
+                    if (valid) { d_dirs[3 * i] = dd[0]; d_dirs[3 * i + 1] = dd[1]; d_dirs[3 * i + 2] = dd[2]; }
+                }
+                stage_hb();
+                publish(ready);
+            }
+
+            // ---- round 6 done: dhb -> db1 = dhb * act'(hb) -> D; enc again -> E -----------------------
+            await_mma(done, phase);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float dl[16], h[16];
+                tmem_ld_cols<16>(Z + 32 * hf + 16 * c, dl);
+                load16<TH>(H, row, 4 * hf + 2 * c, h);
+                mul_hidden_act_grad<16>(hact, dl, h);
+                store16<TD>(D, row, 4 * hf + 2 * c, dl);
+            }
+            stage_enc(i, valid);
+            publish(ready);
+
+            // ---- round 7 done: denc -> HBM ---------------------------------------------------------------
+            await_mma(done, phase);
+            {
+                float de[16];
+                tmem_ld_cols<16>(Z + 16 * hf, de);
+                if (valid) {
+                    float4* out = reinterpret_cast<float4*>(d_enc + i * enc_dim + 16 * hf);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        if (16 * hf + 4 * v4 < enc_dim)
+                            out[v4] = make_float4(de[4 * v4], de[4 * v4 + 1], de[4 * v4 + 2], de[4 * v4 + 3]);
                 }
             }
             tc::tc_fence_before_sync();
@@ -307,48 +596,48 @@ mul_hidden_act_grad<kBwdCols>(f.hidden_act, dl, h);
     // ---- flush the weight-gradient accumulators (M = 64: row m in lane m%16 + 32*(m/16)) ------
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (have_tiles && warp < 4) {
+    if (my_tiles > 0 && warp < 4) {
         tc::tc_fence_after_sync();
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
         const int row = warp * 16 + lane;              // valid for lane < 16
         const bool owner = lane < 16;
         float v[16];
-        for (int c0 = 0; c0 < kHeadIn; c0 += 16) {     // dW1 (64, 31)
-            tmem_ld_cols<16>(tmem_lane + kColDW1 + c0, v);
+        for (int c0 = 0; c0 < kHeadIn; c0 += 16) {     // dW1 (64, 31) | db1 in column 31
+            tmem_ld_cols<16>(tl + kColDW1 + c0, v);
             if (owner)
-                for (int j = 0; j < 16; ++j)
+                for (int j = 0; j < 16; ++j) {
                     if (c0 + j < kShDim + kGeo) atomicAdd(g.w1 + row * (kShDim + kGeo) + c0 + j, v[j]);
+                    else atomicAdd(g.b1 + row, v[j]);
+                }
         }
         for (int c0 = 0; c0 < kWidth; c0 += 16) {      // dW2 (64, 64)
-            tmem_ld_cols<16>(tmem_lane + kColDW2 + c0, v);
+            tmem_ld_cols<16>(tl + kColDW2 + c0, v);
             if (owner)
                 for (int j = 0; j < 16; ++j) atomicAdd(g.w2 + row * kWidth + c0 + j, v[j]);
         }
         for (int c0 = 0; c0 < kEncDim; c0 += 16) {     // dWb1 (64, enc_dim)
-            tmem_ld_cols<16>(tmem_lane + kColDWb1 + c0, v);
+            tmem_ld_cols<16>(tl + kColDWb1 + c0, v);
             if (owner)
                 for (int j = 0; j < 16; ++j)
                     if (c0 + j < enc_dim) atomicAdd(g.wb1 + row * enc_dim + c0 + j, v[j]);
         }
-        tmem_ld_cols<16>(tmem_lane + kColDWb2T, v);    // dWb2^T (in 64, out 16)
+        {
+            float b[8];
+            tmem_ld_cols<8>(tl + kColDW2 + kWidth, b);           // db2
+            if (owner) atomicAdd(g.b2 + row, b[0]);
+            tmem_ld_cols<8>(tl + kColDWb1 + kEncDim, b);         // dbb1
+            if (owner) atomicAdd(g.bb1 + row, b[0]);
+        }
+        tmem_ld_cols<16>(tl + kColDWb2T, v);           // dWb2^T (in 64, out 16)
         if (owner)
             for (int j = 0; j < kBaseOut; ++j) atomicAdd(g.wb2 + j * kWidth + row, v[j]);
-        tmem_ld_cols<16>(tmem_lane + kColDW3T, v);     // dW3^T (in 64, out C)
-        if (owner)
-            for (int j = 0; j < C; ++j) atomicAdd(g.w3 + j * kWidth + row, v[j]);
-        tmem_ld_cols<16>(tmem_lane + kColDB1, v);      // columns 224..239: db1 | db2
-        if (owner) {
-            atomicAdd(g.b1 + row, v[0]);
-            atomicAdd(g.b2 + row, v[8]);
-        }
-        tmem_ld_cols<16>(tmem_lane + kColDBb1, v);
-        if (owner) atomicAdd(g.bb1 + row, v[0]);
-        if (tid < kBaseOut) atomicAdd(g.bb2 + tid, s_small[tid]);
-        if (tid < C) atomicAdd(g.b3 + tid, s_small[16 + tid]);
+        for (int i = tid; i < C * kWidth; i += 128) atomicAdd(g.w3 + i, s_dw3[i]);
+        if (tid < kBaseOut) atomicAdd(g.bb2 + tid, s_dbb2[tid]);
+        if (tid < C) atomicAdd(g.b3 + tid, s_db3[tid]);
     }
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, kBwdTmemCols);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace den
@@ -369,11 +658,14 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
     DEN_CHECK_ARG(enc && rays_o && rays_d && ray_indices && t_starts && t_ends && d_sigmas &&
                       d_rgbs && d_enc,
                   "null pointer");
-    DEN_CHECK_ARG((f->grid.n_levels * 2) % 8 == 0, "encoding width must be a multiple of 8");
-    const int grid = grid_for((n + kTile - 1) / kTile, 1, 1);
+    DEN_CHECK_ARG((f->grid.n_levels * 2) % 4 == 0, "encoding width must be a multiple of 4");
+    DEN_CHECK_ARG(f->channels >= 1 && f->channels <= 3, "1 to 3 radiance channels");
+    // two tiles in flight per CTA: at least two tiles per CTA whenever there are enough of them
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    const int grid = grid_for((n_tiles + 1) / 2, 1, 1);
     cudaFuncSetAttribute(mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)BwdSmem::total);
-    mlp_bwd_tc_kernel<<<grid, kBwdThreads, BwdSmem::total, as_stream(stream)>>>(
+                         (int)bwd::Smem::total);
+    mlp_bwd_tc_kernel<<<grid, bwd::kThreads, bwd::Smem::total, as_stream(stream)>>>(
         *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, d_enc, d_dirs);
     DEN_CHECK_LAUNCH();
     return DEN_OK;

@@ -49,14 +49,23 @@ def _req(t, dtype, name):
 
 _TIME_ALL = False
 _TIMED = None           # {kernel name: [(start_event, end_event), ...]} while timing is on
+_EVENT_POOL = []        # pre-created CUDA events (creation is kept out of the timed region)
 
 
-def enable_kernel_timing(names):
-    """Bracket every launch of the named C-ABI entry points with CUDA events recorded on the
-    launching (current) stream; bench.py derives the roofline from them."""
+def enable_kernel_timing(names, pool_size=4096):
+    """Bracket launches of the named C-ABI entry points (None = all of them) with CUDA events
+    recorded on the launching (current) stream; bench.py derives the roofline from them.  The
+    events come from a pool created here, so the timed region only pays two cudaEventRecord
+    calls per bracketed launch."""
     global _TIMED, _TIME_ALL
     _TIME_ALL = names is None
     _TIMED = {n: [] for n in (names or [])}
+    while len(_EVENT_POOL) < pool_size:
+        _EVENT_POOL.append(torch.cuda.Event(enable_timing=True))
+
+
+def _event():
+    return _EVENT_POOL.pop() if _EVENT_POOL else torch.cuda.Event(enable_timing=True)
 
 
 def kernel_timings():
@@ -69,14 +78,16 @@ def kernel_timings():
 
 def disable_kernel_timing():
     global _TIMED
+    for pairs in (_TIMED or {}).values():
+        for a, b in pairs:
+            _EVENT_POOL.extend((a, b))
     _TIMED = None
 
 
 def _call(name, *args, launches=1):
     if _TIMED is not None and (_TIME_ALL or name in _TIMED):
         _TIMED.setdefault(name, [])
-        start = torch.cuda.Event(enable_timing=True)
-        end = torch.cuda.Event(enable_timing=True)
+        start, end = _event(), _event()
         start.record()
         _lib.lib().call(name, *args)
         end.record()
