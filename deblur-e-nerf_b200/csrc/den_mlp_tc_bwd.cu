@@ -29,6 +29,8 @@
 // dL/dz tile) = 88 KB; 2 slots + 36 KB of weight tiles = 223 KB.  The price of fitting two
 // slots: hb is re-derived from its pre-activation (parked in TMEM) and enc is re-read from
 // L2/HBM for the last round (+12 % epilogue instructions, no extra MMA round).
+#include <stdlib.h>
+
 #include "den_mlp_tc.cuh"
 
 namespace den {
@@ -105,24 +107,39 @@ __device__ __forceinline__ OpDesc mnmajor(const uint8_t* base) {        // K alo
     return {make_desc(base, T::rg, 128), make_desc(base + T::half, T::rg, 128), 2u * T::rg};
 }
 // D (+)= A * B with the 3-product bf16 split, KSTEPS steps of 16 along K
+__device__ __forceinline__ bool elect_one() {
+    uint32_t leader;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(leader));
+    return leader != 0;
+}
+// one tcgen05.mma from the calling (single, elected) thread
+__device__ __forceinline__ void mma1(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D (+)= A * B with the 3-product bf16 split, KSTEPS steps of 16 along K.  Called by the elected
+// lane only (one branch per GEMM instead of one elect.sync + vote per MMA).
 template <int KSTEPS>
 __device__ __forceinline__ void gemm3(uint32_t tmem_d, const OpDesc& a, const OpDesc& b, uint32_t idesc,
                                       bool accumulate) {
-    // short K: fully unrolled; K = 128 (the dW GEMMs): rolled, one running offset per operand, so the
-    // issuing warp does not keep 48 descriptors live (it spilled them)
-    constexpr int kUnroll = KSTEPS <= 4 ? KSTEPS : 2;
-    uint32_t ao = 0, bo = 0;
-#pragma unroll kUnroll
-    for (int ks = 0; ks < KSTEPS; ++ks, ao += a.kstep, bo += b.kstep)
-        tc::mma_bf16(tmem_d, a.hi.at(ao), b.hi.at(bo), idesc, accumulate || ks > 0);
-    ao = 0, bo = 0;
-#pragma unroll kUnroll
-    for (int ks = 0; ks < KSTEPS; ++ks, ao += a.kstep, bo += b.kstep)
-        tc::mma_bf16(tmem_d, a.lo.at(ao), b.hi.at(bo), idesc, true);
-    ao = 0, bo = 0;
-#pragma unroll kUnroll
-    for (int ks = 0; ks < KSTEPS; ++ks, ao += a.kstep, bo += b.kstep)
-        tc::mma_bf16(tmem_d, a.hi.at(ao), b.lo.at(bo), idesc, true);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+        mma1(tmem_d, a.hi.at(ks * a.kstep), b.hi.at(ks * b.kstep), idesc, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+        mma1(tmem_d, a.lo.at(ks * a.kstep), b.hi.at(ks * b.kstep), idesc, 1u);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+        mma1(tmem_d, a.hi.at(ks * a.kstep), b.lo.at(ks * b.kstep), idesc, 1u);
 }
 
 // ---- mbarrier helpers ----------------------------------------------------------------------------
@@ -177,8 +194,24 @@ __device__ __forceinline__ void publish(uint64_t* ready) {
     tc::tc_fence_before_sync();
     mbar_arrive(ready);
 }
-__device__ __forceinline__ void await_mma(uint64_t* done, uint32_t& phase) {
-    tc::mbar_wait(done, phase);
+__device__ __forceinline__ void await_mma(uint64_t* done, uint32_t& phase, int dbg = 0) {
+    if (dbg & 4) {
+        while (!mbar_try(done, phase)) __nanosleep(32);
+    } else if (dbg & 8) {
+        const uint32_t addr = tc::smem_u32(done);
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(addr), "r"(phase), "r"(200000u)
+                : "memory");
+        }
+    } else {
+        tc::mbar_wait(done, phase);
+    }
     phase ^= 1;
     tc::tc_fence_after_sync();
 }
@@ -210,7 +243,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                   const int32_t* __restrict__ ray_indices, const float* __restrict__ t_starts,
                   const float* __restrict__ t_ends, const float* __restrict__ d_sigmas,
                   const float* __restrict__ d_rgbs, int64_t n, float* __restrict__ d_enc,
-                  float* __restrict__ d_dirs) {
+                  float* __restrict__ d_dirs, int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);       // ready[0..1], done[0..1]
@@ -300,7 +333,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 const uint8_t* E = slot + Smem::e;
                 const uint8_t* H = slot + Smem::h;
                 const uint8_t* D = slot + Smem::d;
-                switch (round[s]) {
+                const bool leader = elect_one();
+                if (leader) {
+                switch ((dbg & 1) ? -1 : round[s]) {
+                case -1: break;
                 case 0:     // z_b1 = enc Wb1^T                                    (kept in P)
                     gemm3<kEncDim / 16>(P, kmajor<TE>(E), kmajor<TWb1>(wb1),
                                         tc::instr_desc_bf16(128, kWidth, false, false), false);
@@ -346,7 +382,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                                        tc::instr_desc_bf16(128, kEncDim, false, true), false);
                     break;
                 }
-                tc::mma_commit(&bars[2 + s]);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             ::"r"(tc::smem_u32(&bars[2 + s])) : "memory");
+                }
+                __syncwarp();
                 round[s] = (round[s] + 1) & 7;
                 --rounds_left[s];
             }
@@ -402,6 +441,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         };
 
         for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
+            if (dbg & 2) {
+                for (int r = 0; r < 8; ++r) { publish(ready); await_mma(done, phase, dbg); }
+                continue;
+            }
             const int64_t tile = blockIdx.x + k * gridDim.x;
             const int64_t i = tile * kTile + row;
             const bool valid = i < n;
@@ -424,13 +467,13 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(ready);
 
             // ---- round 0 done: hb ----------------------------------------------------------------
-            await_mma(done, phase);
+            await_mma(done, phase, dbg);
             stage_hb();
             publish(ready);
 
             // ---- round 1 done: y -> raw density, [SH | geo | 1] -> E -------------------------------
             float raw = 0.f;
-            await_mma(done, phase);
+            await_mma(done, phase, dbg);
             {
                 float x[16];
                 if (hf == 0) {
@@ -451,7 +494,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(ready);
 
             // ---- round 2 done: h1 -> H -------------------------------------------------------------
-            await_mma(done, phase);
+            await_mma(done, phase, dbg);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 float h[16];
@@ -470,7 +513,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                     if (c < C) g_rgb[c] = d_rgbs[i * C + c];
                 if (hf == 0) g_sigma = d_sigmas[i];
             }
-            await_mma(done, phase);
+            await_mma(done, phase, dbg);
             {
                 float h2[32];
 #pragma unroll
@@ -525,7 +568,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             }
 
             // ---- round 4 done: dh1 -> d1 = dh1 * act'(h1) -> D ------------------------------------
-            await_mma(done, phase);
+            await_mma(done, phase, dbg);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 float dl[16], h[16];
@@ -537,7 +580,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(ready);
 
             // ---- round 5 done: din1 -> dy (E), hb again (H) -----------------------------------------
-            await_mma(done, phase);
+            await_mma(done, phase, dbg);
             if (hf == 0) {
                 float dgeo[16], dy[16];
                 tmem_ld_cols<16>(Z + kShDim, dgeo);
@@ -564,7 +607,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             }
 
             // ---- round 6 done: dhb -> db1 = dhb * act'(hb) -> D; enc again -> E -----------------------
-            await_mma(done, phase);
+            await_mma(done, phase, dbg);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 float dl[16], h[16];
@@ -577,7 +620,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(ready);
 
             // ---- round 7 done: denc -> HBM ---------------------------------------------------------------
-            await_mma(done, phase);
+            await_mma(done, phase, dbg);
             {
                 float de[16];
                 tmem_ld_cols<16>(Z + 16 * hf, de);
@@ -663,10 +706,12 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
     // two tiles in flight per CTA: at least two tiles per CTA whenever there are enough of them
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int grid = grid_for((n_tiles + 1) / 2, 1, 1);
+    const char* dbg_env = getenv("DEN_MLP_BWD_DEBUG");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     cudaFuncSetAttribute(mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)bwd::Smem::total);
     mlp_bwd_tc_kernel<<<grid, bwd::kThreads, bwd::Smem::total, as_stream(stream)>>>(
-        *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, d_enc, d_dirs);
+        *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, d_enc, d_dirs, dbg);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }
