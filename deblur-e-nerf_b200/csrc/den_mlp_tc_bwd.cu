@@ -21,8 +21,10 @@
 //   * 2 x 8 epilogue warps, one group per slot (warp quadrant q = warp % 4 serves TMEM lanes
 //     32q..32q+31 = tile rows; half hf = (warp / 4) % 2 owns columns [32 hf, 32 hf + 32) of
 //     every 64-wide layer, processed 16 at a time to bound registers);
-//   * 1 MMA warp that polls the two slots' "operands ready" mbarriers and issues whichever
-//     round is ready, so one slot's tensor work overlaps the other slot's SIMT epilogue;
+//   * 1 MMA warp serving the two slots alternately; the hand-off epilogue -> MMA warp is a hardware
+//     named barrier (bar.arrive / bar.sync), MMA -> epilogue a tcgen05.commit mbarrier, so one
+//     slot's tensor work overlaps the other slot's SIMT epilogue; per round the latency-critical
+//     GEMM (forward layer / dX) is committed first, the dW GEMM follows on its own mbarrier;
 //   * the (C <= 3)-row output layer runs on the SIMT side (no 64 x 16 GEMM, no h2 operand tile).
 // Shared memory per slot: E (128 x 40: enc | ones, later [SH | geo | 1], later dy, later enc
 // again), H (128 x 72: hb | ones, later h1, later hb again) and D (128 x 64: the current
@@ -81,7 +83,7 @@ struct Smem {
     static constexpr int w3f = bias + (3 * kWidth + kBaseOut + 16) * 4;   // fp32 W3 rows (3 x 64)
     static constexpr int acc = w3f + 3 * kWidth * 4;      // fp32: dW3 (3 x 64) | dbb2 16 | db3 4 | pad
     static constexpr int zx = acc + (3 * kWidth + 32) * 4;               // per slot (128, 2, 4) fp32
-    static constexpr int bars = zx + kSlots * kTile * 2 * 4 * 4;         // ready[2], done[2]
+    static constexpr int bars = zx + kSlots * kTile * 2 * 4 * 4;         // done[2], dw_done[2]
     static constexpr int tmem_ptr = bars + 4 * 8;
     static constexpr int slot0 = (tmem_ptr + 8 + 127) / 128 * 128;
     static constexpr int e = 0;                            // offsets inside a slot
@@ -188,11 +190,21 @@ __device__ __forceinline__ void load16(const uint8_t* tile, int r, int chunk0, f
         }
     }
 }
-// operands written by this thread are handed to the MMA warp
-__device__ __forceinline__ void publish(uint64_t* ready) {
+// hand-off epilogue group -> MMA warp through a hardware named barrier (3 + slot): the 256 producers
+// arrive without blocking, the MMA warp syncs
+constexpr int kHandoffThreads = kGroupThreads + 32;
+__device__ __forceinline__ void publish(int slot) {
     tc::fence_smem_to_async_proxy();
     tc::tc_fence_before_sync();
-    mbar_arrive(ready);
+    asm volatile("bar.arrive %0, %1;" ::"r"(3 + slot), "r"(kHandoffThreads) : "memory");
+}
+__device__ __forceinline__ void handoff_wait(int slot) {
+    asm volatile("bar.sync %0, %1;" ::"r"(3 + slot), "r"(kHandoffThreads) : "memory");
+}
+__device__ __forceinline__ void commit_to(uint64_t* bar) {      // by the elected issuing thread
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     tc::smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void await_mma(uint64_t* done, uint32_t& phase, int dbg = 0) {
     if (dbg & 4) {
@@ -246,7 +258,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                   float* __restrict__ d_dirs, int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);       // ready[0..1], done[0..1]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);       // done[0..1], dw_done[0..1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::tmem_ptr);
     const float* s_bb1 = reinterpret_cast<const float*>(smem + Smem::bias);
     const float* s_bb2 = s_bb1 + kWidth;
@@ -291,10 +303,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         *reinterpret_cast<uint4*>(slot + Smem::h + TH::half + TH::off(r, 8)) = zero;
     }
     if (tid == 0) {
-        tc::mbar_init(&bars[0], kGroupThreads);
-        tc::mbar_init(&bars[1], kGroupThreads);
-        tc::mbar_init(&bars[2], 1);
-        tc::mbar_init(&bars[3], 1);
+        for (int b = 0; b < 4; ++b) tc::mbar_init(&bars[b], 1);
         tc::fence_barrier_init();
     }
     if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
@@ -308,92 +317,93 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
     const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
     if (warp == kMmaWarp) {
-        // ===================== MMA warp: issue whichever slot has operands ready =====================
+        // ===================== MMA warp =====================
         const uint8_t* wb1 = smem + Smem::wb1;
         const uint8_t* wb2 = smem + Smem::wb2;
         const uint8_t* w1 = smem + Smem::w1;
         const uint8_t* w2 = smem + Smem::w2;
-        int64_t rounds_left[kSlots];
-        int round[kSlots] = {0, 0};
-        uint32_t phase[kSlots] = {0, 0};
-        for (int s = 0; s < kSlots; ++s) rounds_left[s] = 8 * ((my_tiles + 1 - s) / 2);
-        bool acc2 = false, acc1 = false, accb1 = false, accb2 = false;
-        uint32_t idle = 0;
-        while (rounds_left[0] > 0 || rounds_left[1] > 0) {
-            bool progressed = false;
-#pragma unroll
+        // Fixed alternation slot 0, slot 1, slot 0, ...: each hand-off is one named-barrier sync.  Per
+        // round the latency-critical GEMM (forward layer / dX) is issued and committed first; the
+        // weight-gradient GEMM follows with its own commit (dw_done) — nobody waits for it until the
+        // operand tiles it reads are about to be overwritten.
+        // per-slot counters packed in scalars (the slot loop is rolled: no dynamically indexed arrays)
+        int64_t left0 = 8 * ((my_tiles + 1) / 2), left1 = 8 * (my_tiles / 2);
+        int round0 = 0, round1 = 0;
+        uint32_t acc_mask = 0;                           // bit r-4: the dW accumulator of round r holds earlier tiles
+        while (left0 > 0 || left1 > 0) {
+#pragma unroll 1
             for (int s = 0; s < kSlots; ++s) {
-                if (rounds_left[s] <= 0) continue;
-                if (!mbar_try(&bars[s], phase[s])) continue;
-                phase[s] ^= 1;
-                progressed = true;
+                if ((s == 0 ? left0 : left1) <= 0) continue;
+                const int rnd = s == 0 ? round0 : round1;
+                handoff_wait(s);
                 tc::tc_fence_after_sync();
                 uint8_t* slot = smem + Smem::slot0 + s * Smem::slot_bytes;
                 const uint32_t Z = tmem_base + kColZ + 128u * s, P = tmem_base + kColP + 128u * s;
                 const uint8_t* E = slot + Smem::e;
                 const uint8_t* H = slot + Smem::h;
                 const uint8_t* D = slot + Smem::d;
-                const bool leader = elect_one();
-                if (leader) {
-                switch ((dbg & 1) ? -1 : round[s]) {
-                case -1: break;
+                uint64_t* done = &bars[s];
+                uint64_t* dw_done = &bars[2 + s];
+                if (elect_one()) {
+                switch ((dbg & 1) ? -1 : rnd) {
+                case -1: commit_to(done); if (rnd >= 4) commit_to(dw_done); break;
                 case 0:     // z_b1 = enc Wb1^T                                    (kept in P)
                     gemm3<kEncDim / 16>(P, kmajor<TE>(E), kmajor<TWb1>(wb1),
                                         tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    commit_to(done);
                     break;
                 case 1:     // y = hb Wb2^T
                     gemm3<kWidth / 16>(Z, kmajor<TH>(H), kmajor<TWb2>(wb2),
                                        tc::instr_desc_bf16(128, kBaseOut, false, false), false);
+                    commit_to(done);
                     break;
                 case 2:     // z1 = [SH | geo | 1] W1^T
                     gemm3<kHeadIn / 16>(Z, kmajor<TE>(E), kmajor<TW1>(w1),
                                         tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    commit_to(done);
                     break;
                 case 3:     // z2 = h1 W2^T
                     gemm3<kWidth / 16>(Z, kmajor<TH>(H), kmajor<TW2>(w2),
                                        tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    commit_to(done);
                     break;
-                case 4:     // dW2 | db2 += d2^T [h1 | 1];  dh1 = d2 W2
-                    gemm3<kTile / 16>(tmem_base + kColDW2, mnmajor<TD>(D), mnmajor<TH>(H),
-                                      tc::instr_desc_bf16(64, 72, true, true), acc2);
-                    acc2 = true;
+                case 4:     // dh1 = d2 W2;  dW2 | db2 += d2^T [h1 | 1]
                     gemm3<kWidth / 16>(Z, kmajor<TD>(D), mnmajor<TW2>(w2),
                                        tc::instr_desc_bf16(128, kWidth, false, true), false);
+                    commit_to(done);
+                    gemm3<kTile / 16>(tmem_base + kColDW2, mnmajor<TD>(D), mnmajor<TH>(H),
+                                      tc::instr_desc_bf16(64, 72, true, true), (acc_mask >> 0) & 1u);
+                    commit_to(dw_done);
                     break;
-                case 5:     // dW1 | db1 += d1^T [SH | geo | 1];  din1 = d1 W1
-                    gemm3<kTile / 16>(tmem_base + kColDW1, mnmajor<TD>(D), mnmajor<TE>(E),
-                                      tc::instr_desc_bf16(64, kHeadIn, true, true), acc1);
-                    acc1 = true;
+                case 5:     // din1 = d1 W1;  dW1 | db1 += d1^T [SH | geo | 1]
                     gemm3<kWidth / 16>(Z, kmajor<TD>(D), mnmajor<TW1>(w1),
                                        tc::instr_desc_bf16(128, kHeadIn, false, true), false);
+                    commit_to(done);
+                    gemm3<kTile / 16>(tmem_base + kColDW1, mnmajor<TD>(D), mnmajor<TE>(E),
+                                      tc::instr_desc_bf16(64, kHeadIn, true, true), (acc_mask >> 1) & 1u);
+                    commit_to(dw_done);
                     break;
-                case 6:     // dWb2^T += hb^T dy;  dhb = dy Wb2
-                    gemm3<kTile / 16>(tmem_base + kColDWb2T, mnmajor<TH>(H), mnmajor<TE>(E),
-                                      tc::instr_desc_bf16(64, kBaseOut, true, true), accb2);
-                    accb2 = true;
+                case 6:     // dhb = dy Wb2;  dWb2^T += hb^T dy
                     gemm3<kBaseOut / 16>(Z, kmajor<TE>(E), mnmajor<TWb2>(wb2),
                                          tc::instr_desc_bf16(128, kWidth, false, true), false);
+                    commit_to(done);
+                    gemm3<kTile / 16>(tmem_base + kColDWb2T, mnmajor<TH>(H), mnmajor<TE>(E),
+                                      tc::instr_desc_bf16(64, kBaseOut, true, true), (acc_mask >> 2) & 1u);
+                    commit_to(dw_done);
                     break;
-                default:    // dWb1 | dbb1 += db1^T [enc | 1];  denc = db1 Wb1
-                    gemm3<kTile / 16>(tmem_base + kColDWb1, mnmajor<TD>(D), mnmajor<TE>(E),
-                                      tc::instr_desc_bf16(64, 40, true, true), accb1);
-                    accb1 = true;
+                default:    // denc = db1 Wb1;  dWb1 | dbb1 += db1^T [enc | 1]
                     gemm3<kWidth / 16>(Z, kmajor<TD>(D), mnmajor<TWb1>(wb1),
                                        tc::instr_desc_bf16(128, kEncDim, false, true), false);
+                    commit_to(done);
+                    gemm3<kTile / 16>(tmem_base + kColDWb1, mnmajor<TD>(D), mnmajor<TE>(E),
+                                      tc::instr_desc_bf16(64, 40, true, true), (acc_mask >> 3) & 1u);
+                    commit_to(dw_done);
                     break;
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             ::"r"(tc::smem_u32(&bars[2 + s])) : "memory");
                 }
                 __syncwarp();
-                round[s] = (round[s] + 1) & 7;
-                --rounds_left[s];
-            }
-            if (progressed) {
-                idle = 0;
-            } else if (++idle > (1u << 26)) {
-                if (lane == 0) printf("den_b200: mlp_bwd MMA warp starved (block %d)\n", blockIdx.x);
-                __trap();
+                if (rnd >= 4) acc_mask |= 1u << (rnd - 4);
+                if (s == 0) { round0 = (rnd + 1) & 7; --left0; } else { round1 = (rnd + 1) & 7; --left1; }
             }
         }
     } else {
@@ -405,13 +415,19 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         uint8_t* E = slot + Smem::e;
         uint8_t* H = slot + Smem::h;
         uint8_t* D = slot + Smem::d;
-        uint64_t* ready = &bars[slot_id];
-        uint64_t* done = &bars[2 + slot_id];
+        uint64_t* done = &bars[slot_id];
+        uint64_t* dw_done = &bars[2 + slot_id];
         float* zx = reinterpret_cast<float*>(smem + Smem::zx) + slot_id * (kTile * 2 * 4);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t Z = lane_base + kColZ + 128u * slot_id, P = lane_base + kColP + 128u * slot_id;
         const int hact = f.hidden_act;
-        uint32_t phase = 0;
+        uint32_t phase = 0, dw_phase = 0;
+        // the weight-gradient GEMM of the previous round must have consumed its operand tiles before
+        // they are overwritten (it was committed separately, after the latency-critical GEMM)
+        auto await_dw = [&]() {
+            tc::mbar_wait(dw_done, dw_phase);
+            dw_phase ^= 1;
+        };
 
         // load this thread's 16 encoding features of row i into E chunks (2 hf, 2 hf + 1)
         auto stage_enc = [&](int64_t i, bool valid) {
@@ -431,7 +447,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         };
         // hb = act(P + bb1) for this thread's 32 columns -> H
         auto stage_hb = [&]() {
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 float h[16];
                 tmem_ld_cols<16>(P + 32 * hf + 16 * c, h);
@@ -442,7 +458,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
 
         for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
             if (dbg & 2) {
-                for (int r = 0; r < 8; ++r) { publish(ready); await_mma(done, phase, dbg); }
+                for (int r = 0; r < 8; ++r) { publish(slot_id); await_mma(done, phase, dbg); if (r >= 4) await_dw(); }
                 continue;
             }
             const int64_t tile = blockIdx.x + k * gridDim.x;
@@ -464,12 +480,12 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 if (hf == 0) inside = contract_position(f, pos, u);
             }
             stage_enc(i, valid);
-            publish(ready);
+            publish(slot_id);
 
             // ---- round 0 done: hb ----------------------------------------------------------------
             await_mma(done, phase, dbg);
             stage_hb();
-            publish(ready);
+            publish(slot_id);
 
             // ---- round 1 done: y -> raw density, [SH | geo | 1] -> E -------------------------------
             float raw = 0.f;
@@ -491,18 +507,33 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                     store16<TE>(E, row, 0, x);
                 }
             }
-            publish(ready);
+            publish(slot_id);
 
             // ---- round 2 done: h1 -> H -------------------------------------------------------------
             await_mma(done, phase, dbg);
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 float h[16];
                 tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
                 bias_hidden_act<16>(hact, h, s_b1 + 32 * hf + 16 * c);
                 store16<TH>(H, row, 4 * hf + 2 * c, h);
             }
-            publish(ready);
+            publish(slot_id);
+
+            // next tile of this slot: pull its rows towards L2 while this one is in flight
+            if (k + kSlots < my_tiles) {
+                const int64_t ni = (tile + (int64_t)kSlots * gridDim.x) * kTile + row;
+                if (ni < n) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(enc + ni * enc_dim + 16 * hf));
+                    if (hf == 0) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ray_indices + ni));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(t_starts + ni));
+                    } else {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(t_ends + ni));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(d_rgbs + ni * C));
+                    }
+                }
+            }
 
             // ---- round 3 done: h2 (registers), output layer forward + backward on the SIMT side ---
             float g_rgb[3] = {0.f, 0.f, 0.f};
@@ -552,7 +583,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                     }
                     store16<TD>(D, row, 4 * hf + 2 * c2, dl);
                 }
-                publish(ready);
+                publish(slot_id);
                 // dW3 += d3^T h2, db3 += sum d3  (off the critical path: the MMA round is running)
                 for (int c = 0; c < C; ++c) {
                     float t[32];
@@ -569,15 +600,16 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
 
             // ---- round 4 done: dh1 -> d1 = dh1 * act'(h1) -> D ------------------------------------
             await_mma(done, phase, dbg);
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 float dl[16], h[16];
                 tmem_ld_cols<16>(Z + 32 * hf + 16 * c, dl);
                 load16<TH>(H, row, 4 * hf + 2 * c, h);
                 mul_hidden_act_grad<16>(hact, dl, h);
+                if (c == 0) await_dw();                   // dW2 has read d2 (D) and h1 (H)
                 store16<TD>(D, row, 4 * hf + 2 * c, dl);
             }
-            publish(ready);
+            publish(slot_id);
 
             // ---- round 5 done: din1 -> dy (E), hb again (H) -----------------------------------------
             await_mma(done, phase, dbg);
@@ -587,9 +619,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 dy[0] = inside ? g_sigma * density_act_grad(f.density_act, raw) : 0.f;
 #pragma unroll
                 for (int j = 0; j < kGeo; ++j) dy[1 + j] = dgeo[j];
+                await_dw();                               // dW1 has read d1 (D) and [SH | geo | 1] (E)
                 store16<TE>(E, row, 0, dy);
                 stage_hb();
-                publish(ready);
+                publish(slot_id);
                 const float s = warp_transpose_sum<16>(dy, lane & 15);
                 // lanes l and l + 16 hold the two half-warp sums of column l
                 const float tot = s + __shfl_xor_sync(0xffffffffu, s, 16);
@@ -602,13 +635,14 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                     sh_degree4_grad(dir, dsh, dd);
                     if (valid) { d_dirs[3 * i] = dd[0]; d_dirs[3 * i + 1] = dd[1]; d_dirs[3 * i + 2] = dd[2]; }
                 }
+                await_dw();
                 stage_hb();
-                publish(ready);
+                publish(slot_id);
             }
 
             // ---- round 6 done: dhb -> db1 = dhb * act'(hb) -> D; enc again -> E -----------------------
             await_mma(done, phase, dbg);
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 float dl[16], h[16];
                 tmem_ld_cols<16>(Z + 32 * hf + 16 * c, dl);
@@ -616,8 +650,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 mul_hidden_act_grad<16>(hact, dl, h);
                 store16<TD>(D, row, 4 * hf + 2 * c, dl);
             }
+            await_dw();                                   // dWb2^T has read hb (H) and dy (E)
             stage_enc(i, valid);
-            publish(ready);
+            publish(slot_id);
 
             // ---- round 7 done: denc -> HBM ---------------------------------------------------------------
             await_mma(done, phase, dbg);
@@ -632,6 +667,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                             out[v4] = make_float4(de[4 * v4], de[4 * v4 + 1], de[4 * v4 + 2], de[4 * v4 + 3]);
                 }
             }
+            await_dw();                                   // dWb1 has read db1 (D) and enc (E)
             tc::tc_fence_before_sync();
         }
     }
