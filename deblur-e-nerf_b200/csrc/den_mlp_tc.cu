@@ -77,21 +77,22 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
 
     if (warp == kFwdEpiThreads / 32) {
         // ===================== MMA warp: one issue per round =====================
+        // hand-off in: named barrier 1 (producers arrive, this warp syncs); hand-off out: tcgen05.commit
+        // on the mbarrier; one elected lane issues the whole round
+#define DEN_ROUND(...)                                     \
+    handoff_sync(kFwdThreads);                             \
+    if (tc::elect_one()) { __VA_ARGS__; tc::mma_commit_1t(bar); } \
+    __syncwarp();
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            __syncthreads();
-            { tc::tc_fence_after_sync(); mma_fwd<kWidth, kEncDim>(tmem_base, T32, Wb1); tc::mma_commit(bar); }
-            __syncthreads();
-            { tc::tc_fence_after_sync(); mma_fwd<kBaseOut, kWidth>(tmem_base, T64, Wb2); tc::mma_commit(bar); }
+            DEN_ROUND(mma_fwd_1t<kWidth, kEncDim>(tmem_base, T32, Wb1))
+            DEN_ROUND(mma_fwd_1t<kBaseOut, kWidth>(tmem_base, T64, Wb2))
             if (kFull) {
-                __syncthreads();
-                { tc::tc_fence_after_sync(); mma_fwd<kWidth, kHeadIn>(tmem_base, T32, W1); tc::mma_commit(bar); }
-                __syncthreads();
-                { tc::tc_fence_after_sync(); mma_fwd<kWidth, kWidth>(tmem_base, T64, W2); tc::mma_commit(bar); }
-                __syncthreads();
-                { tc::tc_fence_after_sync(); mma_fwd<kOutN, kWidth>(tmem_base, T64, W3); tc::mma_commit(bar); }
+                DEN_ROUND(mma_fwd_1t<kWidth, kHeadIn>(tmem_base, T32, W1))
+                DEN_ROUND(mma_fwd_1t<kWidth, kWidth>(tmem_base, T64, W2))
+                DEN_ROUND(mma_fwd_1t<kOutN, kWidth>(tmem_base, T64, W3))
             }
-            __syncwarp();
         }
+#undef DEN_ROUND
     } else {
         // ===================== epilogue warps =====================
         const int q = warp & 3, cg = warp >> 2;
@@ -126,7 +127,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 if (cg == 0) inside = contract_position(f, pos, u);
             }
             store_cols<16, kEncDim>(T32, row, 16 * cg, x16);
-            publish();
+            publish_arrive(kFwdThreads);
 
             // ---- base layer 1 -------------------------------------------------------------------
             await(bar, phase);
@@ -134,7 +135,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             tmem_ld_cols<kFwdCols>(tmem_lane + kFwdCols * cg, h);
 bias_hidden_act<kFwdCols>(f.hidden_act, h, s_bb1 + kFwdCols * cg);
             store_cols<kFwdCols, kWidth>(T64, row, kFwdCols * cg, h);
-            publish();
+            publish_arrive(kFwdThreads);
 
             // ---- base layer 2: density + geo features; [SH | geo | 0] -> T32 --------------------
             await(bar, phase);
@@ -158,20 +159,20 @@ bias_hidden_act<kFwdCols>(f.hidden_act, h, s_bb1 + kFwdCols * cg);
                 tc::tc_fence_before_sync();
                 continue;
             }
-            publish();
+            publish_arrive(kFwdThreads);
 
             // ---- head layers ----------------------------------------------------------------------
             await(bar, phase);
             tmem_ld_cols<kFwdCols>(tmem_lane + kFwdCols * cg, h);
 bias_hidden_act<kFwdCols>(f.hidden_act, h, s_b1 + kFwdCols * cg);
             store_cols<kFwdCols, kWidth>(T64, row, kFwdCols * cg, h);
-            publish();
+            publish_arrive(kFwdThreads);
 
             await(bar, phase);
             tmem_ld_cols<kFwdCols>(tmem_lane + kFwdCols * cg, h);
 bias_hidden_act<kFwdCols>(f.hidden_act, h, s_b2 + kFwdCols * cg);
             store_cols<kFwdCols, kWidth>(T64, row, kFwdCols * cg, h);
-            publish();
+            publish_arrive(kFwdThreads);
 
             await(bar, phase);
             if (cg == 0) {

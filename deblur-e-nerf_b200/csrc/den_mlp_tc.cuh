@@ -63,6 +63,22 @@ __device__ __forceinline__ void mma_fwd(uint32_t tmem_d, const Tile<kTile, K>& a
     for (int ks = 0; ks < K / 16; ++ks) tc::mma_bf16(tmem_d, ah.at(ks * 256), wl.at(ks * 256), idesc, true);
 }
 
+// the same GEMM issued by the single elected thread (tc::elect_one)
+template <int N, int K>
+__device__ __forceinline__ void mma_fwd_1t(uint32_t tmem_d, const Tile<kTile, K>& a, const Tile<N, K>& w) {
+    constexpr uint32_t idesc = tc::instr_desc_bf16(128, N, false, false);
+    const Desc ah = make_desc(a.hi, 128, Tile<kTile, K>::row_group);
+    const Desc al = make_desc(a.lo, 128, Tile<kTile, K>::row_group);
+    const Desc wh = make_desc(w.hi, 128, Tile<N, K>::row_group);
+    const Desc wl = make_desc(w.lo, 128, Tile<N, K>::row_group);
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) tc::mma_bf16_1t(tmem_d, ah.at(ks * 256), wh.at(ks * 256), idesc, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) tc::mma_bf16_1t(tmem_d, al.at(ks * 256), wh.at(ks * 256), idesc, 1u);
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) tc::mma_bf16_1t(tmem_d, ah.at(ks * 256), wl.at(ks * 256), idesc, 1u);
+}
+
 // D[128 x N] = dY[128 x K] * W, W tile (K rows = out, N feats = in) read MN-major   — dX
 template <int N, int K>
 __device__ __forceinline__ void mma_dx(uint32_t tmem_d, const Tile<kTile, K>& dy, const Tile<K, N>& w) {
@@ -192,6 +208,17 @@ __device__ __forceinline__ void publish() {
     tc::fence_smem_to_async_proxy();
     tc::tc_fence_before_sync();
     __syncthreads();
+}
+// the same hand-off through named barrier 1 without blocking the producers: the epilogue threads
+// arrive and go on to their mbarrier wait, the MMA warp syncs (n_threads = epilogue + 32)
+__device__ __forceinline__ void publish_arrive(int n_threads) {
+    tc::fence_smem_to_async_proxy();
+    tc::tc_fence_before_sync();
+    asm volatile("bar.arrive 1, %0;" ::"r"(n_threads) : "memory");
+}
+__device__ __forceinline__ void handoff_sync(int n_threads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+    tc::tc_fence_after_sync();
 }
 __device__ __forceinline__ void await(uint64_t* bar, uint32_t& phase) {
     tc::mbar_wait(bar, phase);

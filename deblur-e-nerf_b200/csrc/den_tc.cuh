@@ -118,6 +118,35 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
         : "memory");
 }
 
+// Single-thread issue path: the MMA warp elects ONE lane per GEMM round (elect_one), which then
+// issues every tcgen05.mma of the round and the commit from straight-line code.  Descriptor
+// arithmetic lands on the uniform datapath (5 SASS instructions per MMA; the per-MMA elect.sync
+// form above costs 14).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t leader;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(leader));
+    return leader != 0;
+}
+__device__ __forceinline__ void mma_bf16_1t(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_1t(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+
 // ---- TMEM -> registers (warp-collective; thread i of the warp gets lane base+i) -------
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
