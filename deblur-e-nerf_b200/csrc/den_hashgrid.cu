@@ -147,32 +147,34 @@ hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
                 const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
                 const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float w = ((c & 1) ? cf.f[0] : 1.f - cf.f[0]) *
-                              (((c >> 1) & 1) ? cf.f[1] : 1.f - cf.f[1]) *
-                              (((c >> 2) & 1) ? cf.f[2] : 1.f - cf.f[2]);
-                    float ax = w * gx, ay = w * gy;
+                for (int c = 0; c < 8; c += 2) {           // x-neighbour pairs (c, c + 1)
+                    const float wyz = (((c >> 1) & 1) ? cf.f[1] : 1.f - cf.f[1]) *
+                                      (((c >> 2) & 1) ? cf.f[2] : 1.f - cf.f[2]);
+                    const float w0 = (1.f - cf.f[0]) * wyz, w1 = cf.f[0] * wyz;
+                    float a0 = w0 * gx, b0 = w0 * gy, a1 = w1 * gx, b1 = w1 * gy;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
-                        float tx = __shfl_up_sync(0xffffffffu, ax, d);
-                        float ty = __shfl_up_sync(0xffffffffu, ay, d);
-                        if (lane - d >= start) { ax += tx; ay += ty; }
+                        const float t0 = __shfl_up_sync(0xffffffffu, a0, d);
+                        const float t1 = __shfl_up_sync(0xffffffffu, b0, d);
+                        const float t2 = __shfl_up_sync(0xffffffffu, a1, d);
+                        const float t3 = __shfl_up_sync(0xffffffffu, b1, d);
+                        if (lane - d >= start) { a0 += t0; b0 += t1; a1 += t2; b1 += t3; }
                     }
                     if (tail && valid) {
-                        uint32_t idx = entry_index(li, cf.c[0] + (c & 1), cf.c[1] + ((c >> 1) & 1),
-                                                   cf.c[2] + ((c >> 2) & 1));
-                        red_add_v2(gbase + idx, ax, ay);
+                        const uint32_t cy = cf.c[1] + ((c >> 1) & 1), cz = cf.c[2] + ((c >> 2) & 1);
+                        red_add_pair(gbase, entry_index(li, cf.c[0], cy, cz), entry_index(li, cf.c[0] + 1, cy, cz),
+                                     a0, b0, a1, b1);
                     }
                 }
             } else if (valid) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float w = ((c & 1) ? cf.f[0] : 1.f - cf.f[0]) *
-                              (((c >> 1) & 1) ? cf.f[1] : 1.f - cf.f[1]) *
-                              (((c >> 2) & 1) ? cf.f[2] : 1.f - cf.f[2]);
-                    uint32_t idx = entry_index(li, cf.c[0] + (c & 1), cf.c[1] + ((c >> 1) & 1),
-                                               cf.c[2] + ((c >> 2) & 1));
-                    red_add_v2(gbase + idx, w * gx, w * gy);
+                for (int c = 0; c < 8; c += 2) {
+                    const float wyz = (((c >> 1) & 1) ? cf.f[1] : 1.f - cf.f[1]) *
+                                      (((c >> 2) & 1) ? cf.f[2] : 1.f - cf.f[2]);
+                    const float w0 = (1.f - cf.f[0]) * wyz, w1 = cf.f[0] * wyz;
+                    const uint32_t cy = cf.c[1] + ((c >> 1) & 1), cz = cf.c[2] + ((c >> 2) & 1);
+                    red_add_pair(gbase, entry_index(li, cf.c[0], cy, cz), entry_index(li, cf.c[0] + 1, cy, cz),
+                                 w0 * gx, w0 * gy, w1 * gx, w1 * gy);
                 }
             }
 

@@ -70,4 +70,23 @@ __device__ __forceinline__ void red_add_v2(float2* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+__device__ __forceinline__ void red_add_v4(float2* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+// The two x-neighbours (cx, cx + 1) of a cell edge: when their entries are the aligned pair
+// {2k, 2k + 1} (dense levels with an even / odd start, hashed power-of-two levels whenever cx is even:
+// (cx ^ h) and ((cx | 1) ^ h) differ in bit 0 only) one 16-byte vector reduction replaces two 8-byte
+// ones — the L2 atomic unit is the bound of the scatter, not the bytes.
+__device__ __forceinline__ void red_add_pair(float2* base, uint32_t idx0, uint32_t idx1, float a0, float b0,
+                                             float a1, float b1) {
+    if ((idx0 ^ idx1) == 1u) {
+        if (idx0 & 1u) red_add_v4(base + idx1, a1, b1, a0, b0);
+        else red_add_v4(base + idx0, a0, b0, a1, b1);
+    } else {
+        red_add_v2(base + idx0, a0, b0);
+        red_add_v2(base + idx1, a1, b1);
+    }
+}
+
 }  // namespace den
