@@ -126,7 +126,12 @@ hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
             py = __ldg(x + 3 * m + 1);
             pz = __ldg(x + 3 * m + 2);
         }
-        for (int level = warp; level < g.n_levels; level += nwarp) {
+        // coarse (run-merging, expensive) and fine (cheap) levels are paired on the same warp:
+        // warp w takes levels w, L-1-w, w + 2*nwarp, L-1-w - 2*nwarp, ...
+        for (int it = warp; it < g.n_levels; it += nwarp) {
+            const int pair = it / nwarp;                  // 0, 1, 2, ...
+            const int level = (pair & 1) ? g.n_levels - 1 - (it - pair * nwarp) - (pair >> 1) * nwarp
+                                         : (it - pair * nwarp) + (pair >> 1) * nwarp;
             const LevelInfo li = make_level(g, level);
             float2* __restrict__ gbase = dtable + g.offset[level];
             const CellFrac cf = locate(li.scale, px, py, pz);
@@ -146,6 +151,8 @@ hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
                 const uint32_t heads = __ballot_sync(0xffffffffu, head);
                 const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
                 const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+                // scan steps beyond the longest run of this warp cannot contribute (warp-uniform bound)
+                const int max_run = __reduce_max_sync(0xffffffffu, lane - start + 1);
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {           // x-neighbour pairs (c, c + 1)
                     const float wyz = (((c >> 1) & 1) ? cf.f[1] : 1.f - cf.f[1]) *
@@ -154,6 +161,7 @@ hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
                     float a0 = w0 * gx, b0 = w0 * gy, a1 = w1 * gx, b1 = w1 * gy;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
+                        if (d >= max_run) break;
                         const float t0 = __shfl_up_sync(0xffffffffu, a0, d);
                         const float t1 = __shfl_up_sync(0xffffffffu, b0, d);
                         const float t2 = __shfl_up_sync(0xffffffffu, a1, d);

@@ -35,7 +35,10 @@ __device__ __forceinline__ LevelInfo make_level(const den_hashgrid_desc& g, int 
 __device__ __forceinline__ uint32_t entry_index(const LevelInfo& li, uint32_t cx, uint32_t cy, uint32_t cz) {
     uint32_t idx = li.hashed ? (cx ^ (cy * kPrime1) ^ (cz * kPrime2))
                              : (cx * li.st0 + cy * li.st1 + cz * li.st2);
-    return li.mask ? (idx & li.mask) : (idx % li.size);
+    if (li.mask) return idx & li.mask;
+    // dense level: the linear index of an in-range cell is already < size; the (slow) modulo only runs
+    // for out-of-range positions, where tcnn's wrap-around must be reproduced bit for bit
+    return idx < li.size ? idx : idx % li.size;
 }
 
 struct CellFrac {
