@@ -207,6 +207,14 @@ __global__ void accumulate_bwd_kernel(const float* __restrict__ weights,
 }
 
 // ------------------------------------------------------- fused compositor ----
+// Memory-level parallelism: a ray is consumed in groups of kGroupBwd chunks of 32 samples; the loads
+// of a whole group — sigma, t0, t1, rgb: 4 * kGroupBwd independent coalesced 128-byte lines per
+// warp — are issued in one burst before any of the dependent scan arithmetic of the group starts.
+// v1 had one load -> scan -> load chain per chunk and sat at 0.23 of the HBM roofline,
+// long-scoreboard bound (profiles/r01_ncu_full_misc_kernels.md).
+constexpr int kGroupBwd = 8;        // forward
+constexpr int kGroupBwdBwd = 4;     // backward (more live registers per chunk)
+
 template <int C>
 __global__ void __launch_bounds__(kRayThreads)
 composite_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
@@ -219,18 +227,30 @@ composite_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__
         float carry = 0.f, acc_o = 0.f, acc_d = 0.f, acc_c[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) acc_c[k] = 0.f;
-        for (int i0 = beg; i0 < end; i0 += 32) {
-            const int i = i0 + lane;
-            const bool ok = i < end;
-            const float a = ok ? t0[i] : 0.f, b = ok ? t1[i] : 0.f;
-            const float sdt = ok ? sigmas[i] * (b - a) : 0.f;
-            const float inc = warp_inclusive_sum(sdt, lane);
-            const float w = ok ? __expf(-(carry + inc - sdt)) * (1.f - __expf(-sdt)) : 0.f;
-            acc_o += w;
-            acc_d += w * (a + b) * 0.5f;
+        for (int g0 = beg; g0 < end; g0 += 32 * kGroupBwd) {
+            float sg[kGroupBwd], ta[kGroupBwd], tb[kGroupBwd], col[kGroupBwd][C];
 #pragma unroll
-            for (int k = 0; k < C; ++k) acc_c[k] += ok ? w * rgbs[(int64_t)i * C + k] : 0.f;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
+            for (int c = 0; c < kGroupBwd; ++c) {
+                const int i = g0 + 32 * c + lane;
+                const bool ok = i < end;
+                sg[c] = ok ? __ldg(sigmas + i) : 0.f;
+                ta[c] = ok ? __ldg(t0 + i) : 0.f;
+                tb[c] = ok ? __ldg(t1 + i) : 0.f;
+#pragma unroll
+                for (int k = 0; k < C; ++k) col[c][k] = ok ? __ldg(rgbs + (int64_t)i * C + k) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < kGroupBwd; ++c) {
+                if (g0 + 32 * c >= end) break;                     // warp-uniform
+                const float sdt = sg[c] * (tb[c] - ta[c]);         // 0 beyond the ray's end
+                const float inc = warp_inclusive_sum(sdt, lane);
+                const float w = __expf(-(carry + inc - sdt)) * (1.f - __expf(-sdt));
+                acc_o += w;
+                acc_d += w * (ta[c] + tb[c]) * 0.5f;
+#pragma unroll
+                for (int k = 0; k < C; ++k) acc_c[k] += w * col[c][k];
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
         }
         acc_o = warp_sum(acc_o);
         acc_d = warp_sum(acc_d);
@@ -244,6 +264,41 @@ composite_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__
                 colour[r * C + k] = acc_c[k] + (bkgd ? bkgd[k] * (1.f - acc_o) : 0.f);
         }
     }
+}
+
+// one chunk of the back-to-front sweep (shared by the cached and the streaming path)
+template <int C>
+__device__ __forceinline__ void composite_bwd_chunk(int lane, bool ok, float a, float b, float sigma,
+                                                    const float (&rgb)[C], const float (&gc)[C], float g_op,
+                                                    float g_dp, float tot, float& suf_sdt, float& suf_gw,
+                                                    float& d_sigma, float (&d_rgb)[C]) {
+    const float dt = b - a;
+    const float sdt = ok ? sigma * dt : 0.f;
+    float g = g_op + g_dp * (a + b) * 0.5f;               // dL/dw_i
+#pragma unroll
+    for (int k = 0; k < C; ++k) g += gc[k] * rgb[k];
+    if (!ok) g = 0.f;
+    float suf = sdt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float t = __shfl_down_sync(0xffffffffu, suf, d);
+        if (lane + d < 32) suf += t;
+    }
+    const float T = __expf(-(tot - (suf_sdt + suf)));
+    const float keep = __expf(-sdt);
+    const float w = T * (1.f - keep);
+    const float gw = g * w;
+    float sgw = gw;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float t = __shfl_down_sync(0xffffffffu, sgw, d);
+        if (lane + d < 32) sgw += t;
+    }
+    d_sigma = dt * (g * T * keep - (suf_gw + sgw - gw));
+#pragma unroll
+    for (int k = 0; k < C; ++k) d_rgb[k] = gc[k] * w;
+    suf_sdt += __shfl_sync(0xffffffffu, suf, 0);
+    suf_gw += __shfl_sync(0xffffffffu, sgw, 0);
 }
 
 template <int C>
@@ -261,6 +316,7 @@ composite_bwd_kernel(const float* __restrict__ sigmas, const float* __restrict__
 
     DEN_FOR_EACH_RAY(r) {
         const int beg = offsets[r], end = offsets[r + 1];
+        const int n = end - beg;
         float gc[C];
         float g_op = d_opacity ? d_opacity[r] : 0.f;
         const float g_dp = d_depth ? d_depth[r] : 0.f;
@@ -272,50 +328,54 @@ composite_bwd_kernel(const float* __restrict__ sigmas, const float* __restrict__
                 if (lane == 0) bk_acc[k] += gc[k] * (1.f - opacity[r]);
             }
         }
-        if (beg == end) continue;
+        if (n == 0) continue;
+        // pass A: total optical depth of the ray (burst loads, kGroupBwd * 2 chunks in flight)
         float tot = 0.f;
-        for (int i = beg + lane; i < end; i += 32) tot += sigmas[i] * (t1[i] - t0[i]);
+        for (int g0 = beg; g0 < end; g0 += 32 * kGroupBwd) {
+            float sg[kGroupBwd], ta[kGroupBwd], tb[kGroupBwd];
+#pragma unroll
+            for (int c = 0; c < kGroupBwd; ++c) {
+                const int i = g0 + 32 * c + lane;
+                const bool ok = i < end;
+                sg[c] = ok ? __ldg(sigmas + i) : 0.f;
+                ta[c] = ok ? __ldg(t0 + i) : 0.f;
+                tb[c] = ok ? __ldg(t1 + i) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < kGroupBwd; ++c) tot += sg[c] * (tb[c] - ta[c]);
+        }
         tot = warp_sum(tot);
-
+        // pass B: back to front in groups of kGroupBwd chunks (the ray's lines are L1/L2-hot from pass A)
         float suf_sdt = 0.f, suf_gw = 0.f;
-        const int n = end - beg;
-        for (int c = (n + 31) / 32 - 1; c >= 0; --c) {
-            const int i = beg + c * 32 + lane;
-            const bool ok = i < end;
-            const float a = ok ? t0[i] : 0.f, b = ok ? t1[i] : 0.f;
-            const float dt = b - a;
-            const float sdt = ok ? sigmas[i] * dt : 0.f;
-            float g = g_op + g_dp * (a + b) * 0.5f;               // dL/dw_i
-            float rgb[C];
+        const int n_chunks = (n + 31) / 32;
+        for (int c_hi = n_chunks; c_hi > 0; c_hi -= kGroupBwd) {
+            float sg[kGroupBwd], ta[kGroupBwd], tb[kGroupBwd], col[kGroupBwd][C];
 #pragma unroll
-            for (int k = 0; k < C; ++k) {
-                rgb[k] = ok ? rgbs[(int64_t)i * C + k] : 0.f;
-                g += gc[k] * rgb[k];
-            }
-            if (!ok) g = 0.f;
-            float suf = sdt;
+            for (int j = 0; j < kGroupBwd; ++j) {
+                const int c = c_hi - 1 - j;
+                const int i = beg + 32 * c + lane;
+                const bool ok = c >= 0 && i < end;
+                sg[j] = ok ? __ldg(sigmas + i) : 0.f;
+                ta[j] = ok ? __ldg(t0 + i) : 0.f;
+                tb[j] = ok ? __ldg(t1 + i) : 0.f;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                float t = __shfl_down_sync(0xffffffffu, suf, d);
-                if (lane + d < 32) suf += t;
+                for (int k = 0; k < C; ++k) col[j][k] = ok ? __ldg(rgbs + (int64_t)i * C + k) : 0.f;
             }
-            const float T = __expf(-(tot - (suf_sdt + suf)));
-            const float keep = __expf(-sdt);
-            const float w = T * (1.f - keep);
-            const float gw = g * w;
-            float sgw = gw;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                float t = __shfl_down_sync(0xffffffffu, sgw, d);
-                if (lane + d < 32) sgw += t;
-            }
-            if (ok) {
-                d_sigmas[i] = dt * (g * T * keep - (suf_gw + sgw - gw));
+            for (int j = 0; j < kGroupBwd; ++j) {
+                const int c = c_hi - 1 - j;
+                if (c < 0) break;                                  // warp-uniform
+                const int i = beg + 32 * c + lane;
+                const bool ok = i < end;
+                float ds, drgb[C];
+                composite_bwd_chunk<C>(lane, ok, ta[j], tb[j], sg[j], col[j], gc, g_op, g_dp, tot, suf_sdt,
+                                       suf_gw, ds, drgb);
+                if (ok) {
+                    d_sigmas[i] = ds;
 #pragma unroll
-                for (int k = 0; k < C; ++k) d_rgbs[(int64_t)i * C + k] = gc[k] * w;
+                    for (int k = 0; k < C; ++k) d_rgbs[(int64_t)i * C + k] = drgb[k];
+                }
             }
-            suf_sdt += __shfl_sync(0xffffffffu, suf, 0);
-            suf_gw += __shfl_sync(0xffffffffu, sgw, 0);
         }
     }
     if (bkgd && d_bkgd && (threadIdx.x & 31) == 0) {
