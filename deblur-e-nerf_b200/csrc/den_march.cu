@@ -73,7 +73,9 @@ __device__ __forceinline__ bool occupied_at(const float xyz[3], const MarchCtx& 
     return binary[idx] != 0;
 }
 
-template <bool kWrite>
+// kMode 0: count only.  1: write at offsets[r] (second pass of the two-pass scheme).  2: single pass —
+// write into the ray's own segment [offsets[r], offsets[r+1]) of an upper-bound arena AND count.
+template <int kMode>
 __global__ void __launch_bounds__(128)
 march_kernel(const __grid_constant__ den_march_params p, const float* __restrict__ rays_o,
              const float* __restrict__ rays_d, const float* __restrict__ t_min,
@@ -99,8 +101,9 @@ march_kernel(const __grid_constant__ den_march_params p, const float* __restrict
         const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
         const float dir[3] = {rays_d[3 * r], rays_d[3 * r + 1], rays_d[3 * r + 2]};
         const float far = t_max[r];
-        int64_t base = 0;
-        if (kWrite) base = offsets[r];
+        int64_t base = 0, seg = 0;
+        if (kMode >= 1) base = offsets[r];
+        if (kMode == 2) seg = offsets[r + 1] - base;
 
         int j = 0;
         float t0 = t_min[r];
@@ -111,12 +114,17 @@ march_kernel(const __grid_constant__ den_march_params p, const float* __restrict
 #pragma unroll
             for (int d = 0; d < 3; ++d) xyz[d] = fadd(o[d], fmul(tm, dir[d]));
             if (occupied_at(xyz, c, binary)) {
-                if (kWrite) {
+                if (kMode == 1) {
                     const int64_t k = base + j;
                     if (k < capacity) {
                         t_starts[k] = t0;
                         t_ends[k] = t1;
                         ray_indices[k] = (int32_t)r;
+                    }
+                } else if (kMode == 2) {
+                    if (j < seg) {
+                        t_starts[base + j] = t0;
+                        t_ends[base + j] = t1;
                     }
                 }
                 ++j;
@@ -152,7 +160,44 @@ march_kernel(const __grid_constant__ den_march_params p, const float* __restrict
                 tm = fmul(fadd(t0, t1), 0.5f);
             }
         }
-        if (!kWrite) num_steps[r] = j;
+        if (kMode != 1) num_steps[r] = j;
+    }
+}
+
+// Upper bound of the samples ray r can emit: every emitted sample advances t0 by dt >= dt_min and has
+// its midpoint below t_max, so count <= (t_max - t_min) / dt_min + 1 (+1 rounding slack).
+__global__ void march_bound_kernel(const float* __restrict__ t_min, const float* __restrict__ t_max,
+                                   float dt_min, int32_t cap, int32_t* __restrict__ bound, int64_t n_rays) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rays;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const float span = t_max[r] - t_min[r];
+        int32_t b = 0;
+        if (span > 0.f) {
+            const float steps = span / dt_min + 3.0f;
+            b = steps < (float)cap ? (int32_t)steps : cap;
+        }
+        bound[r] = b;
+    }
+}
+
+// One warp per ray: copy the first count[r] samples of the ray's arena segment to their packed place.
+__global__ void __launch_bounds__(256)
+march_pack_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ offsets,
+                  const float* __restrict__ arena_t0, const float* __restrict__ arena_t1,
+                  int64_t n_rays, int32_t* __restrict__ ray_indices, float* __restrict__ t_starts,
+                  float* __restrict__ t_ends) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n_rays; r += nwarps) {
+        const int64_t src = seg_offsets[r];
+        const int64_t dst = offsets[r];
+        const int count = offsets[r + 1] - offsets[r];
+        for (int j = lane; j < count; j += 32) {
+            t_starts[dst + j] = arena_t0[src + j];
+            t_ends[dst + j] = arena_t1[src + j];
+            ray_indices[dst + j] = (int32_t)r;
+        }
     }
 }
 
@@ -379,7 +424,7 @@ int den_march_count(const den_march_params* p, const float* o, const float* d, c
     DEN_CHECK_ARG(n >= 0, "negative ray count");
     if (n == 0) return DEN_OK;
     DEN_CHECK_ARG(o && d && tmin && tmax && binary && num_steps, "null pointer");
-    march_kernel<false><<<grid_for(n, 128, 16), 128, 0, as_stream(stream)>>>(
+    march_kernel<0><<<grid_for(n, 128, 16), 128, 0, as_stream(stream)>>>(
         *p, o, d, tmin, tmax, binary, nullptr, num_steps, nullptr, nullptr, nullptr, n, 0);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
@@ -396,8 +441,51 @@ int den_march_write(const den_march_params* p, const float* o, const float* d, c
     if (n == 0) return DEN_OK;
     DEN_CHECK_ARG(o && d && tmin && tmax && binary && offsets, "null pointer");
     DEN_CHECK_ARG(capacity == 0 || (ray_indices && t_starts && t_ends), "null output");
-    march_kernel<true><<<grid_for(n, 128, 16), 128, 0, as_stream(stream)>>>(
+    march_kernel<1><<<grid_for(n, 128, 16), 128, 0, as_stream(stream)>>>(
         *p, o, d, tmin, tmax, binary, offsets, nullptr, ray_indices, t_starts, t_ends, n, capacity);
+    DEN_CHECK_LAUNCH();
+    return DEN_OK;
+}
+
+int den_march_bound(const den_march_params* p, const float* tmin, const float* tmax,
+                    int32_t max_per_ray, int32_t* bound, int64_t n, void* stream) {
+    using namespace den;
+    int rc = check_march(p);
+    if (rc) return rc;
+    DEN_CHECK_ARG(n >= 0 && max_per_ray > 0, "bad size");
+    if (n == 0) return DEN_OK;
+    DEN_CHECK_ARG(tmin && tmax && bound, "null pointer");
+    march_bound_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(tmin, tmax, p->step_size,
+                                                                          max_per_ray, bound, n);
+    DEN_CHECK_LAUNCH();
+    return DEN_OK;
+}
+
+int den_march_single(const den_march_params* p, const float* o, const float* d, const float* tmin,
+                     const float* tmax, const uint8_t* binary, const int32_t* seg_offsets,
+                     int32_t* num_steps, float* arena_t0, float* arena_t1, int64_t n, void* stream) {
+    using namespace den;
+    int rc = check_march(p);
+    if (rc) return rc;
+    DEN_CHECK_ARG(n >= 0, "negative size");
+    if (n == 0) return DEN_OK;
+    DEN_CHECK_ARG(o && d && tmin && tmax && binary && seg_offsets && num_steps && arena_t0 && arena_t1,
+                  "null pointer");
+    march_kernel<2><<<grid_for(n, 128, 16), 128, 0, as_stream(stream)>>>(
+        *p, o, d, tmin, tmax, binary, seg_offsets, num_steps, nullptr, arena_t0, arena_t1, n, 0);
+    DEN_CHECK_LAUNCH();
+    return DEN_OK;
+}
+
+int den_march_pack(const int32_t* seg_offsets, const int32_t* offsets, const float* arena_t0,
+                   const float* arena_t1, int64_t n, int32_t* ray_indices, float* t_starts,
+                   float* t_ends, void* stream) {
+    using namespace den;
+    DEN_CHECK_ARG(n >= 0, "negative size");
+    if (n == 0) return DEN_OK;
+    DEN_CHECK_ARG(seg_offsets && offsets && arena_t0 && arena_t1, "null pointer");
+    march_pack_kernel<<<grid_for(n, 8, 8), 256, 0, as_stream(stream)>>>(
+        seg_offsets, offsets, arena_t0, arena_t1, n, ray_indices, t_starts, t_ends);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }

@@ -144,7 +144,17 @@ class NeRF(torch.nn.Module):
         params = ops.make_march_params(grid._roi_host, grid._res_host,
                                        self.contraction_type.to_cpp_version(), self._step_host,
                                        self.cone_angle)
-        return ops.march(params, o, d, t_min, t_max, grid.binary)
+        # samples per ray are bounded by the marched span: near..far when both planes are set (the
+        # jitter only moves t_min forward), else the AABB diagonal
+        if self.near_plane is not None and self.far_plane is not None:
+            seg_len = ops.march_segment_length(self.near_plane, self.far_plane, self._step_host)
+        elif self.contraction_type == ContractionType.AABB:
+            a = self._aabb_host
+            diag = sum((a[i + 3] - a[i]) ** 2 for i in range(3)) ** 0.5
+            seg_len = ops.march_segment_length(0.0, diag, self._step_host)
+        else:
+            seg_len = None
+        return ops.march(params, o, d, t_min, t_max, grid.binary, seg_len=seg_len)
 
     def render_chunk(self, o, d, jitter=None):
         """One chunk of rays (R,3),(R,3) -> colour (R,C), opacity (R,), depth (R,), M."""

@@ -205,7 +205,9 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
         ctype = ContractionType.AABB.to_cpp_version()
     params = ops.make_march_params(roi, list(binary.shape), ctype, float(render_step_size),
                                    float(cone_angle))
-    ray_indices, t_starts, t_ends, offsets = ops.march(params, rays_o, rays_d, t_min, t_max, binary)
+    seg_len = ops.march_segment_length(near_plane, far_plane, float(render_step_size))
+    ray_indices, t_starts, t_ends, offsets = ops.march(params, rays_o, rays_d, t_min, t_max, binary,
+                                                       seg_len=seg_len)
     t_starts = t_starts[:, None]
     t_ends = t_ends[:, None]
 

@@ -251,12 +251,41 @@ def clamp_jitter_(t_min, t_max, jitter, near_plane, far_plane, step_size):
           _stream())
 
 
-def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None):
-    """Two-pass occupancy march.  Returns (ray_indices i32, t_starts, t_ends, offsets (R+1)).
+MARCH_MAX_PER_RAY = 8192            # bound-kernel path: a ray whose bound exceeds this takes two passes
+MARCH_ARENA_MAX = 1 << 29           # uniform-segment arena limit (entries; 2 x 4 B each = 4 GiB)
+_ARENA = {}                         # device -> (t0, t1) grow-only scratch arena
+_SEG_OFFSETS = {}                   # (device, n, seg_len) -> int32 arange(n + 1) * seg_len
 
-    With ``capacity=None`` the total is read back (one host sync, as upstream does) and
-    the outputs are exact-size; with a capacity the arena is caller-bounded, nothing is
-    synchronised and ``offsets[-1]`` (device) holds the true total.
+
+def _arena(dev, n):
+    cur = _ARENA.get(dev)
+    if cur is None or cur[0].numel() < n:
+        cur = (torch.empty(n, dtype=torch.float32, device=dev),
+               torch.empty(n, dtype=torch.float32, device=dev))
+        _ARENA[dev] = cur
+    return cur
+
+
+def march_segment_length(t_lo, t_hi, step_size):
+    """Most samples a ray can emit between distances t_lo and t_hi (host arithmetic, + slack)."""
+    if t_lo is None or t_hi is None or not math.isfinite(t_hi - t_lo):
+        return None
+    return int(max(t_hi - t_lo, 0.0) / float(step_size)) + 4
+
+
+def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=None,
+          single_pass=True):
+    """Occupancy march.  Returns (ray_indices i32, t_starts, t_ends, offsets (R+1)).
+
+    Default: ONE marching pass into an upper-bound arena, then a coalesced pack — the sequential
+    marching loop, the expensive part, runs once instead of twice.  With ``seg_len`` (a host-known
+    bound of the samples per ray, e.g. (far - near) / step) every ray owns a fixed segment of a
+    cached scratch arena and the only host read is the sample total; without it the per-ray bounds
+    come from ``den_march_bound`` (one more host read for the arena size).
+    ``single_pass=False`` (or a caller-given ``capacity``) selects the count + write scheme: with
+    ``capacity=None`` the total is read back (one host sync, as upstream does) and the outputs are
+    exact-size; with a capacity the arena is caller-bounded, nothing is synchronised and
+    ``offsets[-1]`` (device) holds the true total.
     """
     rays_o = _req(rays_o, torch.float32, "rays_o")
     rays_d = _req(rays_d, torch.float32, "rays_d")
@@ -268,11 +297,43 @@ def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None):
     n = rays_o.shape[0]
     dev = rays_o.device
     counts = torch.empty(n, dtype=torch.int32, device=dev)
-    _call("den_march_count", ctypes.byref(params), _ptr(rays_o), _ptr(rays_d), _ptr(t_min),
-          _ptr(t_max), _ptr(binary), _ptr(counts), n, _stream())
-    offsets = exclusive_scan_i32(counts)
-    if capacity is None:
-        capacity = int(offsets[-1].item())
+    if single_pass and capacity is None and n > 0:
+        if seg_len is not None and n * seg_len <= MARCH_ARENA_MAX:
+            key = (dev, n, seg_len)
+            seg = _SEG_OFFSETS.get(key)
+            if seg is None:
+                seg = (torch.arange(n + 1, dtype=torch.int64, device=dev) * seg_len).to(torch.int32)
+                if len(_SEG_OFFSETS) > 16:
+                    _SEG_OFFSETS.clear()
+                _SEG_OFFSETS[key] = seg
+            bound = None
+            arena_t0, arena_t1 = _arena(dev, n * seg_len)
+        else:
+            bound = torch.empty(n, dtype=torch.int32, device=dev)
+            _call("den_march_bound", ctypes.byref(params), _ptr(t_min), _ptr(t_max),
+                  MARCH_MAX_PER_RAY, _ptr(bound), n, _stream())
+            seg = exclusive_scan_i32(bound)
+            arena_t0, arena_t1 = _arena(dev, max(int(seg[-1].item()), 1))    # host read: arena size
+        _call("den_march_single", ctypes.byref(params), _ptr(rays_o), _ptr(rays_d), _ptr(t_min),
+              _ptr(t_max), _ptr(binary), _ptr(seg), _ptr(counts), _ptr(arena_t0), _ptr(arena_t1), n,
+              _stream())
+        offsets = exclusive_scan_i32(counts)
+        over = (counts > (seg_len if bound is None else bound)).any().to(torch.int32)
+        total, overflow = (int(v) for v in torch.stack((offsets[-1], over)).tolist())   # host read
+        if not overflow:
+            ray_indices = torch.empty(total, dtype=torch.int32, device=dev)
+            t_starts = torch.empty(total, dtype=torch.float32, device=dev)
+            t_ends = torch.empty(total, dtype=torch.float32, device=dev)
+            _call("den_march_pack", _ptr(seg), _ptr(offsets), _ptr(arena_t0), _ptr(arena_t1), n,
+                  _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _stream())
+            return ray_indices, t_starts, t_ends, offsets
+        capacity = total            # a ray outgrew its segment: exact write pass instead
+    else:
+        _call("den_march_count", ctypes.byref(params), _ptr(rays_o), _ptr(rays_d), _ptr(t_min),
+              _ptr(t_max), _ptr(binary), _ptr(counts), n, _stream())
+        offsets = exclusive_scan_i32(counts)
+        if capacity is None:
+            capacity = int(offsets[-1].item())
     ray_indices = torch.empty(capacity, dtype=torch.int32, device=dev)
     t_starts = torch.empty(capacity, dtype=torch.float32, device=dev)
     t_ends = torch.empty(capacity, dtype=torch.float32, device=dev)

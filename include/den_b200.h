@@ -115,6 +115,23 @@ int den_march_write(const den_march_params* p, const float* rays_o, const float*
                     const int32_t* offsets, int32_t* ray_indices, float* t_starts, float* t_ends,
                     int64_t n_rays, int64_t capacity, void* stream);
 
+/* Single-pass alternative to count + write (the marching loop runs once): den_march_bound gives a
+ * per-ray upper bound of the samples ray r can emit (<= max_per_ray); after an exclusive scan of the
+ * bounds (seg_offsets, n_rays+1) den_march_single marches every ray once, writing t_starts/t_ends
+ * into the ray's own segment of the arena and its true count into num_steps; after a scan of the
+ * counts (offsets) den_march_pack copies the segments to their packed place and fills ray_indices.
+ * A ray whose count exceeds its segment keeps counting but stops writing (the caller compares
+ * num_steps with the bounds and falls back to den_march_write). */
+int den_march_bound(const den_march_params* p, const float* t_min, const float* t_max,
+                    int32_t max_per_ray, int32_t* bound, int64_t n_rays, void* stream);
+int den_march_single(const den_march_params* p, const float* rays_o, const float* rays_d,
+                     const float* t_min, const float* t_max, const uint8_t* binary,
+                     const int32_t* seg_offsets, int32_t* num_steps, float* arena_t0,
+                     float* arena_t1, int64_t n_rays, void* stream);
+int den_march_pack(const int32_t* seg_offsets, const int32_t* offsets, const float* arena_t0,
+                   const float* arena_t1, int64_t n_rays, int32_t* ray_indices, float* t_starts,
+                   float* t_ends, void* stream);
+
 /* Visibility filter + compaction — replaces nerfacc.render_visibility and the
  * three boolean-mask compactions inside nerfacc.ray_marching. */
 /* alpha = 1 - exp(-sigma * (t1 - t0)) */

@@ -163,6 +163,28 @@ def test_march_bit_exact(den_lib, cuda, case):
     assert torch.equal(te.cpu(), te_ref)
 
 
+@pytest.mark.parametrize("seg", ["uniform", "bound", "overflow"])
+def test_march_single_pass_equals_two_pass(den_lib, cuda, seg):
+    """The one-pass march (upper-bound arena + pack) returns exactly what count + write returns,
+    for fixed segments, for den_march_bound segments, and when a too-small segment forces the
+    fall-back write pass."""
+    from deblur_e_nerf_b200 import nerfacc as nf, ops
+    roi, res, step = [-1.5] * 3 + [1.5] * 3, 64, 3 ** 0.5 * 3 / 1024
+    grid_ref = _grid(res, nerfacc_ref.ContractionType.AABB, roi, 0.2, seed=11)
+    binary = grid_ref._binary.to(cuda)
+    o, d = _rays(5000, 21)
+    o, d = o.to(cuda), d.to(cuda)
+    t_min, t_max = ops.ray_aabb_intersect(o, d, roi)
+    ops.clamp_jitter_(t_min, t_max, torch.rand_like(t_min), 1.43, 6.63, step)
+    params = ops.make_march_params(roi, [res] * 3, nf.ContractionType.AABB.to_cpp_version(), step, 0.0)
+    ref = ops.march(params, o, d, t_min, t_max, binary, single_pass=False)
+    seg_len = {"uniform": ops.march_segment_length(1.43, 6.63, step), "bound": None, "overflow": 5}[seg]
+    out = ops.march(params, o, d, t_min, t_max, binary, seg_len=seg_len)
+    assert ref[0].numel() > 10000
+    for a, b in zip(out, ref):
+        assert a.dtype == b.dtype and torch.equal(a, b)
+
+
 def test_march_with_sigma_fn_and_visibility(den_lib, cuda):
     """Full ray_marching path: density callback -> alphas -> visibility -> compaction.
     alphas come from the same fp32 formula on both sides only up to exp() ulps, so the
