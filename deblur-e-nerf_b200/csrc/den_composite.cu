@@ -207,13 +207,13 @@ __global__ void accumulate_bwd_kernel(const float* __restrict__ weights,
 }
 
 // ------------------------------------------------------- fused compositor ----
-// Memory-level parallelism: a ray is consumed in groups of kGroupBwd chunks of 32 samples; the loads
-// of a whole group — sigma, t0, t1, rgb: 4 * kGroupBwd independent coalesced 128-byte lines per
+// Memory-level parallelism: a ray is consumed in groups of kGroup chunks of 32 samples; the loads
+// of a whole group — sigma, t0, t1, rgb: 4 * kGroup independent coalesced 128-byte lines per
 // warp — are issued in one burst before any of the dependent scan arithmetic of the group starts.
 // v1 had one load -> scan -> load chain per chunk and sat at 0.23 of the HBM roofline,
 // long-scoreboard bound (profiles/r01_ncu_full_misc_kernels.md).
-constexpr int kGroupBwd = 8;        // forward
-constexpr int kGroupBwdBwd = 4;     // backward (more live registers per chunk)
+constexpr int kGroup = 8;        // forward
+constexpr int kGroupBwd = 4;     // backward (more live registers per chunk)
 
 template <int C>
 __global__ void __launch_bounds__(kRayThreads)
@@ -227,10 +227,10 @@ composite_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__
         float carry = 0.f, acc_o = 0.f, acc_d = 0.f, acc_c[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) acc_c[k] = 0.f;
-        for (int g0 = beg; g0 < end; g0 += 32 * kGroupBwd) {
-            float sg[kGroupBwd], ta[kGroupBwd], tb[kGroupBwd], col[kGroupBwd][C];
+        for (int g0 = beg; g0 < end; g0 += 32 * kGroup) {
+            float sg[kGroup], ta[kGroup], tb[kGroup], col[kGroup][C];
 #pragma unroll
-            for (int c = 0; c < kGroupBwd; ++c) {
+            for (int c = 0; c < kGroup; ++c) {
                 const int i = g0 + 32 * c + lane;
                 const bool ok = i < end;
                 sg[c] = ok ? __ldg(sigmas + i) : 0.f;
@@ -240,7 +240,7 @@ composite_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__
                 for (int k = 0; k < C; ++k) col[c][k] = ok ? __ldg(rgbs + (int64_t)i * C + k) : 0.f;
             }
 #pragma unroll
-            for (int c = 0; c < kGroupBwd; ++c) {
+            for (int c = 0; c < kGroup; ++c) {
                 if (g0 + 32 * c >= end) break;                     // warp-uniform
                 const float sdt = sg[c] * (tb[c] - ta[c]);         // 0 beyond the ray's end
                 const float inc = warp_inclusive_sum(sdt, lane);

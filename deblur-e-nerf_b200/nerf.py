@@ -128,7 +128,7 @@ class NeRF(torch.nn.Module):
         return T_wc_position, d
 
     # ------------------------------------------------------------------- render ------
-    def _march(self, o, d, jitter):
+    def _march(self, o, d, jitter, probe=None):
         grid = self.occupancy_grid
         if self.contraction_type == ContractionType.AABB:
             t_min, t_max = ops.ray_aabb_intersect(o, d, self._aabb_host)
@@ -154,13 +154,22 @@ class NeRF(torch.nn.Module):
             seg_len = ops.march_segment_length(0.0, diag, self._step_host)
         else:
             seg_len = None
-        return ops.march(params, o, d, t_min, t_max, grid.binary, seg_len=seg_len)
+        return ops.march(params, o, d, t_min, t_max, grid.binary, seg_len=seg_len, probe=probe)
 
-    def render_chunk(self, o, d, jitter=None):
-        """One chunk of rays (R,3),(R,3) -> colour (R,C), opacity (R,), depth (R,), M."""
+    def render_chunk(self, o, d, jitter=None, groups=1):
+        """One chunk of rays (R,3),(R,3) -> colour (R,C), opacity (R,), depth (R,), M.
+        With ``groups`` > 1 the rays are `groups` equal consecutive blocks (the render calls of one
+        training step batched into a single launch sequence) and M is the list of per-block sample
+        counts; the counts ride along with the host read of the total (no extra sync)."""
         field = self.radiance_field
         n_rays = o.shape[0]
-        ray_idx, t0, t1, offsets = self._march(o, d, jitter)
+        probe = None
+        if groups > 1:
+            assert n_rays % groups == 0
+            probe = torch.arange(0, groups + 1, device=o.device) * (n_rays // groups)
+        marched = self._march(o, d, jitter, probe)
+        ray_idx, t0, t1, offsets = marched[:4]
+        bounds = marched[4] if groups > 1 else None
 
         needs_grad = torch.is_grad_enabled() and any(
             p.requires_grad for p in field.parameters())
@@ -173,7 +182,11 @@ class NeRF(torch.nn.Module):
             alphas = ops.alpha_from_sigma(pre[0], t0, t1)
             mask, counts = ops.visibility(alphas, offsets, self.early_stop_eps, alpha_thre)
             offsets_out = ops.exclusive_scan_i32(counts)
-            total = int(offsets_out[-1].item())
+            if groups > 1:
+                bounds = [int(v) for v in offsets_out[probe].tolist()]          # host read
+                total = bounds[-1]
+            else:
+                total = int(offsets_out[-1].item())                             # host read
             if total < ray_idx.numel():
                 ray_idx, t0, t1 = ops.compact(mask, offsets, offsets_out, ray_idx, t0, t1, total)
                 offsets = offsets_out
@@ -191,13 +204,29 @@ class NeRF(torch.nn.Module):
                                            precomputed=(sigma, rgb))
         bkgd = self.render_bkgd
         colour, opacity, depth = ops.composite(sigma, rgb, t0, t1, offsets, bkgd)
+        if groups > 1:
+            return colour, opacity, depth, [bounds[g + 1] - bounds[g] for g in range(groups)]
         return colour, opacity, depth, ray_idx.numel()
 
-    def forward(self, ray_origin, ray_direction, jitter=None):
+    def forward(self, ray_origin, ray_direction, jitter=None, groups=1):
+        """``groups`` > 1 (training only): the leading dimension of the rays indexes `groups`
+        independent render calls evaluated as one; the fourth return value is then the list of
+        their mean samples per ray."""
         shape = ray_origin.shape
         o = ray_origin.reshape(-1, 3).float().contiguous()
         d = ray_direction.reshape(-1, 3).float().contiguous()
         n_rays = o.shape[0]
+        if groups > 1:
+            assert self.radiance_field.training and shape[0] == groups
+            per = n_rays // groups
+            if jitter is None:
+                # one draw per render call, in call order: the RNG stream of `groups` separate calls
+                jitter = torch.cat([torch.rand(per, device=o.device) for _ in range(groups)])
+            col, opa, dep, counts = self.render_chunk(o, d, jitter.reshape(-1).contiguous(), groups)
+            radiance = col.view(*shape[:-1], -1).squeeze(dim=-1)
+            opacity = opa.view(*shape[:-1])
+            depth = dep.view(*shape[:-1]) / (opacity + self.opacity_eps)
+            return radiance, opacity, depth, [c / max(per, 1) for c in counts]
         chunk = n_rays if self.radiance_field.training else self.test_chunk_size
         cols, opas, deps, total = [], [], [], 0
         for i in range(0, max(n_rays, 1), max(chunk, 1)):

@@ -39,6 +39,25 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_ROW_QUANTUM = 1 << 18      # sample-sized buffers are allocated in multiples of 262 144 rows
+
+
+def _rows(n, tail, dtype, device):
+    """(n, *tail) buffer for per-sample data.  The sample count changes a little from one render
+    call to the next (stratified jitter, fresh batch); allocating the exact size makes the caching
+    allocator miss on every slightly larger request (a cudaMalloc + implicit device sync in the
+    middle of the step).  Rounding the ROW count up to a quantum and handing out the leading view
+    keeps the block sizes constant from step to step."""
+    n = int(n)
+    cap = n if n < (1 << 16) else -(-n // _ROW_QUANTUM) * _ROW_QUANTUM
+    buf = torch.empty((cap, *tail), dtype=dtype, device=device)
+    return buf if cap == n else buf[:n]
+
+
+def _rows_like(t):
+    return _rows(t.shape[0], tuple(t.shape[1:]), t.dtype, t.device)
+
+
 def _req(t, dtype, name):
     if not t.is_cuda:
         raise NotImplementedError(f"{name}: only CUDA tensors are supported (no CPU fallback)")
@@ -147,7 +166,7 @@ def hashgrid_fwd(desc, x, table):
     x = _req(x, torch.float32, "x")
     table = _req(table, torch.float32, "table")
     n = x.shape[0]
-    out = torch.empty((n, desc.n_levels * desc.n_features), dtype=torch.float32, device=x.device)
+    out = _rows(n, (desc.n_levels * desc.n_features,), torch.float32, x.device)
     _call("den_hashgrid_fwd", ctypes.byref(desc), _ptr(x), _ptr(table), _ptr(out), n, _stream())
     return out
 
@@ -158,7 +177,7 @@ def hashgrid_bwd(desc, x, dout, table, need_dx, dtable=None):
     n = x.shape[0]
     if dtable is None:
         dtable = torch.zeros_like(table)
-    dx = torch.empty_like(x) if need_dx else None
+    dx = _rows_like(x) if need_dx else None
     _call("den_hashgrid_bwd", ctypes.byref(desc), _ptr(x), _ptr(dout), _ptr(table), _ptr(dtable),
           _ptr(dx), n, _stream())
     return dtable, dx
@@ -252,7 +271,7 @@ def clamp_jitter_(t_min, t_max, jitter, near_plane, far_plane, step_size):
 
 
 MARCH_MAX_PER_RAY = 8192            # bound-kernel path: a ray whose bound exceeds this takes two passes
-MARCH_ARENA_MAX = 1 << 29           # uniform-segment arena limit (entries; 2 x 4 B each = 4 GiB)
+MARCH_ARENA_MAX = (1 << 31) - 1     # uniform-segment arena limit: int32 segment offsets (2 x 4 B per entry)
 _ARENA = {}                         # device -> (t0, t1) grow-only scratch arena
 _SEG_OFFSETS = {}                   # (device, n, seg_len) -> int32 arange(n + 1) * seg_len
 
@@ -274,7 +293,7 @@ def march_segment_length(t_lo, t_hi, step_size):
 
 
 def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=None,
-          single_pass=True):
+          single_pass=True, probe=None):
     """Occupancy march.  Returns (ray_indices i32, t_starts, t_ends, offsets (R+1)).
 
     Default: ONE marching pass into an upper-bound arena, then a coalesced pack — the sequential
@@ -286,6 +305,10 @@ def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=N
     ``capacity=None`` the total is read back (one host sync, as upstream does) and the outputs are
     exact-size; with a capacity the arena is caller-bounded, nothing is synchronised and
     ``offsets[-1]`` (device) holds the true total.
+
+    ``probe`` (int64 index tensor into ``offsets``): those entries ride along with the host read of
+    the total and come back as a fifth return value (a list of ints) — per-group sample counts
+    without a second synchronisation.
     """
     rays_o = _req(rays_o, torch.float32, "rays_o")
     rays_d = _req(rays_d, torch.float32, "rays_d")
@@ -319,14 +342,19 @@ def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=N
               _stream())
         offsets = exclusive_scan_i32(counts)
         over = (counts > (seg_len if bound is None else bound)).any().to(torch.int32)
-        total, overflow = (int(v) for v in torch.stack((offsets[-1], over)).tolist())   # host read
+        head = torch.stack((offsets[-1], over))
+        if probe is not None:
+            head = torch.cat((head, offsets[probe]))
+        vals = [int(v) for v in head.tolist()]                                        # host read
+        total, overflow, probed = vals[0], vals[1], vals[2:]
         if not overflow:
-            ray_indices = torch.empty(total, dtype=torch.int32, device=dev)
-            t_starts = torch.empty(total, dtype=torch.float32, device=dev)
-            t_ends = torch.empty(total, dtype=torch.float32, device=dev)
+            ray_indices = _rows(total, (), torch.int32, dev)
+            t_starts = _rows(total, (), torch.float32, dev)
+            t_ends = _rows(total, (), torch.float32, dev)
             _call("den_march_pack", _ptr(seg), _ptr(offsets), _ptr(arena_t0), _ptr(arena_t1), n,
                   _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _stream())
-            return ray_indices, t_starts, t_ends, offsets
+            out = (ray_indices, t_starts, t_ends, offsets)
+            return out if probe is None else out + (probed,)
         capacity = total            # a ray outgrew its segment: exact write pass instead
     else:
         _call("den_march_count", ctypes.byref(params), _ptr(rays_o), _ptr(rays_d), _ptr(t_min),
@@ -334,18 +362,19 @@ def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=N
         offsets = exclusive_scan_i32(counts)
         if capacity is None:
             capacity = int(offsets[-1].item())
-    ray_indices = torch.empty(capacity, dtype=torch.int32, device=dev)
-    t_starts = torch.empty(capacity, dtype=torch.float32, device=dev)
-    t_ends = torch.empty(capacity, dtype=torch.float32, device=dev)
+    ray_indices = _rows(capacity, (), torch.int32, dev)
+    t_starts = _rows(capacity, (), torch.float32, dev)
+    t_ends = _rows(capacity, (), torch.float32, dev)
     _call("den_march_write", ctypes.byref(params), _ptr(rays_o), _ptr(rays_d), _ptr(t_min),
           _ptr(t_max), _ptr(binary), _ptr(offsets), _ptr(ray_indices), _ptr(t_starts),
           _ptr(t_ends), n, capacity, _stream())
-    return ray_indices, t_starts, t_ends, offsets
+    out = (ray_indices, t_starts, t_ends, offsets)
+    return out if probe is None else out + ([int(v) for v in offsets[probe].tolist()],)
 
 
 def alpha_from_sigma(sigmas, t_starts, t_ends):
     sigmas = _req(sigmas.reshape(-1), torch.float32, "sigmas")
-    out = torch.empty_like(sigmas)
+    out = _rows_like(sigmas)
     _call("den_alpha_from_sigma", _ptr(sigmas), _ptr(t_starts), _ptr(t_ends), _ptr(out),
           sigmas.numel(), _stream())
     return out
@@ -355,7 +384,7 @@ def visibility(alphas, offsets, early_stop_eps, alpha_thre):
     alphas = _req(alphas.reshape(-1), torch.float32, "alphas")
     offsets = _req(offsets, torch.int32, "offsets")
     n_rays = offsets.numel() - 1
-    mask = torch.empty(alphas.numel(), dtype=torch.uint8, device=alphas.device)
+    mask = _rows(alphas.numel(), (), torch.uint8, alphas.device)
     counts = torch.empty(n_rays, dtype=torch.int32, device=alphas.device)
     _call("den_visibility", _ptr(alphas), _ptr(offsets), n_rays, float(early_stop_eps),
           float(alpha_thre), _ptr(mask), _ptr(counts), _stream())
@@ -365,9 +394,9 @@ def visibility(alphas, offsets, early_stop_eps, alpha_thre):
 def compact(mask, offsets_in, offsets_out, ray_indices, t_starts, t_ends, capacity):
     dev = mask.device
     n_rays = offsets_in.numel() - 1
-    ro = torch.empty(capacity, dtype=torch.int32, device=dev)
-    t0 = torch.empty(capacity, dtype=torch.float32, device=dev)
-    t1 = torch.empty(capacity, dtype=torch.float32, device=dev)
+    ro = _rows(capacity, (), torch.int32, dev)
+    t0 = _rows(capacity, (), torch.float32, dev)
+    t1 = _rows(capacity, (), torch.float32, dev)
     _call("den_compact_samples", _ptr(mask), _ptr(offsets_in), _ptr(offsets_out),
           _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _ptr(ro), _ptr(t0), _ptr(t1), n_rays,
           _stream())
@@ -390,7 +419,7 @@ class _WeightFromDensityFn(torch.autograd.Function):
         t_starts = _req(t_starts.reshape(-1), torch.float32, "t_starts")
         t_ends = _req(t_ends.reshape(-1), torch.float32, "t_ends")
         n_rays = offsets.numel() - 1
-        w = torch.empty_like(sigmas)
+        w = _rows_like(sigmas)
         _call("den_weight_from_density_fwd", _ptr(sigmas), _ptr(t_starts), _ptr(t_ends),
               _ptr(offsets), n_rays, _ptr(w), _stream())
         ctx.save_for_backward(sigmas, t_starts, t_ends, offsets)
@@ -400,7 +429,7 @@ class _WeightFromDensityFn(torch.autograd.Function):
     def backward(ctx, dw):
         sigmas, t_starts, t_ends, offsets = ctx.saved_tensors
         dw = _req(dw.reshape(-1), torch.float32, "dweights")
-        ds = torch.empty_like(sigmas)
+        ds = _rows_like(sigmas)
         _call("den_weight_from_density_bwd", _ptr(sigmas), _ptr(t_starts), _ptr(t_ends),
               _ptr(offsets), offsets.numel() - 1, _ptr(dw), _ptr(ds), _stream())
         return ds, None, None, None
@@ -410,7 +439,7 @@ class _WeightFromAlphaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, alphas, offsets):
         alphas = _req(alphas.reshape(-1), torch.float32, "alphas")
-        w = torch.empty_like(alphas)
+        w = _rows_like(alphas)
         _call("den_weight_from_alpha_fwd", _ptr(alphas), _ptr(offsets), offsets.numel() - 1,
               _ptr(w), _stream())
         ctx.save_for_backward(alphas, offsets)
@@ -420,7 +449,7 @@ class _WeightFromAlphaFn(torch.autograd.Function):
     def backward(ctx, dw):
         alphas, offsets = ctx.saved_tensors
         dw = _req(dw.reshape(-1), torch.float32, "dweights")
-        da = torch.empty_like(alphas)
+        da = _rows_like(alphas)
         _call("den_weight_from_alpha_bwd", _ptr(alphas), _ptr(offsets), offsets.numel() - 1,
               _ptr(dw), _ptr(da), _stream())
         return da, None
@@ -450,8 +479,8 @@ class _AccumulateFn(torch.autograd.Function):
             values = None
         dout = _req(dout, torch.float32, "dout")
         n = weights.numel()
-        dw = torch.empty_like(weights) if ctx.needs_input_grad[0] else None
-        dv = (torch.empty_like(values)
+        dw = _rows_like(weights) if ctx.needs_input_grad[0] else None
+        dv = (_rows_like(values)
               if (values is not None and ctx.needs_input_grad[1]) else None)
         _call("den_accumulate_bwd", _ptr(weights), _ptr(values), _ptr(ray_indices), _ptr(dout), n,
               ctx.dim, _ptr(dw), _ptr(dv), _stream())
@@ -490,8 +519,8 @@ class _CompositeFn(torch.autograd.Function):
         d_colour = _req(d_colour, torch.float32, "d_colour")
         d_opacity = _req(d_opacity, torch.float32, "d_opacity")
         d_depth = _req(d_depth, torch.float32, "d_depth")
-        d_sigmas = torch.empty_like(sigmas)
-        d_rgbs = torch.empty_like(rgbs)
+        d_sigmas = _rows_like(sigmas)
+        d_rgbs = _rows_like(rgbs)
         d_bk = torch.zeros_like(bk) if (bk is not None and ctx.needs_input_grad[5]) else None
         _call("den_composite_bwd", _ptr(sigmas), _ptr(rgbs), _ptr(t_starts), _ptr(t_ends),
               _ptr(offsets), n_rays, ctx.channels, _ptr(bk), _ptr(opacity), _ptr(d_colour),
@@ -541,8 +570,8 @@ def field_fwd(desc, params, rays_o, rays_d, ray_indices, t_starts, t_ends, chann
     t_ends = _req(t_ends.reshape(-1), torch.float32, "t_ends")
     n = ray_indices.numel()
     dev = rays_o.device
-    sig = torch.empty(n, dtype=torch.float32, device=dev)
-    rgb = torch.empty((n, channels), dtype=torch.float32, device=dev) if channels else None
+    sig = _rows(n, (), torch.float32, dev)
+    rgb = _rows(n, (channels,), torch.float32, dev) if channels else None
     _call("den_field_fwd", ctypes.byref(desc), ctypes.byref(params), _ptr(rays_o), _ptr(rays_d),
           _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(n_dev), _ptr(sig), _ptr(rgb),
           _stream())
@@ -554,7 +583,7 @@ def field_fwd(desc, params, rays_o, rays_d, ray_indices, t_starts, t_ends, chann
 # --------------------------------------------------------------------------- #
 def contract_samples(desc, rays_o, rays_d, ray_indices, t_starts, t_ends):
     n = ray_indices.numel()
-    out = torch.empty((n, 3), dtype=torch.float32, device=rays_o.device)
+    out = _rows(n, (3,), torch.float32, rays_o.device)
     _call("den_contract_samples", ctypes.byref(desc), _ptr(rays_o), _ptr(rays_d),
           _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(out), _stream())
     return out
@@ -564,8 +593,8 @@ def mlp_fwd(desc, params, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, ch
     enc = _req(enc, torch.float32, "enc")
     n = ray_indices.numel()
     dev = enc.device
-    sig = torch.empty(n, dtype=torch.float32, device=dev)
-    rgb = torch.empty((n, channels), dtype=torch.float32, device=dev) if channels else None
+    sig = _rows(n, (), torch.float32, dev)
+    rgb = _rows(n, (channels,), torch.float32, dev) if channels else None
     _call("den_mlp_fwd", ctypes.byref(desc), ctypes.byref(params), _ptr(enc), _ptr(rays_o),
           _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(sig), _ptr(rgb),
           _stream())
@@ -577,7 +606,7 @@ def mlp_bwd(desc, params, grads_struct, enc, rays_o, rays_d, ray_indices, t_star
     """dL/denc (M, L*2) [and dL/d(view dir) (M,3)]; weight gradients are accumulated into the
     buffers of `grads_struct`."""
     n = ray_indices.numel()
-    d_enc = torch.empty_like(enc)
+    d_enc = _rows_like(enc)
     d_dirs = torch.zeros((n, 3), dtype=torch.float32, device=enc.device) if need_d_dirs else None
     d_sigmas = _req(d_sigmas.reshape(-1), torch.float32, "d_sigmas")
     d_rgbs = _req(d_rgbs, torch.float32, "d_rgbs")
@@ -612,8 +641,8 @@ class _ContractSamplesFn(torch.autograd.Function):
         rays_o, rays_d, ray_indices, t_starts, t_ends, offsets = ctx.saved_tensors
         n = ray_indices.numel()
         d_unit = _req(d_unit, torch.float32, "d_unit")
-        d_pos = torch.empty_like(d_unit)
-        d_pos_t = torch.empty_like(d_unit)
+        d_pos = _rows_like(d_unit)
+        d_pos_t = _rows_like(d_unit)
         _call("den_contract_samples_bwd", ctypes.byref(ctx.desc), _ptr(rays_o), _ptr(rays_d),
               _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _ptr(d_unit), n, _ptr(d_pos),
               _ptr(d_pos_t), _stream())

@@ -42,6 +42,10 @@ class EventRenderer(torch.nn.Module):
         self.next_train_batch_size = None
         self._jitters = None
         self.mean_samples_reduce_fn = None              # set by ddp.attach(): all-reduce mean
+        # evaluate the (up to) four render calls of a training step as ONE march / field /
+        # compositing launch sequence over 4x the rays (same arithmetic per ray, same RNG draws in
+        # the same order): a quarter of the launches and host synchronisations per step
+        self.batch_render_calls = True
 
     # ------------------------------------------------------------- render helpers ----
     def render_pixels(self, intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation):
@@ -75,6 +79,38 @@ class EventRenderer(torch.nn.Module):
         intensity, occ_rate, mean_samples, is_valid = self.render_train_pixels(
             timestamp, pixel_position, pixel_channel_idx)
         return intensity.log(), occ_rate, mean_samples, is_valid
+
+    def render_log_intensity_batched(self, requests, pixel_position, normalized_interval_gen):
+        """`render_log_intensity` for several (timestamp, reset_diff) requests of the same pixels
+        at once.  Returns one (log_intensity, occ_rate, mean_samples, is_valid) tuple per request,
+        in order (the pixel-bandwidth reset state is carried from request to request exactly as
+        the sequential calls do)."""
+        pb = self.pixel_bandwidth
+        K = len(requests)
+        if pb is not None:
+            ts_all = torch.stack([(ts - pb.sample_lifetimes(normalized_interval_gen)).clamp(
+                min=pb.min_ts) for ts, _ in requests])                   # (K, S, N)
+        else:
+            ts_all = torch.stack([ts for ts, _ in requests])             # (K, N)
+        pos, rot = self.trajectory(ts_all)
+        o, d = self.nerf.pixel_params_to_ray(self.train_intrinsics_inv, pixel_position, pos, rot)
+        jitter = None
+        if self._jitters:
+            jitter = torch.cat([self._jitters.pop(0).reshape(-1) for _ in range(K)])
+        intensity, opacity, _, means = self.nerf(o, d, jitter=jitter, groups=K)
+        intensity = intensity + self.min_modeled_intensity
+        hit = opacity > 0
+        is_valid = hit if self.render_bkgd is None else torch.ones_like(hit)
+        occ = hit.reshape(K, -1).to(torch.get_default_dtype()).mean(dim=1)
+        out = []
+        for k, (ts, reset_diff) in enumerate(requests):
+            if pb is not None:
+                cached = (intensity[k], occ[k], means[k], is_valid[k])
+                log_it, aux = pb(normalized_interval_gen, ts, lambda _ts, c=cached: c, reset_diff)
+                out.append((log_it, aux[0], aux[1], aux[2].any(dim=0)))
+            else:
+                out.append((intensity[k].log(), occ[k], means[k], is_valid[k]))
+        return out
 
     # ------------------------------------------------------------------ the step -----
     @staticmethod
@@ -122,13 +158,23 @@ class EventRenderer(torch.nn.Module):
                                       T_wc_position=self.trajectory.T_wc_position)
 
         mean_samples, occ_rates, valid_rates = [], [], []
-        for seg, is_diff in ((diff, True), (subdiff, False)):
-            if seg is None:
-                continue
-            a, occ_a, ms_a, va = self.render_log_intensity(
-                seg["start_ts"], event["position"], None, gen, reset_diff=is_diff)
-            b, occ_b, ms_b, vb = self.render_log_intensity(
-                seg["end_ts"], event["position"], None, gen)
+        segs = [(seg, is_diff) for seg, is_diff in ((diff, True), (subdiff, False))
+                if seg is not None]
+        batched = None
+        if self.batch_render_calls and self.nerf.radiance_field.training and segs:
+            requests = []
+            for seg, is_diff in segs:
+                requests += [(seg["start_ts"], is_diff), (seg["end_ts"], False)]
+            batched = self.render_log_intensity_batched(requests, event["position"], gen)
+        for seg, is_diff in segs:
+            if batched is not None:
+                (a, occ_a, ms_a, va), (b, occ_b, ms_b, vb) = batched[0], batched[1]
+                batched = batched[2:]
+            else:
+                a, occ_a, ms_a, va = self.render_log_intensity(
+                    seg["start_ts"], event["position"], None, gen, reset_diff=is_diff)
+                b, occ_b, ms_b, vb = self.render_log_intensity(
+                    seg["end_ts"], event["position"], None, gen)
             seg["log_intensity_diff"] = b - a
             seg["is_valid"] = va | vb
             mean_samples += [ms_a, ms_b]

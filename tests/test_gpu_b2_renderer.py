@@ -147,6 +147,38 @@ def _run_training_step_golden(cuda, pb_on):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("pb_on", [False, True], ids=["pb_off", "pb_on"])
+def test_batched_render_calls_equal_sequential_calls(den_lib, cuda, pb_on):
+    """The four render calls of a step evaluated as one launch sequence (the default) give the
+    loss, logged terms and gradients of four separate calls (same per-ray arithmetic; only the
+    order of the atomic gradient accumulation differs)."""
+    golden = _scene.load_golden("training_step_pb_on" if pb_on else "training_step_pb_off")
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    results = []
+    for batched in (True, False):
+        model, poses = _scene.build_product_renderer(cfg, cuda, 8, pixel_bandwidth=pb_on)
+        for name in ["nerf", "contrast_threshold", "refractory_period"] + (
+                ["pixel_bandwidth"] if pb_on else []):
+            _scene.load_golden_state(getattr(model, name), golden, name, cuda)
+        batch = {"event": _scene.golden_section(golden, "event", cuda),
+                 "normalized": _scene.golden_section(golden, "normalized", cuda)}
+        jitters = [v for _, v in sorted(_scene.golden_section(golden, "jitter", cuda).items(),
+                                        key=lambda kv: int(kv[0]))]
+        model.train()
+        model.batch_render_calls = batched
+        model.nerf.update_occ_grid = lambda *a, **k: None
+        loss = model.training_step(batch, 0, 0, jitters=jitters)
+        loss.backward()
+        results.append((loss.detach(), dict(model.logged), _scene.flat_named_grads(model)))
+    (la, ga, gra), (lb, gb, grb) = results
+    assert _rel(la, lb) < 1e-6
+    assert abs(ga["train/mean_num_samples_per_ray"] - gb["train/mean_num_samples_per_ray"]) < 1e-9
+    assert _rel(ga["train/mean_ray_occ_rate"], gb["train/mean_ray_occ_rate"]) < 1e-6
+    assert set(gra) == set(grb)
+    for key in gra:
+        assert _rel(gra[key], grb[key]) < 2e-4, key      # fp32 accumulation order differs
+
+
 def test_training_step_pb_off_matches_reference_golden(den_lib, cuda):
     _run_training_step_golden(cuda, pb_on=False)
 
