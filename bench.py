@@ -459,12 +459,21 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+def _shutdown():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        try:
+            run_ours(args)
+        finally:
+            _shutdown()
 
 
 if __name__ == "__main__":
