@@ -398,7 +398,6 @@ def run_ours(args):
     tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     per_step_samples = samples_seen / args.steps
-    samples_per_launch = per_step_samples / 4        # one launch per render call per kernel
     kernel_table = {k: {"launches": v[0], "ms_per_launch": round(v[1] / v[0], 4),
                         "share_of_step": round(v[1] / profile_ms, 4)}
                     for k, v in profile_timings.items() if v[0] > 0}
@@ -406,6 +405,9 @@ def run_ours(args):
     def roof(name):
         n_launch, ms_k = timings[name]
         avg_s = ms_k / n_launch * 1e-3
+        # every rated kernel runs once per render launch sequence over all of its samples / rays
+        samples_per_launch = samples_seen / n_launch
+        rays_per_launch = rays_per_step(n_events) * args.steps / n_launch
         if name in KERNEL_FLOP_PER_SAMPLE:
             achieved = KERNEL_FLOP_PER_SAMPLE[name] * samples_per_launch / avg_s / 1e12
             return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
@@ -418,7 +420,7 @@ def run_ours(args):
                             "on the launching stream); the kernel is bound by its SIMT epilogue "
                             "(activation MUFU + bf16 hi/lo split), not by the tensor pipe"}
         nbytes_launch = (KERNEL_BYTES_PER_SAMPLE[name] * samples_per_launch +
-                         KERNEL_BYTES_PER_RAY.get(name, 0) * w["S"] * n_events)
+                         KERNEL_BYTES_PER_RAY.get(name, 0) * rays_per_launch)
         achieved = nbytes_launch / avg_s / 1e9
         return {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -101,7 +101,7 @@ _SIGNATURES = {
                                         _P, _P]),
     "den_lpf_fwd": (_INT, [_P, _P, _P, _I32, _I64, _I32, _P, _P]),
     "den_lpf_bwd": (_INT, [_P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
-    "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P,
+    "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
 }
 

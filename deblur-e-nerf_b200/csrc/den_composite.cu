@@ -385,6 +385,90 @@ composite_bwd_kernel(const float* __restrict__ sigmas, const float* __restrict__
     }
 }
 
+// Single-sweep backward: with the forward outputs at hand the suffix sum_{j>i} g_j w_j is
+// total - prefix, where total = sum_i g_i w_i = g_op * opacity + g_depth * depth + sum_k g_c[k] * colour_acc[k]
+// needs no pass over the samples — so the ray is read ONCE, front to back, exactly like the forward
+// (28 B/sample of real traffic instead of 44).  The cancellation error of total - prefix is
+// ~1e-7 * |total| absolute, i.e. only visible on samples whose gradient is itself negligible.
+template <int C>
+__global__ void __launch_bounds__(kRayThreads)
+composite_bwd_sweep_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                           const float* __restrict__ t0, const float* __restrict__ t1,
+                           const int32_t* __restrict__ offsets, int64_t n_rays,
+                           const float* __restrict__ bkgd, const float* __restrict__ colour,
+                           const float* __restrict__ opacity, const float* __restrict__ depth,
+                           const float* __restrict__ d_colour, const float* __restrict__ d_opacity,
+                           const float* __restrict__ d_depth, float* __restrict__ d_sigmas,
+                           float* __restrict__ d_rgbs, float* __restrict__ d_bkgd) {
+    float bk_acc[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k) bk_acc[k] = 0.f;
+
+    DEN_FOR_EACH_RAY(r) {
+        const int beg = offsets[r], end = offsets[r + 1];
+        const float opa = opacity[r];
+        float gc[C];
+        float g_op = d_opacity ? d_opacity[r] : 0.f;
+        const float g_dp = d_depth ? d_depth[r] : 0.f;
+        float total = g_dp * depth[r];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            gc[k] = d_colour ? d_colour[r * C + k] : 0.f;
+            float acc = colour[r * C + k];
+            if (bkgd) {
+                g_op -= gc[k] * bkgd[k];
+                acc -= bkgd[k] * (1.f - opa);
+                if (lane == 0) bk_acc[k] += gc[k] * (1.f - opa);
+            }
+            total += gc[k] * acc;
+        }
+        total += g_op * opa;
+        float carry = 0.f, carry_gw = 0.f;
+        for (int g0 = beg; g0 < end; g0 += 32 * kGroup) {
+            float sg[kGroup], ta[kGroup], tb[kGroup], col[kGroup][C];
+#pragma unroll
+            for (int c = 0; c < kGroup; ++c) {
+                const int i = g0 + 32 * c + lane;
+                const bool ok = i < end;
+                sg[c] = ok ? __ldg(sigmas + i) : 0.f;
+                ta[c] = ok ? __ldg(t0 + i) : 0.f;
+                tb[c] = ok ? __ldg(t1 + i) : 0.f;
+#pragma unroll
+                for (int k = 0; k < C; ++k) col[c][k] = ok ? __ldg(rgbs + (int64_t)i * C + k) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < kGroup; ++c) {
+                if (g0 + 32 * c >= end) break;                     // warp-uniform
+                const int i = g0 + 32 * c + lane;
+                const bool ok = i < end;
+                const float dt = tb[c] - ta[c];
+                const float sdt = sg[c] * dt;                      // 0 beyond the ray's end
+                float g = g_op + g_dp * (ta[c] + tb[c]) * 0.5f;
+#pragma unroll
+                for (int k = 0; k < C; ++k) g += gc[k] * col[c][k];
+                const float inc = warp_inclusive_sum(sdt, lane);
+                const float T = __expf(-(carry + inc - sdt));
+                const float keep = __expf(-sdt);
+                const float w = T * (1.f - keep);
+                const float gw = ok ? g * w : 0.f;
+                const float ginc = warp_inclusive_sum(gw, lane);
+                if (ok) {
+                    d_sigmas[i] = dt * (g * T * keep - (total - (carry_gw + ginc)));
+#pragma unroll
+                    for (int k = 0; k < C; ++k) d_rgbs[(int64_t)i * C + k] = gc[k] * w;
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+                carry_gw += __shfl_sync(0xffffffffu, ginc, 31);
+            }
+        }
+    }
+    if (bkgd && d_bkgd && (threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            if (bk_acc[k] != 0.f) atomicAdd(d_bkgd + k, bk_acc[k]);
+    }
+}
+
 inline int ray_grid(int64_t n_rays) { return grid_for(n_rays, kRayWarpsPerCta, 8); }
 
 }  // namespace den
@@ -486,23 +570,35 @@ int den_composite_fwd(const float* sigmas, const float* rgbs, const float* t0, c
 
 int den_composite_bwd(const float* sigmas, const float* rgbs, const float* t0, const float* t1,
                       const int32_t* offsets, int64_t n_rays, int32_t channels, const float* bkgd,
-                      const float* opacity, const float* d_colour, const float* d_opacity,
-                      const float* d_depth, float* d_sigmas, float* d_rgbs, float* d_bkgd,
-                      void* stream) {
+                      const float* colour, const float* opacity, const float* depth,
+                      const float* d_colour, const float* d_opacity, const float* d_depth,
+                      float* d_sigmas, float* d_rgbs, float* d_bkgd, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(n_rays >= 0, "negative ray count");
     DEN_CHECK_ARG(channels == 1 || channels == 3, "channels must be 1 or 3");
     if (n_rays == 0) return DEN_OK;
     DEN_CHECK_ARG(offsets, "null offsets");
     DEN_CHECK_ARG(!bkgd || opacity, "background blend needs the forward opacity");
-    if (channels == 1)
-        composite_bwd_kernel<1><<<ray_grid(n_rays), kRayThreads, 0, as_stream(stream)>>>(
+    const int grid = ray_grid(n_rays);
+    if (colour && opacity && depth) {
+        // forward outputs available: single sweep
+        if (channels == 1)
+            composite_bwd_sweep_kernel<1><<<grid, kRayThreads, 0, as_stream(stream)>>>(
+                sigmas, rgbs, t0, t1, offsets, n_rays, bkgd, colour, opacity, depth, d_colour, d_opacity,
+                d_depth, d_sigmas, d_rgbs, d_bkgd);
+        else
+            composite_bwd_sweep_kernel<3><<<grid, kRayThreads, 0, as_stream(stream)>>>(
+                sigmas, rgbs, t0, t1, offsets, n_rays, bkgd, colour, opacity, depth, d_colour, d_opacity,
+                d_depth, d_sigmas, d_rgbs, d_bkgd);
+    } else if (channels == 1) {
+        composite_bwd_kernel<1><<<grid, kRayThreads, 0, as_stream(stream)>>>(
             sigmas, rgbs, t0, t1, offsets, n_rays, bkgd, opacity, d_colour, d_opacity, d_depth,
             d_sigmas, d_rgbs, d_bkgd);
-    else
-        composite_bwd_kernel<3><<<ray_grid(n_rays), kRayThreads, 0, as_stream(stream)>>>(
+    } else {
+        composite_bwd_kernel<3><<<grid, kRayThreads, 0, as_stream(stream)>>>(
             sigmas, rgbs, t0, t1, offsets, n_rays, bkgd, opacity, d_colour, d_opacity, d_depth,
             d_sigmas, d_rgbs, d_bkgd);
+    }
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }

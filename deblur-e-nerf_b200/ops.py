@@ -507,12 +507,12 @@ class _CompositeFn(torch.autograd.Function):
         ctx.channels = channels
         ctx.has_bkgd = bk is not None
         ctx.save_for_backward(sigmas, rgbs, t_starts, t_ends, offsets,
-                              bk if bk is not None else opacity, opacity)
+                              bk if bk is not None else opacity, opacity, colour, depth)
         return colour, opacity, depth
 
     @staticmethod
     def backward(ctx, d_colour, d_opacity, d_depth):
-        sigmas, rgbs, t_starts, t_ends, offsets, bk, opacity = ctx.saved_tensors
+        sigmas, rgbs, t_starts, t_ends, offsets, bk, opacity, colour, depth = ctx.saved_tensors
         if not ctx.has_bkgd:
             bk = None
         n_rays = offsets.numel() - 1
@@ -523,7 +523,8 @@ class _CompositeFn(torch.autograd.Function):
         d_rgbs = _rows_like(rgbs)
         d_bk = torch.zeros_like(bk) if (bk is not None and ctx.needs_input_grad[5]) else None
         _call("den_composite_bwd", _ptr(sigmas), _ptr(rgbs), _ptr(t_starts), _ptr(t_ends),
-              _ptr(offsets), n_rays, ctx.channels, _ptr(bk), _ptr(opacity), _ptr(d_colour),
+              _ptr(offsets), n_rays, ctx.channels, _ptr(bk), _ptr(colour), _ptr(opacity), _ptr(depth),
+              _ptr(d_colour),
               _ptr(d_opacity), _ptr(d_depth), _ptr(d_sigmas), _ptr(d_rgbs), _ptr(d_bk), _stream())
         return d_sigmas, d_rgbs, None, None, None, d_bk
 

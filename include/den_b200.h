@@ -173,12 +173,16 @@ int den_accumulate_bwd(const float* weights, const float* values, const int32_t*
 int den_composite_fwd(const float* sigmas, const float* rgbs, const float* t_starts,
                       const float* t_ends, const int32_t* offsets, int64_t n_rays, int32_t channels,
                       const float* bkgd, float* colour, float* opacity, float* depth, void* stream);
-/* d_bkgd (C) is accumulated with atomics (pre-zeroed by the caller); may be NULL */
+/* d_bkgd (C) is accumulated with atomics (pre-zeroed by the caller); may be NULL.
+ * colour / opacity / depth are den_composite_fwd's outputs: with all three the backward is a single
+ * front-to-back sweep (the suffix sums come from total - prefix); colour and depth may be NULL, which
+ * selects the two-pass form (total optical depth, then a back-to-front sweep). */
 int den_composite_bwd(const float* sigmas, const float* rgbs, const float* t_starts,
                       const float* t_ends, const int32_t* offsets, int64_t n_rays, int32_t channels,
-                      const float* bkgd, const float* opacity, const float* d_colour,
-                      const float* d_opacity, const float* d_depth, float* d_sigmas, float* d_rgbs,
-                      float* d_bkgd, void* stream);
+                      const float* bkgd, const float* colour, const float* opacity,
+                      const float* depth, const float* d_colour, const float* d_opacity,
+                      const float* d_depth, float* d_sigmas, float* d_rgbs, float* d_bkgd,
+                      void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused radiance field — replaces NGPradianceField.query_density / forward

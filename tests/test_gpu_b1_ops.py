@@ -301,13 +301,14 @@ def test_accumulate_along_rays(den_lib, cuda, dim):
     assert torch.all(out.cpu()[counts == 0] == 0)
 
 
+@pytest.mark.parametrize("max_count", [260, 900], ids=["rays<=260", "rays<=900"])
 @pytest.mark.parametrize("channels,with_bkgd", [(1, True), (1, False), (3, True)])
-def test_fused_composite_matches_rendering(den_lib, cuda, channels, with_bkgd):
+def test_fused_composite_matches_rendering(den_lib, cuda, channels, with_bkgd, max_count):
     """den_composite_{fwd,bwd} == weights + 3 accumulations + background blend
     (external/vol_rendering.py:89-126), values and all gradients."""
     from deblur_e_nerf_b200 import ops
     n_rays = 600
-    counts, ri, g = _random_packing(n_rays, 260, 61)
+    counts, ri, g = _random_packing(n_rays, max_count, 61)     # incl. empty rays; > 384: streaming path
     m = ri.shape[0]
     ts = torch.rand(m, 1, generator=g) * 5
     te = ts + 0.005
