@@ -29,8 +29,8 @@
 // Shared memory per slot: E (128 x 40: enc | ones, later [SH | geo | 1], later dy, later enc
 // again), H (128 x 72: hb | ones, later h1, later hb again) and D (128 x 64: the current
 // dL/dz tile) = 88 KB; 2 slots + 36 KB of weight tiles = 223 KB.  The price of fitting two
-// slots: hb is re-derived from its pre-activation (parked in TMEM) and enc is re-read from
-// L2/HBM for the last round (+12 % epilogue instructions, no extra MMA round).
+// slots: the split hb tile is parked in TMEM (64 columns of packed bf16 words per slot) while h1
+// occupies H and copied back afterwards, and enc is re-read from L2/HBM for the last round.
 #include <stdlib.h>
 
 #include "den_mlp_tc.cuh"
@@ -50,7 +50,7 @@ constexpr uint32_t kTmemCols = 512;
 
 // TMEM column plan
 constexpr uint32_t kColZ = 0;            // + 128 * slot : 64 scratch columns (forward / dX results)
-constexpr uint32_t kColP = 64;           // + 128 * slot : 64 columns, base-layer pre-activation (kept)
+constexpr uint32_t kColP = 64;           // + 128 * slot : 64 columns, the split hb tile parked as packed bf16 words
 constexpr uint32_t kColDW2 = 256;        // 72: dW2 (out 64 x in 64) | db2 x 8
 constexpr uint32_t kColDW1 = 336;        // 32: dW1 (64 x 31) | db1 in column 31
 constexpr uint32_t kColDWb1 = 368;       // 40: dWb1 (64 x 32) | dbb1 x 8
@@ -175,6 +175,47 @@ __device__ __forceinline__ void store16(uint8_t* tile, int r, int chunk0, const 
         *reinterpret_cast<uint4*>(tile + T::half + o) = lo;
     }
 }
+// the same store, also handing back the 16 packed words (hi chunk 0, lo chunk 0, hi chunk 1, lo chunk 1)
+template <class T>
+__device__ __forceinline__ void store16_keep(uint8_t* tile, int r, int chunk0, const float (&v)[16],
+                                             uint32_t (&words)[16]) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint4 hi, lo;
+        split8(&v[8 * c], hi, lo);
+        const uint32_t o = T::off(r, chunk0 + c);
+        *reinterpret_cast<uint4*>(tile + o) = hi;
+        *reinterpret_cast<uint4*>(tile + T::half + o) = lo;
+        words[8 * c + 0] = hi.x; words[8 * c + 1] = hi.y; words[8 * c + 2] = hi.z; words[8 * c + 3] = hi.w;
+        words[8 * c + 4] = lo.x; words[8 * c + 5] = lo.y; words[8 * c + 6] = lo.z; words[8 * c + 7] = lo.w;
+    }
+}
+template <class T>
+__device__ __forceinline__ void store16_words(uint8_t* tile, int r, int chunk0, const uint32_t (&words)[16]) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t o = T::off(r, chunk0 + c);
+        *reinterpret_cast<uint4*>(tile + o) =
+            make_uint4(words[8 * c + 0], words[8 * c + 1], words[8 * c + 2], words[8 * c + 3]);
+        *reinterpret_cast<uint4*>(tile + T::half + o) =
+            make_uint4(words[8 * c + 4], words[8 * c + 5], words[8 * c + 6], words[8 * c + 7]);
+    }
+}
+// registers <-> TMEM, 16 words per thread (warp-collective; thread i addresses lane base + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_words(uint32_t taddr, uint32_t (&r)[16]) {
+    tmem_ld16_nowait(taddr, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <class T>
 __device__ __forceinline__ void load16(const uint8_t* tile, int r, int chunk0, float (&v)[16]) {
 #pragma unroll
@@ -338,7 +379,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 handoff_wait(s);
                 tc::tc_fence_after_sync();
                 uint8_t* slot = smem + Smem::slot0 + s * Smem::slot_bytes;
-                const uint32_t Z = tmem_base + kColZ + 128u * s, P = tmem_base + kColP + 128u * s;
+                const uint32_t Z = tmem_base + kColZ + 128u * s;
                 const uint8_t* E = slot + Smem::e;
                 const uint8_t* H = slot + Smem::h;
                 const uint8_t* D = slot + Smem::d;
@@ -347,8 +388,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 if (elect_one()) {
                 switch ((dbg & 1) ? -1 : rnd) {
                 case -1: commit_to(done); if (rnd >= 4) commit_to(dw_done); break;
-                case 0:     // z_b1 = enc Wb1^T                                    (kept in P)
-                    gemm3<kEncDim / 16>(P, kmajor<TE>(E), kmajor<TWb1>(wb1),
+                case 0:     // z_b1 = enc Wb1^T
+                    gemm3<kEncDim / 16>(Z, kmajor<TE>(E), kmajor<TWb1>(wb1),
                                         tc::instr_desc_bf16(128, kWidth, false, false), false);
                     commit_to(done);
                     break;
@@ -445,14 +486,27 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             }
             store16<TE>(E, row, 2 * hf, x);
         };
-        // hb = act(P + bb1) for this thread's 32 columns -> H
+        // hb = act(z_b1 + bb1) for this thread's 32 columns -> H, and the packed hi/lo words parked in
+        // TMEM: hb is needed again after h1 has overwritten H (dWb2^T += hb^T dy, act'(hb)), and copying
+        // 32 words back costs a twentieth of re-deriving them (softplus = 2 MUFU, split = 3 instr / element)
         auto stage_hb = [&]() {
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 float h[16];
-                tmem_ld_cols<16>(P + 32 * hf + 16 * c, h);
+                uint32_t words[16];
+                tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
                 bias_hidden_act<16>(hact, h, s_bb1 + 32 * hf + 16 * c);
-                store16<TH>(H, row, 4 * hf + 2 * c, h);
+                store16_keep<TH>(H, row, 4 * hf + 2 * c, h, words);
+                tmem_st16(P + 32 * hf + 16 * c, words);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        };
+        auto restore_hb = [&]() {
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t words[16];
+                tmem_ld16_words(P + 32 * hf + 16 * c, words);
+                store16_words<TH>(H, row, 4 * hf + 2 * c, words);
             }
         };
 
@@ -621,7 +675,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 for (int j = 0; j < kGeo; ++j) dy[1 + j] = dgeo[j];
                 await_dw();                               // dW1 has read d1 (D) and [SH | geo | 1] (E)
                 store16<TE>(E, row, 0, dy);
-                stage_hb();
+                restore_hb();
                 publish(slot_id);
                 const float s = warp_transpose_sum<16>(dy, lane & 15);
                 // lanes l and l + 16 hold the two half-warp sums of column l
@@ -636,7 +690,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                     if (valid) { d_dirs[3 * i] = dd[0]; d_dirs[3 * i + 1] = dd[1]; d_dirs[3 * i + 2] = dd[2]; }
                 }
                 await_dw();
-                stage_hb();
+                restore_hb();
                 publish(slot_id);
             }
 

@@ -115,3 +115,32 @@ def test_pixel_bandwidth_schedule_and_coefficients(S):
     _close(c[2] * it, wn_sq, 1e-6)
     _close(c[3], 1 / ora.param("tau_sf").double(), 1e-6)
     _close(c[4], 1 / ora.param("tau_diff").double(), 1e-6)
+
+
+def test_march_segment_length_bounds_the_sample_count():
+    """Host-side bound of the samples a ray can emit between near and far (single-pass march)."""
+    from deblur_e_nerf_b200 import ops
+    step = 3 ** 0.5 * 3 / 1024
+    seg = ops.march_segment_length(1.43, 6.63, step)
+    assert seg >= int((6.63 - 1.43) / step) + 1            # every emitted sample advances >= one step
+    assert seg <= int((6.63 - 1.43) / step) + 8
+    assert ops.march_segment_length(None, 6.63, step) is None
+    assert ops.march_segment_length(0.0, float("inf"), step) is None
+    assert ops.march_segment_length(2.0, 1.0, step) == 4     # empty span: slack only
+
+
+def test_sample_buffers_are_allocated_in_row_quanta():
+    """Per-sample buffers round their ROW count up to a quantum (stable block sizes for the caching
+    allocator) and hand out the leading, contiguous view."""
+    import torch
+    from deblur_e_nerf_b200 import ops
+    small = ops._rows(1000, (3,), torch.float32, "cpu")
+    assert small.shape == (1000, 3) and small.untyped_storage().nbytes() == 1000 * 3 * 4
+    n = (1 << 18) + 5
+    big = ops._rows(n, (2,), torch.float32, "cpu")
+    assert big.shape == (n, 2) and big.is_contiguous()
+    assert big.untyped_storage().nbytes() == 2 * (1 << 18) * 2 * 4
+    like = ops._rows_like(big)
+    assert like.shape == big.shape and like.dtype == big.dtype
+    exact = ops._rows(2 << 18, (), torch.int32, "cpu")
+    assert exact.numel() == 2 << 18 and exact.untyped_storage().nbytes() == (2 << 18) * 4
