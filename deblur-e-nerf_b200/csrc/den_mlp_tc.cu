@@ -14,180 +14,296 @@
 // product, measured against the fp32 evaluation in tests/test_gpu_mlp_tc.py (single-pass TF32
 // measured 2e-3 on the head-weight gradients, outside the 1e-3 parity bound).
 //
-// Thread layout: see den_mlp_tc.cuh (S = 2: 8 epilogue warps + 1 MMA warp, 2 CTAs per SM).
-#include "den_mlp_tc.cuh"
+// Thread layout and pipeline: see namespace fwd below (three tiles in flight per CTA).
+#include "den_mlp_ops.cuh"
 
 namespace den {
 
 using namespace mlp;
 
-constexpr int kFwdS = 2;
-constexpr int kFwdCols = kWidth / kFwdS;                 // 32 accumulator columns per thread
-constexpr int kFwdEpiThreads = 128 * kFwdS;
-constexpr int kFwdThreads = kFwdEpiThreads + 32;
-constexpr uint32_t kFwdTmemCols = 64;
+namespace fwd {
 
-struct FwdSmem {
-    static constexpr int a32 = (Weights::end + 127) / 128 * 128;      // (128, 32): enc, then [SH|geo]
-    static constexpr int a64 = a32 + Tile<kTile, kEncDim>::bytes;     // (128, 64): hb, h1, h2
-    static constexpr int bar = a64 + Tile<kTile, kWidth>::bytes;
-    static constexpr int tmem_ptr = bar + 8;
-    static constexpr int total = tmem_ptr + 8;
+// Pipeline (v3).  v2 ran 2 CTAs per SM, each a single tile through 5 serial rounds (epilogue ->
+// hand-off -> MMA -> commit -> wait): 39 % issue-active, 39 % MUFU, every round paying ~1.2 k cycles of
+// hand-shake + MMA latency.  v3 is ONE persistent CTA per SM with THREE tiles ("slots") in flight:
+// 3 x 8 epilogue warps (warp quadrant q = warp % 4 serves TMEM lanes 32q.. = tile rows; half
+// hf = (warp / 4) % 2 owns columns [32 hf, 32 hf + 32) of every 64-wide layer, 16 at a time) + 1 MMA
+// warp serving the slots round-robin.  The C-row output layer runs on the SIMT side (dot product
+// with fp32 W3 rows, halves combined through shared memory): no fifth GEMM round, no h2 operand
+// tile.  Per slot: A32 (128 x 32: enc, then [SH | geo | 0]) + A64 (128 x 64: hb, then h1) = 48 KB;
+// 3 slots + 36 KB of weight tiles = 181 KB of shared memory, 192 TMEM columns.
+constexpr int kSlots = 3;
+constexpr int kGroupThreads = 256;
+constexpr int kEpiThreads = kSlots * kGroupThreads;
+constexpr int kThreads = kEpiThreads + 32;
+constexpr int kMmaWarp = kEpiThreads / 32;
+constexpr int kHandoff = kGroupThreads + 32;
+constexpr uint32_t kTmemCols = 256;
+
+using TA32 = OpTile<kTile, 4>;
+using TA64 = OpTile<kTile, 8>;
+using TWb1 = OpTile<kWidth, 4>;
+using TWb2 = OpTile<kBaseOut, 8>;
+using TW1 = OpTile<kWidth, 4>;
+using TW2 = OpTile<kWidth, 8>;
+
+struct Smem {
+    static constexpr int wb1 = 0;
+    static constexpr int wb2 = wb1 + TWb1::bytes;
+    static constexpr int w1 = wb2 + TWb2::bytes;
+    static constexpr int w2 = w1 + TW1::bytes;
+    static constexpr int bias = w2 + TW2::bytes;          // fp32: bb1 64 | bb2 16 | b1 64 | b2 64 | b3 16
+    static constexpr int w3f = bias + (3 * kWidth + kBaseOut + 16) * 4;   // fp32 W3 rows (3 x 64)
+    static constexpr int zx = w3f + 3 * kWidth * 4;       // per slot (128, 2) float4: output-layer partials
+    static constexpr int bars = zx + kSlots * kTile * 2 * 16;             // done[kSlots]
+    static constexpr int tmem_ptr = bars + 4 * 8;
+    static constexpr int slot0 = (tmem_ptr + 8 + 127) / 128 * 128;
+    static constexpr int a32 = 0;
+    static constexpr int a64 = a32 + TA32::bytes;
+    static constexpr int slot_bytes = a64 + TA64::bytes;
+    static constexpr int total = slot0 + kSlots * slot_bytes;
 };
+static_assert(Smem::slot_bytes % 128 == 0 && Smem::slot0 % 128 == 0, "tile alignment");
+static_assert(Smem::total <= 227 * 1024, "shared-memory plan exceeds 227 KB");
+
+}  // namespace fwd
 
 template <bool kFull>
-__global__ void __launch_bounds__(kFwdThreads, 2)
+__global__ void __launch_bounds__(fwd::kThreads, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constant__ den_field_params p,
                   const float* __restrict__ enc, const float* __restrict__ rays_o,
                   const float* __restrict__ rays_d, const int32_t* __restrict__ ray_indices,
                   const float* __restrict__ t_starts, const float* __restrict__ t_ends, int64_t n,
                   float* __restrict__ sigmas, float* __restrict__ rgbs) {
+    using namespace fwd;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + FwdSmem::bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FwdSmem::tmem_ptr);
-    const float* s_bb1 = reinterpret_cast<const float*>(smem + Weights::bias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::tmem_ptr);
+    const float* s_bb1 = reinterpret_cast<const float*>(smem + Smem::bias);
     const float* s_bb2 = s_bb1 + kWidth;
     const float* s_b1 = s_bb2 + kBaseOut;
     const float* s_b2 = s_b1 + kWidth;
     const float* s_b3 = s_b2 + kWidth;
+    float* s_w3f = reinterpret_cast<float*>(smem + Smem::w3f);
+    const int enc_dim = f.grid.n_levels * 2;
+    const int C = f.channels;
+    constexpr int kRounds = kFull ? 4 : 2;
 
-    const Tile<kWidth, kEncDim> Wb1(smem + Weights::wb1);
-    const Tile<kBaseOut, kWidth> Wb2(smem + Weights::wb2);
-    const Tile<kWidth, kHeadIn> W1(smem + Weights::w1);
-    const Tile<kWidth, kWidth> W2(smem + Weights::w2);
-    const Tile<kOutN, kWidth> W3(smem + Weights::w3);
-    const Tile<kTile, kEncDim> T32(smem + FwdSmem::a32);
-    const Tile<kTile, kWidth> T64(smem + FwdSmem::a64);
-
-    load_all_weights(smem, f, p, kFull);
+    // ---- setup ---------------------------------------------------------------------------------
+    tc::load_weight_split(smem + Smem::wb1, smem + Smem::wb1 + TWb1::half, p.wb1, kWidth, enc_dim, kWidth, kEncDim);
+    tc::load_weight_split(smem + Smem::wb2, smem + Smem::wb2 + TWb2::half, p.wb2, kBaseOut, kWidth, kBaseOut, kWidth);
+    {
+        float* b = reinterpret_cast<float*>(smem + Smem::bias);
+        load_padded(b, p.bb1, kWidth, kWidth);
+        load_padded(b + kWidth, p.bb2, kBaseOut, kBaseOut);
+        if (kFull) {
+            load_padded(b + kWidth + kBaseOut, p.b1, kWidth, kWidth);
+            load_padded(b + 2 * kWidth + kBaseOut, p.b2, kWidth, kWidth);
+            load_padded(b + 3 * kWidth + kBaseOut, p.b3, C, 16);
+        }
+    }
+    if (kFull) {
+        tc::load_weight_split(smem + Smem::w1, smem + Smem::w1 + TW1::half, p.w1, kWidth, kShDim + kGeo, kWidth, kHeadIn);
+        tc::load_weight_split(smem + Smem::w2, smem + Smem::w2 + TW2::half, p.w2, kWidth, kWidth, kWidth, kWidth);
+        for (int i = tid; i < 3 * kWidth; i += kThreads) s_w3f[i] = (i / kWidth) < C ? __ldg(p.w3 + i) : 0.f;
+    }
     if (tid == 0) {
-        tc::mbar_init(bar, 1);
+        for (int b = 0; b < kSlots; ++b) tc::mbar_init(&bars[b], 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, kFwdTmemCols);
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
     tc::fence_smem_to_async_proxy();
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_tiles = (n + kTile - 1) / kTile;
-    const int enc_dim = f.grid.n_levels * 2;
-    const int C = f.channels;
+    // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0 .. my_tiles-1; slot s takes k = s, s+3, ...
+    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
-    if (warp == kFwdEpiThreads / 32) {
-        // ===================== MMA warp: one issue per round =====================
-        // hand-off in: named barrier 1 (producers arrive, this warp syncs); hand-off out: tcgen05.commit
-        // on the mbarrier; one elected lane issues the whole round
-#define DEN_ROUND(...)                                     \
-    handoff_sync(kFwdThreads);                             \
-    if (tc::elect_one()) { __VA_ARGS__; tc::mma_commit_1t(bar); } \
-    __syncwarp();
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            DEN_ROUND(mma_fwd_1t<kWidth, kEncDim>(tmem_base, T32, Wb1))
-            DEN_ROUND(mma_fwd_1t<kBaseOut, kWidth>(tmem_base, T64, Wb2))
-            if (kFull) {
-                DEN_ROUND(mma_fwd_1t<kWidth, kHeadIn>(tmem_base, T32, W1))
-                DEN_ROUND(mma_fwd_1t<kWidth, kWidth>(tmem_base, T64, W2))
-                DEN_ROUND(mma_fwd_1t<kOutN, kWidth>(tmem_base, T64, W3))
+    if (warp == kMmaWarp) {
+        // ===================== MMA warp: the slots round-robin, one elected lane issues a round =====
+        const uint8_t* wb1 = smem + Smem::wb1;
+        const uint8_t* wb2 = smem + Smem::wb2;
+        const uint8_t* w1 = smem + Smem::w1;
+        const uint8_t* w2 = smem + Smem::w2;
+        int64_t left[kSlots];
+        int rnd[kSlots];
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            left[s] = kRounds * ((my_tiles + kSlots - 1 - s) / kSlots);
+            rnd[s] = 0;
+        }
+        bool any = true;
+        while (any) {
+            any = false;
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (left[s] <= 0) continue;
+                any = true;
+                handoff_from(4 + s, kHandoff);
+                const uint8_t* slot = smem + Smem::slot0 + s * Smem::slot_bytes;
+                const uint32_t Z = tmem_base + 64u * s;
+                if (elect_one()) {
+                    switch (rnd[s]) {
+                    case 0:     // z_b1 = enc Wb1^T
+                        gemm3<kEncDim / 16>(Z, kmajor<TA32>(slot + Smem::a32), kmajor<TWb1>(wb1),
+                                            tc::instr_desc_bf16(128, kWidth, false, false), false);
+                        break;
+                    case 1:     // y = hb Wb2^T
+                        gemm3<kWidth / 16>(Z, kmajor<TA64>(slot + Smem::a64), kmajor<TWb2>(wb2),
+                                           tc::instr_desc_bf16(128, kBaseOut, false, false), false);
+                        break;
+                    case 2:     // z1 = [SH | geo | 0] W1^T
+                        gemm3<kHeadIn / 16>(Z, kmajor<TA32>(slot + Smem::a32), kmajor<TW1>(w1),
+                                            tc::instr_desc_bf16(128, kWidth, false, false), false);
+                        break;
+                    default:    // z2 = h1 W2^T
+                        gemm3<kWidth / 16>(Z, kmajor<TA64>(slot + Smem::a64), kmajor<TW2>(w2),
+                                           tc::instr_desc_bf16(128, kWidth, false, false), false);
+                        break;
+                    }
+                    tc::mma_commit_1t(&bars[s]);
+                }
+                __syncwarp();
+                rnd[s] = rnd[s] + 1 == kRounds ? 0 : rnd[s] + 1;
+                --left[s];
             }
         }
-#undef DEN_ROUND
     } else {
-        // ===================== epilogue warps =====================
-        const int q = warp & 3, cg = warp >> 2;
+        // ===================== epilogue warps: one group of 8 per slot =====================
+        const int slot_id = warp >> 3;
+        const int q = warp & 3, hf = (warp >> 2) & 1;
         const int row = q * 32 + lane;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint8_t* slot = smem + Smem::slot0 + slot_id * Smem::slot_bytes;
+        uint8_t* A32 = slot + Smem::a32;
+        uint8_t* A64 = slot + Smem::a64;
+        uint64_t* done = &bars[slot_id];
+        float* zx = reinterpret_cast<float*>(smem + Smem::zx) + slot_id * (kTile * 2 * 4);
+        const uint32_t Z = tmem_base + ((uint32_t)(q * 32) << 16) + 64u * slot_id;
+        const int hact = f.hidden_act;
+        const int ready = 4 + slot_id;
         uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+
+        for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
+            const int64_t tile = blockIdx.x + k * gridDim.x;
             const int64_t i = tile * kTile + row;
             const bool valid = i < n;
-            // ---- stage 0: 16 of the 32 encoding features of this row -> T32 ------------------
-            float x16[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) x16[k] = 0.f;
+
+            // ---- operands of round 0: this thread's 16 encoding features -------------------------
             float dir[3] = {0.f, 0.f, 1.f};
             bool inside = false;
-            if (valid) {
-                const float4* src = reinterpret_cast<const float4*>(enc + i * enc_dim + 16 * cg);
+            {
+                float x[16];
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4)
-                    if (16 * cg + 4 * v4 < enc_dim) {
-                        const float4 v = __ldg(src + v4);
-                        x16[4 * v4] = v.x; x16[4 * v4 + 1] = v.y; x16[4 * v4 + 2] = v.z; x16[4 * v4 + 3] = v.w;
+                for (int c = 0; c < 16; ++c) x[c] = 0.f;
+                if (valid) {
+                    const float4* src = reinterpret_cast<const float4*>(enc + i * enc_dim + 16 * hf);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        if (16 * hf + 4 * v4 < enc_dim) {
+                            const float4 v = __ldg(src + v4);
+                            x[4 * v4] = v.x; x[4 * v4 + 1] = v.y; x[4 * v4 + 2] = v.z; x[4 * v4 + 3] = v.w;
+                        }
+                    const int64_t r = ray_indices[i];
+                    const float tm = t_starts[i] + t_ends[i];
+                    float pos[3], u[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        dir[d] = __ldg(rays_d + 3 * r + d);
+                        pos[d] = __ldg(rays_o + 3 * r + d) + (dir[d] * tm) * 0.5f;
                     }
-                const int64_t r = ray_indices[i];
-                const float tm = t_starts[i] + t_ends[i];
-                float pos[3], u[3];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    dir[d] = __ldg(rays_d + 3 * r + d);
-                    pos[d] = __ldg(rays_o + 3 * r + d) + (dir[d] * tm) * 0.5f;
+                    if (hf == 0) inside = contract_position(f, pos, u);
                 }
-                if (cg == 0) inside = contract_position(f, pos, u);
+                store16<TA32>(A32, row, 2 * hf, x);
             }
-            store_cols<16, kEncDim>(T32, row, 16 * cg, x16);
-            publish_arrive(kFwdThreads);
+            publish_to(ready, kHandoff);
 
-            // ---- base layer 1 -------------------------------------------------------------------
-            await(bar, phase);
-            float h[kFwdCols];
-            tmem_ld_cols<kFwdCols>(tmem_lane + kFwdCols * cg, h);
-bias_hidden_act<kFwdCols>(f.hidden_act, h, s_bb1 + kFwdCols * cg);
-            store_cols<kFwdCols, kWidth>(T64, row, kFwdCols * cg, h);
-            publish_arrive(kFwdThreads);
+            // ---- round 0 done: hb -> A64 ---------------------------------------------------------------
+            tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                float h[16];
+                tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
+                bias_hidden_act<16>(hact, h, s_bb1 + 32 * hf + 16 * c);
+                store16<TA64>(A64, row, 4 * hf + 2 * c, h);
+            }
+            publish_to(ready, kHandoff);
 
-            // ---- base layer 2: density + geo features; [SH | geo | 0] -> T32 --------------------
-            await(bar, phase);
-            if (cg == 0) {
-                float y[kBaseOut];
-                tmem_ld_cols<kBaseOut>(tmem_lane, y);
+            // ---- round 1 done: density; [SH | geo | 0] -> A32 --------------------------------------------
+            tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
+            if (hf == 0) {
+                float y[16];
+                tmem_ld_cols<16>(Z, y);
 #pragma unroll
                 for (int j = 0; j < kBaseOut; ++j) y[j] += s_bb2[j];
                 if (valid) sigmas[i] = inside ? density_act(f.density_act, y[0]) : 0.f;
                 if (kFull) {
+                    float x[16];
 #pragma unroll
-                    for (int j = 0; j < kGeo; ++j) x16[j] = y[1 + j];
-                    x16[15] = 0.f;
-                    store_cols<16, kHeadIn>(T32, row, 16, x16);
+                    for (int j = 0; j < kGeo; ++j) x[j] = y[1 + j];
+                    x[15] = 0.f;
+                    store16<TA32>(A32, row, 2, x);
                 }
             } else if (kFull) {
-                sh_degree4(dir, x16);
-                store_cols<16, kHeadIn>(T32, row, 0, x16);
+                float x[16];
+                sh_degree4(dir, x);
+                store16<TA32>(A32, row, 0, x);
             }
             if (!kFull) {
                 tc::tc_fence_before_sync();
                 continue;
             }
-            publish_arrive(kFwdThreads);
+            publish_to(ready, kHandoff);
 
-            // ---- head layers ----------------------------------------------------------------------
-            await(bar, phase);
-            tmem_ld_cols<kFwdCols>(tmem_lane + kFwdCols * cg, h);
-bias_hidden_act<kFwdCols>(f.hidden_act, h, s_b1 + kFwdCols * cg);
-            store_cols<kFwdCols, kWidth>(T64, row, kFwdCols * cg, h);
-            publish_arrive(kFwdThreads);
-
-            await(bar, phase);
-            tmem_ld_cols<kFwdCols>(tmem_lane + kFwdCols * cg, h);
-bias_hidden_act<kFwdCols>(f.hidden_act, h, s_b2 + kFwdCols * cg);
-            store_cols<kFwdCols, kWidth>(T64, row, kFwdCols * cg, h);
-            publish_arrive(kFwdThreads);
-
-            await(bar, phase);
-            if (cg == 0) {
-                float out[kOutN];
-                tmem_ld_cols<kOutN>(tmem_lane, out);
-                if (valid)
-                    for (int c = 0; c < C; ++c) rgbs[i * C + c] = radiance_act(f.radiance_act, out[c] + s_b3[c]);
+            // ---- round 2 done: h1 -> A64 ---------------------------------------------------------------------
+            tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                float h[16];
+                tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
+                bias_hidden_act<16>(hact, h, s_b1 + 32 * hf + 16 * c);
+                store16<TA64>(A64, row, 4 * hf + 2 * c, h);
             }
-            tc::tc_fence_before_sync();
+            publish_to(ready, kHandoff);
+
+            // ---- round 3 done: h2 stays in registers; output layer = dot with the fp32 W3 rows ----------------
+            tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
+            {
+                float z3[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    float h[16];
+                    tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
+                    bias_hidden_act<16>(hact, h, s_b2 + 32 * hf + 16 * c);
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        if (ch < C) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                z3[ch] = fmaf(h[j], s_w3f[ch * kWidth + 32 * hf + 16 * c + j], z3[ch]);
+                        }
+                }
+                tc::tc_fence_before_sync();
+                if (hf == 1) *reinterpret_cast<float4*>(zx + row * 4) = make_float4(z3[0], z3[1], z3[2], 0.f);
+                named_sync(1 + slot_id, kGroupThreads);
+                if (hf == 0) {
+                    const float4 other = *reinterpret_cast<const float4*>(zx + row * 4);
+                    z3[0] += other.x; z3[1] += other.y; z3[2] += other.z;
+                    if (valid) {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            if (ch < C) rgbs[i * C + ch] = radiance_act(f.radiance_act, z3[ch] + s_b3[ch]);
+                    }
+                }
+            }
         }
     }
 
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, kFwdTmemCols);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, fwd::kTmemCols);
 }
 
 // positions of marched samples in the field's unit cube (input of the hash-grid kernels)
@@ -288,15 +404,18 @@ int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float*
     DEN_CHECK_ARG(enc && rays_o && rays_d && ray_indices && t_starts && t_ends && sigmas,
                   "null pointer");
     DEN_CHECK_ARG((f->grid.n_levels * 2) % 4 == 0, "encoding width must be a multiple of 4");
-    const int grid = grid_for((n + kTile - 1) / kTile, 1, 2);
-    const size_t smem = FwdSmem::total;
+    DEN_CHECK_ARG(!full || (f->channels >= 1 && f->channels <= 3), "1 to 3 radiance channels");
+    // three tiles in flight per CTA: one persistent CTA per SM, at least three tiles each when there are enough
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    const int grid = grid_for((n_tiles + fwd::kSlots - 1) / fwd::kSlots, 1, 1);
+    const size_t smem = fwd::Smem::total;
     if (full) {
         cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mlp_fwd_tc_kernel<true><<<grid, kFwdThreads, smem, as_stream(stream)>>>(
+        mlp_fwd_tc_kernel<true><<<grid, fwd::kThreads, smem, as_stream(stream)>>>(
             *f, *p, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, n, sigmas, rgbs);
     } else {
         cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mlp_fwd_tc_kernel<false><<<grid, kFwdThreads, smem, as_stream(stream)>>>(
+        mlp_fwd_tc_kernel<false><<<grid, fwd::kThreads, smem, as_stream(stream)>>>(
             *f, *p, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, n, sigmas, nullptr);
     }
     DEN_CHECK_LAUNCH();
