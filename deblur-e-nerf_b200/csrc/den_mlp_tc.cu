@@ -35,9 +35,7 @@ namespace fwd {
 constexpr int kSlots = 3;
 constexpr int kGroupThreads = 256;
 constexpr int kEpiThreads = kSlots * kGroupThreads;
-constexpr int kThreads = kEpiThreads + 32;
-constexpr int kMmaWarp = kEpiThreads / 32;
-constexpr int kHandoff = kGroupThreads + 32;
+constexpr int kThreads = kEpiThreads;              // no dedicated MMA warp: each group issues its own GEMMs
 constexpr uint32_t kTmemCols = 256;
 
 using TA32 = OpTile<kTile, 4>;
@@ -88,7 +86,6 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
     float* s_w3f = reinterpret_cast<float*>(smem + Smem::w3f);
     const int enc_dim = f.grid.n_levels * 2;
     const int C = f.channels;
-    constexpr int kRounds = kFull ? 4 : 2;
 
     // ---- setup ---------------------------------------------------------------------------------
     tc::load_weight_split(smem + Smem::wb1, smem + Smem::wb1 + TWb1::half, p.wb1, kWidth, enc_dim, kWidth, kEncDim);
@@ -122,56 +119,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
     // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0 .. my_tiles-1; slot s takes k = s, s+3, ...
     const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
-    if (warp == kMmaWarp) {
-        // ===================== MMA warp: the slots round-robin, one elected lane issues a round =====
-        const uint8_t* wb1 = smem + Smem::wb1;
-        const uint8_t* wb2 = smem + Smem::wb2;
-        const uint8_t* w1 = smem + Smem::w1;
-        const uint8_t* w2 = smem + Smem::w2;
-        int64_t left[kSlots];
-        int rnd[kSlots];
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-            left[s] = kRounds * ((my_tiles + kSlots - 1 - s) / kSlots);
-            rnd[s] = 0;
-        }
-        bool any = true;
-        while (any) {
-            any = false;
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                if (left[s] <= 0) continue;
-                any = true;
-                handoff_from(4 + s, kHandoff);
-                const uint8_t* slot = smem + Smem::slot0 + s * Smem::slot_bytes;
-                const uint32_t Z = tmem_base + 64u * s;
-                if (elect_one()) {
-                    switch (rnd[s]) {
-                    case 0:     // z_b1 = enc Wb1^T
-                        gemm3<kEncDim / 16>(Z, kmajor<TA32>(slot + Smem::a32), kmajor<TWb1>(wb1),
-                                            tc::instr_desc_bf16(128, kWidth, false, false), false);
-                        break;
-                    case 1:     // y = hb Wb2^T
-                        gemm3<kWidth / 16>(Z, kmajor<TA64>(slot + Smem::a64), kmajor<TWb2>(wb2),
-                                           tc::instr_desc_bf16(128, kBaseOut, false, false), false);
-                        break;
-                    case 2:     // z1 = [SH | geo | 0] W1^T
-                        gemm3<kHeadIn / 16>(Z, kmajor<TA32>(slot + Smem::a32), kmajor<TW1>(w1),
-                                            tc::instr_desc_bf16(128, kWidth, false, false), false);
-                        break;
-                    default:    // z2 = h1 W2^T
-                        gemm3<kWidth / 16>(Z, kmajor<TA64>(slot + Smem::a64), kmajor<TW2>(w2),
-                                           tc::instr_desc_bf16(128, kWidth, false, false), false);
-                        break;
-                    }
-                    tc::mma_commit_1t(&bars[s]);
-                }
-                __syncwarp();
-                rnd[s] = rnd[s] + 1 == kRounds ? 0 : rnd[s] + 1;
-                --left[s];
-            }
-        }
-    } else {
+    {
         // ===================== epilogue warps: one group of 8 per slot =====================
         const int slot_id = warp >> 3;
         const int q = warp & 3, hf = (warp >> 2) & 1;
@@ -183,8 +131,41 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         float* zx = reinterpret_cast<float*>(smem + Smem::zx) + slot_id * (kTile * 2 * 4);
         const uint32_t Z = tmem_base + ((uint32_t)(q * 32) << 16) + 64u * slot_id;
         const int hact = f.hidden_act;
-        const int ready = 4 + slot_id;
         uint32_t phase = 0;
+        const uint8_t* wb1 = smem + Smem::wb1;
+        const uint8_t* wb2 = smem + Smem::wb2;
+        const uint8_t* w1 = smem + Smem::w1;
+        const uint8_t* w2 = smem + Smem::w2;
+        const uint32_t Zd = tmem_base + 64u * slot_id;            // accumulator address (lane 0) for the MMAs
+        // Hand the operand tiles to the tensor core: every thread makes its shared-memory writes
+        // visible to the async proxy, the 8 warps of the group meet at a hardware named barrier, then
+        // ONE elected lane of the group's first warp issues the round's GEMM and its commit — the
+        // slots own disjoint accumulators, so the three issuing threads never touch the same TMEM
+        // columns and no dedicated MMA warp (and no second hand-off hop) is needed.
+        auto launch_round = [&](int round) {
+            tc::fence_smem_to_async_proxy();
+            tc::tc_fence_before_sync();
+            named_sync(4 + slot_id, kGroupThreads);
+            if ((warp & 7) == 0) {
+                tc::tc_fence_after_sync();
+                if (elect_one()) {
+                    if (round == 0)        // z_b1 = enc Wb1^T
+                        gemm3<kEncDim / 16>(Zd, kmajor<TA32>(A32), kmajor<TWb1>(wb1),
+                                            tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    else if (round == 1)   // y = hb Wb2^T
+                        gemm3<kWidth / 16>(Zd, kmajor<TA64>(A64), kmajor<TWb2>(wb2),
+                                           tc::instr_desc_bf16(128, kBaseOut, false, false), false);
+                    else if (round == 2)   // z1 = [SH | geo | 0] W1^T
+                        gemm3<kHeadIn / 16>(Zd, kmajor<TA32>(A32), kmajor<TW1>(w1),
+                                            tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    else                   // z2 = h1 W2^T
+                        gemm3<kWidth / 16>(Zd, kmajor<TA64>(A64), kmajor<TW2>(w2),
+                                           tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    tc::mma_commit_1t(done);
+                }
+                __syncwarp();
+            }
+        };
 
         for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
             const int64_t tile = blockIdx.x + k * gridDim.x;
@@ -218,7 +199,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 }
                 store16<TA32>(A32, row, 2 * hf, x);
             }
-            publish_to(ready, kHandoff);
+            launch_round(0);
 
             // ---- round 0 done: hb -> A64 ---------------------------------------------------------------
             tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
@@ -229,7 +210,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 bias_hidden_act<16>(hact, h, s_bb1 + 32 * hf + 16 * c);
                 store16<TA64>(A64, row, 4 * hf + 2 * c, h);
             }
-            publish_to(ready, kHandoff);
+            launch_round(1);
 
             // ---- round 1 done: density; [SH | geo | 0] -> A32 --------------------------------------------
             tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
@@ -255,7 +236,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 tc::tc_fence_before_sync();
                 continue;
             }
-            publish_to(ready, kHandoff);
+            launch_round(2);
 
             // ---- round 2 done: h1 -> A64 ---------------------------------------------------------------------
             tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
@@ -266,7 +247,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 bias_hidden_act<16>(hact, h, s_b1 + 32 * hf + 16 * c);
                 store16<TA64>(A64, row, 4 * hf + 2 * c, h);
             }
-            publish_to(ready, kHandoff);
+            launch_round(3);
 
             // ---- round 3 done: h2 stays in registers; output layer = dot with the fp32 W3 rows ----------------
             tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
