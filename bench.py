@@ -18,6 +18,8 @@ Workloads (BASELINE.json `configs`):
   synthetic_budget   reading (R): N = budget(2^17 samples)/mean samples per ray, PB on
   eds                configs[3] shape (sphere contraction, cone 0.004, res 256, no background)
   plumbing           configs[0]: 4096 events x 8 samples, small hash grid (CPU-runnable)
+  render_sweep       configs[4]: eval-mode 800x800 novel views in 16 384-ray chunks (march + hash grid +
+                     MLP + compositing, no event loss); a step is one view, `value` is rays/s
 `--impl reference` times the reference's path on the host cores instead: the CPU oracle
 (oracle/path_ref.py = the reference's own files restated and pinned against them; nerfacc /
 tiny-cuda-nn are CUDA-only, so their pure-PyTorch equivalents are used and labelled).
@@ -45,6 +47,9 @@ WORKLOADS = {
     "eds": dict(config="eds", pb=True, S=30, rays_per_call=1 << 17, small=False, occ_res=256),
     "plumbing": dict(config="synthetic", pb=True, S=8, rays_per_call=4096 * 8, small=True,
                      occ_res=32),
+    # configs[4]: test-mode novel-view sweep, 800x800 views in 16 384-ray chunks, forward only
+    "render_sweep": dict(config="synthetic", pb=False, S=1, rays_per_call=800 * 800, small=False,
+                         occ_res=128, sweep=True),
 }
 
 # algorithmic bytes per sample (SURVEY.md §8(d) / BASELINE.md §3), 16 levels x 8 corners x 8 B
@@ -204,9 +209,50 @@ def cpu_reference_rate(workload, n_events, steps=1, warmup=0):
     }, rays_per_step
 
 
+def cpu_sweep_rate(workload, n_rays, steps=1, warmup=0):
+    """rays/s of the reference's eval-mode render (CPU oracle) on `n_rays` pixels of an 800x800 view."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, _, _, w = _oracle_scene(workload, 8)
+    model.eval()
+    side = 800
+    kinv = torch.linalg.inv(torch.tensor([[side * 1.2, 0, side / 2], [0, side * 1.2, side / 2],
+                                          [0, 0, 1.0]]))
+    g = torch.Generator().manual_seed(5)
+    pix = torch.rand(n_rays, 2, generator=g) * (side - 1)
+    ts = model.trajectory.T_wc_timestamp[len(model.trajectory.T_wc_timestamp) // 2].double().expand(n_rays)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            pos, rot = model.trajectory(ts)
+            o, d = model.nerf.pixel_params_to_ray(kinv, pix, pos, rot)
+            model.nerf(o, d)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    mean_t = sum(times) / len(times)
+    return {"value": n_rays / mean_t, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": (f"{n_rays} pixels of one 800x800 view, eval mode, forward only, {len(times)} timed "
+                       "pass(es); reference's own files restated in oracle/path_ref.py, nerfacc / "
+                       "tiny-cuda-nn replaced by their pure-PyTorch equivalents"),
+            "ms_per_step": mean_t * 1e3}, n_rays
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if WORKLOADS[args.workload].get("sweep"):
+        base, _ = cpu_sweep_rate(args.workload, 4096, steps=args.steps, warmup=min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": "render rays/s (eval, fwd only)", "value": base["value"],
+            "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "view": "800x800", "bounded_sample": True},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "rays/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}))
         return
     base, rays_per_step = cpu_reference_rate(args.workload, args.cpu_events, steps=args.steps,
                                              warmup=min(args.warmup, 1))
@@ -236,6 +282,99 @@ def workload_config(name, w, n_events, bounded=False):
         "l2_policy": "inputs larger than L2: per-step sample arena + 48 MiB table + gradients "
                      "exceed 126 MB; a fresh batch every step",
     }
+
+
+# ------------------------------------------------------------------ render sweep ------
+def run_sweep(args):
+    """BASELINE.json configs[4]: 800x800 novel views, eval mode (deterministic march, 16 384-ray
+    chunks, no gradients), one view per step; every rank renders its own views."""
+    import torch
+    import __graft_entry__ as entry
+    from deblur_e_nerf_b200 import ddp, factory, ops, synthetic
+
+    rank, local_rank, world = ddp.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if rank == 0:
+        entry.build()
+    ddp.barrier()
+    w = WORKLOADS[args.workload]
+    model, cfg, poses = factory.build_renderer(w["config"], dev, pixel_bandwidth=False,
+                                               occ_resolution=w["occ_res"], seed=0)
+    sphere = synthetic.solid_sphere_occupancy(w["occ_res"]).to(dev)
+    model.nerf.occupancy_grid._binary = sphere
+    ddp.broadcast_parameters(model)
+    model.eval()
+    side = 800
+    kinv = torch.linalg.inv(torch.tensor([[side * 1.2, 0, side / 2], [0, side * 1.2, side / 2],
+                                          [0, 0, 1.0]])).to(dev)
+    v, u = torch.meshgrid(torch.arange(side, dtype=torch.float32),
+                          torch.arange(side, dtype=torch.float32), indexing="ij")
+    pix_host = torch.stack((u, v), dim=-1).reshape(-1, 2).pin_memory()
+    n_views = args.warmup + args.steps
+    view_ts = torch.linspace(float(poses[2][10]), float(poses[2][-10]), world * n_views,
+                             dtype=torch.float64)[rank::world].to(dev)
+
+    def render_view(i, pix):
+        ts = view_ts[i].expand(pix.shape[0])
+        pos, rot = model.trajectory(ts)
+        o, d = model.nerf.pixel_params_to_ray(kinv, pix, pos, rot)
+        with torch.no_grad():
+            radiance, opacity, depth, mean_samples = model.nerf(o, d)
+        return radiance, mean_samples
+
+    pix_dev = pix_host.to(dev)
+    for i in range(args.warmup):
+        render_view(i, pix_dev)
+    ddp.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = ops.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    samples = 0.0
+    for i in range(args.steps):
+        _, ms = render_view(args.warmup + i, pix_dev)
+        samples += ms * side * side
+    end.record()
+    ddp.barrier()
+    torch.cuda.synchronize()
+    ms_step = ddp.max_over_ranks(start.elapsed_time(end) / args.steps, dev)
+    launches = ops.launch_count() - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    # end to end: pixels from pinned host memory, the rendered view read back
+    start.record()
+    for i in range(args.steps):
+        img, _ = render_view(args.warmup + i, pix_host.to(dev, non_blocking=True))
+        img_host = img.to("cpu")
+    end.record()
+    ddp.barrier()
+    torch.cuda.synchronize()
+    ms_e2e = ddp.max_over_ranks(start.elapsed_time(end) / args.steps, dev)
+    rays = ddp.sum_over_ranks(side * side, dev)
+    if rank != 0:
+        return
+    line = {
+        "metric": "render rays/s (eval, fwd only)", "value": rays / (ms_step * 1e-3), "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "yaml": "configs/test/synthetic.yaml shape",
+                   "view": "800x800", "test_chunk_size": cfg["test_chunk_size"],
+                   "occupancy": "controlled solid sphere r=0.75", "field": "random init",
+                   "l2_policy": "a fresh view (camera pose) every step; the 48 MiB table is L2-resident "
+                                "by design"},
+        "views_per_s": world / (ms_step * 1e-3),
+        "samples_per_s": world * samples / args.steps / (ms_step * 1e-3),
+        "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s",
+                "h2d_bytes_per_step": pix_host.numel() * 4, "d2h_bytes_per_step": img_host.numel() * 4,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "clocks": clock_info, "roofline": None, "cpu_baseline": None,
+    }
+    print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------- ours ------
@@ -473,7 +612,10 @@ def main():
         run_reference(args)
     else:
         try:
-            run_ours(args)
+            if WORKLOADS[args.workload].get("sweep"):
+                run_sweep(args)
+            else:
+                run_ours(args)
         finally:
             _shutdown()
 

@@ -77,6 +77,8 @@ _SIGNATURES = {
     "den_march_bound": (_INT, [_c.POINTER(MarchParams), _P, _P, _I32, _P, _I64, _P]),
     "den_march_single": (_INT, [_c.POINTER(MarchParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "den_march_pack": (_INT, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "den_rays_from_trajectory": (_INT, [_P, _P, _I64, _P, _P, _P, _I32, _c.POINTER(_F), _P, _P, _I64,
+                                        _P]),
     "den_alpha_from_sigma": (_INT, [_P, _P, _P, _P, _I64, _P]),
     "den_visibility": (_INT, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "den_compact_samples": (_INT, [_P] * 9 + [_I64, _P]),

@@ -94,6 +94,11 @@ class NeRF(torch.nn.Module):
             dir_encoding_config=dict(_get(arch_config, "dir_encoding")),
             mlp_base_config=base, mlp_head_config=head)
         self.last_num_samples = None        # device int32 scalar of the latest render call
+        # eval mode: the reference renders `test_chunk_size` rays at a time to bound memory
+        # (external/utils.py:99-103); rays are independent and the eval march is deterministic, so any
+        # chunking gives the same image — on a 180 GB part the chunks are merged up to this many rays
+        # (40 launches sequences per 800x800 view become one)
+        self.eval_chunk_rays = 1 << 20
 
     # ---------------------------------------------------------------- occupancy ------
     def update_occ_grid(self, step, T_wc_position=None):
@@ -227,7 +232,8 @@ class NeRF(torch.nn.Module):
             opacity = opa.view(*shape[:-1])
             depth = dep.view(*shape[:-1]) / (opacity + self.opacity_eps)
             return radiance, opacity, depth, [c / max(per, 1) for c in counts]
-        chunk = n_rays if self.radiance_field.training else self.test_chunk_size
+        chunk = n_rays if self.radiance_field.training else max(self.test_chunk_size,
+                                                                   self.eval_chunk_rays)
         cols, opas, deps, total = [], [], [], 0
         for i in range(0, max(n_rays, 1), max(chunk, 1)):
             jit = None if jitter is None else jitter.reshape(-1)[i:i + chunk].contiguous()

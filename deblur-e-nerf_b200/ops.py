@@ -655,6 +655,29 @@ def contract_samples_autograd(desc, rays_o, rays_d, ray_indices, t_starts, t_end
 
 
 # --------------------------------------------------------------------------- #
+# trajectory + camera model -> rays
+# --------------------------------------------------------------------------- #
+def rays_from_trajectory(timestamps, pixels, pose_ts, pose_pos, pose_quat, kinv_host):
+    """timestamps (..., N) f64 ns, pixels (N, 2) f32 -> rays_o, rays_d (..., N, 3) in one launch
+    (no gradient: callers keep the torch autograd path when the timestamps require grad).
+    `kinv_host`: the 9 floats of K^-1, row-major, on the host."""
+    shape = tuple(timestamps.shape)
+    ts = _req(timestamps.detach().reshape(-1), torch.float64, "timestamps")
+    pixels = _req(pixels.reshape(-1, 2), torch.float32, "pixels")
+    pose_ts = _req(pose_ts, torch.int64, "pose_ts")
+    pose_pos = _req(pose_pos, torch.float32, "pose_pos")
+    pose_quat = _req(pose_quat, torch.float32, "pose_quat")
+    n = ts.numel()
+    assert pixels.shape[0] > 0 and n % pixels.shape[0] == 0 and shape[-1] == pixels.shape[0]
+    o = torch.empty((n, 3), dtype=torch.float32, device=ts.device)
+    d = torch.empty((n, 3), dtype=torch.float32, device=ts.device)
+    host = (ctypes.c_float * 9)(*[float(v) for v in kinv_host])
+    _call("den_rays_from_trajectory", _ptr(ts), _ptr(pixels), pixels.shape[0], _ptr(pose_ts),
+          _ptr(pose_pos), _ptr(pose_quat), pose_ts.numel(), host, _ptr(o), _ptr(d), n, _stream())
+    return o.view(*shape, 3), d.view(*shape, 3)
+
+
+# --------------------------------------------------------------------------- #
 # pixel-bandwidth low-pass filter
 # --------------------------------------------------------------------------- #
 class _LpfFn(torch.autograd.Function):

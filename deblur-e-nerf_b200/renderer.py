@@ -48,6 +48,24 @@ class EventRenderer(torch.nn.Module):
         self.batch_render_calls = True
 
     # ------------------------------------------------------------- render helpers ----
+    def _kinv_host(self):
+        """K^-1 as 9 host floats (read back once; the intrinsics are a constant buffer)."""
+        if getattr(self, "_kinv_cache", None) is None:
+            self._kinv_cache = [float(v) for v in self.train_intrinsics_inv.detach().cpu().reshape(-1)]
+        return self._kinv_cache
+
+    def rays(self, timestamp, pixel_position):
+        """Camera rays of `pixel_position` (N,2) at `timestamp` (..., N): one fused kernel
+        (trajectory interpolation + pinhole model) unless the timestamps carry a gradient (the
+        refractory-period path), which keeps the torch autograd form."""
+        if timestamp.requires_grad or pixel_position.requires_grad or not timestamp.is_cuda:
+            pos, rot = self.trajectory(timestamp)
+            return self.nerf.pixel_params_to_ray(self.train_intrinsics_inv, pixel_position, pos, rot)
+        from . import ops
+        tr = self.trajectory
+        return ops.rays_from_trajectory(timestamp, pixel_position, tr.T_wc_timestamp, tr.T_wc_position,
+                                        tr.T_wc_orientation_quat, self._kinv_host())
+
     def render_pixels(self, intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation):
         o, d = self.nerf.pixel_params_to_ray(intrinsics_inverse, pixel_position, T_wc_position,
                                              T_wc_orientation)
@@ -92,8 +110,7 @@ class EventRenderer(torch.nn.Module):
                 min=pb.min_ts) for ts, _ in requests])                   # (K, S, N)
         else:
             ts_all = torch.stack([ts for ts, _ in requests])             # (K, N)
-        pos, rot = self.trajectory(ts_all)
-        o, d = self.nerf.pixel_params_to_ray(self.train_intrinsics_inv, pixel_position, pos, rot)
+        o, d = self.rays(ts_all, pixel_position)
         jitter = None
         if self._jitters:
             jitter = torch.cat([self._jitters.pop(0).reshape(-1) for _ in range(K)])

@@ -132,6 +132,16 @@ int den_march_pack(const int32_t* seg_offsets, const int32_t* offsets, const flo
                    const float* arena_t1, int64_t n_rays, int32_t* ray_indices, float* t_starts,
                    float* t_ends, void* stream);
 
+/* Timestamps + pixels -> rays: LinearTrajectory.forward (models/trajectories.py:30-90: searchsorted,
+ * f64 weight, LERP, shortest-path SLERP via utils/tensor_ops.py:118-184, quaternion -> R) fused with
+ * NeRF.pixel_params_to_ray (models/nerf.py:206-228).  timestamps (n_rays) f64 ns; ray i looks through
+ * pixel i % n_pixels of pixels (n_pixels, 2); pose_ts (C) int64 ascending, pose_pos (C,3), pose_quat
+ * (C,4) xyzw; kinv9_host: row-major K^-1 on the HOST.  No gradient (the tau path stays in autograd). */
+int den_rays_from_trajectory(const double* timestamps, const float* pixels, int64_t n_pixels,
+                             const int64_t* pose_ts, const float* pose_pos, const float* pose_quat,
+                             int32_t n_poses, const float* kinv9_host, float* rays_o, float* rays_d,
+                             int64_t n_rays, void* stream);
+
 /* Visibility filter + compaction — replaces nerfacc.render_visibility and the
  * three boolean-mask compactions inside nerfacc.ray_marching. */
 /* alpha = 1 - exp(-sigma * (t1 - t0)) */

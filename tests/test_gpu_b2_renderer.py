@@ -179,6 +179,29 @@ def test_batched_render_calls_equal_sequential_calls(den_lib, cuda, pb_on):
         assert _rel(gra[key], grb[key]) < 2e-4, key      # fp32 accumulation order differs
 
 
+def test_fused_rays_match_the_torch_trajectory_path(den_lib, cuda):
+    """den_rays_from_trajectory == LinearTrajectory.forward + pixel_params_to_ray (torch ops), incl.
+    timestamps exactly on a pose stamp, on the first / last stamp and a (K, S, N) batch shape."""
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    model, poses = _scene.build_product_renderer(cfg, cuda, 8, pixel_bandwidth=False)
+    tr = model.trajectory
+    g = torch.Generator().manual_seed(4)
+    n = 700
+    t0, t1 = float(tr.T_wc_timestamp[0]), float(tr.T_wc_timestamp[-1])
+    ts = t0 + torch.rand(3, 5, n, generator=g, dtype=torch.float64) * (t1 - t0)
+    ts[0, 0, :8] = tr.T_wc_timestamp[:8].double().cpu()          # exactly on pose stamps (incl. the first)
+    ts[0, 0, 8] = t1
+    ts = ts.to(cuda)
+    pix = (torch.rand(n, 2, generator=g) * 300).to(cuda)
+    pos, rot = tr(ts)
+    o_ref, d_ref = model.nerf.pixel_params_to_ray(model.train_intrinsics_inv, pix, pos, rot)
+    o, d = model.rays(ts, pix)
+    assert o.shape == (3, 5, n, 3) and d.shape == (3, 5, n, 3)
+    assert (o - o_ref).abs().max().item() < 2e-6 * o_ref.abs().max().item() + 1e-6
+    assert (d - d_ref).abs().max().item() < 5e-6
+    assert torch.allclose(d.norm(dim=-1), torch.ones_like(d[..., 0]), atol=1e-6)
+
+
 def test_training_step_pb_off_matches_reference_golden(den_lib, cuda):
     _run_training_step_golden(cuda, pb_on=False)
 
