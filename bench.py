@@ -65,10 +65,11 @@ KERNEL_BYTES_PER_SAMPLE = {
 KERNEL_BYTES_PER_RAY = {"den_composite_fwd": 12, "den_composite_bwd": 12}
 # tensor-pipe kernels: algorithmic FLOP per sample
 KERNEL_FLOP_PER_SAMPLE = {"den_mlp_fwd": 18432, "den_mlp_bwd": 55296}
-# dram__bytes_read.sum + dram__bytes_write.sum per sample from the ncu --set full capture of
-# profiles/r01_ncu_full_top_kernels.md (1.284 M samples per launch)
-NCU_DRAM_BYTES_PER_SAMPLE = {"den_mlp_bwd": (190.64e6 + 122.26e6) / 1284068,
-                             "den_hashgrid_bwd": (225.43e6 + 5.47e6) / 1284068}
+# dram__bytes_read.sum + dram__bytes_write.sum per sample from the ncu --set full captures of
+# profiles/r01_ncu_mlp_final.md (10.2 M samples per launch) and profiles/r01_ncu_misc_kernels.md
+NCU_DRAM_BYTES_PER_SAMPLE = {"den_mlp_bwd": (1.513147e9 + 1.266210e9) / 10200012,
+                             "den_mlp_fwd": (1.432741e9 + 0.081466e9) / 10200012,
+                             "den_hashgrid_bwd": (402.03e6 + 8.46e6) / 2531605}
 
 
 def parse_args():

@@ -26,13 +26,14 @@
 //     slot's tensor work overlaps the other slot's SIMT epilogue; per round the latency-critical
 //     GEMM (forward layer / dX) is committed first, the dW GEMM follows on its own mbarrier;
 //   * the (C <= 3)-row output layer runs on the SIMT side (no 64 x 16 GEMM, no h2 operand tile).
+// (Tried and rejected, measured: all 16 warps on ONE slot's phase at a time, alternating slots, with a
+// CTA-wide barrier per phase — every warp then hits the same tcgen05.ld / fence / barrier latencies at
+// the same moment and nothing is left to hide them: 6.9 ms against 5.3 ms for the form below.)
 // Shared memory per slot: E (128 x 40: enc | ones, later [SH | geo | 1], later dy, later enc
 // again), H (128 x 72: hb | ones, later h1, later hb again) and D (128 x 64: the current
 // dL/dz tile) = 88 KB; 2 slots + 36 KB of weight tiles = 223 KB.  The price of fitting two
 // slots: the split hb tile is parked in TMEM (64 columns of packed bf16 words per slot) while h1
 // occupies H and copied back afterwards, and enc is re-read from L2/HBM for the last round.
-#include <stdlib.h>
-
 #include "den_mlp_ops.cuh"
 
 namespace den {
@@ -85,21 +86,6 @@ struct Smem {
 static_assert(Smem::slot_bytes % 128 == 0 && Smem::slot0 % 128 == 0, "tile alignment");
 static_assert(Smem::total <= 227 * 1024, "shared-memory plan exceeds 227 KB");
 
-// ---- mbarrier helpers ----------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(tc::smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
 __device__ __forceinline__ void group_sync(int slot) {       // the 8 epilogue warps of one slot
     asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(kGroupThreads) : "memory");
 }
@@ -121,24 +107,8 @@ __device__ __forceinline__ void commit_to(uint64_t* bar) {      // by the electe
                      tc::smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void await_mma(uint64_t* done, uint32_t& phase, int dbg = 0) {
-    if (dbg & 4) {
-        while (!mbar_try(done, phase)) __nanosleep(32);
-    } else if (dbg & 8) {
-        const uint32_t addr = tc::smem_u32(done);
-        uint32_t ok = 0;
-        while (!ok) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok)
-                : "r"(addr), "r"(phase), "r"(200000u)
-                : "memory");
-        }
-    } else {
-        tc::mbar_wait(done, phase);
-    }
+__device__ __forceinline__ void await_mma(uint64_t* done, uint32_t& phase) {
+    tc::mbar_wait(done, phase);
     phase ^= 1;
     tc::tc_fence_after_sync();
 }
@@ -153,7 +123,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                   const int32_t* __restrict__ ray_indices, const float* __restrict__ t_starts,
                   const float* __restrict__ t_ends, const float* __restrict__ d_sigmas,
                   const float* __restrict__ d_rgbs, int64_t n, float* __restrict__ d_enc,
-                  float* __restrict__ d_dirs, int dbg) {
+                  float* __restrict__ d_dirs) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);       // done[0..1], dw_done[0..1]
@@ -243,8 +213,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 uint64_t* done = &bars[s];
                 uint64_t* dw_done = &bars[2 + s];
                 if (elect_one()) {
-                switch ((dbg & 1) ? -1 : rnd) {
-                case -1: commit_to(done); if (rnd >= 4) commit_to(dw_done); break;
+                switch (rnd) {
                 case 0:     // z_b1 = enc Wb1^T
                     gemm3<kEncDim / 16>(Z, kmajor<TE>(E), kmajor<TWb1>(wb1),
                                         tc::instr_desc_bf16(128, kWidth, false, false), false);
@@ -368,10 +337,6 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         };
 
         for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
-            if (dbg & 2) {
-                for (int r = 0; r < 8; ++r) { publish(slot_id); await_mma(done, phase, dbg); if (r >= 4) await_dw(); }
-                continue;
-            }
             const int64_t tile = blockIdx.x + k * gridDim.x;
             const int64_t i = tile * kTile + row;
             const bool valid = i < n;
@@ -394,13 +359,13 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(slot_id);
 
             // ---- round 0 done: hb ----------------------------------------------------------------
-            await_mma(done, phase, dbg);
+            await_mma(done, phase);
             stage_hb();
             publish(slot_id);
 
             // ---- round 1 done: y -> raw density, [SH | geo | 1] -> E -------------------------------
             float raw = 0.f;
-            await_mma(done, phase, dbg);
+            await_mma(done, phase);
             {
                 float x[16];
                 if (hf == 0) {
@@ -421,7 +386,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(slot_id);
 
             // ---- round 2 done: h1 -> H -------------------------------------------------------------
-            await_mma(done, phase, dbg);
+            await_mma(done, phase);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 float h[16];
@@ -455,7 +420,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                     if (c < C) g_rgb[c] = d_rgbs[i * C + c];
                 if (hf == 0) g_sigma = d_sigmas[i];
             }
-            await_mma(done, phase, dbg);
+            await_mma(done, phase);
             {
                 float h2[32];
 #pragma unroll
@@ -510,7 +475,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             }
 
             // ---- round 4 done: dh1 -> d1 = dh1 * act'(h1) -> D ------------------------------------
-            await_mma(done, phase, dbg);
+            await_mma(done, phase);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 float dl[16], h[16];
@@ -523,7 +488,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(slot_id);
 
             // ---- round 5 done: din1 -> dy (E), hb again (H) -----------------------------------------
-            await_mma(done, phase, dbg);
+            await_mma(done, phase);
             if (hf == 0) {
                 float dgeo[16], dy[16];
                 tmem_ld_cols<16>(Z + kShDim, dgeo);
@@ -552,7 +517,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             }
 
             // ---- round 6 done: dhb -> db1 = dhb * act'(hb) -> D; enc again -> E -----------------------
-            await_mma(done, phase, dbg);
+            await_mma(done, phase);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 float dl[16], h[16];
@@ -566,7 +531,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(slot_id);
 
             // ---- round 7 done: denc -> HBM ---------------------------------------------------------------
-            await_mma(done, phase, dbg);
+            await_mma(done, phase);
             {
                 float de[16];
                 tmem_ld_cols<16>(Z + 16 * hf, de);
@@ -653,12 +618,10 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
     // two tiles in flight per CTA: at least two tiles per CTA whenever there are enough of them
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int grid = grid_for((n_tiles + 1) / 2, 1, 1);
-    const char* dbg_env = getenv("DEN_MLP_BWD_DEBUG");
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     cudaFuncSetAttribute(mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)bwd::Smem::total);
     mlp_bwd_tc_kernel<<<grid, bwd::kThreads, bwd::Smem::total, as_stream(stream)>>>(
-        *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, d_enc, d_dirs, dbg);
+        *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, d_enc, d_dirs);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }

@@ -1,6 +1,6 @@
 """Time den_mlp_fwd / den_mlp_bwd alone (CUDA events) on a synthetic.yaml-shaped sample set.
 
-    python profiles/time_mlp.py [n_rays] [modes...]     (modes = DEN_MLP_BWD_DEBUG values)
+    python profiles/time_mlp.py [n_rays]
 """
 import os
 import sys
@@ -15,7 +15,6 @@ from deblur_e_nerf_b200 import factory, ops, synthetic  # noqa: E402
 
 def main():
     n_rays = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
-    modes = sys.argv[2:] or ["0"]
     dev = torch.device("cuda:0")
     model, cfg, poses = factory.build_renderer("synthetic", dev, pixel_bandwidth=False)
     nerf = model.nerf
@@ -54,10 +53,8 @@ def main():
     print("samples", n)
     print("mlp_fwd full ms", timeit(lambda: ops.mlp_fwd(desc, params, enc, o, d, ray_idx, t0, t1, 1)))
     print("mlp_fwd density ms", timeit(lambda: ops.mlp_fwd(desc, params, enc, o, d, ray_idx, t0, t1, 0)))
-    for m in modes:
-        os.environ["DEN_MLP_BWD_DEBUG"] = m
-        ms = timeit(lambda: ops.mlp_bwd(desc, params, grads, enc, o, d, ray_idx, t0, t1, d_sig, d_rgb))
-        print(f"mlp_bwd mode {m}: {ms:.3f} ms")
+    ms = timeit(lambda: ops.mlp_bwd(desc, params, grads, enc, o, d, ray_idx, t0, t1, d_sig, d_rgb))
+    print(f"mlp_bwd ms {ms:.3f}")
 
 
 if __name__ == "__main__":
