@@ -48,6 +48,11 @@ constexpr int kEpiThreads = kSlots * kGroupThreads;
 constexpr int kThreads = kEpiThreads + 32;                 // + the MMA warp
 constexpr int kMmaWarp = kEpiThreads / 32;
 constexpr uint32_t kTmemCols = 512;
+// The tensor core accumulates with truncation: the error of a TMEM weight-gradient accumulator grows
+// linearly with the tiles summed into it (measured against an fp64 evaluation, profiles/wgrad_check.py:
+// 2.9e-4 of max|dW| after 539 tiles, 6.7e-5 after 135, 1.2e-5 after 8).  The accumulators are therefore
+// flushed to global memory (fp32 atomics, round-to-nearest) every kFlushTiles tiles of a CTA.
+constexpr int kFlushTiles = 128;
 
 // TMEM column plan
 constexpr uint32_t kColZ = 0;            // + 128 * slot : 64 scratch columns (forward / dX results)
@@ -184,6 +189,45 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
     // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0 .. my_tiles-1; slot s takes k = s, s+2, ...
     const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
+    // TMEM weight-gradient accumulators -> global (warps 0..3; M = 64: row m in lane m%16 + 32*(m/16))
+    auto flush_tmem = [&]() {
+        tc::tc_fence_after_sync();
+        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int row = warp * 16 + lane;              // valid for lane < 16
+        const bool owner = lane < 16;
+        float v[16];
+        for (int c0 = 0; c0 < kHeadIn; c0 += 16) {     // dW1 (64, 31) | db1 in column 31
+            tmem_ld_cols<16>(tl + kColDW1 + c0, v);
+            if (owner)
+                for (int j = 0; j < 16; ++j) {
+                    if (c0 + j < kShDim + kGeo) atomicAdd(g.w1 + row * (kShDim + kGeo) + c0 + j, v[j]);
+                    else atomicAdd(g.b1 + row, v[j]);
+                }
+        }
+        for (int c0 = 0; c0 < kWidth; c0 += 16) {      // dW2 (64, 64)
+            tmem_ld_cols<16>(tl + kColDW2 + c0, v);
+            if (owner)
+                for (int j = 0; j < 16; ++j) atomicAdd(g.w2 + row * kWidth + c0 + j, v[j]);
+        }
+        for (int c0 = 0; c0 < kEncDim; c0 += 16) {     // dWb1 (64, enc_dim)
+            tmem_ld_cols<16>(tl + kColDWb1 + c0, v);
+            if (owner)
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < enc_dim) atomicAdd(g.wb1 + row * enc_dim + c0 + j, v[j]);
+        }
+        {
+            float b[8];
+            tmem_ld_cols<8>(tl + kColDW2 + kWidth, b);           // db2
+            if (owner) atomicAdd(g.b2 + row, b[0]);
+            tmem_ld_cols<8>(tl + kColDWb1 + kEncDim, b);         // dbb1
+            if (owner) atomicAdd(g.bb1 + row, b[0]);
+        }
+        tmem_ld_cols<16>(tl + kColDWb2T, v);           // dWb2^T (in 64, out 16)
+        if (owner)
+            for (int j = 0; j < kBaseOut; ++j) atomicAdd(g.wb2 + j * kWidth + row, v[j]);
+        tc::tc_fence_before_sync();
+    };
+
     if (warp == kMmaWarp) {
         // ===================== MMA warp =====================
         const uint8_t* wb1 = smem + Smem::wb1;
@@ -195,7 +239,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         // weight-gradient GEMM follows with its own commit (dw_done) — nobody waits for it until the
         // operand tiles it reads are about to be overwritten.
         // per-slot counters packed in scalars (the slot loop is rolled: no dynamically indexed arrays)
-        int64_t left0 = 8 * ((my_tiles + 1) / 2), left1 = 8 * (my_tiles / 2);
+        for (int64_t c0 = 0; c0 < my_tiles; c0 += kFlushTiles) {
+        const int64_t nt = min((int64_t)kFlushTiles, my_tiles - c0);          // tiles of this flush period
+        int64_t left0 = 8 * ((nt + 1) / 2), left1 = 8 * (nt / 2);
         int round0 = 0, round1 = 0;
         uint32_t acc_mask = 0;                           // bit r-4: the dW accumulator of round r holds earlier tiles
         while (left0 > 0 || left1 > 0) {
@@ -273,6 +319,13 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 if (s == 0) { round0 = (rnd + 1) & 7; --left0; } else { round1 = (rnd + 1) & 7; --left1; }
             }
         }
+        // end of the flush period: the epilogue groups have awaited every GEMM; warps 0..3 drain the
+        // accumulators between the two barriers, the next period starts them afresh (accumulate = 0)
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        __syncthreads();
+        tc::tc_fence_after_sync();
+        }
     } else {
         // ===================== epilogue warps: one group of 8 per slot =====================
         const int slot_id = warp >> 3;
@@ -336,7 +389,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             }
         };
 
-        for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
+        for (int64_t c0 = 0; c0 < my_tiles; c0 += kFlushTiles) {
+        const int64_t c1 = min(c0 + (int64_t)kFlushTiles, my_tiles);
+        for (int64_t k = c0 + slot_id; k < c1; k += kSlots) {
             const int64_t tile = blockIdx.x + k * gridDim.x;
             const int64_t i = tile * kTile + row;
             const bool valid = i < n;
@@ -546,46 +601,19 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             await_dw();                                   // dWb1 has read db1 (D) and enc (E)
             tc::tc_fence_before_sync();
         }
+        // end of the flush period (see the MMA warp): every GEMM of both slots has been awaited
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        if (warp < 4) flush_tmem();
+        __syncthreads();
+        tc::tc_fence_after_sync();
+        }
     }
 
-    // ---- flush the weight-gradient accumulators (M = 64: row m in lane m%16 + 32*(m/16)) ------
+    // ---- the SIMT-side accumulators (dW3, dbb2, db3: fp32 shared-memory atomics) go out once ----------
     tc::tc_fence_before_sync();
     __syncthreads();
     if (my_tiles > 0 && warp < 4) {
-        tc::tc_fence_after_sync();
-        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int row = warp * 16 + lane;              // valid for lane < 16
-        const bool owner = lane < 16;
-        float v[16];
-        for (int c0 = 0; c0 < kHeadIn; c0 += 16) {     // dW1 (64, 31) | db1 in column 31
-            tmem_ld_cols<16>(tl + kColDW1 + c0, v);
-            if (owner)
-                for (int j = 0; j < 16; ++j) {
-                    if (c0 + j < kShDim + kGeo) atomicAdd(g.w1 + row * (kShDim + kGeo) + c0 + j, v[j]);
-                    else atomicAdd(g.b1 + row, v[j]);
-                }
-        }
-        for (int c0 = 0; c0 < kWidth; c0 += 16) {      // dW2 (64, 64)
-            tmem_ld_cols<16>(tl + kColDW2 + c0, v);
-            if (owner)
-                for (int j = 0; j < 16; ++j) atomicAdd(g.w2 + row * kWidth + c0 + j, v[j]);
-        }
-        for (int c0 = 0; c0 < kEncDim; c0 += 16) {     // dWb1 (64, enc_dim)
-            tmem_ld_cols<16>(tl + kColDWb1 + c0, v);
-            if (owner)
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < enc_dim) atomicAdd(g.wb1 + row * enc_dim + c0 + j, v[j]);
-        }
-        {
-            float b[8];
-            tmem_ld_cols<8>(tl + kColDW2 + kWidth, b);           // db2
-            if (owner) atomicAdd(g.b2 + row, b[0]);
-            tmem_ld_cols<8>(tl + kColDWb1 + kEncDim, b);         // dbb1
-            if (owner) atomicAdd(g.bb1 + row, b[0]);
-        }
-        tmem_ld_cols<16>(tl + kColDWb2T, v);           // dWb2^T (in 64, out 16)
-        if (owner)
-            for (int j = 0; j < kBaseOut; ++j) atomicAdd(g.wb2 + j * kWidth + row, v[j]);
         for (int i = tid; i < C * kWidth; i += 128) atomicAdd(g.w3 + i, s_dw3[i]);
         if (tid < kBaseOut) atomicAdd(g.bb2 + tid, s_dbb2[tid]);
         if (tid < C) atomicAdd(g.b3 + tid, s_db3[tid]);

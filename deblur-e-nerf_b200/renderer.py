@@ -80,10 +80,15 @@ class EventRenderer(torch.nn.Module):
         return intensity, opacity, depth, mean_samples, is_valid
 
     def render_train_pixels(self, timestamp, pixel_position, pixel_channel_idx=None):
-        pos, rot = self.trajectory(timestamp)
-        intensity, opacity, _, mean_samples, is_valid = self.render_pixels(
-            self.train_intrinsics_inv, pixel_position, pos, rot)
-        occ_rate = torch.mean(opacity > 0, dtype=torch.get_default_dtype())
+        """models/deblur_e_nerf.py:1162-1183 (training never uses the depth, so the camera-z
+        correction of render_pixels is skipped and the rays come from the fused kernel)."""
+        o, d = self.rays(timestamp, pixel_position)
+        jitter = self._jitters.pop(0) if self._jitters else None
+        intensity, opacity, _, mean_samples = self.nerf(o, d, jitter=jitter)
+        intensity = intensity + self.min_modeled_intensity
+        hit = opacity > 0
+        is_valid = hit if self.render_bkgd is None else torch.ones_like(hit)
+        occ_rate = torch.mean(hit, dtype=torch.get_default_dtype())
         return intensity, occ_rate, mean_samples, is_valid
 
     def render_log_intensity(self, timestamp, pixel_position, pixel_channel_idx=None,
