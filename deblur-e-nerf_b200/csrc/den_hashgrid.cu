@@ -51,21 +51,18 @@ hashgrid_fwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
             const LevelInfo li = make_level(g, level);
             const float2* __restrict__ base = table + g.offset[level];
             const CellFrac cf = locate(li.scale, px, py, pz);
+            uint32_t idx[8];
+            float w[8];
             float2 v[8];
+            corner_indices(li, cf, idx);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint32_t idx = entry_index(li, cf.c[0] + (c & 1), cf.c[1] + ((c >> 1) & 1),
-                                           cf.c[2] + ((c >> 2) & 1));
-                v[c] = valid ? __ldg(base + idx) : make_float2(0.f, 0.f);
-            }
+            for (int c = 0; c < 8; ++c) v[c] = valid ? __ldg(base + idx[c]) : make_float2(0.f, 0.f);
+            corner_weights(cf, w);
             float ax = 0.f, ay = 0.f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float w = ((c & 1) ? cf.f[0] : 1.f - cf.f[0]) *
-                          (((c >> 1) & 1) ? cf.f[1] : 1.f - cf.f[1]) *
-                          (((c >> 2) & 1) ? cf.f[2] : 1.f - cf.f[2]);
-                ax = fmaf(w, v[c].x, ax);
-                ay = fmaf(w, v[c].y, ay);
+                ax = fmaf(w[c], v[c].x, ax);
+                ay = fmaf(w[c], v[c].y, ay);
             }
             s_tile[lane * ld + 2 * level + 0] = ax;
             s_tile[lane * ld + 2 * level + 1] = ay;
@@ -137,6 +134,8 @@ hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
             const CellFrac cf = locate(li.scale, px, py, pz);
             const float gx = valid ? s_tile[lane * ld + 2 * level + 0] : 0.f;
             const float gy = valid ? s_tile[lane * ld + 2 * level + 1] : 0.f;
+            uint32_t idx[8];
+            corner_indices(li, cf, idx);
 
             if (level < g.n_agg_levels) {
                 // runs of consecutive lanes in the same cell -> one atomic per run & corner
@@ -168,11 +167,7 @@ hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
                         const float t3 = __shfl_up_sync(0xffffffffu, b1, d);
                         if (lane - d >= start) { a0 += t0; b0 += t1; a1 += t2; b1 += t3; }
                     }
-                    if (tail && valid) {
-                        const uint32_t cy = cf.c[1] + ((c >> 1) & 1), cz = cf.c[2] + ((c >> 2) & 1);
-                        red_add_pair(gbase, entry_index(li, cf.c[0], cy, cz), entry_index(li, cf.c[0] + 1, cy, cz),
-                                     a0, b0, a1, b1);
-                    }
+                    if (tail && valid) red_add_pair(gbase, idx[c], idx[c + 1], a0, b0, a1, b1);
                 }
             } else if (valid) {
 #pragma unroll
@@ -180,9 +175,7 @@ hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
                     const float wyz = (((c >> 1) & 1) ? cf.f[1] : 1.f - cf.f[1]) *
                                       (((c >> 2) & 1) ? cf.f[2] : 1.f - cf.f[2]);
                     const float w0 = (1.f - cf.f[0]) * wyz, w1 = cf.f[0] * wyz;
-                    const uint32_t cy = cf.c[1] + ((c >> 1) & 1), cz = cf.c[2] + ((c >> 2) & 1);
-                    red_add_pair(gbase, entry_index(li, cf.c[0], cy, cz), entry_index(li, cf.c[0] + 1, cy, cz),
-                                 w0 * gx, w0 * gy, w1 * gx, w1 * gy);
+                    red_add_pair(gbase, idx[c], idx[c + 1], w0 * gx, w0 * gy, w1 * gx, w1 * gy);
                 }
             }
 
@@ -192,9 +185,7 @@ hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __
                 float dpos[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    uint32_t idx = entry_index(li, cf.c[0] + (c & 1), cf.c[1] + ((c >> 1) & 1),
-                                               cf.c[2] + ((c >> 2) & 1));
-                    float2 t = __ldg(base + idx);
+                    float2 t = __ldg(base + idx[c]);
                     float dotv = t.x * gx + t.y * gy;
                     float w0 = (c & 1) ? cf.f[0] : 1.f - cf.f[0];
                     float w1 = ((c >> 1) & 1) ? cf.f[1] : 1.f - cf.f[1];

@@ -69,6 +69,45 @@ __device__ __forceinline__ uint32_t corner_index(const LevelInfo& li, const Cell
     return entry_index(li, cf.c[0] + (c & 1), cf.c[1] + ((c >> 1) & 1), cf.c[2] + ((c >> 2) & 1));
 }
 
+// All eight corner entries of a cell at once: the dense / hashed decision is taken once per level
+// (warp-uniform), the neighbours come from additions (dense: + stride, hashed: + prime before the
+// XOR) instead of eight independent index evaluations.  Bit-identical to corner_index(): unsigned
+// arithmetic is modular, (c + 1) * k == c * k + k.  Corner c = dx + 2 dy + 4 dz.
+__device__ __forceinline__ void corner_indices(const LevelInfo& li, const CellFrac& cf, uint32_t (&idx)[8]) {
+    if (li.hashed) {
+        const uint32_t x[2] = {cf.c[0], cf.c[0] + 1u};
+        const uint32_t y0 = cf.c[1] * kPrime1, z0 = cf.c[2] * kPrime2;
+        const uint32_t y[2] = {y0, y0 + kPrime1};
+        const uint32_t z[2] = {z0, z0 + kPrime2};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idx[c] = x[c & 1] ^ y[(c >> 1) & 1] ^ z[c >> 2];
+        if (li.mask) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) idx[c] &= li.mask;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) idx[c] %= li.size;
+        }
+    } else {
+        const uint32_t b = cf.c[0] * li.st0 + cf.c[1] * li.st1 + cf.c[2] * li.st2;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t i = b + ((c & 1) ? li.st0 : 0u) + ((c & 2) ? li.st1 : 0u) + ((c & 4) ? li.st2 : 0u);
+            if (li.mask) i &= li.mask;
+            else if (i >= li.size) i %= li.size;       // only out-of-range positions wrap (tcnn semantics)
+            idx[c] = i;
+        }
+    }
+}
+// trilinear weights of the eight corners from three pairs
+__device__ __forceinline__ void corner_weights(const CellFrac& cf, float (&w)[8]) {
+    const float wx[2] = {1.f - cf.f[0], cf.f[0]};
+    const float wy[2] = {1.f - cf.f[1], cf.f[1]};
+    const float wz[2] = {1.f - cf.f[2], cf.f[2]};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = wx[c & 1] * wy[(c >> 1) & 1] * wz[c >> 2];
+}
+
 __device__ __forceinline__ void red_add_v2(float2* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
