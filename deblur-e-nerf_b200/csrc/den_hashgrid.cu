@@ -27,7 +27,7 @@ constexpr int kTile = 32;            // samples per tile (one per lane)
 constexpr int kHashThreads = 256;    // 8 warps
 
 // ------------------------------------------------------------------ forward --
-__global__ void __launch_bounds__(kHashThreads)
+__global__ void __launch_bounds__(kHashThreads, 6)
 hashgrid_fwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __restrict__ x,
                     const float2* __restrict__ table, float* __restrict__ out, int64_t n) {
     extern __shared__ float s_tile[];            // kTile x (LF + 1)
