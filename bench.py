@@ -114,7 +114,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Keep the samples taken inside [t0, t1] (the sampler is started before the warm-up steps:
+        nvidia-smi needs a few hundred ms to deliver its first line)."""
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        self.rows = inside if inside else self.rows[-3:]
 
     def stop(self):
         if self.proc is None:
@@ -126,7 +132,7 @@ class ClockSampler:
             self.proc.kill()
         sm, sm_max, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        for _, row in self.rows:
             try:
                 sm.append(float(row[0]))
                 sm_max = float(row[1])
@@ -454,13 +460,14 @@ def run_ours(args):
 
     # ---- device-resident loop (value) ------------------------------------------------
     samples_seen = 0.0
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         one_step(dev_batches[i], 1 + i)
     ddp.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    t_wall0 = time.time()
     launches0 = ops.launch_count()
     mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     ops.enable_kernel_timing(rated_kernels)
@@ -472,12 +479,16 @@ def run_ours(args):
     end.record()
     ddp.barrier()
     torch.cuda.synchronize()
+    t_wall1 = time.time()
     ms_total = start.elapsed_time(end)
     ms_step = ddp.max_over_ranks(ms_total / args.steps, dev)
     timings = ops.kernel_timings()
     ops.disable_kernel_timing()
     launches = (ops.launch_count() - launches0)
     mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
+    if rank == 0:
+        time.sleep(0.15)                    # let the last in-window sample arrive
+        clocks.window(t_wall0, t_wall1)
     clock_info = clocks.stop() if rank == 0 else None
     global_rays = ddp.sum_over_ranks(rays_per_step(n_events), dev)
     global_samples = ddp.sum_over_ranks(samples_seen / args.steps, dev)
