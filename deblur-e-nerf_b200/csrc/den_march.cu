@@ -109,6 +109,83 @@ march_kernel(const __grid_constant__ den_march_params p, const float* __restrict
         float t0 = t_min[r];
         float t1 = fadd(t0, calc_dt(t0, c));
         float tm = fmul(fadd(t0, t1), 0.5f);
+        if (c.contraction == DEN_CONTRACT_AABB) {
+            // AABB: the unit-cube coordinate u of the sample is needed both by the occupancy lookup and by
+            // the voxel skip — computed once per step; 1/dir, sign(dir) are per-ray constants; the division
+            // by a power-of-two grid resolution is an exact multiplication.  Every value is bit-identical
+            // to the per-use evaluation (same IEEE operations on the same operands).
+            float inv[3], half_sgn[3], rres[3];
+            bool pow2[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                inv[d] = fdiv(1.0f, dir[d]);
+                half_sgn[d] = fmul(0.5f, copysignf(1.0f, dir[d]));
+                pow2[d] = (c.res[d] & (c.res[d] - 1)) == 0;
+                rres[d] = fdiv(1.0f, c.resf[d]);
+            }
+            while (tm < far) {
+                float xyz[3], u[3];
+                bool in_box = true;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    xyz[d] = fadd(o[d], fmul(tm, dir[d]));
+                    in_box = in_box && (xyz[d] >= c.roi_min[d] && xyz[d] <= c.roi_max[d]);
+                    u[d] = fdiv(fsub(xyz[d], c.roi_min[d]), c.extent[d]);
+                }
+                bool occ = false;
+                if (in_box) {
+                    int ijk[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const float sc = fmul(u[d], c.resf[d]);
+                        const int i = isfinite(sc) ? (int)sc : 0;
+                        ijk[d] = min(max(i, 0), c.res[d] - 1);
+                    }
+                    occ = binary[((int64_t)ijk[0] * c.res[1] + ijk[1]) * c.res[2] + ijk[2]] != 0;
+                }
+                if (occ) {
+                    if (kMode == 1) {
+                        const int64_t k = base + j;
+                        if (k < capacity) {
+                            t_starts[k] = t0;
+                            t_ends[k] = t1;
+                            ray_indices[k] = (int32_t)r;
+                        }
+                    } else if (kMode == 2) {
+                        if (j < seg) {
+                            t_starts[base + j] = t0;
+                            t_ends[base + j] = t1;
+                        }
+                    }
+                    ++j;
+                    t0 = t1;
+                    t1 = fadd(t0, calc_dt(t0, c));
+                    tm = fmul(fadd(t0, t1), 0.5f);
+                } else {
+                    // DDA-like skip to the next voxel face, then catch up in whole steps
+                    float tnext = 3.4e38f;
+                    bool any = false;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const float ug = fmul(u[d], c.resf[d]);
+                        const float face = floorf(fadd(fadd(ug, 0.5f), half_sgn[d]));
+                        const float num = fmul(fsub(face, ug), inv[d]);
+                        const float tx = fmul(pow2[d] ? fmul(num, rres[d]) : fdiv(num, c.resf[d]), c.extent[d]);
+                        // fminf semantics: ignore NaN
+                        if (!isnan(tx)) { tnext = any ? fminf(tnext, tx) : tx; any = true; }
+                    }
+                    if (!any) tnext = __int_as_float(0x7fc00000);   // all-NaN -> NaN, fmaxf(NaN,0)=0
+                    const float dist = fmaxf(tnext, 0.0f);
+                    const float target = fadd(tm, dist);
+                    float t = tm;
+                    do { t = fadd(t, c.dt_min); } while (t < target);
+                    tm = t;
+                    const float dt = calc_dt(tm, c);
+                    t0 = fsub(tm, fmul(dt, 0.5f));
+                    t1 = fadd(tm, fmul(dt, 0.5f));
+                }
+            }
+        } else
         while (tm < far) {
             float xyz[3];
 #pragma unroll
@@ -131,29 +208,6 @@ march_kernel(const __grid_constant__ den_march_params p, const float* __restrict
                 t0 = t1;
                 t1 = fadd(t0, calc_dt(t0, c));
                 tm = fmul(fadd(t0, t1), 0.5f);
-            } else if (c.contraction == DEN_CONTRACT_AABB) {
-                // DDA-like skip to the next voxel face, then catch up in whole steps
-                float tnext = 3.4e38f;
-                bool any = false;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const float u = fmul(fdiv(fsub(xyz[d], c.roi_min[d]), c.extent[d]), c.resf[d]);
-                    const float sgn = copysignf(1.0f, dir[d]);
-                    const float inv = fdiv(1.0f, dir[d]);
-                    const float face = floorf(fadd(fadd(u, 0.5f), fmul(0.5f, sgn)));
-                    const float tx = fmul(fdiv(fmul(fsub(face, u), inv), c.resf[d]), c.extent[d]);
-                    // fminf semantics: ignore NaN
-                    if (!isnan(tx)) { tnext = any ? fminf(tnext, tx) : tx; any = true; }
-                }
-                if (!any) tnext = __int_as_float(0x7fc00000);   // all-NaN -> NaN, fmaxf(NaN,0)=0
-                const float dist = fmaxf(tnext, 0.0f);
-                const float target = fadd(tm, dist);
-                float t = tm;
-                do { t = fadd(t, c.dt_min); } while (t < target);
-                tm = t;
-                const float dt = calc_dt(tm, c);
-                t0 = fsub(tm, fmul(dt, 0.5f));
-                t1 = fadd(tm, fmul(dt, 0.5f));
             } else {
                 t0 = t1;
                 t1 = fadd(t0, calc_dt(t0, c));
