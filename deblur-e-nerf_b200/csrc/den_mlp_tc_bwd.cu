@@ -61,6 +61,7 @@ constexpr uint32_t kColDW2 = 256;        // 72: dW2 (out 64 x in 64) | db2 x 8
 constexpr uint32_t kColDW1 = 336;        // 32: dW1 (64 x 31) | db1 in column 31
 constexpr uint32_t kColDWb1 = 368;       // 40: dWb1 (64 x 32) | dbb1 x 8
 constexpr uint32_t kColDWb2T = 408;      // 16: dWb2^T (in 64 x out 16)
+constexpr uint32_t kColEncPark = 424;    // + 32 * slot : 32 columns, the split enc tile parked as packed bf16 words
 
 using TE = OpTile<kTile, 5>;     // enc | ones     /  [SH | geo | 1]  /  dy
 using TH = OpTile<kTile, 9>;     // hb | ones      /  h1
@@ -342,6 +343,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         const uint32_t Z = lane_base + kColZ + 128u * slot_id, P = lane_base + kColP + 128u * slot_id;
         const int hact = f.hidden_act;
         uint32_t phase = 0, dw_phase = 0;
+        bool dw_pending = false;         // the slot's previous tile left its last dW GEMM un-awaited
         // the weight-gradient GEMM of the previous round must have consumed its operand tiles before
         // they are overwritten (it was committed separately, after the latency-critical GEMM)
         auto await_dw = [&]() {
@@ -350,8 +352,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         };
 
         // load this thread's 16 encoding features of row i into E chunks (2 hf, 2 hf + 1)
-        auto stage_enc = [&](int64_t i, bool valid) {
-            float x[16];
+        // this thread's 16 encoding features of row i: global -> registers ...
+        auto load_enc = [&](int64_t i, bool valid, float (&x)[16]) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) x[k] = 0.f;
             if (valid) {
@@ -363,7 +365,20 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                         x[4 * v4] = v.x; x[4 * v4 + 1] = v.y; x[4 * v4 + 2] = v.z; x[4 * v4 + 3] = v.w;
                     }
             }
-            store16<TE>(E, row, 2 * hf, x);
+        };
+        // ... -> split -> E chunks (2 hf, 2 hf + 1), and the packed words parked in TMEM: enc is needed
+        // again for the last round (dWb1 += db1^T enc) after [SH | geo] and dy have passed through E
+        const uint32_t EP = lane_base + kColEncPark + 32u * slot_id + 16u * hf;
+        auto stage_enc = [&](const float (&x)[16]) {
+            uint32_t words[16];
+            store16_keep<TE>(E, row, 2 * hf, x, words);
+            tmem_st16(EP, words);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        };
+        auto restore_enc = [&]() {
+            uint32_t words[16];
+            tmem_ld16_words(EP, words);
+            store16_words<TE>(E, row, 2 * hf, words);
         };
         // hb = act(z_b1 + bb1) for this thread's 32 columns -> H, and the packed hi/lo words parked in
         // TMEM: hb is needed again after h1 has overwritten H (dWb2^T += hb^T dy, act'(hb)), and copying
@@ -410,7 +425,13 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 }
                 if (hf == 0) inside = contract_position(f, pos, u);
             }
-            stage_enc(i, valid);
+            float xe[16];
+            load_enc(i, valid, xe);
+            // the last weight-gradient GEMM of this slot's previous tile (dWb1: reads D and E) is awaited
+            // here, under the latency of the loads above, not at the end of that tile
+            if (dw_pending) await_dw();
+            dw_pending = true;
+            stage_enc(xe);
             publish(slot_id);
 
             // ---- round 0 done: hb ----------------------------------------------------------------
@@ -582,7 +603,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 store16<TD>(D, row, 4 * hf + 2 * c, dl);
             }
             await_dw();                                   // dWb2^T has read hb (H) and dy (E)
-            stage_enc(i, valid);
+            restore_enc();
             publish(slot_id);
 
             // ---- round 7 done: denc -> HBM ---------------------------------------------------------------
@@ -598,10 +619,11 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                             out[v4] = make_float4(de[4 * v4], de[4 * v4 + 1], de[4 * v4 + 2], de[4 * v4 + 3]);
                 }
             }
-            await_dw();                                   // dWb1 has read db1 (D) and enc (E)
             tc::tc_fence_before_sync();
         }
         // end of the flush period (see the MMA warp): every GEMM of both slots has been awaited
+        if (dw_pending) await_dw();                       // dWb1 of the slot's last tile
+        dw_pending = false;
         tc::tc_fence_before_sync();
         __syncthreads();
         if (warp < 4) flush_tmem();
