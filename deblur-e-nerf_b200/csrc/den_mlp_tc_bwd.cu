@@ -404,31 +404,33 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             }
         };
 
+        // software pipeline over this slot's tiles: the encoding row and the ray index of tile k + 2 are
+        // loaded while tile k drains, so a tile never starts on an HBM miss
+        float xe[16];
+        int64_t i = ((int64_t)blockIdx.x + (int64_t)slot_id * gridDim.x) * kTile + row;
+        bool valid = slot_id < my_tiles && i < n;
+        int64_t ray = 0;
+        float tmid2 = 0.f;                       // t_start + t_end
+        load_enc(i, valid, xe);
+        if (valid) { ray = ray_indices[i]; tmid2 = t_starts[i] + t_ends[i]; }
+
         for (int64_t c0 = 0; c0 < my_tiles; c0 += kFlushTiles) {
         const int64_t c1 = min(c0 + (int64_t)kFlushTiles, my_tiles);
         for (int64_t k = c0 + slot_id; k < c1; k += kSlots) {
-            const int64_t tile = blockIdx.x + k * gridDim.x;
-            const int64_t i = tile * kTile + row;
-            const bool valid = i < n;
-
             // ---- operands of round 0: enc -------------------------------------------------------
             float dir[3] = {0.f, 0.f, 1.f};
             bool inside = false;
             if (valid) {
-                const int64_t r = ray_indices[i];
-                const float tm = t_starts[i] + t_ends[i];
                 float pos[3], u[3];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    dir[d] = __ldg(rays_d + 3 * r + d);
-                    pos[d] = __ldg(rays_o + 3 * r + d) + (dir[d] * tm) * 0.5f;
+                    dir[d] = __ldg(rays_d + 3 * ray + d);
+                    pos[d] = __ldg(rays_o + 3 * ray + d) + (dir[d] * tmid2) * 0.5f;
                 }
                 if (hf == 0) inside = contract_position(f, pos, u);
             }
-            float xe[16];
-            load_enc(i, valid, xe);
             // the last weight-gradient GEMM of this slot's previous tile (dWb1: reads D and E) is awaited
-            // here, under the latency of the loads above, not at the end of that tile
+            // here, not at the end of that tile
             if (dw_pending) await_dw();
             dw_pending = true;
             stage_enc(xe);
@@ -474,7 +476,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
 
             // next tile of this slot: pull its rows towards L2 while this one is in flight
             if (k + kSlots < my_tiles) {
-                const int64_t ni = (tile + (int64_t)kSlots * gridDim.x) * kTile + row;
+                const int64_t ni = i + (int64_t)kSlots * gridDim.x * kTile;
                 if (ni < n) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(enc + ni * enc_dim + 16 * hf));
                     if (hf == 0) {
@@ -607,12 +609,19 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             publish(slot_id);
 
             // ---- round 7 done: denc -> HBM ---------------------------------------------------------------
+            const int64_t i_cur = i;
+            const bool valid_cur = valid;
+            i += (int64_t)kSlots * gridDim.x * kTile;     // this slot's next tile: loads in flight across the wait
+            valid = k + kSlots < my_tiles && i < n;
+            load_enc(i, valid, xe);
+            ray = 0; tmid2 = 0.f;
+            if (valid) { ray = ray_indices[i]; tmid2 = t_starts[i] + t_ends[i]; }
             await_mma(done, phase);
             {
                 float de[16];
                 tmem_ld_cols<16>(Z + 16 * hf, de);
-                if (valid) {
-                    float4* out = reinterpret_cast<float4*>(d_enc + i * enc_dim + 16 * hf);
+                if (valid_cur) {
+                    float4* out = reinterpret_cast<float4*>(d_enc + i_cur * enc_dim + 16 * hf);
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4)
                         if (16 * hf + 4 * v4 < enc_dim)
