@@ -67,8 +67,8 @@ KERNEL_BYTES_PER_RAY = {"den_composite_fwd": 12, "den_composite_bwd": 12}
 KERNEL_FLOP_PER_SAMPLE = {"den_mlp_fwd": 18432, "den_mlp_bwd": 55296}
 # dram__bytes_read.sum + dram__bytes_write.sum per sample from the ncu --set full captures of
 # profiles/r01_ncu_mlp_final.md (10.2 M samples per launch) and profiles/r01_ncu_misc_kernels.md
-NCU_DRAM_BYTES_PER_SAMPLE = {"den_mlp_bwd": (1.513147e9 + 1.266210e9) / 10200012,
-                             "den_mlp_fwd": (1.432741e9 + 0.081466e9) / 10200012,
+NCU_DRAM_BYTES_PER_SAMPLE = {"den_mlp_bwd": (1.520543e9 + 1.275103e9) / 10200012,
+                             "den_mlp_fwd": (1.431510e9 + 0.081907e9) / 10200012,
                              "den_hashgrid_bwd": (402.03e6 + 8.46e6) / 2531605}
 
 
