@@ -97,8 +97,11 @@ class NeRF(torch.nn.Module):
         # eval mode: the reference renders `test_chunk_size` rays at a time to bound memory
         # (external/utils.py:99-103); rays are independent and the eval march is deterministic, so any
         # chunking gives the same image — on a 180 GB part the chunks are merged up to this many rays
-        # (40 launches sequences per 800x800 view become one)
+        # (40 launch sequences per 800x800 view become three).  The merged chunk is sized from the
+        # samples per ray seen so far so that one chunk stays below `eval_chunk_samples` samples
+        # (~0.4 KB of per-sample buffers each): the first chunk is `test_chunk_size` rays.
         self.eval_chunk_rays = 1 << 20
+        self.eval_chunk_samples = 1 << 25
 
     # ---------------------------------------------------------------- occupancy ------
     def update_occ_grid(self, step, T_wc_position=None):
@@ -232,16 +235,23 @@ class NeRF(torch.nn.Module):
             opacity = opa.view(*shape[:-1])
             depth = dep.view(*shape[:-1]) / (opacity + self.opacity_eps)
             return radiance, opacity, depth, [c / max(per, 1) for c in counts]
-        chunk = n_rays if self.radiance_field.training else max(self.test_chunk_size,
-                                                                   self.eval_chunk_rays)
+        training = self.radiance_field.training
+        chunk = n_rays if training else self.test_chunk_size
         cols, opas, deps, total = [], [], [], 0
-        for i in range(0, max(n_rays, 1), max(chunk, 1)):
+        i = 0
+        while i < max(n_rays, 1):
             jit = None if jitter is None else jitter.reshape(-1)[i:i + chunk].contiguous()
             col, opa, dep, m = self.render_chunk(o[i:i + chunk], d[i:i + chunk], jit)
             cols.append(col)
             opas.append(opa)
             deps.append(dep)
             total += m
+            done = min(i + chunk, n_rays) - i
+            i += max(chunk, 1)
+            if not training:
+                per_ray = max(m / max(done, 1), 1.0)
+                chunk = int(min(max(self.eval_chunk_samples / per_ray, self.test_chunk_size),
+                                max(self.eval_chunk_rays, self.test_chunk_size)))
         colour = torch.cat(cols).view(*shape[:-1], -1)
         opacity = torch.cat(opas).view(*shape[:-1])
         depth = torch.cat(deps).view(*shape[:-1])
