@@ -55,6 +55,13 @@ class FieldParams(_c.Structure):
         "table", "wb1", "bb1", "wb2", "bb2", "w1", "b1", "w2", "b2", "w3", "b3")]
 
 
+class AdamTensor(_c.Structure):
+    """den_adam_tensor (include/den_b200.h)."""
+    _fields_ = [("param", _c.c_void_p), ("grad", _c.c_void_p), ("exp_avg", _c.c_void_p),
+                ("exp_avg_sq", _c.c_void_p), ("n", _c.c_int64), ("lr", _c.c_float),
+                ("weight_decay", _c.c_float)]
+
+
 class FieldGrads(_c.Structure):
     _fields_ = [(name, _P) for name in (
         "wb1", "bb1", "wb2", "bb2", "w1", "b1", "w2", "b2", "w3", "b3")]
@@ -79,6 +86,7 @@ _SIGNATURES = {
     "den_march_pack": (_INT, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "den_rays_from_trajectory": (_INT, [_P, _P, _I64, _P, _P, _P, _I32, _c.POINTER(_F), _P, _P, _I64,
                                         _P]),
+    "den_adam_step": (_INT, [_c.POINTER(AdamTensor), _I32, _c.c_double, _c.c_double, _c.c_double, _I64, _P]),
     "den_alpha_from_sigma": (_INT, [_P, _P, _P, _P, _I64, _P]),
     "den_visibility": (_INT, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "den_compact_samples": (_INT, [_P] * 9 + [_I64, _P]),

@@ -84,4 +84,7 @@ def configure_optimizer(model, lr=0.01, weight_decay=1e-6, refractory_relative_l
     take(lambda n: True)
     if fused is None:
         fused = all(p.is_cuda for _, p in named)
-    return torch.optim.Adam(groups, lr=lr, fused=fused)
+    if fused:
+        from .optim import FusedAdam          # den_adam_step: two launches per step
+        return FusedAdam(groups, lr=lr)
+    return torch.optim.Adam(groups, lr=lr)

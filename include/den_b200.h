@@ -306,6 +306,26 @@ int den_lpf_bwd(const float* intensity, const float* sample_dt_ns, const double*
 int den_tc_probe_gemm(int mode, const float* x, const float* w, float* d, int n, int k,
                       void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Optimiser — replaces torch.optim.Adam as set up by DeblurENeRF.configure_optimizers
+ * (models/deblur_e_nerf.py:1055-1112) for the fp32 parameters: one step t (1-based) of
+ *   g = grad + weight_decay * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+ * over a HOST array of tensor descriptors (device pointers inside), each with its own lr / decay.
+ * ------------------------------------------------------------------------- */
+typedef struct den_adam_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t n;
+    float lr;
+    float weight_decay;
+} den_adam_tensor;
+
+int den_adam_step(const den_adam_tensor* tensors_host, int32_t n_tensors, double beta1, double beta2,
+                  double eps, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
