@@ -197,20 +197,6 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// thread `r` stores its row x[0..K) into the hi / lo operand tiles
-template <int K>
-__device__ __forceinline__ void store_row_split(uint8_t* tile_hi, uint8_t* tile_lo, int r,
-                                                const float (&x)[K]) {
-#pragma unroll
-    for (int c = 0; c < K / 8; ++c) {
-        uint4 hi, lo;
-        split8(&x[8 * c], hi, lo);
-        const uint32_t off = chunk_offset(r, c, K);
-        *reinterpret_cast<uint4*>(tile_hi + off) = hi;
-        *reinterpret_cast<uint4*>(tile_lo + off) = lo;
-    }
-}
-
 // cooperative load of an nn.Linear weight (n_out, n_in) fp32 row-major from global into hi / lo
 // bf16 operand tiles of logical shape (n_pad, k_pad), zero padded
 __device__ __forceinline__ void load_weight_split(uint8_t* tile_hi, uint8_t* tile_lo,
@@ -225,30 +211,6 @@ __device__ __forceinline__ void load_weight_split(uint8_t* tile_hi, uint8_t* til
         *reinterpret_cast<__nv_bfloat16*>(tile_hi + off) = h;
         *reinterpret_cast<__nv_bfloat16*>(tile_lo + off) = l;
     }
-}
-
-// One GEMM round: D[128 x N] = A[128 x K] * B[N x K]^T with the 3-product bf16 split
-// (Ah*Bh + Al*Bh + Ah*Bl).  Issued by a single thread; completion arrives on `bar`.
-template <int N, int K>
-__device__ __forceinline__ void gemm_split_kmajor(uint32_t tmem_d, const uint8_t* a_hi,
-                                                  const uint8_t* a_lo, const uint8_t* b_hi,
-                                                  const uint8_t* b_lo, uint64_t* bar) {
-    constexpr uint32_t idesc = instr_desc_bf16(128, N, false, false);
-    constexpr uint32_t sbo = (K / 8) * 128;
-    const uint32_t a_addr[3] = {smem_u32(a_hi), smem_u32(a_lo), smem_u32(a_hi)};
-    const uint32_t b_addr[3] = {smem_u32(b_hi), smem_u32(b_hi), smem_u32(b_lo)};
-    bool acc = false;
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-#pragma unroll
-        for (int ks = 0; ks < K / 16; ++ks) {
-            const uint64_t ad = smem_desc(a_addr[t] + ks * 256, 128, sbo);
-            const uint64_t bd = smem_desc(b_addr[t] + ks * 256, 128, sbo);
-            mma_bf16(tmem_d, ad, bd, idesc, acc);
-            acc = true;
-        }
-    }
-    mma_commit(bar);
 }
 
 }  // namespace tc
