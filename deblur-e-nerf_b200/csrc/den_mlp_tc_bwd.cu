@@ -242,8 +242,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         // per-slot counters packed in scalars (the slot loop is rolled: no dynamically indexed arrays)
         for (int64_t c0 = 0; c0 < my_tiles; c0 += kFlushTiles) {
         const int64_t nt = min((int64_t)kFlushTiles, my_tiles - c0);          // tiles of this flush period
-        int64_t left0 = 8 * ((nt + 1) / 2), left1 = 8 * (nt / 2);
-        int round0 = 0, round1 = 0;
+        // the forward rounds 0..3 (private accumulators) are issued by the slots themselves; this warp
+        // issues the backward rounds 4..7, whose dW GEMMs share the weight-gradient accumulators
+        int64_t left0 = 4 * ((nt + 1) / 2), left1 = 4 * (nt / 2);
+        int round0 = 4, round1 = 4;
         uint32_t acc_mask = 0;                           // bit r-4: the dW accumulator of round r holds earlier tiles
         while (left0 > 0 || left1 > 0) {
 #pragma unroll 1
@@ -261,26 +263,6 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 uint64_t* dw_done = &bars[2 + s];
                 if (elect_one()) {
                 switch (rnd) {
-                case 0:     // z_b1 = enc Wb1^T
-                    gemm3<kEncDim / 16>(Z, kmajor<TE>(E), kmajor<TWb1>(wb1),
-                                        tc::instr_desc_bf16(128, kWidth, false, false), false);
-                    commit_to(done);
-                    break;
-                case 1:     // y = hb Wb2^T
-                    gemm3<kWidth / 16>(Z, kmajor<TH>(H), kmajor<TWb2>(wb2),
-                                       tc::instr_desc_bf16(128, kBaseOut, false, false), false);
-                    commit_to(done);
-                    break;
-                case 2:     // z1 = [SH | geo | 1] W1^T
-                    gemm3<kHeadIn / 16>(Z, kmajor<TE>(E), kmajor<TW1>(w1),
-                                        tc::instr_desc_bf16(128, kWidth, false, false), false);
-                    commit_to(done);
-                    break;
-                case 3:     // z2 = h1 W2^T
-                    gemm3<kWidth / 16>(Z, kmajor<TH>(H), kmajor<TW2>(w2),
-                                       tc::instr_desc_bf16(128, kWidth, false, false), false);
-                    commit_to(done);
-                    break;
                 case 4:     // dh1 = d2 W2;  dW2 | db2 += d2^T [h1 | 1]
                     gemm3<kWidth / 16>(Z, kmajor<TD>(D), mnmajor<TW2>(w2),
                                        tc::instr_desc_bf16(128, kWidth, false, true), false);
@@ -317,7 +299,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 }
                 __syncwarp();
                 if (rnd >= 4) acc_mask |= 1u << (rnd - 4);
-                if (s == 0) { round0 = (rnd + 1) & 7; --left0; } else { round1 = (rnd + 1) & 7; --left1; }
+                if (s == 0) { round0 = 4 + ((rnd + 1) & 3); --left0; } else { round1 = 4 + ((rnd + 1) & 3); --left1; }
             }
         }
         // end of the flush period: the epilogue groups have awaited every GEMM; warps 0..3 drain the
@@ -352,6 +334,34 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         };
 
         // load this thread's 16 encoding features of row i into E chunks (2 hf, 2 hf + 1)
+        // forward rounds: the 8 warps of the slot meet at their named barrier and the slot's first warp
+        // elects the thread that issues the GEMM (it only writes this slot's own scratch columns)
+        const uint32_t Zd = tmem_base + kColZ + 128u * slot_id;
+        auto launch_fwd = [&](int round) {
+            tc::fence_smem_to_async_proxy();
+            tc::tc_fence_before_sync();
+            group_sync(slot_id);
+            if ((warp & 7) == 0) {
+                tc::tc_fence_after_sync();
+                if (elect_one()) {
+                    if (round == 0)        // z_b1 = enc Wb1^T
+                        gemm3<kEncDim / 16>(Zd, kmajor<TE>(E), kmajor<TWb1>(smem + Smem::wb1),
+                                            tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    else if (round == 1)   // y = hb Wb2^T
+                        gemm3<kWidth / 16>(Zd, kmajor<TH>(H), kmajor<TWb2>(smem + Smem::wb2),
+                                           tc::instr_desc_bf16(128, kBaseOut, false, false), false);
+                    else if (round == 2)   // z1 = [SH | geo | 1] W1^T
+                        gemm3<kHeadIn / 16>(Zd, kmajor<TE>(E), kmajor<TW1>(smem + Smem::w1),
+                                            tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    else                   // z2 = h1 W2^T
+                        gemm3<kWidth / 16>(Zd, kmajor<TH>(H), kmajor<TW2>(smem + Smem::w2),
+                                           tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    commit_to(done);
+                }
+                __syncwarp();
+            }
+        };
+
         // this thread's 16 encoding features of row i: global -> registers ...
         auto load_enc = [&](int64_t i, bool valid, float (&x)[16]) {
 #pragma unroll
@@ -434,12 +444,12 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             if (dw_pending) await_dw();
             dw_pending = true;
             stage_enc(xe);
-            publish(slot_id);
+            launch_fwd(0);
 
             // ---- round 0 done: hb ----------------------------------------------------------------
             await_mma(done, phase);
             stage_hb();
-            publish(slot_id);
+            launch_fwd(1);
 
             // ---- round 1 done: y -> raw density, [SH | geo | 1] -> E -------------------------------
             float raw = 0.f;
@@ -461,7 +471,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                     store16<TE>(E, row, 0, x);
                 }
             }
-            publish(slot_id);
+            launch_fwd(2);
 
             // ---- round 2 done: h1 -> H -------------------------------------------------------------
             await_mma(done, phase);
@@ -472,7 +482,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 bias_hidden_act<16>(hact, h, s_b1 + 32 * hf + 16 * c);
                 store16<TH>(H, row, 4 * hf + 2 * c, h);
             }
-            publish(slot_id);
+            launch_fwd(3);
 
             // next tile of this slot: pull its rows towards L2 while this one is in flight
             if (k + kSlots < my_tiles) {
