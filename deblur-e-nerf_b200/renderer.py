@@ -46,6 +46,8 @@ class EventRenderer(torch.nn.Module):
         # compositing launch sequence over 4x the rays (same arithmetic per ray, same RNG draws in
         # the same order): a quarter of the launches and host synchronisations per step
         self.batch_render_calls = True
+        self.batch_bytes_per_sample = 448        # encodings + their gradient + the per-sample scalars
+        self._last_mean_samples = None           # samples per ray of the previous step (memory guard)
 
     # ------------------------------------------------------------- render helpers ----
     def _kinv_host(self):
@@ -183,7 +185,8 @@ class EventRenderer(torch.nn.Module):
         segs = [(seg, is_diff) for seg, is_diff in ((diff, True), (subdiff, False))
                 if seg is not None]
         batched = None
-        if self.batch_render_calls and self.nerf.radiance_field.training and segs:
+        if self.batch_render_calls and self.nerf.radiance_field.training and segs \
+                and self._batch_fits(2 * len(segs) * size, gen):
             requests = []
             for seg, is_diff in segs:
                 requests += [(seg["start_ts"], is_diff), (seg["end_ts"], False)]
@@ -203,6 +206,7 @@ class EventRenderer(torch.nn.Module):
             occ_rates += [occ_a, occ_b]
             valid_rates += [va, vb]
 
+        self._last_mean_samples = max(mean_samples) if mean_samples else None
         mean_samples = self.update_train_batch_size(mean_samples, batch_index)
         terms = self.loss.compute(event, diff, subdiff,
                                   self.contrast_threshold.mean_contrast_threshold)
@@ -214,6 +218,19 @@ class EventRenderer(torch.nn.Module):
             self.logged[f"train/{key}"] = value.detach()
         self.logged["train/mean_ray_occ_rate"] = sum(occ_rates) / len(occ_rates)
         return loss
+
+    def _batch_fits(self, n_render_rays, gen):
+        """Memory guard of the batched render calls: estimated per-sample buffers (from the samples
+        per ray of the previous step; 128 before the first) against 70 % of the free device memory."""
+        if not torch.cuda.is_available():
+            return True
+        rays = n_render_rays * (gen.shape[0] + 1 if (gen is not None and self.pixel_bandwidth is not None)
+                                else 1)
+        per_ray = self._last_mean_samples if self._last_mean_samples else 128.0
+        free, _ = torch.cuda.mem_get_info()
+        # blocks the caching allocator holds but has not handed out are available too
+        free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+        return rays * per_ray * self.batch_bytes_per_sample < 0.7 * free
 
     def update_train_batch_size(self, mean_samples_per_call, batch_index):
         """models/deblur_e_nerf.py:1252-1308: N_next = int(budget / mean samples per ray)."""
