@@ -227,9 +227,11 @@ class EventRenderer(torch.nn.Module):
         rays = n_render_rays * (gen.shape[0] + 1 if (gen is not None and self.pixel_bandwidth is not None)
                                 else 1)
         per_ray = self._last_mean_samples if self._last_mean_samples else 128.0
-        free, _ = torch.cuda.mem_get_info()
-        # blocks the caching allocator holds but has not handed out are available too
-        free += torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+        # device capacity minus what this process holds (allocator statistics: no driver call — the
+        # cudaMemGetInfo behind torch.cuda.mem_get_info costs milliseconds per step)
+        if getattr(self, "_device_bytes", None) is None:
+            self._device_bytes = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+        free = self._device_bytes - torch.cuda.memory_allocated()
         return rays * per_ray * self.batch_bytes_per_sample < 0.7 * free
 
     def update_train_batch_size(self, mean_samples_per_call, batch_index):

@@ -144,3 +144,35 @@ def test_sample_buffers_are_allocated_in_row_quanta():
     assert like.shape == big.shape and like.dtype == big.dtype
     exact = ops._rows(2 << 18, (), torch.int32, "cpu")
     assert exact.numel() == 2 << 18 and exact.untyped_storage().nbytes() == (2 << 18) * 4
+
+
+def test_event_batch_producer_shapes_and_distributions():
+    """Device-side batch producer (here on CPU tensors): layout, dtypes, ranges, per-rank streams and
+    the batch-size controller hook."""
+    import torch
+    from deblur_e_nerf_b200.data import EventBatchProducer
+    g = torch.Generator().manual_seed(0)
+    n = 20000
+    events = {"position": torch.rand(n, 2, generator=g) * 100,
+              "start_ts": torch.arange(n) * 1000, "end_ts": torch.arange(n) * 1000 + 500,
+              "num_pos": torch.ones(n, dtype=torch.int64), "num_neg": torch.zeros(n, dtype=torch.int64)}
+    prod = EventBatchProducer(events, 4096, it_sample_size=30, device="cpu", seed=5, rank=0)
+    b = prod.next_batch()
+    ev, nm = b["event"], b["normalized"]
+    assert ev["position"].shape == (4096, 2) and ev["position"].dtype == torch.float32
+    assert ev["end_ts"].dtype == torch.int64 and torch.equal(ev["end_ts"] - ev["start_ts"],
+                                                             torch.full((4096,), 500))
+    assert nm["interval_gen"].shape == (29, 4096) and bool((nm["interval_gen"] == 0.5).all())
+    assert bool((nm["ts_diff"] == 1).all())
+    for k in ("diff_start_ts", "ts_subdiff", "subdiff_start_ts"):
+        assert nm[k].dtype == torch.float64 and 0 <= float(nm[k].min()) and float(nm[k].max()) < 1
+    # triangular with mode 0: mean 1/3; uniform: mean 1/2
+    assert abs(float(nm["ts_subdiff"].mean()) - 1 / 3) < 0.02
+    assert abs(float(nm["diff_start_ts"].mean()) - 0.5) < 0.02
+    other = EventBatchProducer(events, 4096, it_sample_size=None, device="cpu", seed=5, rank=1).next_batch()
+    assert "interval_gen" not in other["normalized"]
+    assert not torch.equal(other["event"]["end_ts"], ev["end_ts"])          # rank-offset stream
+    prod.set_batch_size(100)
+    assert prod.next_batch()["event"]["num_pos"].shape == (100,)
+    trimmed = EventBatchProducer(events, 64, device="cpu", dataset_len=10)
+    assert int(trimmed.next_batch()["event"]["end_ts"].max()) <= 9 * 1000 + 500

@@ -179,3 +179,49 @@ def test_training_step(pb_on):
     for k in gr:
         tol = 5e-3 if "pixel_bandwidth" in k or "refractory" in k else 2e-4
         _close(go[k], gr[k], tol)
+
+
+def test_event_batch_producer_reproduces_the_reference_samplers():
+    """deblur_e_nerf_b200.data.EventBatchProducer on CPU tensors + a CPU generator == the reference's
+    IterableMapDataset (utils/datasets.py:19-32) + UniformSampler / TriangularSampler /
+    DiracDeltaSampler (data/samplers.py) drawing from one shared generator in the dataloader's order
+    (event batch first, then the normalised samplers: data/datamodule.py:151-247), bit for bit."""
+    from deblur_e_nerf_b200.data import EventBatchProducer
+    ref_datasets = ref_shim.load("utils.datasets")
+    ref_samplers = ref_shim.load("data.samplers")
+    g0 = torch.Generator().manual_seed(3)
+    n_events, batch, S = 5000, 257, 8
+    events = {
+        "position": torch.rand(n_events, 2, generator=g0) * 300,
+        "start_ts": torch.randint(0, 10 ** 9, (n_events,), generator=g0),
+        "end_ts": torch.randint(10 ** 9, 2 * 10 ** 9, (n_events,), generator=g0),
+        "num_pos": torch.randint(0, 2, (n_events,), generator=g0),
+        "num_neg": torch.randint(0, 2, (n_events,), generator=g0),
+    }
+
+    class MapEvents(torch.utils.data.Dataset):           # Event.__getitem__: index every array
+        def __len__(self):
+            return n_events
+
+        def __getitem__(self, index):
+            return {k: v[index] for k, v in events.items()}
+
+    gen = torch.Generator().manual_seed(11)
+    ref_events = iter(ref_datasets.IterableMapDataset(MapEvents(), batch, generator=gen))
+    f64 = torch.float64
+    ref_norm = iter(ref_datasets.JoinDataset(
+        [ref_samplers.DiracDeltaSampler(center=1, size=batch, dtype=f64),
+         ref_samplers.UniformSampler(low=0, high=1, size=batch, dtype=f64, generator=gen),
+         ref_samplers.TriangularSampler(low=0, high=1, size=batch, mode=0, dtype=f64, generator=gen),
+         ref_samplers.UniformSampler(low=0, high=1, size=batch, dtype=f64, generator=gen),
+         ref_samplers.DiracDeltaSampler(center=0.5, size=(S - 1, batch), dtype=f64)],
+        ["ts_diff", "diff_start_ts", "ts_subdiff", "subdiff_start_ts", "interval_gen"]))
+    ours = EventBatchProducer(events, batch, it_sample_size=S, device="cpu", seed=11)
+    for _ in range(3):
+        ev, nm = next(ref_events), next(ref_norm)
+        out = ours.next_batch()
+        assert set(out["event"]) == set(ev) and set(out["normalized"]) == set(nm)
+        for k in ev:
+            assert out["event"][k].dtype == ev[k].dtype and torch.equal(out["event"][k], ev[k]), k
+        for k in nm:
+            assert out["normalized"][k].dtype == nm[k].dtype and torch.equal(out["normalized"][k], nm[k]), k
