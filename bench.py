@@ -66,10 +66,12 @@ KERNEL_BYTES_PER_RAY = {"den_composite_fwd": 12, "den_composite_bwd": 12}
 # tensor-pipe kernels: algorithmic FLOP per sample
 KERNEL_FLOP_PER_SAMPLE = {"den_mlp_fwd": 18432, "den_mlp_bwd": 55296}
 # dram__bytes_read.sum + dram__bytes_write.sum per sample from the ncu --set full captures of
-# profiles/r01_ncu_mlp_final.md (10.2 M samples per launch) and profiles/r01_ncu_misc_kernels.md
+# profiles/r01_ncu_mlp_final.md (10.2 M samples per launch)
 NCU_DRAM_BYTES_PER_SAMPLE = {"den_mlp_bwd": (1.520543e9 + 1.275103e9) / 10200012,
                              "den_mlp_fwd": (1.431510e9 + 0.081907e9) / 10200012,
-                             "den_hashgrid_bwd": (402.03e6 + 8.46e6) / 2531605}
+                             # profiles/r01_ncu_hashgrid_final.md (10.2 M samples per launch)
+                             "den_hashgrid_fwd": (0.390110e9 + 1.285446e9) / 10200038,
+                             "den_hashgrid_bwd": (1.486487e9 + 0.021163e9) / 10200038}
 
 
 def parse_args():
