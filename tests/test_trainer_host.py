@@ -1,0 +1,136 @@
+"""CPU tests of the optimizer-step loop (trainer.py) on a stand-in model: the Lightning behaviours
+the hot path relies on — step / epoch counting, gradient accumulation,
+the two-batch lag of the batch controller, scheduler interval, checkpoint round trip."""
+
+import torch
+
+from deblur_e_nerf_b200 import trainer as trainer_mod
+
+
+class _Producer:
+    def __init__(self, batch_size):
+        self.batch_size = batch_size
+        self.drawn = []
+        self.g = torch.Generator().manual_seed(0)
+
+    def set_batch_size(self, n):
+        self.batch_size = int(n)
+
+    def next_batch(self):
+        self.drawn.append(self.batch_size)
+        return {"x": torch.randn(self.batch_size, 3, generator=self.g, dtype=torch.float64)}
+
+
+class _Model(torch.nn.Module):
+    """Least squares on w; the 'controller' asks for batch size 10 + number of steps seen."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(3, dtype=torch.float64))
+        self.next_train_batch_size = None
+        self.accumulate_grad_batches = 1
+        self.logged = {}
+        self.calls = []
+
+    def training_step(self, batch, batch_index, global_step):
+        self.calls.append((batch_index, global_step, batch["x"].shape[0]))
+        self.next_train_batch_size = 10 + len(self.calls)
+        loss = ((batch["x"] @ self.w - batch["x"].sum(-1)) ** 2).mean()
+        self.logged = {"train/loss": loss.detach(), "train/batch_size": batch["x"].shape[0]}
+        return loss
+
+
+def test_step_and_epoch_counting_and_controller_lag():
+    model, prod = _Model(), _Producer(8)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1], gamma=0.5)
+    tr = trainer_mod.Trainer(max_epochs=2, limit_train_batches=5, log_every_n_steps=2)
+    out = tr.fit(model, prod, opt, sched)
+    assert tr.global_step == 10 and tr.current_epoch == 2
+    assert [c[0] for c in model.calls] == [0, 1, 2, 3, 4] * 2
+    assert [c[1] for c in model.calls] == list(range(10))
+    # one prefetched batch: the size chosen in batch k (10 + k + 1) is first seen by batch k + 2
+    seen = [c[2] for c in model.calls]
+    assert seen[:2] == [8, 8]
+    assert seen[2:] == [10 + k + 1 for k in range(8)]
+    assert opt.param_groups[0]["lr"] == 0.05 * 0.5          # epoch interval: one milestone passed
+    assert [s for s, _ in tr.history] == [2, 4, 6, 8, 10]
+    assert out["train/loss"] < 3.0 and isinstance(out["train/loss"], float)
+
+
+def test_gradient_accumulation_equals_the_mean_gradient():
+    torch.manual_seed(0)
+    xs = [torch.randn(6, 3, dtype=torch.float64) for _ in range(4)]
+
+    class Fixed:
+        def __init__(self):
+            self.i = 0
+
+        def set_batch_size(self, n):
+            pass
+
+        def next_batch(self):
+            self.i += 1
+            return {"x": xs[(self.i - 1) % 4]}
+
+    model = _Model()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    tr = trainer_mod.Trainer(max_epochs=1, limit_train_batches=4, accumulate_grad_batches=4,
+                             lr_scheduler_interval="step")
+    tr.fit(model, Fixed(), opt)
+    assert tr.global_step == 1 and model.accumulate_grad_batches == 4
+    ref = _Model()
+    loss = sum(((x @ ref.w - x.sum(-1)) ** 2).mean() for x in xs) / 4
+    loss.backward()
+    assert torch.allclose(model.w.detach(), -0.1 * ref.w.grad, rtol=1e-12, atol=0)
+
+    # an epoch that is not a multiple of the window still steps on its last batch
+    model2 = _Model()
+    opt2 = torch.optim.SGD(model2.parameters(), lr=0.1)
+    tr2 = trainer_mod.Trainer(max_epochs=1, limit_train_batches=3, accumulate_grad_batches=2)
+    tr2.fit(model2, Fixed(), opt2)
+    assert tr2.global_step == 2
+
+
+def test_checkpoint_round_trip_and_resume(tmp_path):
+    def run(epochs):
+        model, prod = _Model(), _Producer(8)
+        opt = torch.optim.Adam(model.parameters(), lr=0.05)
+        sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1, 2], gamma=0.5)
+        tr = trainer_mod.Trainer(max_epochs=epochs, limit_train_batches=3,
+                                 checkpoint_dir=str(tmp_path))
+        tr.fit(model, prod, opt, sched)
+        return model, opt, tr, prod
+
+    model_a, _, tr_a, prod_a = run(1)
+    ckpt_path = str(tmp_path / "last.ckpt")
+    ckpt = torch.load(ckpt_path, weights_only=False)
+    assert set(ckpt) >= {"epoch", "global_step", "state_dict", "optimizer_states", "lr_schedulers"}
+    assert ckpt["epoch"] == 1 and ckpt["global_step"] == 3
+    assert ckpt["train_batch_size"]["next"] == model_a.next_train_batch_size
+    assert tr_a.max_steps is None
+    # `max_steps` stops inside an epoch
+    model_s, prod_s = _Model(), _Producer(8)
+    tr_s = trainer_mod.Trainer(max_epochs=5, limit_train_batches=3, max_steps=4)
+    tr_s.fit(model_s, prod_s, torch.optim.SGD(model_s.parameters(), lr=0.01))
+    assert tr_s.global_step == 4 and tr_s.current_epoch == 1
+    # resuming restores the counters, the optimizer moments, the schedule and the controller
+    model_b, prod_b = _Model(), _Producer(8)
+    opt_b = torch.optim.Adam(model_b.parameters(), lr=0.05)
+    sched_b = torch.optim.lr_scheduler.MultiStepLR(opt_b, milestones=[1, 2], gamma=0.5)
+    tr_b = trainer_mod.Trainer(max_epochs=2, limit_train_batches=3)
+    tr_b.load_checkpoint(ckpt_path, model_b, opt_b, sched_b)
+    assert tr_b.current_epoch == 1 and tr_b.global_step == 3
+    assert torch.equal(model_b.w.detach(), model_a.w.detach())
+    assert opt_b.param_groups[0]["lr"] == 0.05 * 0.5
+    assert opt_b.state_dict()["state"][0]["step"] == 3
+    tr_b.fit(model_b, prod_b, opt_b, sched_b)
+    assert tr_b.current_epoch == 2 and tr_b.global_step == 6
+    assert prod_b.drawn[0] == model_a.next_train_batch_size
+
+
+def test_seed_everything_reseeds_torch():
+    trainer_mod.seed_everything(7)
+    a = torch.rand(3)
+    trainer_mod.seed_everything(7)
+    assert torch.equal(a, torch.rand(3))
