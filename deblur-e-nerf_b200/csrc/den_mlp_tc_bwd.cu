@@ -35,6 +35,14 @@
 // (Tried and rejected, measured: all 16 warps on ONE slot's phase at a time, alternating slots, with a
 // CTA-wide barrier per phase — every warp then hits the same tcgen05.ld / fence / barrier latencies at
 // the same moment and nothing is left to hide them: 6.9 ms against 5.3 ms for the form below.)
+// (Also tried and rejected, measured at 10.2 M samples: SAVING the forward activations in den_mlp_fwd
+// (832 B/sample, tile-blocked so that every warp access is 512 contiguous bytes) and reading them back
+// here instead of recomputing them — four MMA rounds per tile instead of eight, no TMEM parking, results
+// bit-identical.  Forward 1.71 -> 2.05 ms, backward 4.85 -> 5.27 ms (5.68 ms with the loads hoisted
+// across the MMA waits: the 96-register cap turns the extra live values into spills).  The recompute
+// rounds of one slot hide under the backward rounds of the other, so removing them buys nothing; what
+// bounds the kernel is the chain hand-off -> GEMM -> mbarrier -> epilogue of the four backward rounds
+// with only two tiles in flight.)
 // Shared memory per slot: E (128 x 40: enc | ones, later [SH | geo | 1], later dy, later enc
 // again), H (128 x 72: hb | ones, later h1, later hb again) and D (128 x 64: the current
 // dL/dz tile) = 88 KB; 2 slots + 36 KB of weight tiles = 223 KB.  The price of fitting two
