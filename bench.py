@@ -525,19 +525,22 @@ def run_ours(args):
         pool = synthetic.event_batch(1 << 21, cfg, poses[2], g)          # 2 M queued events, uploaded once
         producer = EventBatchProducer(pool, n_events, it_sample_size=w["S"] if w["pb"] else None,
                                       device=dev, seed=1234, rank=rank)
-        for i in range(2):
+        for i in range(max(args.warmup, 3)):
             one_step(producer.next_batch(), 1 + i)
         ddp.barrier()
         torch.cuda.synchronize()
+        mallocs_p = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         start.record()
         for i in range(args.steps):
             one_step(producer.next_batch(), 1 + args.warmup + i)
         end.record()
         ddp.barrier()
         torch.cuda.synchronize()
+        mallocs_p = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs_p
         ms_prod = ddp.max_over_ranks(start.elapsed_time(end) / args.steps, dev)
         producer_line = {"value": global_rays / (ms_prod * 1e-3), "unit": "rays/s", "ms_per_step": ms_prod,
-                         "events_in_hbm": len(producer),
+                         "events_in_hbm": len(producer), "cuda_mallocs": mallocs_p,
+                         "mean_samples_per_ray": float(model.logged["train/mean_num_samples_per_ray"]),
                          "note": "batches drawn by data.EventBatchProducer on the device (random event "
                                  "gather + normalised samplers), no host batch, no copy"}
 
