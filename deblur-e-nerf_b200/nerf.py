@@ -198,8 +198,11 @@ class NeRF(torch.nn.Module):
             if total < ray_idx.numel():
                 ray_idx, t0, t1 = ops.compact(mask, offsets, offsets_out, ray_idx, t0, t1, total)
                 offsets = offsets_out
-                keep = mask.bool()      # survivors keep their positions: outputs stay valid
-                pre = tuple(t[keep] for t in pre)
+                # survivors keep their order: the pre-pass outputs stay valid.  The survivor count is
+                # already on the host, so the row gather needs no further synchronisation (boolean
+                # indexing would read the count back once per tensor)
+                keep = torch.nonzero_static(mask.reshape(-1), size=total).reshape(-1)
+                pre = tuple(t.index_select(0, keep) for t in pre)
         if pre is None:
             pre = field.eval_samples_tc(o, d, ray_idx, t0, t1, full=True) if ray_idx.numel() \
                 else (torch.empty(0, device=o.device),

@@ -73,6 +73,65 @@ def test_world_size_2_gloo(tmp_path):
     assert res[0]["sum"] == res[1]["sum"] == 7.0
 
 
+def _trainer_worker(rank, world, port, out_dir):
+    """trainer.Trainer under world_size 2: every rank trains on its own event shard
+    (EventBatchProducer seeded with seed + rank), gradients are mean all-reduced once per optimizer
+    step (also with accumulation), rank 0 alone writes the checkpoint."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from deblur_e_nerf_b200 import data, ddp, trainer
+    ddp.init_from_env(backend="gloo")
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.randn(2, dtype=torch.float64))
+            self.next_train_batch_size = None
+            self.accumulate_grad_batches = 1
+            self.logged = {}
+            self.seen = []
+
+        def training_step(self, batch, batch_index, global_step):
+            pos = batch["event"]["position"].double()
+            self.seen.append(pos[:, 0].sum().item())
+            loss = ((pos @ self.w - batch["normalized"]["diff_start_ts"]) ** 2).mean()
+            self.logged = {"train/loss": loss.detach()}
+            return loss
+
+    torch.manual_seed(50 + rank)
+    model = Model()
+    ddp.broadcast_parameters(model)
+    g = torch.Generator().manual_seed(0)                 # the same event pool on every rank
+    n = 64
+    events = {"position": torch.rand(n, 2, generator=g), "start_ts": torch.arange(n),
+              "end_ts": torch.arange(n) + 5, "num_pos": torch.ones(n, dtype=torch.int64),
+              "num_neg": torch.zeros(n, dtype=torch.int64)}
+    producer = data.EventBatchProducer(events, 8, None, "cpu", seed=3, rank=rank)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    tr = trainer.Trainer(max_epochs=2, limit_train_batches=4, accumulate_grad_batches=2,
+                         checkpoint_dir=os.path.join(out_dir, "ckpt"))
+    tr.fit(model, producer, opt)
+    torch.save({"w": model.w.detach().clone(), "seen": model.seen, "steps": tr.global_step},
+               os.path.join(out_dir, f"trainer_rank{rank}.pt"))
+    ddp.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_trainer_world_size_2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_trainer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"trainer_rank{r}.pt") for r in range(world)]
+    assert res[0]["steps"] == res[1]["steps"] == 4              # 2 epochs x 4 batches / 2 accumulated
+    assert res[0]["seen"] != res[1]["seen"]                     # rank-offset seeds: different shards
+    assert torch.equal(res[0]["w"], res[1]["w"])                # mean all-reduce keeps replicas equal
+    ckpts = os.listdir(tmp_path / "ckpt")
+    assert ckpts == ["last.ckpt"]
+    ckpt = torch.load(tmp_path / "ckpt" / "last.ckpt", weights_only=False)
+    assert ckpt["global_step"] == 4 and torch.equal(ckpt["state_dict"]["w"], res[0]["w"])
+
+
 def test_single_process_is_a_noop():
     sys.path.insert(0, ROOT)
     from deblur_e_nerf_b200 import ddp

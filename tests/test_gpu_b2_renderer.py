@@ -91,6 +91,51 @@ def test_nerf_render_matches_oracle(den_lib, cuda, scene, training):
         assert _rel(gp[key], go[key]) < TOL, key
 
 
+def test_nerf_render_with_culled_samples_matches_oracle(den_lib, cuda):
+    """A dense field (density bias +5: sigma ~ 150) makes the transmittance test of the visibility
+    pre-pass cull most marched samples (external/utils.py:68-81, early_stop_eps 1e-4): covers the
+    survivor gather of the pre-pass outputs and the grad pass on the compacted sample set."""
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    ora = _scene.build_oracle_nerf(cfg)
+    with torch.no_grad():
+        ora.radiance_field.mlp_base[1].output_layer.bias[0] += 5.0
+    prod = _scene.build_product_nerf(cfg, cuda)
+    _scene.copy_params(ora, prod)
+    ora.train()
+    prod.train()
+    poses = _scene.synthetic.camera_poses(cfg, n_poses=50)
+    torch.manual_seed(3)
+    ora.update_occ_grid(0, poses[0])
+    prod.occupancy_grid._binary = ora.occupancy_grid.binary.to(cuda)
+    prod.occupancy_grid.occs.copy_(ora.occupancy_grid.occs)
+    traj = _scene.path_ref.LinearTrajectory(*poses)
+    g = torch.Generator().manual_seed(5)
+    n = 600
+    ts = torch.rand(n, generator=g, dtype=torch.float64) * float(poses[2][-1])
+    px = torch.stack([torch.rand(n, generator=g) * cfg["width"],
+                      torch.rand(n, generator=g) * cfg["height"]], -1)
+    pos, rot = traj(ts)
+    kinv = torch.linalg.inv(torch.from_numpy(_scene.synthetic.intrinsics(cfg)))
+    o, d = _scene.path_ref.NeRF.pixel_params_to_ray(kinv, px, pos, rot)
+    jitter = torch.rand(n, generator=g)
+    marched = prod._march(o.to(cuda).float().contiguous(), d.to(cuda).float().contiguous(),
+                          jitter.to(cuda))[0].numel()
+    rad_o, opa_o, dep_o, ms_o = ora(o, d, jitter=jitter)
+    rad_p, opa_p, dep_p, ms_p = prod(o.to(cuda), d.to(cuda), jitter=jitter.to(cuda))
+    assert 1 < ms_o * n < 0.5 * marched, (ms_o * n, marched)     # most samples were culled
+    assert abs(ms_p - ms_o) * n <= 3, (ms_p, ms_o)
+    assert _rel(rad_p, rad_o) < TOL
+    assert _rel(opa_p, opa_o) < TOL
+    assert _rel(dep_p, dep_o) < TOL
+    w = torch.randn(n, generator=g)
+    ((rad_o + 1e-3).log() * w).sum().backward()
+    ((rad_p + 1e-3).log() * w.to(cuda)).sum().backward()
+    go, gp = _scene.flat_named_grads(ora), _scene.flat_named_grads(prod)
+    assert set(go) == set(gp)
+    for key in go:
+        assert _rel(gp[key], go[key]) < TOL, key
+
+
 def test_occupancy_update_bit_exact_given_same_draws(den_lib, cuda):
     """Occupancy booleans must match the oracle exactly given identical upstream inputs:
     the jittered cell positions are injected (CUDA and CPU Philox streams differ)."""
