@@ -71,7 +71,9 @@ NCU_DRAM_BYTES_PER_SAMPLE = {"den_mlp_bwd": (1.520543e9 + 1.275103e9) / 10200012
                              "den_mlp_fwd": (1.431510e9 + 0.081907e9) / 10200012,
                              # profiles/r01_ncu_hashgrid_final.md (10.2 M samples per launch)
                              "den_hashgrid_fwd": (0.390110e9 + 1.285446e9) / 10200038,
-                             "den_hashgrid_bwd": (1.486487e9 + 0.021163e9) / 10200038}
+                             "den_hashgrid_bwd": (1.486487e9 + 0.021163e9) / 10200038,
+                             # profiles/r01_ncu_misc_kernels.md (burst-load kernel, 10.2 M samples)
+                             "den_composite_fwd": (165.532416e6 + 3.671552e6) / 10200012}
 
 
 def parse_args():
