@@ -94,15 +94,21 @@ class PixelBandwidth(torch.nn.Module):
         return -torch.log1p(-(self.target_cumprob_max_sample_lifetime * life)) / rate
 
     def forward(self, normalized_interval_gen, output_ts, intensity_sampling_fn,
-                reset_diff=False):
-        sample_ts = output_ts - self.sample_lifetimes(normalized_interval_gen)
+                reset_diff=False, lifetimes=None, coefficients=None):
+        """`lifetimes` / `coefficients`: values of sample_lifetimes(normalized_interval_gen) /
+        coefficients() computed by the caller once for several calls of the same step (they depend
+        only on the interval generator and the parameters)."""
+        if lifetimes is None:
+            lifetimes = self.sample_lifetimes(normalized_interval_gen)
+        sample_ts = output_ts - lifetimes
         sampled = intensity_sampling_fn(sample_ts.clamp(min=self.min_ts))
         intensity, aux = sampled[0], sampled[1:]
         sample_dt = sample_ts.detach().diff(dim=0).to(intensity.dtype)
         batch_shape = intensity.shape[1:]
         S = intensity.shape[0]
         out = ops.lpf(intensity.reshape(S, -1), sample_dt.reshape(S - 1, -1),
-                      self.coefficients(), 2 if reset_diff else 1)
+                      self.coefficients() if coefficients is None else coefficients,
+                      2 if reset_diff else 1)
         if reset_diff:
             sf = out[:, 0].reshape(batch_shape)
             before = out[:, 1].reshape(batch_shape)
