@@ -176,3 +176,27 @@ def test_event_batch_producer_shapes_and_distributions():
     assert prod.next_batch()["event"]["num_pos"].shape == (100,)
     trimmed = EventBatchProducer(events, 64, device="cpu", dataset_len=10)
     assert int(trimmed.next_batch()["event"]["end_ts"].max()) <= 9 * 1000 + 500
+
+
+def test_batch_controller_gating_follows_the_reference():
+    """models/deblur_e_nerf.py:1252-1308: N_next = int(budget / mean samples per ray); with gradient
+    accumulation only the second-to-last micro-batch of a window updates it (so that, with the one
+    prefetched batch, every micro-batch of the next window has the same size); the cross-rank mean
+    is taken before the division."""
+    import types
+    stub = types.SimpleNamespace(mean_samples_reduce_fn=None, accumulate_grad_batches=1,
+                                 train_ray_sample_batch_size=131072, next_train_batch_size=None)
+    update = renderer.EventRenderer.update_train_batch_size
+    assert update(stub, [80.0, 70.0, 90.0, 80.0], 0) == 80.0
+    assert stub.next_train_batch_size == int(131072 / 80.0)
+    stub.accumulate_grad_batches, stub.next_train_batch_size = 4, None
+    for batch_index in (0, 1, 3, 4, 5, 7):
+        update(stub, [50.0], batch_index)
+        assert stub.next_train_batch_size is None, batch_index
+    update(stub, [50.0], 2)
+    assert stub.next_train_batch_size == int(131072 / 50.0)
+    update(stub, [64.0], 6)
+    assert stub.next_train_batch_size == 2048
+    stub.accumulate_grad_batches = 1
+    stub.mean_samples_reduce_fn = lambda mean: (mean + 3 * mean) / 2        # two ranks: m and 3 m
+    assert update(stub, [32.0], 0) == 64.0 and stub.next_train_batch_size == 2048
