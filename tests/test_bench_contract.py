@@ -50,3 +50,29 @@ def test_reference_arm_other_ranks_exit_silently():
     res = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
     assert res.returncode == 0, res.stderr[-2000:]
     assert not [l for l in res.stdout.splitlines() if l.startswith("{")]
+
+
+def test_product_ops_refuse_cpu_tensors():
+    """The product path has no CPU / PyTorch fallback: the tensor wrappers of the C ABI raise on CPU
+    tensors instead of computing anything (upstream raises NotImplementedError on CPU
+    tensors too), the optimizer refuses CPU parameters, and the bench's own arm asserts a device."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from deblur_e_nerf_b200 import ops, optim
+    x = torch.zeros(4, 3)
+    idx = torch.zeros(4, dtype=torch.int32)
+    t = torch.zeros(4)
+    offsets = torch.tensor([0, 4], dtype=torch.int32)
+    with pytest.raises(NotImplementedError):
+        ops.composite(t, torch.zeros(4, 1), t, t, offsets, None)
+    with pytest.raises(NotImplementedError):
+        ops.segment_sum(x, offsets)
+    with pytest.raises(NotImplementedError):
+        opt = optim.FusedAdam([torch.nn.Parameter(torch.zeros(3))], lr=0.01)
+        opt.param_groups[0]["params"][0].grad = torch.ones(3)
+        opt.step()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0",
+                          "--no-cpu-baseline"], capture_output=True, text=True, cwd=ROOT, timeout=300,
+                         env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert res.returncode != 0 and "needs a GPU" in res.stderr
+    assert not [l for l in res.stdout.splitlines() if l.startswith("{")]
