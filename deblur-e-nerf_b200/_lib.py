@@ -41,6 +41,10 @@ class MarchParams(_c.Structure):
     ]
 
 
+class OccGridDesc(_c.Structure):
+    _fields_ = [("roi", _F * 6), ("res", _I32 * 3), ("contraction", _I32)]
+
+
 class FieldDesc(_c.Structure):
     _fields_ = [
         ("grid", HashGridDesc), ("aabb", _F * 6), ("contraction", _I32), ("channels", _I32),
@@ -84,6 +88,11 @@ _SIGNATURES = {
     "den_march_bound": (_INT, [_c.POINTER(MarchParams), _P, _P, _I32, _P, _I64, _P]),
     "den_march_single": (_INT, [_c.POINTER(MarchParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "den_march_pack": (_INT, [_P, _P, _P, _P, _I64, _P, _P, _P, _P]),
+    "den_occgrid_cell_points": (_INT, [_c.POINTER(OccGridDesc), _P, _P, _I64, _P, _P, _P]),
+    "den_occgrid_occ": (_INT, [_P, _P, _P, _P, _F, _F, _INT, _F, _F, _I64, _P, _P]),
+    "den_occgrid_workspace_bytes": (_SZ, [_I64]),
+    "den_occgrid_workspace_init": (_INT, [_P, _I64, _P]),
+    "den_occgrid_ema_update": (_INT, [_P, _P, _P, _I64, _F, _F, _P, _I64, _P, _P, _P, _P]),
     "den_rays_from_trajectory": (_INT, [_P, _P, _I64, _P, _P, _P, _I32, _c.POINTER(_F), _P, _P, _I64,
                                         _P]),
     "den_adam_step": (_INT, [_c.POINTER(AdamTensor), _I32, _c.c_double, _c.c_double, _c.c_double, _I64, _P]),

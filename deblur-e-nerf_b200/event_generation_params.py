@@ -81,7 +81,7 @@ class RefractoryPeriod(torch.nn.Module):
         tau = torch.from_numpy(np.asarray(calib["refractory_period"]))
         if max_refractory_period is None:
             path = os.path.join(dataset_directory, "max_refractory_period.pt")
-            max_refractory_period = torch.load(path)
+            max_refractory_period = torch.load(path, weights_only=True)     # a 0-d tensor
         tau_max = torch.as_tensor(max_refractory_period)
         if not (0 <= tau < tau_max):
             warnings.warn(f"Calibrated refractory period ({tau}) >= max. possible ({tau_max}).")

@@ -61,29 +61,53 @@ def freeze_like_synthetic_yaml(model):
     return model
 
 
+# configs/train/*.yaml `optimizer.lr` (synthetic.yaml:146-157): per-parameter learning rates of the
+# multi-parameter components, in YAML order (the order fixes the optimizer's group indices)
+COMPONENT_LR = {
+    "contrast_threshold": {"p2n_contrast_threshold_ratio": 0.1, "mean_contrast_threshold": 0.1},
+    "pixel_bandwidth": {"tau_mil_it_eff_prod": 0.01, "A_amp_inv": 0.01, "A_loop_inv": 0.01,
+                        "tau_out": 0.01, "tau_sf": 0.01, "tau_diff": 0.01},
+}
+
+
+def optimizer_param_groups(model, weight_decay=1e-6, refractory_relative_lr=50.0, component_lr=None):
+    """The parameter groups of DeblurENeRF.configure_optimizers (models/deblur_e_nerf.py:1055-1090),
+    group for group: [0] the refractory-period parameters at lr = tau_max * relative_lr, [1] every
+    parameter named `nerf.radiance_field.mlp*` (hash table included) with the weight decay, then ONE
+    group per `.original` parameter of each multi-parameter component (contrast threshold, and the
+    pixel bandwidth when enabled) with its own lr in YAML order, then the remaining parameters.
+    Frozen parameters stay in their groups like upstream (Adam skips parameters without a gradient), so
+    `optimizer.load_state_dict` of a reference checkpoint finds the group layout it saved.  The last
+    group is a `set` difference upstream (unordered); here it follows `named_parameters()`."""
+    component_lr = COMPONENT_LR if component_lr is None else component_lr
+    tau_lr = float(model.refractory_period.max_refractory_period) * refractory_relative_lr
+    groups = [
+        dict(params=list(model.refractory_period.parameters()), lr=tau_lr),
+        dict(params=[p for n, p in model.named_parameters()
+                     if n.startswith("nerf.radiance_field.mlp")], weight_decay=weight_decay),
+    ]
+    for component in ("contrast_threshold", "pixel_bandwidth"):      # MULTI_PARAM_MODEL_COMPONENTS
+        module = getattr(model, component, None)
+        if module is None:
+            continue
+        for name, lr in component_lr.get(component, {}).items():
+            if not hasattr(module.parametrizations, name):
+                if component == "contrast_threshold" and name == "mean_contrast_threshold":
+                    continue        # only a parameter when `parameterize_mean_ct` is true (yaml:149)
+                raise AttributeError(f"{component} has no parametrized `{name}`")
+            groups.append(dict(params=[getattr(module.parametrizations, name).original], lr=lr))
+    taken = {id(p) for g in groups for p in g["params"]}
+    groups.append(dict(params=[p for p in model.parameters() if id(p) not in taken]))
+    assert sum(len(g["params"]) for g in groups) == len(list(model.parameters()))
+    return groups
+
+
 def configure_optimizer(model, lr=0.01, weight_decay=1e-6, refractory_relative_lr=50.0,
                         component_lr=None, fused=None):
-    """Adam with the reference's groups: tau at lr = tau_max * 50; every parameter whose name
-    starts with `nerf.radiance_field.mlp` (this includes the hash table) gets weight decay
-    1e-6; C_p / Omega `.original` parameters get their own lr; the rest default."""
-    component_lr = component_lr or {"contrast_threshold": 0.1, "pixel_bandwidth": 0.01}
-    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-    groups, taken = [], set()
-
-    def take(pred, **opts):
-        params = [p for n, p in named if pred(n) and id(p) not in taken]
-        taken.update(id(p) for p in params)
-        if params:
-            groups.append(dict(params=params, **opts))
-
-    tau_lr = float(model.refractory_period.max_refractory_period) * refractory_relative_lr
-    take(lambda n: n.startswith("refractory_period."), lr=tau_lr)
-    take(lambda n: n.startswith("nerf.radiance_field.mlp"), weight_decay=weight_decay)
-    for comp, comp_lr in component_lr.items():
-        take(lambda n, c=comp: n.startswith(c + "."), lr=comp_lr)
-    take(lambda n: True)
+    """Adam over `optimizer_param_groups` (den_adam_step through optim.FusedAdam on CUDA)."""
+    groups = optimizer_param_groups(model, weight_decay, refractory_relative_lr, component_lr)
     if fused is None:
-        fused = all(p.is_cuda for _, p in named)
+        fused = all(p.is_cuda for p in model.parameters())
     if fused:
         from .optim import FusedAdam          # den_adam_step: two launches per step
         return FusedAdam(groups, lr=lr)

@@ -1,6 +1,6 @@
 """B2 host mirror of ``Loss`` (loss_metric/loss.py:8-96): per-event Huber / L1 / MSE on the
 normalised log-intensity difference + the TV term, masked means.  Masked means are written
-as sum(err * mask) / sum(mask) so no host synchronisation is needed (the reference's
+as sum(where(mask, err, 0)) / sum(mask) so no host synchronisation is needed (the reference's
 boolean indexing syncs twice)."""
 
 import torch
@@ -40,8 +40,11 @@ class Loss(torch.nn.Module):
 
     @staticmethod
     def _masked_mean(err, mask):
-        m = mask.to(err.dtype)
-        return (err * m).sum() / m.sum()
+        # the reference indexes `err[is_valid]` (loss_metric/loss.py:80,94): a non-finite error at an
+        # invalid event must not reach the loss or its gradient, so masked-out entries are replaced
+        # (torch.where routes a zero gradient to them), not multiplied by zero
+        kept = torch.where(mask, err, torch.zeros_like(err))
+        return kept.sum() / mask.sum().to(err.dtype)
 
     def compute(self, batch_event, batch_diff=None, batch_subdiff=None,
                 mean_contrast_threshold=None):

@@ -105,20 +105,17 @@ class NeRF(torch.nn.Module):
 
     # ---------------------------------------------------------------- occupancy ------
     def update_occ_grid(self, step, T_wc_position=None):
-        """models/nerf.py:170-204: density * step size per cell through the fused density
-        kernel; EMA-max + threshold as upstream."""
+        """models/nerf.py:170-204: density (fused gather + MLP kernel) times the cone-aware step
+        size per drawn cell (`den_occgrid_occ`), handed to the grid's EMA-max / threshold kernels."""
         def occ_eval_fn(x):
+            camera_ids = None
             if self.cone_angle > 0.0:
+                # the reference's draw (models/nerf.py:177-180), after the grid's own draws
                 camera_ids = torch.randint(0, len(T_wc_position), (x.shape[0],),
                                            device=T_wc_position.device)
-                t = (T_wc_position[camera_ids, :] - x).norm(dim=-1, keepdim=True)
-                step_size = torch.clamp(t * self.cone_angle, min=self.render_step_size)
-                if self.near_plane is not None and self.far_plane is not None:
-                    step_size = torch.where((t > self.near_plane) & (t < self.far_plane),
-                                            step_size, torch.zeros_like(step_size))
-            else:
-                step_size = self.render_step_size
-            return self.radiance_field.density_at(x) * step_size
+            sigma = self.radiance_field.density_at(x)
+            return ops.occgrid_occ(sigma, x, camera_ids, T_wc_position, self.cone_angle,
+                                   self._step_host, self.near_plane, self.far_plane)[:, None]
 
         self.occupancy_grid.every_n_step(
             step, occ_eval_fn, _get(self.occ_grid_config, "occ_thre"),

@@ -36,101 +36,82 @@ class ContractionType(enum.Enum):
 
 
 # --------------------------------------------------------------------------- #
-def contract_inv(x, roi, type=ContractionType.AABB):
-    """Unit cube -> world (nerfacc helpers_contraction.h; used by the grid update).
-
-    Elementwise torch ops on (n_cells, 3): the heavy part of the occupancy update is
-    the density query, which runs on the den_b200 field kernels.
-    """
-    roi_min, roi_max = roi[:3], roi[3:]
-    if type == ContractionType.AABB:
-        u = x
-    elif type == ContractionType.UN_BOUNDED_TANH:
-        u = torch.atanh((x - 0.5) * 2.0) + 0.5
-    elif type == ContractionType.UN_BOUNDED_SPHERE:
-        u = (x - 0.5) * 4.0
-        norm = torch.sqrt((u[..., 0] * u[..., 0] + u[..., 1] * u[..., 1]) + u[..., 2] * u[..., 2])
-        outside = norm > 1.0
-        safe = torch.where(outside, norm, torch.ones_like(norm))
-        warped = (u / safe[..., None]) * (1.0 / (2.0 - safe))[..., None]
-        u = torch.where(outside[..., None], warped, u)
-        u = u * 0.5 + 0.5
-    else:
-        raise ValueError(type)
-    return u * (roi_max - roi_min) + roi_min
-
-
 class OccupancyGrid(torch.nn.Module):
-    """nerfacc ``OccupancyGrid`` (grid.py): same buffers / state-dict keys / update rule."""
+    """``nerfacc.OccupancyGrid`` (grid.py): the same constructor, buffers /
+    state-dict keys (``_roi_aabb, resolution, occs, _binary, grid_coords, grid_indices``),
+    properties and ``every_n_step`` / ``_update`` contract, evaluated by the
+    ``den_occgrid_*`` kernels: one launch turns the drawn cells + jitter into world points
+    (``grid_coords`` gather, jitter, divide, ball test, inverse contraction upstream), three more
+    apply the EMA-max, the fp64 mean and the threshold.  The random draws are torch calls in
+    upstream order — ``randint`` (uniform cells), [``randint`` (occupied sub-sample)],
+    ``rand_like`` (jitter) — so the Philox stream is consumed as upstream consumes it."""
 
     NUM_DIM = 3
 
     def __init__(self, roi_aabb, resolution=128, contraction_type=ContractionType.AABB):
         super().__init__()
-        if isinstance(resolution, int):
-            resolution = [resolution] * self.NUM_DIM
-        if isinstance(resolution, (list, tuple)):
-            resolution = torch.tensor(resolution, dtype=torch.int32)
-        if isinstance(roi_aabb, (list, tuple)):
-            roi_aabb = torch.tensor(roi_aabb, dtype=torch.float32)
-        assert isinstance(resolution, torch.Tensor) and resolution.shape == (self.NUM_DIM,)
-        assert isinstance(roi_aabb, torch.Tensor) and roi_aabb.shape == (2 * self.NUM_DIM,)
+        res = [resolution] * self.NUM_DIM if isinstance(resolution, int) else \
+            [int(r) for r in (resolution.tolist() if torch.is_tensor(resolution) else resolution)]
+        roi = roi_aabb.tolist() if torch.is_tensor(roi_aabb) else list(roi_aabb)
+        if len(res) != self.NUM_DIM or len(roi) != 2 * self.NUM_DIM:
+            raise AssertionError("resolution must have 3 entries and roi_aabb 6")
         self._contraction_type = contraction_type
-        self.num_cells = int(resolution.prod().item())
-        self._res_host = [int(r) for r in resolution.tolist()]
-        self._roi_host = [float(v) for v in roi_aabb.tolist()]
-        self.register_buffer("_roi_aabb", roi_aabb.to(torch.float32))
-        self.register_buffer("resolution", resolution)
+        self._res_host = res
+        self._roi_host = [float(v) for v in roi]
+        self.num_cells = res[0] * res[1] * res[2]
+        self.register_buffer("_roi_aabb", torch.tensor(self._roi_host, dtype=torch.float32))
+        self.register_buffer("resolution", torch.tensor(res, dtype=torch.int32))
         self.register_buffer("occs", torch.zeros(self.num_cells))
-        self.register_buffer("_binary", torch.zeros(self._res_host, dtype=torch.bool))
-        coords = torch.stack(torch.meshgrid(
-            [torch.arange(r) for r in self._res_host], indexing="ij"), dim=-1)
-        self.register_buffer("grid_coords", coords.reshape(self.num_cells, self.NUM_DIM))
+        self.register_buffer("_binary", torch.zeros(res, dtype=torch.bool))
+        # checkpoint keys of upstream; the kernels derive the lattice coordinates from the index
+        axes = [torch.arange(r) for r in res]
+        self.register_buffer("grid_coords", torch.cartesian_prod(*axes).reshape(self.num_cells, 3))
         self.register_buffer("grid_indices", torch.arange(self.num_cells))
+        self._desc = ops.make_occgrid_desc(self._roi_host, res, contraction_type.to_cpp_version())
 
-    @property
-    def roi_aabb(self):
-        return self._roi_aabb
+    roi_aabb = property(lambda self: self._roi_aabb)
+    binary = property(lambda self: self._binary)
+    contraction_type = property(lambda self: self._contraction_type)
+    device = property(lambda self: self.occs.device)
 
-    @property
-    def binary(self):
-        return self._binary
+    # the three draws of an update, overridable per instance (the parity tests inject the oracle's)
+    def _draw_randint(self, high, n):
+        return torch.randint(high, (n,), device=self.device)
 
-    @property
-    def contraction_type(self):
-        return self._contraction_type
-
-    @property
-    def device(self):
-        return self.occs.device
+    def _draw_jitter(self, n):
+        return torch.rand((n, self.NUM_DIM), dtype=torch.float32, device=self.device)
 
     @torch.no_grad()
     def _sample_uniform_and_occupied_cells(self, n):
-        uniform = torch.randint(self.num_cells, (n,), device=self.device)
+        uniform = self._draw_randint(self.num_cells, n)
         occupied = torch.nonzero(self._binary.flatten())[:, 0]
         if n < len(occupied):
-            pick = torch.randint(len(occupied), (n,), device=self.device)
-            occupied = occupied[pick]
+            occupied = occupied[self._draw_randint(len(occupied), n)]
         return torch.cat([uniform, occupied], dim=0)
 
     @torch.no_grad()
     def _update(self, step, occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256):
+        if not self.occs.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")
         if step < warmup_steps:
-            indices = self.grid_indices
+            indices, n = None, self.num_cells          # every cell, in order
         else:
             indices = self._sample_uniform_and_occupied_cells(self.num_cells // 4)
-        coords = self.grid_coords[indices]
-        x = (coords + torch.rand_like(coords, dtype=torch.float32)) / self.resolution
-        if self._contraction_type == ContractionType.UN_BOUNDED_SPHERE:
-            inside = (x - 0.5).norm(dim=1) < 0.5
-            x = x[inside]
-            indices = indices[inside]
-        x = contract_inv(x, roi=self._roi_aabb, type=self._contraction_type)
+            n = indices.numel()
+        sphere = self._contraction_type == ContractionType.UN_BOUNDED_SPHERE
+        x, keep = ops.occgrid_cell_points(self._desc, indices, self._draw_jitter(n), sphere)
+        if sphere:
+            # upstream hands occ_eval_fn only the points inside the unit ball (its own draws
+            # depend on that count): compact like upstream does
+            kept = torch.nonzero(keep)[:, 0]
+            x = x[kept]
+            indices = kept if indices is None else indices[kept]
         occ = occ_eval_fn(x).squeeze(-1)
-        self.occs[indices] = torch.maximum(self.occs[indices] * ema_decay, occ)
-        self._binary = (
-            self.occs > torch.clamp(self.occs.mean(), max=occ_thre)
-        ).view(self._binary.shape)
+        binary = self._binary if (self._binary.is_contiguous() and self._binary.is_cuda) \
+            else torch.empty(self._res_host, dtype=torch.bool, device=self.device)
+        self.last_mean = ops.occgrid_ema_update(indices, occ.float(), self.occs,
+                                                binary.view(torch.uint8), ema_decay, occ_thre)
+        self._binary = binary
 
     @torch.no_grad()
     def every_n_step(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95,
@@ -140,7 +121,7 @@ class OccupancyGrid(torch.nn.Module):
                 "You should only call this function only during training. "
                 "Please call _update() directly if you want to update the "
                 "field during inference.")
-        if step % n == 0 and self.training:
+        if step % n == 0:
             self._update(step=step, occ_eval_fn=occ_eval_fn, occ_thre=occ_thre,
                          ema_decay=ema_decay, warmup_steps=warmup_steps)
 

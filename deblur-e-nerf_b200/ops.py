@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HashGridDesc, MarchParams
+from ._lib import HashGridDesc, MarchParams, OccGridDesc
 
 _LAUNCHES = 0           # kernels launched through the C ABI (bench.py reports it)
 
@@ -407,6 +407,78 @@ def offsets_from_ray_indices(ray_indices, n_rays):
     """(R+1) int32 packing offsets of a sorted ``ray_indices`` (B1 callers pass indices)."""
     counts = torch.bincount(ray_indices.long(), minlength=n_rays).to(torch.int32)
     return exclusive_scan_i32(counts)
+
+
+# --------------------------------------------------------------------------- #
+# occupancy-grid update
+# --------------------------------------------------------------------------- #
+def make_occgrid_desc(roi, res, contraction):
+    d = OccGridDesc()
+    for i in range(6):
+        d.roi[i] = float(roi[i])
+    for i in range(3):
+        d.res[i] = int(res[i])
+    d.contraction = int(contraction)
+    return d
+
+
+def occgrid_cell_points(desc, indices, jitter, want_keep):
+    """Cell indices (n,) int64 or None (= every cell in order) + jitter (n,3) -> world points (n,3)
+    and, if asked, the mask of the points upstream keeps (sphere contraction: inside the unit ball)."""
+    jitter = _req(jitter, torch.float32, "jitter")
+    n = jitter.shape[0]
+    if indices is not None:
+        indices = _req(indices, torch.int64, "indices")
+        assert indices.numel() == n
+    world = torch.empty((n, 3), dtype=torch.float32, device=jitter.device)
+    keep = torch.empty(n, dtype=torch.uint8, device=jitter.device) if want_keep else None
+    _call("den_occgrid_cell_points", ctypes.byref(desc), _ptr(indices), _ptr(jitter), n, _ptr(world),
+          _ptr(keep), _stream())
+    return world, keep
+
+
+def occgrid_occ(sigma, world, camera_ids, camera_pos, cone_angle, step_size, near_plane, far_plane):
+    """density -> density * step size of the cell (models/nerf.py:175-198)."""
+    sigma = _req(sigma.reshape(-1), torch.float32, "sigma")
+    n = sigma.numel()
+    occ = torch.empty_like(sigma)
+    has_planes = near_plane is not None and far_plane is not None
+    if cone_angle > 0.0:
+        world = _req(world, torch.float32, "world")
+        camera_ids = _req(camera_ids, torch.int64, "camera_ids")
+        camera_pos = _req(camera_pos, torch.float32, "camera_pos")
+    _call("den_occgrid_occ", _ptr(sigma), _ptr(world) if cone_angle > 0.0 else None,
+          _ptr(camera_ids) if cone_angle > 0.0 else None,
+          _ptr(camera_pos) if cone_angle > 0.0 else None, float(cone_angle),
+          float(np.float32(step_size)), int(has_planes), float(near_plane or 0.0),
+          float(far_plane or 0.0), n, _ptr(occ), _stream())
+    return occ
+
+
+_OCC_WS = {}        # (device, n_cells) -> initialised workspace
+
+
+def occgrid_ema_update(indices, occ, occs, binary_u8, ema_decay, occ_thre):
+    """occs[indices] = max(occs[indices] * decay, occ); binary = occs > min(mean(occs), thre).
+    Returns mean(occs) as a device scalar."""
+    occ = _req(occ.reshape(-1), torch.float32, "occ")
+    occs = _req(occs, torch.float32, "occs")
+    n_cells = occs.numel()
+    if indices is not None:
+        indices = _req(indices, torch.int64, "indices")
+        assert indices.numel() == occ.numel()
+    key = (occs.device, n_cells)
+    ws = _OCC_WS.get(key)
+    if ws is None:
+        nbytes = _lib.lib().raw("den_occgrid_workspace_bytes")(n_cells)
+        ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=occs.device)
+        _call("den_occgrid_workspace_init", _ptr(ws), n_cells, _stream())
+        _OCC_WS[key] = ws
+    mean = torch.empty((), dtype=torch.float32, device=occs.device)
+    _call("den_occgrid_ema_update", _ptr(indices), None, _ptr(occ), occ.numel(), float(ema_decay),
+          float(np.float32(occ_thre)), _ptr(occs), n_cells, _ptr(binary_u8), _ptr(mean), _ptr(ws),
+          _stream(), launches=3)
+    return mean
 
 
 # --------------------------------------------------------------------------- #

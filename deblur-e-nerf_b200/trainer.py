@@ -77,8 +77,13 @@ class Trainer:
         torch.save(self.checkpoint(model, optimizer, scheduler), tmp)
         os.replace(tmp, path)           # a crash never leaves a truncated checkpoint behind
 
-    def load_checkpoint(self, path, model, optimizer=None, scheduler=None, strict=True):
-        ckpt = torch.load(path, map_location=next(model.parameters()).device, weights_only=False)
+    def load_checkpoint(self, path, model, optimizer=None, scheduler=None, strict=True,
+                        trust_pickle=False):
+        """Checkpoints are loaded with `weights_only=True` (tensors and plain containers only): a
+        public checkpoint cannot run code on load.  A Lightning checkpoint that pickles other objects
+        (e.g. hyper-parameter containers) needs the explicit `trust_pickle=True`."""
+        ckpt = torch.load(path, map_location=next(model.parameters()).device,
+                          weights_only=not trust_pickle)
         model.load_state_dict(ckpt["state_dict"], strict=strict)
         if optimizer is not None and ckpt.get("optimizer_states"):
             optimizer.load_state_dict(ckpt["optimizer_states"][0])

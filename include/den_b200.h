@@ -132,6 +132,40 @@ int den_march_pack(const int32_t* seg_offsets, const int32_t* offsets, const flo
                    const float* arena_t1, int64_t n_rays, int32_t* ray_indices, float* t_starts,
                    float* t_ends, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Occupancy-grid update — replaces nerfacc.OccupancyGrid._update (grid.py)
+ * as called through every_n_step at models/nerf.py:200-204, and the cone-aware
+ * occ_eval_fn of NeRF.update_occ_grid (models/nerf.py:171-198).  The random draws (cell
+ * indices, jitter, camera ids) are made by the caller in upstream order and passed in.
+ * ------------------------------------------------------------------------- */
+typedef struct den_occgrid_desc {
+    float roi[6];                       /* grid.roi_aabb */
+    int32_t res[3];                     /* grid.resolution */
+    int32_t contraction;                /* den_contraction */
+} den_occgrid_desc;
+
+/* point i: cell = indices ? indices[i] : i (x-slowest flat index); unit = (coords + jitter[i]) /
+ * res; world[i] = contract_inv(unit) (AABB: unit_to_roi; sphere: v = 4(unit - 0.5), n > 1:
+ * v /= max(2n - n^2, 1e-10)); keep[i] (may be NULL) = sphere ? ||unit - 0.5|| < 0.5 : 1 */
+int den_occgrid_cell_points(const den_occgrid_desc* g, const int64_t* indices, const float* jitter,
+                            int64_t n, float* world, uint8_t* keep, void* stream);
+/* occ[i] = sigma[i] * step_i; cone_angle > 0: t = ||camera_pos[camera_ids[i]] - world[i]||,
+ * step_i = max(t * cone_angle, step_size), 0 outside (near, far) when has_planes; else step_size */
+int den_occgrid_occ(const float* sigma, const float* world, const int64_t* camera_ids,
+                    const float* camera_pos, float cone_angle, float step_size, int has_planes,
+                    float near_plane, float far_plane, int64_t n, float* occ, void* stream);
+/* occs[cell] = max(occs[cell] * ema_decay, occ) over the n points (duplicates: the largest
+ * candidate wins — one of the outcomes of upstream's unordered indexed assignment; points with
+ * keep[i] == 0 are skipped), then binary = occs > min(mean(occs), occ_thre) with the mean
+ * accumulated in fp64 in a fixed order; mean_out (device, may be NULL) receives mean(occs).
+ * workspace: den_occgrid_workspace_bytes(n_cells), initialised ONCE by den_occgrid_workspace_init
+ * (the update leaves it ready for the next call). */
+size_t den_occgrid_workspace_bytes(int64_t n_cells);
+int den_occgrid_workspace_init(void* workspace, int64_t n_cells, void* stream);
+int den_occgrid_ema_update(const int64_t* indices, const uint8_t* keep, const float* occ, int64_t n,
+                           float ema_decay, float occ_thre, float* occs, int64_t n_cells,
+                           uint8_t* binary, float* mean_out, void* workspace, void* stream);
+
 /* Timestamps + pixels -> rays: LinearTrajectory.forward (models/trajectories.py:30-90: searchsorted,
  * f64 weight, LERP, shortest-path SLERP via utils/tensor_ops.py:118-184, quaternion -> R) fused with
  * NeRF.pixel_params_to_ray (models/nerf.py:206-228).  timestamps (n_rays) f64 ns; ray i looks through

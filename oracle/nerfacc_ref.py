@@ -51,6 +51,9 @@ def _roi_split(roi):
     return roi[:3], roi[3:]
 
 
+SPHERE_INV_EPS = 1e-10      # helpers_contraction.h: fmaxf(2n - n^2, 1e-10f) in the sphere inverse
+
+
 def _dot3(u):
     return (u[..., 0] * u[..., 0] + u[..., 1] * u[..., 1]) + u[..., 2] * u[..., 2]
 
@@ -82,12 +85,12 @@ def contract_inv(x, roi, type=ContractionType.AABB):
     elif type == ContractionType.UN_BOUNDED_TANH:
         u = torch.atanh((x - 0.5) * 2.0) + 0.5
     elif type == ContractionType.UN_BOUNDED_SPHERE:
+        # helpers_contraction.h `unit_sphere_to_inf`: v / max(2n - n^2, eps)
         u = (x - 0.5) * 4.0
-        norm = torch.sqrt(_dot3(u))
-        outside = norm > 1.0
-        safe = torch.where(outside, norm, torch.ones_like(norm))
-        warped = (u / safe[..., None]) * (1.0 / (2.0 - safe))[..., None]
-        u = torch.where(outside[..., None], warped, u)
+        norm_sq = _dot3(u)
+        norm = torch.sqrt(norm_sq)
+        denom = torch.clamp(2.0 * norm - norm_sq, min=SPHERE_INV_EPS)
+        u = torch.where((norm > 1.0)[..., None], u / denom[..., None], u)
         u = u * 0.5 + 0.5
     else:
         raise ValueError(type)
