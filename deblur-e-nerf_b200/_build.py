@@ -21,6 +21,9 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libden_b200.so")
 STAMP = os.path.join(LIB_DIR, "libden_b200.stamp")
+# test-only probe kernels (tests/csrc/*.cu): built into their own library, never into the product's
+PROBE_SRC_DIR = os.path.join(REPO_ROOT, "tests", "csrc")
+PROBE_LIB_PATH = os.path.join(LIB_DIR, "libden_b200_probe.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,13 +47,18 @@ def _sources():
 
 
 def _digest():
+    """Content hash of flags + sources; file names enter RELATIVE to the repository root so the
+    snapshot copied to another directory (the GPU box) still matches its stamp."""
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
     files = _sources() + sorted(
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files += [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
+    if os.path.isdir(PROBE_SRC_DIR):
+        files += sorted(os.path.join(PROBE_SRC_DIR, f) for f in os.listdir(PROBE_SRC_DIR)
+                        if f.endswith(".cu"))
     for path in files:
-        h.update(path.encode())
+        h.update(os.path.relpath(path, REPO_ROOT).encode())
         with open(path, "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -61,6 +69,10 @@ def is_current():
         return False
     with open(STAMP) as fh:
         return fh.read().strip() == _digest()
+
+
+def have_nvcc():
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
 
 
 def _compile(src, verbose):
@@ -80,16 +92,22 @@ def build(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = _sources()
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as pool:
-        results = list(pool.map(lambda s: _compile(s, verbose), srcs))
+    probes = sorted(os.path.join(PROBE_SRC_DIR, f) for f in os.listdir(PROBE_SRC_DIR)
+                    if f.endswith(".cu")) if os.path.isdir(PROBE_SRC_DIR) else []
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(12, len(srcs) + len(probes))) as pool:
+        results = list(pool.map(lambda s: _compile(s, verbose), srcs + probes))
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
-    objs = [o for o, _ in results]
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    objs = [o for o, _ in results[:len(srcs)]]
+    for out, members in ((LIB_PATH, objs),
+                         (PROBE_LIB_PATH, [o for o, _ in results[len(srcs):]]
+                          + [os.path.join(OBJ_DIR, "den_api.o")])):
+        if out == PROBE_LIB_PATH and not probes:
+            continue
+        res = subprocess.run([_nvcc(), "-shared", "-o", out, *members], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     with open(STAMP, "w") as fh:
         fh.write(_digest())
     return LIB_PATH

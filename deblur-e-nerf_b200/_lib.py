@@ -113,7 +113,6 @@ _SIGNATURES = {
     "den_contract_samples": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _I64, _P, _P]),
     "den_mlp_fwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _P, _P, _P, _P, _P, _P,
                            _I64, _P, _P, _P]),
-    "den_tc_probe_gemm": (_INT, [_INT, _P, _P, _P, _INT, _INT, _P]),
     "den_mlp_bwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _c.POINTER(FieldGrads),
                            _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "den_contract_samples_bwd": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _I64, _P,
@@ -146,6 +145,14 @@ class _Library:
                 f"{path} is missing: the CUDA extension has not been built. Run "
                 "`python -c 'import __graft_entry__ as g; g.build()'` — there is no "
                 "CPU or PyTorch fallback for the den_b200 kernels.")
+        # a library older than its sources must not be used silently: rebuild where nvcc exists,
+        # otherwise refuse (DEN_ALLOW_STALE_LIB=1 overrides, for debugging only)
+        if not _build.is_current() and os.environ.get("DEN_ALLOW_STALE_LIB") != "1":
+            if not _build.have_nvcc():
+                raise DenError(
+                    f"{path} is stale (csrc/ or include/ changed since it was built) and nvcc is "
+                    "not available to rebuild it; there is no CPU or PyTorch fallback.")
+            _build.build()
         self.path = path
         self.cdll = _c.CDLL(path)
         for name, (restype, argtypes) in _SIGNATURES.items():

@@ -335,11 +335,6 @@ int den_lpf_bwd(const float* intensity, const float* sample_dt_ns, const double*
                 int64_t N, int32_t n_channels, const float* d_out, float* d_intensity,
                 double* d_coef, void* stream);
 
-/* Diagnostic: one tcgen05 GEMM in each operand-major flavour the MLP kernels use (see
- * csrc/den_tc_probe.cu); pinned by tests/test_gpu_mlp_tc.py. */
-int den_tc_probe_gemm(int mode, const float* x, const float* w, float* d, int n, int k,
-                      void* stream);
-
 /* ------------------------------------------------------------------------- *
  * Optimiser — replaces torch.optim.Adam as set up by DeblurENeRF.configure_optimizers
  * (models/deblur_e_nerf.py:1055-1112) for the fp32 parameters: one step t (1-based) of

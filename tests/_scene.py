@@ -80,7 +80,8 @@ def make_batch(cfg, poses, n_events, it_sample_size, seed, pixel_bandwidth=True)
 # --------------------------------------------------------------------------- #
 # the reference's own modules (build container only)
 # --------------------------------------------------------------------------- #
-def build_reference_renderer(cfg, it_sample_size=8, pixel_bandwidth=True, seed=0, n_poses=200):
+def build_reference_renderer(cfg, it_sample_size=8, pixel_bandwidth=True, seed=0, n_poses=200,
+                             freeze_refractory_period=True, accumulate_grad_batches=1):
     from oracle import ref_shim
     ref_shim.load_lightning_module()
     import easydict
@@ -124,10 +125,11 @@ def build_reference_renderer(cfg, it_sample_size=8, pixel_bandwidth=True, seed=0
         min_modeled_intensity=0.001,
         pixel_bandwidth=dict(enable=pixel_bandwidth, it_sample_size=it_sample_size),
         loss=loss_cfg,
-        refractory_period=dict(freeze=True),
+        refractory_period=dict(freeze=freeze_refractory_period),
         nerf=dict(),
     )
     module = ref_shim.make_reference_module(hparams, components)
+    module.trainer.accumulate_grad_batches = accumulate_grad_batches
     module.render_bkgd = cfg["render_bkgd"]
     module.register_buffer("train_intrinsics_inv",
                            torch.linalg.inv(torch.from_numpy(synthetic.intrinsics(cfg))),

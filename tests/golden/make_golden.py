@@ -3,7 +3,7 @@ oracle/ref_shim, CPU fp32).  Build container only (needs /root/reference):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{training_step_pb_on,training_step_pb_off,field_small}.npz.  Each
+Writes tests/golden/{training_step_pb_on,training_step_pb_off,training_step_eds,field_small}.npz.  Each
 file carries the parameters, the inputs (events, normalised samples, the stratified
 jitter the reference drew, the occupancy grid after its step-0 update) and the
 reference's outputs (loss, loss terms, mean samples per ray, every parameter gradient),
@@ -71,6 +71,54 @@ def training_step_golden(pb_on, path):
           f"{len(jitters)} render calls")
 
 
+def training_step_eds_golden(path, n_micro=2):
+    """08_peanuts_running.yaml shape: sphere contraction, cone angle 0.004, no background
+    (validity = opacity > 0), pixel bandwidth on, `refractory_period.freeze: false` and the
+    contrast-threshold / pixel-bandwidth parameters trainable (:31-55), `accumulate_grad_batches`
+    micro-batches whose gradients are accumulated with loss / n (models/deblur_e_nerf.py:465-469,
+    Lightning's accumulation)."""
+    cfg = _scene.scene_config("eds", occ_resolution=32, small=True)
+    ref, poses = _scene.build_reference_renderer(cfg, IT_SAMPLE_SIZE, pixel_bandwidth=True,
+                                                 freeze_refractory_period=False,
+                                                 accumulate_grad_batches=n_micro)
+    ref.train()
+    ref.zero_grad()
+    out = {"n_micro": np.asarray(n_micro)}
+    torch.manual_seed(13)
+    for m in range(n_micro):
+        event, normalized = _scene.make_batch(cfg, poses, N_EVENTS, IT_SAMPLE_SIZE, seed=21 + m,
+                                              pixel_bandwidth=True)
+        nerfacc_ref.JITTER_LOG = []
+        loss = ref.training_step(_scene.reference_batch(event, normalized), m)
+        jitters = nerfacc_ref.JITTER_LOG
+        nerfacc_ref.JITTER_LOG = None
+        (loss / n_micro).backward()
+        out[f"loss/{m}"] = _np(loss)
+        for key, value in ref.logged.items():
+            if key.startswith("train/log_intensity") or key in ("train/mean_num_samples_per_ray",
+                                                                 "train/mean_valid_rate"):
+                out[f"logged/{m}/{key}"] = np.asarray(float(value))
+        for key, value in event.items():
+            out[f"event/{m}/{key}"] = _np(value)
+        for key, value in normalized.items():
+            out[f"normalized/{m}/{key}"] = _np(value)
+        for i, jit in enumerate(jitters):
+            out[f"jitter/{m}/{i}"] = _np(jit)
+        if m == 0:
+            # parameters are untouched between the micro-batches; the grid was updated once (batch 0)
+            for name in ("nerf", "contrast_threshold", "refractory_period", "pixel_bandwidth"):
+                for key, value in getattr(ref, name).state_dict().items():
+                    if key.rsplit(".", 1)[-1] in SKIP_BUFFERS:
+                        continue
+                    out[f"state/{name}/{key}"] = _np(value)
+    for key, value in _scene.flat_named_grads(ref).items():
+        out["grad/" + key] = _np(value)
+    np.savez_compressed(path, **out)
+    print(path, "losses", [float(out[f"loss/{m}"]) for m in range(n_micro)],
+          f"{os.path.getsize(path) / 1e6:.2f} MB", "mean samples/ray",
+          [float(out[f"logged/{m}/train/mean_num_samples_per_ray"]) for m in range(n_micro)])
+
+
 def field_golden(path):
     cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
     ref, _ = _scene.build_reference_renderer(cfg, IT_SAMPLE_SIZE, pixel_bandwidth=False)
@@ -99,3 +147,4 @@ if __name__ == "__main__":
     training_step_golden(True, os.path.join(HERE, "training_step_pb_on.npz"))
     training_step_golden(False, os.path.join(HERE, "training_step_pb_off.npz"))
     field_golden(os.path.join(HERE, "field_small.npz"))
+    training_step_eds_golden(os.path.join(HERE, "training_step_eds.npz"))

@@ -136,9 +136,10 @@ def test_nerf_render_with_culled_samples_matches_oracle(den_lib, cuda):
         assert _rel(gp[key], go[key]) < TOL, key
 
 
-def test_occupancy_update_bit_exact_given_same_draws(den_lib, cuda):
-    """Occupancy booleans must match the oracle exactly given identical upstream inputs:
-    the jittered cell positions are injected (CUDA and CPU Philox streams differ)."""
+def test_cell_densities_match_oracle_field(den_lib, cuda):
+    """The fused density kernel of the occupancy update (`den_field_density_at`) against the oracle
+    field at jittered cell centres.  The grid logic itself (draws, EMA, threshold, booleans bit for
+    bit) is pinned by tests/test_gpu_occgrid.py through the product's `every_n_step`."""
     cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
     ora = _scene.build_oracle_nerf(cfg)
     prod = _scene.build_product_nerf(cfg, cuda)
@@ -151,11 +152,6 @@ def test_occupancy_update_bit_exact_given_same_draws(den_lib, cuda):
     occ_o = ora.radiance_field.query_density(world).squeeze(-1) * cfg["step"]
     occ_p = prod.radiance_field.density_at(world.to(cuda)).squeeze(-1).cpu() * cfg["step"]
     assert _rel(occ_p, occ_o) < 1e-4
-    thr = torch.clamp(occ_o.mean(), max=1e-2)
-    # cells whose occupancy sits within fp32 noise of the threshold may flip; none here
-    safe = (occ_o - thr).abs() > 1e-4 * thr
-    assert torch.equal((occ_p > thr)[safe], (occ_o > thr)[safe])
-    assert safe.float().mean() > 0.999
 
 
 def _run_training_step_golden(cuda, pb_on):
@@ -187,6 +183,9 @@ def _run_training_step_golden(cuda, pb_on):
     worst = {}
     for key in ref:
         worst[key] = _rel(grads[key], ref[key])
+    print("golden pb_on" if pb_on else "golden pb_off", "worst relative gradient errors:",
+          {k.split(".")[-2] if k.endswith("original") else k.split("radiance_field.")[-1]: f"{v:.1e}"
+           for k, v in worst.items()})
     bad = {k: v for k, v in worst.items()
            if v > (5e-3 if ("pixel_bandwidth" in k or "refractory" in k) else TOL)}
     assert not bad, bad
@@ -300,3 +299,83 @@ def test_pixel_bandwidth_filter_matches_oracle(den_lib, cuda, S):
 
 def test_training_step_pb_on_matches_reference_golden(den_lib, cuda):
     _run_training_step_golden(cuda, pb_on=True)
+
+
+def test_training_step_eds_two_microbatches_matches_reference_golden(den_lib, cuda):
+    """BASELINE configs[3] shape (08_peanuts_running.yaml:57-70,203): sphere contraction, cone
+    angle 0.004, no background (validity = opacity > 0), pixel bandwidth on, tau / Omega / C_p
+    trainable, `accumulate_grad_batches` micro-batches accumulated with loss / n
+    (models/deblur_e_nerf.py:465-469,1055-1112).  Golden: the reference's own files, CPU fp32.
+    Exercises together: the sphere contraction reverse mode, cone-angle marching, the tau gradient
+    through rays / samples / SH, the Omega gradients of the filter and the C_p gradients."""
+    golden = _scene.load_golden("training_step_eds")
+    n_micro = int(golden["n_micro"])
+    cfg = _scene.scene_config("eds", occ_resolution=32, small=True)
+    model, poses = _scene.build_product_renderer(cfg, cuda, 8, pixel_bandwidth=True)
+    for name in ("nerf", "contrast_threshold", "refractory_period", "pixel_bandwidth"):
+        _scene.load_golden_state(getattr(model, name), golden, name, cuda)
+    model.train()
+    model.accumulate_grad_batches = n_micro
+    model.nerf.update_occ_grid = lambda *a, **k: None      # the golden holds the grid after its update
+    model.zero_grad()
+    for m in range(n_micro):
+        batch = {"event": _scene.golden_section(golden, f"event/{m}", cuda),
+                 "normalized": _scene.golden_section(golden, f"normalized/{m}", cuda)}
+        jitters = [v for _, v in sorted(_scene.golden_section(golden, f"jitter/{m}", cuda).items(),
+                                        key=lambda kv: int(kv[0]))]
+        loss = model.training_step(batch, m, 0, jitters=jitters)
+        assert _rel(loss, golden[f"loss/{m}"]) < TOL, (m, float(loss), float(golden[f"loss/{m}"]))
+        for key in ("log_intensity_diff", "log_intensity_tv"):
+            assert _rel(model.logged[f"train/{key}"], golden[f"logged/{m}/train/{key}"]) < TOL
+        assert abs(model.logged["train/mean_num_samples_per_ray"]
+                   - float(golden[f"logged/{m}/train/mean_num_samples_per_ray"])) < 0.05
+        (loss / n_micro).backward()
+    grads = _scene.flat_named_grads(model)
+    ref = _scene.golden_section(golden, "grad")
+    assert set(ref) <= set(grads), set(ref) - set(grads)
+    worst = {key: _rel(grads[key], ref[key]) for key in ref}
+    print("EDS golden, worst relative gradient errors:",
+          {k.split(".")[-2] if k.endswith("original") else k.split("radiance_field.")[-1]: f"{v:.1e}"
+           for k, v in worst.items()})
+    bad = {k: v for k, v in worst.items() if v > TOL}
+    assert not bad, bad
+
+
+def test_eval_render_of_merged_chunks_matches_oracle(den_lib, cuda):
+    """Eval mode with more rays than `test_chunk_size` (external/utils.py:99-103): the reference
+    renders 16 384-ray chunks; the product merges chunks (first `test_chunk_size` rays, then sized
+    from the samples per ray) — rays are independent and the eval march is deterministic, so the
+    image must be the same.  40 000 rays = three reference chunks."""
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    ora = _scene.build_oracle_nerf(cfg)
+    prod = _scene.build_product_nerf(cfg, cuda)
+    _scene.copy_params(ora, prod)
+    ora.train()
+    prod.train()
+    poses = _scene.synthetic.camera_poses(cfg, n_poses=50)
+    torch.manual_seed(3)
+    ora.update_occ_grid(0, poses[0])
+    prod.occupancy_grid._binary = ora.occupancy_grid.binary.to(cuda)
+    prod.occupancy_grid.occs.copy_(ora.occupancy_grid.occs)
+    ora.eval()
+    prod.eval()
+    n = 40_000
+    assert n > 2 * cfg["test_chunk_size"]
+    traj = _scene.path_ref.LinearTrajectory(*poses)
+    g = torch.Generator().manual_seed(8)
+    ts = torch.full((n,), float(poses[2][20]), dtype=torch.float64)
+    px = torch.stack([torch.rand(n, generator=g) * cfg["width"],
+                      torch.rand(n, generator=g) * cfg["height"]], -1)
+    pos, rot = traj(ts)
+    kinv = torch.linalg.inv(torch.from_numpy(_scene.synthetic.intrinsics(cfg)))
+    o, d = _scene.path_ref.NeRF.pixel_params_to_ray(kinv, px, pos, rot)
+    with torch.no_grad():
+        rad_o, opa_o, dep_o, ms_o = ora(o, d)
+        chunks = []
+        render_chunk = prod.render_chunk
+        prod.render_chunk = lambda o_, d_, *a, **k: (chunks.append(o_.shape[0]), render_chunk(o_, d_, *a, **k))[1]
+        rad_p, opa_p, dep_p, ms_p = prod(o.to(cuda), d.to(cuda))
+    assert len(chunks) >= 2 and max(chunks) > cfg["test_chunk_size"], chunks   # merged chunks were used
+    assert sum(chunks) == n
+    assert abs(ms_p - ms_o) * n <= 3, (ms_p, ms_o)
+    assert _rel(rad_p, rad_o) < TOL and _rel(opa_p, opa_o) < TOL and _rel(dep_p, dep_o) < TOL

@@ -73,8 +73,11 @@ def test_tc_probe_gemm_flavours(den_lib, cuda, mode, n, k):
     xd, wd = x.to(cuda).contiguous(), w.to(cuda).contiguous()
     out = torch.full((rows, n), float("nan"), device=cuda)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    den_lib.call("den_tc_probe_gemm", mode, ctypes.c_void_p(xd.data_ptr()),
-                 ctypes.c_void_p(wd.data_ptr()), ctypes.c_void_p(out.data_ptr()), n, k, stream)
+    from deblur_e_nerf_b200 import _build
+    probe = ctypes.CDLL(_build.PROBE_LIB_PATH)          # test-only kernels, not part of the product .so
+    rc = probe.den_tc_probe_gemm(mode, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(wd.data_ptr()),
+                                 ctypes.c_void_p(out.data_ptr()), n, k, stream)
+    assert rc == 0
     torch.cuda.synchronize()
     assert _rel(out, ref) < 1e-5, (out.cpu()[:2, :4], ref[:2, :4])
 
