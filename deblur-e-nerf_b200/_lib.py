@@ -66,6 +66,11 @@ class AdamTensor(_c.Structure):
                 ("weight_decay", _c.c_float)]
 
 
+class LpfLossDesc(_c.Structure):
+    _fields_ = [("it_sample_size", _I32), ("n_requests", _I32), ("has_reset", _I32),
+                ("error_kind", _I32 * 4), ("has_target", _I32 * 4)]
+
+
 class FieldGrads(_c.Structure):
     _fields_ = [(name, _P) for name in (
         "wb1", "bb1", "wb2", "bb2", "w1", "b1", "w2", "b2", "w3", "b3")]
@@ -119,6 +124,11 @@ _SIGNATURES = {
                                         _P, _P]),
     "den_lpf_fwd": (_INT, [_P, _P, _P, _I32, _I64, _I32, _P, _P]),
     "den_lpf_bwd": (_INT, [_P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
+    "den_lpf_loss_workspace_bytes": (_SZ, [_I32, _I64]),
+    "den_lpf_loss_fwd": (_INT, [_c.POINTER(LpfLossDesc), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P,
+                                _P]),
+    "den_lpf_loss_bwd": (_INT, [_c.POINTER(LpfLossDesc), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P,
+                                _P, _P, _P, _P]),
     "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
 }

@@ -1,5 +1,6 @@
 // Pixel-bandwidth low-pass filter: intensity samples -> band-limited log-intensity, forward and
-// reverse mode, one thread per event, all internal arithmetic in fp64 (sm_100a).
+// reverse mode, all internal arithmetic in fp64 (sm_100a).  S <= 32: one warp per event, one lane per
+// interval (den_lpf_loss.cu); 32 < S <= 64: one thread per event (this file).
 //
 // Replaces PixelBandwidth.intensity_sample_to_weight / linearize_sys / linearized_sys_params /
 // discretized_sys_to_weight / the normalisation half of weighted_it_sample_to_output_log_it
@@ -26,153 +27,9 @@
 // in one descending sweep, then out = sum (w / sum w) log I.
 // Reverse mode: the adjoint of expm is the Frechet derivative at the transposed argument,
 // L(M^T, Gbar), evaluated with the block-triangular pair recurrence (no stored intermediates).
-#include "den_common.cuh"
+#include "den_lpf.cuh"
 
 namespace den {
-
-constexpr int kLpfMaxS = 64;
-constexpr int kLpfThreads = 64;
-constexpr int kTaylor = 12;
-
-struct Mat4 {
-    double m[16];
-};
-
-__device__ __forceinline__ void mat_mul(const double* __restrict__ a, const double* __restrict__ b,
-                                        double* __restrict__ c) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) s = fma(a[4 * i + k], b[4 * k + j], s);
-            c[4 * i + j] = s;
-        }
-}
-
-__device__ __forceinline__ int scaling_power(const double* m) {
-    double norm = 0.0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        double col = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) col += fabs(m[4 * i + j]);
-        norm = fmax(norm, col);
-    }
-    if (!(norm > 0.5)) return 0;
-    int e;
-    frexp(norm, &e);            // norm = f * 2^e, f in [0.5, 1)
-    return min(e + 1, 60);      // ||m / 2^s|| <= 0.5
-}
-
-// E = expm(M)
-__device__ void expm4(const double* M, double* E) {
-    const int s = scaling_power(M);
-    const double sc = ldexp(1.0, -s);
-    double X[16], T[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) X[i] = M[i] * sc;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) E[i] = (i % 5 == 0) ? 1.0 : 0.0;
-    for (int k = kTaylor; k >= 1; --k) {
-        mat_mul(X, E, T);
-        const double inv = 1.0 / k;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) E[i] = ((i % 5 == 0) ? 1.0 : 0.0) + T[i] * inv;
-    }
-    for (int q = 0; q < s; ++q) {
-        mat_mul(E, E, T);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) E[i] = T[i];
-    }
-}
-
-// Lout = L(M^T, G): adjoint of expm at M applied to the output adjoint G
-__device__ void expm4_adjoint(const double* M, const double* G, double* Lout) {
-    const int s = scaling_power(M);
-    const double sc = ldexp(1.0, -s);
-    double X[16], Y[16], E[16], F[16], T1[16], T2[16], T3[16];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) X[4 * i + j] = M[4 * j + i] * sc;      // transpose
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        Y[i] = G[i] * sc;
-        E[i] = (i % 5 == 0) ? 1.0 : 0.0;
-        F[i] = 0.0;
-    }
-    for (int k = kTaylor; k >= 1; --k) {
-        mat_mul(X, E, T1);
-        mat_mul(X, F, T2);
-        mat_mul(Y, E, T3);
-        const double inv = 1.0 / k;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            E[i] = ((i % 5 == 0) ? 1.0 : 0.0) + T1[i] * inv;
-            F[i] = (T2[i] + T3[i]) * inv;
-        }
-    }
-    for (int q = 0; q < s; ++q) {
-        mat_mul(E, F, T1);
-        mat_mul(F, E, T2);
-        mat_mul(E, E, T3);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            F[i] = T1[i] + T2[i];
-            E[i] = T3[i];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) Lout[i] = F[i];
-}
-
-struct Interval {
-    double a, wn, wsf, wd, dt;      // balanced rates and the step in seconds
-    double phi[16];                 // expm(A' dt)
-    double u[4];                    // A'^-1 G1
-    double bd[4], bt[4];            // Bd', Bt' (balanced coordinates)
-};
-
-__device__ __forceinline__ void build_balanced(double a, double wn, double wsf, double wd, double dt,
-                                               double* M) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) M[i] = 0.0;
-    M[0] = -a * dt;
-    M[1] = -wn * dt;
-    M[4] = wn * dt;
-    M[9] = wsf * dt;
-    M[10] = -wsf * dt;
-    M[14] = wd * dt;
-    M[15] = -wd * dt;
-}
-
-__device__ void discretize(double I, double dt_s, const double* coef, Interval& iv) {
-    iv.a = coef[0] + coef[1] * I;
-    iv.wn = sqrt(coef[2] * I);
-    iv.wsf = coef[3];
-    iv.wd = coef[4];
-    iv.dt = dt_s;
-    double M[16];
-    build_balanced(iv.a, iv.wn, iv.wsf, iv.wd, dt_s, M);
-    expm4(M, iv.phi);
-    // G1 = e - Phi e, e = (0,1,1,1)
-    double g1[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-        g1[r] = (r > 0 ? 1.0 : 0.0) - (iv.phi[4 * r + 1] + iv.phi[4 * r + 2] + iv.phi[4 * r + 3]);
-    // u = A'^-1 G1
-    iv.u[0] = g1[1] / iv.wn;
-    iv.u[1] = -(g1[0] + iv.a * iv.u[0]) / iv.wn;
-    iv.u[2] = iv.u[1] - g1[2] / iv.wsf;
-    iv.u[3] = iv.u[2] - g1[3] / iv.wd;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        iv.bt[r] = iv.u[r] / dt_s + (r > 0 ? 1.0 : 0.0);      // G2
-        iv.bd[r] = g1[r] - iv.bt[r];                          // G1 - G2
-    }
-}
 
 // one descending sweep over the intervals; r_hist (optional) records r_{j+1} per interval
 template <bool kRecord>
@@ -296,41 +153,8 @@ lpf_bwd_kernel(const float* __restrict__ intensity, const float* __restrict__ dt
                 rbar[c][2] = rpbar[2];
                 rbar[c][3] = rpbar[3];
             }
-            // Bd = G1 - G2, Bt = G2
-            double g1bar[4], g2bar[4], ub[4], v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { g1bar[k] = bdbar[k]; g2bar[k] = btbar[k] - bdbar[k]; }
-            // G2 = u / dt + e, u = A'^-1 G1
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ub[k] = g2bar[k] / iv.dt;
-            v[3] = -ub[3] / iv.wd;                                  // v = A'^-T ub
-            v[2] = (iv.wd * v[3] - ub[2]) / iv.wsf;
-            v[0] = (iv.wsf * v[2] - ub[1]) / iv.wn;
-            v[1] = (ub[0] + iv.a * v[0]) / iv.wn;
-            double Abar[16];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                g1bar[r] += v[r];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) Abar[4 * r + q] = -v[r] * iv.u[q];
-            }
-            // G1 = e - Phi e
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                phibar[4 * r + 1] -= g1bar[r];
-                phibar[4 * r + 2] -= g1bar[r];
-                phibar[4 * r + 3] -= g1bar[r];
-            }
-            double M[16], Mbar[16];
-            build_balanced(iv.a, iv.wn, iv.wsf, iv.wd, iv.dt, M);
-            expm4_adjoint(M, phibar, Mbar);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) Abar[i] += iv.dt * Mbar[i];
-            const double abar = -Abar[0];
-            wnbar += -Abar[1] + Abar[4];
-            const double wsfbar = Abar[9] - Abar[10];
-            const double wdbar = Abar[14] - Abar[15];
-            const double bbar = wnbar / (2.0 * iv.wn);              // wn = sqrt(b)
+            double abar, bbar, wsfbar, wdbar;
+            interval_adjoint(iv, phibar, bdbar, btbar, wnbar, abar, bbar, wsfbar, wdbar);
             dI[j + 1] += abar * coef[1] + bbar * coef[2];
             dcoef[0] += abar;
             dcoef[1] += abar * Ij;
@@ -365,6 +189,11 @@ int den_lpf_fwd(const float* intensity, const float* sample_dt_ns, const double*
     DEN_CHECK_ARG(N >= 0, "negative event count");
     if (N == 0) return DEN_OK;
     DEN_CHECK_ARG(intensity && sample_dt_ns && coef && out, "null pointer");
+    if (S <= 32) {          // one warp per event, one lane per interval
+        lpf_warp_fwd(intensity, sample_dt_ns, coef, S, N, n_channels, out, as_stream(stream));
+        DEN_CHECK_LAUNCH();
+        return DEN_OK;
+    }
     const unsigned grid = (unsigned)((N + kLpfThreads - 1) / kLpfThreads);
     lpf_fwd_kernel<<<grid, kLpfThreads, 0, as_stream(stream)>>>(intensity, sample_dt_ns, coef, S, N,
                                                                n_channels, out);
@@ -381,6 +210,12 @@ int den_lpf_bwd(const float* intensity, const float* sample_dt_ns, const double*
     DEN_CHECK_ARG(N >= 0, "negative event count");
     if (N == 0) return DEN_OK;
     DEN_CHECK_ARG(intensity && sample_dt_ns && coef && d_out && d_intensity, "null pointer");
+    if (S <= 32) {
+        lpf_warp_bwd(intensity, sample_dt_ns, coef, S, N, n_channels, d_out, d_intensity, d_coef,
+                     as_stream(stream));
+        DEN_CHECK_LAUNCH();
+        return DEN_OK;
+    }
     const unsigned grid = (unsigned)((N + kLpfThreads - 1) / kLpfThreads);
     lpf_bwd_kernel<<<grid, kLpfThreads, 0, as_stream(stream)>>>(intensity, sample_dt_ns, coef, S, N,
                                                                n_channels, d_out, d_intensity, d_coef);

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HashGridDesc, MarchParams, OccGridDesc
+from ._lib import HashGridDesc, LpfLossDesc, MarchParams, OccGridDesc
 
 _LAUNCHES = 0           # kernels launched through the C ABI (bench.py reports it)
 
@@ -790,3 +790,95 @@ class _LpfFn(torch.autograd.Function):
 def lpf(intensity, sample_dt, coef, n_channels):
     """(S,N) intensities, (S-1,N) sample spacings [ns], 5 fp64 coefficients -> (N, n_channels)."""
     return _LpfFn.apply(intensity, sample_dt, coef, n_channels)
+
+
+# --------------------------------------------------------------------------- #
+# pixel-bandwidth filter fused with the event loss (all requests of a step, one launch)
+# --------------------------------------------------------------------------- #
+LPF_LOSS_MAX_S = 32
+ERROR_KINDS = {"l1": 0, "mse": 1, "huber": 2, "mape": 3}
+_LPF_LOSS_WS = {}       # (device, P, N) -> zero-initialised workspace (the kernel leaves it zeroed)
+
+
+def _lpf_loss_workspace(dev, P, N):
+    key = (dev, P, N)
+    ws = _LPF_LOSS_WS.get(key)
+    if ws is None:
+        nbytes = _lib.lib().raw("den_lpf_loss_workspace_bytes")(P, N)
+        ws = torch.zeros(nbytes // 8 + 1, dtype=torch.float64, device=dev)
+        if len(_LPF_LOSS_WS) > 8:
+            _LPF_LOSS_WS.clear()
+        _LPF_LOSS_WS[key] = ws
+    return ws
+
+
+class _LpfLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, intensity, sample_dt, coef, reset_dt, target, inv_k, valid, desc):
+        intensity = _req(intensity, torch.float32, "intensity")
+        sample_dt = _req(sample_dt, torch.float32, "sample_dt")
+        coef = _req(coef, torch.float64, "coef")
+        inv_k = _req(inv_k, torch.float32, "inv_k")
+        valid = _req(valid, torch.uint8, "valid")
+        K, S, N = intensity.shape
+        P = K // 2
+        assert sample_dt.shape == (K, S - 1, N) and valid.shape == (P, N) and inv_k.shape == (P,)
+        if reset_dt is not None:
+            reset_dt = _req(reset_dt, torch.float64, "reset_dt")
+            assert reset_dt.shape == (K, N)
+        if target is not None:
+            target = _req(target, torch.float32, "target")
+            assert target.shape == (P, N)
+        dev = intensity.device
+        terms = torch.empty(P, dtype=torch.float32, device=dev)
+        counts = torch.empty(P, dtype=torch.int32, device=dev)
+        log_it = torch.empty((K, N), dtype=torch.float32, device=dev)
+        _call("den_lpf_loss_fwd", ctypes.byref(desc), _ptr(intensity), _ptr(sample_dt), _ptr(coef),
+              _ptr(reset_dt), _ptr(target), _ptr(inv_k), _ptr(valid), N, _ptr(terms), _ptr(counts),
+              _ptr(log_it), _ptr(_lpf_loss_workspace(dev, P, N)), _stream())
+        ctx.desc = desc
+        ctx.has = (reset_dt is not None, target is not None)
+        ctx.save_for_backward(intensity, sample_dt, coef, inv_k, valid, counts,
+                              reset_dt if reset_dt is not None else coef,
+                              target if target is not None else inv_k)
+        ctx.mark_non_differentiable(counts, log_it)
+        return terms, log_it, counts
+
+    @staticmethod
+    def backward(ctx, d_terms, _d_log_it, _d_counts):
+        intensity, sample_dt, coef, inv_k, valid, counts, reset_dt, target = ctx.saved_tensors
+        has_reset_dt, has_target = ctx.has
+        reset_dt = reset_dt if has_reset_dt else None
+        target = target if has_target else None
+        N = intensity.shape[2]
+        need = ctx.needs_input_grad
+        d_terms = _req(d_terms, torch.float32, "d_terms")
+        d_int = torch.empty_like(intensity)
+        d_coef = torch.zeros_like(coef) if need[2] else None
+        d_reset = torch.empty_like(reset_dt) if (has_reset_dt and need[3]) else None
+        d_target = torch.zeros_like(target) if (has_target and need[4]) else None
+        d_inv_k = torch.zeros(inv_k.shape, dtype=torch.float64, device=inv_k.device) if need[5] else None
+        _call("den_lpf_loss_bwd", ctypes.byref(ctx.desc), _ptr(intensity), _ptr(sample_dt), _ptr(coef),
+              _ptr(reset_dt), _ptr(target), _ptr(inv_k), _ptr(valid), N, _ptr(counts), _ptr(d_terms),
+              _ptr(d_int), _ptr(d_coef), _ptr(d_reset), _ptr(d_target), _ptr(d_inv_k), _stream())
+        return (d_int, None, d_coef, d_reset, d_target,
+                d_inv_k.to(inv_k.dtype) if d_inv_k is not None else None, None, None)
+
+
+def lpf_loss(intensity, sample_dt, coef, reset_dt, target, inv_k, valid, kinds, has_target,
+             has_reset=True):
+    """Filter + loss of the K = 2P render requests of a step.  intensity (K,S,N), sample_dt (K,S-1,N)
+    [ns], coef (5) f64, reset_dt (K,N) f64 [ns] or None, target (P,N) or None, inv_k (P), valid (P,N)
+    uint8/bool; kinds / has_target: per pair.  Returns (terms (P) — masked means of the per-event
+    errors —, log_intensity (K,N) no-grad, counts (P) int32)."""
+    K, S, _ = intensity.shape
+    if S > LPF_LOSS_MAX_S or K % 2 or not 2 <= K <= 8:
+        raise NotImplementedError("lpf_loss: it_sample_size <= 32 and an even number of requests <= 8")
+    desc = LpfLossDesc()
+    desc.it_sample_size, desc.n_requests, desc.has_reset = S, K, int(bool(has_reset))
+    for p in range(K // 2):
+        desc.error_kind[p] = ERROR_KINDS[kinds[p]]
+        desc.has_target[p] = int(bool(has_target[p]))
+    if valid.dtype == torch.bool:
+        valid = valid.view(torch.uint8)
+    return _LpfLossFn.apply(intensity, sample_dt, coef, reset_dt, target, inv_k, valid, desc)

@@ -46,6 +46,9 @@ class EventRenderer(torch.nn.Module):
         # compositing launch sequence over 4x the rays (same arithmetic per ray, same RNG draws in
         # the same order): a quarter of the launches and host synchronisations per step
         self.batch_render_calls = True
+        # with the pixel-bandwidth model on, filter + reset + loss of all requests run as ONE kernel per
+        # direction (den_lpf_loss_fwd / _bwd) instead of a filter launch per request + eager loss ops
+        self.fuse_lpf_loss = True
         self.batch_bytes_per_sample = 448        # encodings + their gradient + the per-sample scalars
         self._last_mean_samples = None           # samples per ray of the previous step (memory guard)
 
@@ -141,6 +144,64 @@ class EventRenderer(torch.nn.Module):
                 out.append((intensity[k].log(), occ[k], means[k], is_valid[k]))
         return out
 
+    def render_and_loss_fused(self, event, segs, pixel_position, normalized_interval_gen, mean_ct):
+        """All render requests of the step as one launch sequence, then the pixel-bandwidth filter of
+        every request, the reset carried from the first one, the pair differences and the masked loss
+        means in ONE kernel (`den_lpf_loss_fwd`; reverse mode `den_lpf_loss_bwd`).  `segs`: the
+        supervision intervals [(seg dict, is_diff)], at most two.  Returns (terms {name: mean},
+        mean samples per ray per request, occupancy rate per request)."""
+        from . import ops
+        pb, loss = self.pixel_bandwidth, self.loss
+        life = pb.sample_lifetimes(normalized_interval_gen)                    # (S, N) f64, no grad
+        stamps = []
+        for seg, _ in segs:
+            stamps += [seg["start_ts"], seg["end_ts"]]
+        out_ts = torch.stack(stamps)                                           # (K, N) f64
+        K = out_ts.shape[0]
+        sample_ts = out_ts[:, None, :] - life[None]                            # (K, S, N)
+        o, d = self.rays(sample_ts.clamp(min=pb.min_ts), pixel_position)
+        jitter = None
+        if self._jitters:
+            jitter = torch.cat([self._jitters.pop(0).reshape(-1) for _ in range(K)])
+        intensity, opacity, _, means = self.nerf(o, d, jitter=jitter, groups=K)
+        intensity = intensity + self.min_modeled_intensity                    # (K, S, N)
+        hit = opacity > 0
+        occ = hit.reshape(K, -1).to(torch.get_default_dtype()).mean(dim=1)
+        P = K // 2
+        if self.render_bkgd is None:
+            per_request = hit.any(dim=1)                                       # (K, N)
+            valid = per_request[0::2] | per_request[1::2]                      # (P, N)
+        else:
+            valid = torch.ones((P, out_ts.shape[1]), dtype=torch.bool, device=out_ts.device)
+        sample_dt = sample_ts.detach().diff(dim=1).to(intensity.dtype)         # (K, S-1, N) ns
+        has_reset = segs[0][1]
+        reset_dt = out_ts - out_ts[0] if has_reset else None
+        names, kinds, has_target, inv_k, rows = [], [], [], [], []
+        for seg, is_diff in segs:
+            name = "log_intensity_diff" if is_diff else "log_intensity_tv"
+            names.append(name)
+            kinds.append(_get(loss.error_fn, name))
+            k = mean_ct if _get(loss.normalize, name) else torch.ones_like(mean_ct)
+            inv_k.append(1.0 / k)
+            has_target.append(is_diff)
+            if is_diff:         # loss_metric/loss.py:44-60: target = ts_diff * dL/dt of the event / k
+                grad = event["log_intensity_diff"] / (event["end_ts"] - event["start_ts"])
+                event["log_intensity_grad"] = grad
+                rows.append((seg["ts_diff"] * grad / k).to(intensity.dtype))
+            else:               # :82-94: total variation, target zero
+                rows.append(None)
+        target = None
+        if any(r is not None for r in rows):
+            zero = torch.zeros_like(next(r for r in rows if r is not None))
+            target = torch.stack([zero if r is None else r for r in rows])
+        terms, log_it, _ = ops.lpf_loss(intensity, sample_dt, pb.coefficients(), reset_dt, target,
+                                        torch.stack(inv_k).to(intensity.dtype), valid, kinds,
+                                        has_target, has_reset)
+        for p, (seg, _) in enumerate(segs):
+            seg["log_intensity_diff"] = log_it[2 * p + 1] - log_it[2 * p]
+            seg["is_valid"] = valid[p]
+        return {name: terms[p] for p, name in enumerate(names)}, list(means), list(occ.unbind(0))
+
     # ------------------------------------------------------------------ the step -----
     @staticmethod
     def supervision_timestamps(event, normalized, use_diff, use_tv):
@@ -196,8 +257,14 @@ class EventRenderer(torch.nn.Module):
         segs = [(seg, is_diff) for seg, is_diff in ((diff, True), (subdiff, False))
                 if seg is not None]
         batched = None
-        if self.batch_render_calls and self.nerf.radiance_field.training and segs \
-                and self._batch_fits(2 * len(segs) * size, gen):
+        fits = self.batch_render_calls and self.nerf.radiance_field.training and segs \
+            and self._batch_fits(2 * len(segs) * size, gen)
+        if fits and self.fuse_lpf_loss and self.pixel_bandwidth is not None \
+                and event["position"].is_cuda and gen.shape[0] + 1 <= 32 and segs[0][1]:
+            terms, mean_samples, occ_rates = self.render_and_loss_fused(
+                event, segs, event["position"], gen, self.contrast_threshold.mean_contrast_threshold)
+            return self._finish_step(terms, mean_samples, occ_rates, weight, size, batch_index)
+        if fits:
             requests = []
             for seg, is_diff in segs:
                 requests += [(seg["start_ts"], is_diff), (seg["end_ts"], False)]
@@ -217,10 +284,13 @@ class EventRenderer(torch.nn.Module):
             occ_rates += [occ_a, occ_b]
             valid_rates += [va, vb]
 
-        self._last_mean_samples = max(mean_samples) if mean_samples else None
-        mean_samples = self.update_train_batch_size(mean_samples, batch_index)
         terms = self.loss.compute(event, diff, subdiff,
                                   self.contrast_threshold.mean_contrast_threshold)
+        return self._finish_step(terms, mean_samples, occ_rates, weight, size, batch_index)
+
+    def _finish_step(self, terms, mean_samples, occ_rates, weight, size, batch_index):
+        self._last_mean_samples = max(mean_samples) if mean_samples else None
+        mean_samples = self.update_train_batch_size(mean_samples, batch_index)
         loss = sum(v * _get(weight, k) for k, v in terms.items())
 
         self.logged = {"train/loss": loss.detach(), "train/batch_size": size,

@@ -336,6 +336,45 @@ int den_lpf_bwd(const float* intensity, const float* sample_dt_ns, const double*
                 double* d_coef, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Pixel-bandwidth filter fused with the event loss, every render request of a training step in
+ * ONE launch — replaces, per step, the filter half of the 2P calls of PixelBandwidth.forward
+ * (models/pixel_bandwidth.py:369-448, including the differencing-amplifier reset carried from the
+ * first request to the others, :419-446) and Loss.compute (loss_metric/loss.py:34-96).
+ * Requests k = 0 .. K-1 come in P = K/2 pairs (2p, 2p+1) = (start, end) of a supervision interval
+ * (models/deblur_e_nerf.py:472-521: pair 0 = `diff`, pair 1 = `subdiff`); with has_reset request 0 is
+ * the reset call: delta = diff-amp output - source-follower output, its own value is the
+ * source-follower output, and request k >= 1 yields out_k - delta exp(-omega_diff 1e-9 reset_dt_k).
+ *   pred_p = final[2p+1] - final[2p];   err_p = E_kind(pred_p inv_k[p], target[p]);
+ *   terms[p] = mean of err_p over the events with valid[p] != 0   (counts[p] of them).
+ * intensity (K,S,N) fp32; sample_dt_ns (K,S-1,N) fp32; coef 5 fp64 (den_lpf_fwd); reset_dt_ns (K,N)
+ * fp64 = output_ts[k] - output_ts[0] (row 0 unused; NULL without reset); target (P,N) fp32 or NULL;
+ * inv_k (P) fp32 on the device; valid (P,N) uint8.  S <= 32, K even <= 8.  fp64 inside; the means are
+ * summed in event order by the last CTA to finish (deterministic).  log_intensity (K,N), optional:
+ * the K filter outputs after the reset.  workspace: den_lpf_loss_workspace_bytes(P, N), zeroed ONCE.
+ * ------------------------------------------------------------------------- */
+typedef struct den_lpf_loss_desc {
+    int32_t it_sample_size;             /* S */
+    int32_t n_requests;                 /* K */
+    int32_t has_reset;
+    int32_t error_kind[4];              /* per pair: 0 l1, 1 mse, 2 huber (delta 1), 3 mape */
+    int32_t has_target[4];              /* per pair: 0 -> target is zero (the TV term) */
+} den_lpf_loss_desc;
+
+size_t den_lpf_loss_workspace_bytes(int32_t n_pairs, int64_t N);
+int den_lpf_loss_fwd(const den_lpf_loss_desc* d, const float* intensity, const float* sample_dt_ns,
+                     const double* coef, const double* reset_dt_ns, const float* target,
+                     const float* inv_k, const uint8_t* valid, int64_t N, float* terms, int32_t* counts,
+                     float* log_intensity, void* workspace, void* stream);
+/* d_terms (P) fp32 on the device; d_intensity (K,S,N) written; d_coef (5 fp64), d_inv_k (P fp64)
+ * accumulated with atomics (pre-zeroed, may be NULL); d_reset_dt_ns (K,N) fp64 and d_target (P,N)
+ * fp32 written (may be NULL; rows of pairs without a target are left untouched). */
+int den_lpf_loss_bwd(const den_lpf_loss_desc* d, const float* intensity, const float* sample_dt_ns,
+                     const double* coef, const double* reset_dt_ns, const float* target,
+                     const float* inv_k, const uint8_t* valid, int64_t N, const int32_t* counts,
+                     const float* d_terms, float* d_intensity, double* d_coef, double* d_reset_dt_ns,
+                     float* d_target, double* d_inv_k, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Optimiser — replaces torch.optim.Adam as set up by DeblurENeRF.configure_optimizers
  * (models/deblur_e_nerf.py:1055-1112) for the fp32 parameters: one step t (1-based) of
  *   g = grad + weight_decay * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;

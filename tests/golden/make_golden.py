@@ -119,6 +119,57 @@ def training_step_eds_golden(path, n_micro=2):
           [float(out[f"logged/{m}/train/mean_num_samples_per_ray"]) for m in range(n_micro)])
 
 
+def _step_gradients(cfg, pb_on, eds, perturb_seed):
+    """Gradients of the reference's training step(s) with every field parameter multiplied by
+    1 + u * 2^-23, u in {-1, 0, 1} (a one-ulp relative perturbation; seed 0 = unperturbed)."""
+    n_micro = 2 if eds else 1
+    ref, poses = _scene.build_reference_renderer(
+        cfg, IT_SAMPLE_SIZE, pixel_bandwidth=pb_on, freeze_refractory_period=not eds,
+        accumulate_grad_batches=n_micro)
+    ref.train()
+    ref.zero_grad()
+    if perturb_seed:
+        g = torch.Generator().manual_seed(perturb_seed)
+        with torch.no_grad():
+            for p in ref.nerf.radiance_field.parameters():
+                p.mul_(1 + (torch.randint(0, 3, p.shape, generator=g).float() - 1) * 2.0 ** -23)
+    torch.manual_seed(13 if eds else 11)
+    for m in range(n_micro):
+        event, normalized = _scene.make_batch(cfg, poses, N_EVENTS, IT_SAMPLE_SIZE,
+                                              seed=(21 + m) if eds else 7, pixel_bandwidth=pb_on)
+        loss = ref.training_step(_scene.reference_batch(event, normalized), m)
+        (loss / n_micro).backward()
+    return {k: v.double() for k, v in _scene.flat_named_grads(ref).items()}
+
+
+def conditioning_golden(path, trials=3):
+    """How far the REFERENCE'S OWN fp32 gradients move when its field parameters are perturbed by one
+    ulp: `<scene>/<parameter>` = max over `trials` perturbations of max|g' - g| / max|g|.  A gradient
+    that the reference's arithmetic cannot reproduce to better than c under a one-ulp change of its
+    inputs cannot be pinned to better than a small multiple of c by any other fp32 evaluation (a
+    GPU run of the reference itself included: atomics reorder its sums); the training-step parity
+    tests use max(1e-3, 16 c) as the bound of such keys.  On the shipped shapes c stays below 3e-5
+    except for the sums that cancel almost completely: the pixel-bandwidth parameters, the mean
+    contrast threshold and the output-layer bias on the EDS shape (1e-3 .. 4e-3)."""
+    out = {}
+    scenes = {"pb_on": ("synthetic", True, False), "pb_off": ("synthetic", False, False),
+              "eds": ("eds", True, True)}
+    for name, (scene, pb_on, eds) in scenes.items():
+        cfg = _scene.scene_config(scene, occ_resolution=32, small=True)
+        base = _step_gradients(cfg, pb_on, eds, 0)
+        spread = {k: 0.0 for k in base}
+        for t in range(1, trials + 1):
+            g = _step_gradients(cfg, pb_on, eds, t)
+            for k in base:
+                rel = float((g[k] - base[k]).abs().max() / base[k].abs().max().clamp(min=1e-300))
+                spread[k] = max(spread[k], rel)
+        for k, v in spread.items():
+            out[f"{name}/{k}"] = np.asarray(v)
+        print(name, {k.split(".")[-2] if k.endswith("original") else k.split(".")[-2] + "." + k.split(".")[-1]:
+                     f"{v:.1e}" for k, v in spread.items()})
+    np.savez_compressed(path, **out)
+
+
 def field_golden(path):
     cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
     ref, _ = _scene.build_reference_renderer(cfg, IT_SAMPLE_SIZE, pixel_bandwidth=False)
@@ -148,3 +199,4 @@ if __name__ == "__main__":
     training_step_golden(False, os.path.join(HERE, "training_step_pb_off.npz"))
     field_golden(os.path.join(HERE, "field_small.npz"))
     training_step_eds_golden(os.path.join(HERE, "training_step_eds.npz"))
+    conditioning_golden(os.path.join(HERE, "gradient_conditioning.npz"))
