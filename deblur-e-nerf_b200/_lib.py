@@ -22,6 +22,7 @@ _SZ = _c.c_size_t
 _INT = _c.c_int
 
 DEN_MAX_LEVELS = 32
+ABI_VERSION = 2         # DEN_ABI_VERSION of include/den_b200.h
 
 
 class HashGridDesc(_c.Structure):
@@ -100,7 +101,8 @@ _SIGNATURES = {
     "den_occgrid_ema_update": (_INT, [_P, _P, _P, _I64, _F, _F, _P, _I64, _P, _P, _P, _P]),
     "den_rays_from_trajectory": (_INT, [_P, _P, _I64, _P, _P, _P, _I32, _c.POINTER(_F), _P, _P, _I64,
                                         _P]),
-    "den_adam_step": (_INT, [_c.POINTER(AdamTensor), _I32, _c.c_double, _c.c_double, _c.c_double, _I64, _P]),
+    "den_adam_step": (_INT, [_c.POINTER(AdamTensor), _I32, _c.c_double, _c.c_double, _c.c_double, _I64,
+                             _c.c_double, _P]),
     "den_alpha_from_sigma": (_INT, [_P, _P, _P, _P, _I64, _P]),
     "den_visibility": (_INT, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "den_compact_samples": (_INT, [_P] * 9 + [_I64, _P]),
@@ -173,7 +175,7 @@ class _Library:
             fn.restype = restype
             fn.argtypes = argtypes
         version = self.cdll.den_version()
-        if version != 1:
+        if version != ABI_VERSION:
             raise DenError(f"unexpected den_b200 ABI version {version}")
 
     def last_error(self):

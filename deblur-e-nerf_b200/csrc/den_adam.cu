@@ -5,7 +5,8 @@
 // (0.9, 0.999), eps 1e-8, L2 weight decay added to the gradient, no amsgrad) for the fp32
 // parameters — the 12.6 M-entry hash table is 99.9 % of them.  Semantics of one step t (1-based),
 // exactly torch's single-tensor formula:
-//     g  = grad + weight_decay * p
+//     g  = grad_scale * grad + weight_decay * p        (grad_scale: 1 / world size folded in under
+//                                                       data parallelism — the all-reduce sums)
 //     m  = beta1 * m + (1 - beta1) * g
 //     v  = beta2 * v + (1 - beta2) * g * g
 //     p -= (lr / (1 - beta1^t)) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
@@ -29,8 +30,8 @@ struct AdamBatch {
 // omb1 = 1 - beta1, omb2 = 1 - beta2 come from the host in double precision (1.f - 0.999f is off by 1.3e-5)
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float wd, float b1, float b2,
                                             float omb1, float omb2, float step_size, float inv_sqrt_bias2,
-                                            float eps) {
-    g = fmaf(wd, p, g);
+                                            float eps, float gs) {
+    g = fmaf(wd, p, g * gs);
     m = fmaf(b1, m, omb1 * g);
     v = fmaf(b2, v, omb2 * g * g);
     const float denom = sqrtf(v) * inv_sqrt_bias2 + eps;
@@ -41,7 +42,7 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 // 16-byte aligned — every torch allocation is)
 __global__ void __launch_bounds__(256)
 adam_kernel(const __grid_constant__ AdamBatch b, float beta1, float beta2, float omb1, float omb2, float eps,
-            float bias1, float inv_sqrt_bias2) {
+            float bias1, float inv_sqrt_bias2, float gs) {
     const int t = blockIdx.y;
     float* __restrict__ p = b.p[t];
     const float* __restrict__ g = b.g[t];
@@ -60,17 +61,17 @@ adam_kernel(const __grid_constant__ AdamBatch b, float beta1, float beta2, float
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
         float4 m4 = reinterpret_cast<float4*>(m)[i];
         float4 v4 = reinterpret_cast<float4*>(v)[i];
-        adam_update(p4.x, g4.x, m4.x, v4.x, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps);
-        adam_update(p4.y, g4.y, m4.y, v4.y, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps);
-        adam_update(p4.z, g4.z, m4.z, v4.z, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps);
-        adam_update(p4.w, g4.w, m4.w, v4.w, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps);
+        adam_update(p4.x, g4.x, m4.x, v4.x, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps, gs);
+        adam_update(p4.y, g4.y, m4.y, v4.y, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps, gs);
+        adam_update(p4.z, g4.z, m4.z, v4.z, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps, gs);
+        adam_update(p4.w, g4.w, m4.w, v4.w, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps, gs);
         reinterpret_cast<float4*>(p)[i] = p4;
         reinterpret_cast<float4*>(m)[i] = m4;
         reinterpret_cast<float4*>(v)[i] = v4;
     }
     for (int64_t i = 4 * n4 + tid; i < n; i += stride) {
         float pi = p[i], mi = m[i], vi = v[i];
-        adam_update(pi, g[i], mi, vi, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps);
+        adam_update(pi, g[i], mi, vi, wd, beta1, beta2, omb1, omb2, step_size, inv_sqrt_bias2, eps, gs);
         p[i] = pi;
         m[i] = mi;
         v[i] = vi;
@@ -80,7 +81,7 @@ adam_kernel(const __grid_constant__ AdamBatch b, float beta1, float beta2, float
 }  // namespace den
 
 extern "C" int den_adam_step(const den_adam_tensor* tensors, int32_t n_tensors, double beta1_d, double beta2_d,
-                             double eps_d, int64_t step, void* stream) {
+                             double eps_d, int64_t step, double grad_scale, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(n_tensors >= 0 && step >= 1, "bad tensor count / step");
     DEN_CHECK_ARG(n_tensors == 0 || tensors != nullptr, "null tensor list");
@@ -99,7 +100,7 @@ extern "C" int den_adam_step(const den_adam_tensor* tensors, int32_t n_tensors, 
             dim3 grid((unsigned)grid_for(blocks > 0 ? blocks : 1, 1, 8), (unsigned)count);
             adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(b, beta1, beta2, (float)(1.0 - (double)beta1_d),
                                                              (float)(1.0 - (double)beta2_d), eps, (float)bias1,
-                                                             inv_sqrt_bias2);
+                                                             inv_sqrt_bias2, (float)grad_scale);
             cudaError_t e = cudaGetLastError();
             count = 0;
             largest = 0;

@@ -2,8 +2,9 @@
 (``gloo`` on CPU for the tests), mirroring what the reference gets from Lightning's
 ``DDPPlugin`` (scripts/run.py:84-100): every rank renders its own shard of the event batch
 (per-GPU sample budget, models/deblur_e_nerf.py:72-75), parameters / occupancy grid are
-replicated, and the gradients are MEAN all-reduced once per optimizer step over ONE flat
-fp32 buffer (12 609 346 floats = 50.4 MB for synthetic.yaml).  The batch controller's mean
+replicated, and the gradients are all-reduced once per optimizer step over ONE flat fp32 buffer
+(12 609 346 floats = 50.4 MB for synthetic.yaml) that the parameters' ``.grad`` tensors are views of
+(`GradReducer`: no copy in or out, SUM over NVLink, the 1 / N folded into ``den_adam_step``).  The batch controller's mean
 samples-per-ray is averaged across ranks like ``self.all_gather(...).mean()``
 (models/deblur_e_nerf.py:1269-1272).
 
@@ -54,8 +55,87 @@ def broadcast_parameters(module, src=0):
             data.copy_(packed)
 
 
+class GradReducer:
+    """Gradient reduction of one optimizer step with NO copy passes: every trainable parameter's
+    ``.grad`` is a VIEW into one flat buffer per dtype that this object owns (the 12.6 M-entry hash
+    table gradient is 99.9 % of it), autograd accumulates into the views, and a step is ONE
+    ``all_reduce(SUM)`` over the flat buffer — the division by the world size is folded into the
+    Adam update (``optimizer.grad_scale = 1 / world``, applied inside ``den_adam_step``).  Replaces
+    Lightning's ``DDPPlugin`` gradient averaging (scripts/run.py:84-100).
+
+    The same parameters take part at every world size: the views exist for a single process too, so a
+    parameter that received no gradient in a step is stepped with a zero gradient (moments decay,
+    weight decay applies) at N = 1 exactly as at N > 1 — under DDP every trainable parameter gets a
+    gradient every step, a parameter that never does is frozen and holds no view.
+
+    Usage: ``reducer = GradReducer(model); reducer.bind(optimizer)``; per step
+    ``optimizer.zero_grad(set_to_none=False)`` (or ``reducer.zero_()``: one memset), backward, then
+    ``reducer()`` and ``optimizer.step()``.  ``zero_grad(set_to_none=True)`` drops the views;
+    ``reducer()`` re-attaches them (copying what autograd produced) so nothing silently breaks."""
+
+    def __init__(self, module_or_params, async_op=False):
+        params = module_or_params.parameters() if hasattr(module_or_params, "parameters") \
+            else module_or_params
+        self.params = [p for p in params if p.requires_grad]
+        self.flat = {}              # dtype -> flat gradient buffer
+        self.views = {}             # id(param) -> its view
+        by_dtype = {}
+        for p in self.params:
+            by_dtype.setdefault((p.dtype, p.device), []).append(p)
+        for (dtype, device), group in by_dtype.items():
+            # every view starts on a 16-byte boundary (the Adam kernel reads float4)
+            align = max(16 // torch.empty((), dtype=dtype).element_size(), 1)
+            sizes = [-(-p.numel() // align) * align for p in group]
+            flat = torch.zeros(sum(sizes), dtype=dtype, device=device)
+            off = 0
+            for p, size in zip(group, sizes):
+                self.views[id(p)] = flat[off:off + p.numel()].view_as(p)
+                off += size
+            self.flat[(dtype, device)] = flat
+        self.attach()
+        self._work = []
+
+    def attach(self):
+        """Point every ``.grad`` at its view (keeping whatever gradient autograd left there)."""
+        for p in self.params:
+            view = self.views[id(p)]
+            if p.grad is None:
+                view.zero_()
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            else:
+                continue
+            p.grad = view
+
+    def zero_(self):
+        for flat in self.flat.values():
+            flat.zero_()
+        self.attach()
+
+    def bind(self, optimizer):
+        """Fold the mean into the optimizer's update instead of a division pass over the buffer."""
+        optimizer.grad_scale = 1.0 / world_size()
+        return optimizer
+
+    @property
+    def nbytes(self):
+        return sum(f.numel() * f.element_size() for f in self.flat.values())
+
+    def __call__(self):
+        """SUM all-reduce of the flat buffer(s) on the current stream; returns the bytes reduced."""
+        self.attach()
+        if world_size() == 1:
+            return 0
+        for flat in self.flat.values():
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return self.nbytes
+
+
 class FlatGradAllReduce:
-    """Mean all-reduce of every parameter gradient through one flat buffer per dtype."""
+    """Mean all-reduce of the parameter gradients through one flat buffer per dtype, for ANY optimizer
+    (the copy-in / copy-out form; `GradReducer` is the copy-free one the hot path uses with FusedAdam).
+    A parameter whose gradient is None on EVERY rank keeps None (the optimizer skips it, as in a
+    single process); one that has a gradient on some rank takes part everywhere (zeros elsewhere)."""
 
     def __init__(self, parameters):
         self.params = [p for p in parameters if p.requires_grad]
@@ -65,9 +145,16 @@ class FlatGradAllReduce:
         n = world_size()
         if n == 1:
             return 0
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        used = torch.tensor([0 if p.grad is None else 1 for p in self.params], dtype=torch.int32,
+                            device=dev)
+        dist.all_reduce(used, op=dist.ReduceOp.MAX)          # the same participant set on all ranks
+        used = used.tolist()
         nbytes = 0
         by_dtype = {}
-        for p in self.params:
+        for p, flag in zip(self.params, used):
+            if not flag:
+                continue
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
             by_dtype.setdefault(p.grad.dtype, []).append(p)

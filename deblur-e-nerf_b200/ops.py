@@ -729,10 +729,10 @@ def contract_samples_autograd(desc, rays_o, rays_d, ray_indices, t_starts, t_end
 # --------------------------------------------------------------------------- #
 # optimiser
 # --------------------------------------------------------------------------- #
-def adam_step(tensor_array, n_tensors, beta1, beta2, eps, step):
+def adam_step(tensor_array, n_tensors, beta1, beta2, eps, step, grad_scale=1.0):
     """One Adam step over a ctypes array of ``AdamTensor`` descriptors (see optim.FusedAdam)."""
     _call("den_adam_step", tensor_array, int(n_tensors), float(beta1), float(beta2), float(eps),
-          int(step), _stream(), launches=2)
+          int(step), float(grad_scale), _stream(), launches=2)
 
 
 # --------------------------------------------------------------------------- #

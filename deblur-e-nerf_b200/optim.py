@@ -22,6 +22,9 @@ class FusedAdam(torch.optim.Optimizer):
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
             raise ValueError("invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        # gradients are multiplied by this inside the update: ddp.GradReducer sets 1 / world_size so the
+        # SUM all-reduce needs no separate division pass
+        self.grad_scale = 1.0
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -54,12 +57,13 @@ class FusedAdam(torch.optim.Optimizer):
                     raise NotImplementedError("FusedAdam: only CUDA parameters are supported (no CPU fallback)")
                 else:
                     # e.g. the float64 refractory-period scalar: the same formula in torch
-                    g = p.grad.add(p, alpha=group["weight_decay"]) if group["weight_decay"] else p.grad
+                    g = p.grad * self.grad_scale if self.grad_scale != 1.0 else p.grad
+                    g = g.add(p, alpha=group["weight_decay"]) if group["weight_decay"] else g
                     m.mul_(beta1).add_(g, alpha=1 - beta1)
                     v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
                     denom = (v.sqrt() / math.sqrt(1 - beta2 ** t)).add_(group["eps"])
                     p.addcdiv_(m, denom, value=-group["lr"] / (1 - beta1 ** t))
         for (beta1, beta2, eps, t), entries in launches.items():
             arr = (AdamTensor * len(entries))(*[e for e, _ in entries])
-            ops.adam_step(arr, len(entries), beta1, beta2, eps, t)
+            ops.adam_step(arr, len(entries), beta1, beta2, eps, t, self.grad_scale)
         return loss

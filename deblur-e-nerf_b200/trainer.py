@@ -104,14 +104,19 @@ class Trainer:
         model.accumulate_grad_batches = acc
         model.train()
         if reducer is None:
-            reducer = ddp.FlatGradAllReduce(model.parameters())
+            if hasattr(optimizer, "grad_scale"):        # FusedAdam: copy-free reduction, mean folded in
+                reducer = ddp.GradReducer(model)
+                reducer.bind(optimizer)
+            else:
+                reducer = ddp.FlatGradAllReduce(model.parameters())
+        keep_views = isinstance(reducer, ddp.GradReducer)
         if getattr(model, "next_train_batch_size", None):
             producer.set_batch_size(model.next_train_batch_size)
         logged = {}
         prefetched = producer.next_batch()
         done = False
         while self.current_epoch < self.max_epochs and not done:
-            optimizer.zero_grad(set_to_none=True)
+            optimizer.zero_grad(set_to_none=not keep_views)
             for batch_index in range(self.limit_train_batches):
                 batch = prefetched
                 prefetched = producer.next_batch()      # drawn BEFORE this batch's controller update
@@ -125,7 +130,7 @@ class Trainer:
                     continue
                 reducer()
                 optimizer.step()
-                optimizer.zero_grad(set_to_none=True)
+                optimizer.zero_grad(set_to_none=not keep_views)
                 self.global_step += 1
                 if scheduler is not None and self.lr_scheduler_interval == "step":
                     scheduler.step()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DEN_ABI_VERSION 1
+#define DEN_ABI_VERSION 2
 #define DEN_MAX_LEVELS 32
 
 typedef enum den_status {
@@ -377,7 +377,7 @@ int den_lpf_loss_bwd(const den_lpf_loss_desc* d, const float* intensity, const f
 /* ------------------------------------------------------------------------- *
  * Optimiser — replaces torch.optim.Adam as set up by DeblurENeRF.configure_optimizers
  * (models/deblur_e_nerf.py:1055-1112) for the fp32 parameters: one step t (1-based) of
- *   g = grad + weight_decay * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   g = grad_scale * grad + weight_decay * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
  *   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
  * over a HOST array of tensor descriptors (device pointers inside), each with its own lr / decay.
  * ------------------------------------------------------------------------- */
@@ -391,8 +391,10 @@ typedef struct den_adam_tensor {
     float weight_decay;
 } den_adam_tensor;
 
+/* grad_scale: 1 for a single process; 1 / world_size when the gradients were SUM all-reduced
+ * (the mean of Lightning's DDP, scripts/run.py:84-89, folded into the update). */
 int den_adam_step(const den_adam_tensor* tensors_host, int32_t n_tensors, double beta1, double beta2,
-                  double eps, int64_t step, void* stream);
+                  double eps, int64_t step, double grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

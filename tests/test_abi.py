@@ -13,7 +13,7 @@ def test_library_builds_and_exports_every_declared_symbol(den_lib):
         assert hasattr(den_lib.cdll, name), f"{name} declared in den_b200.h but not exported"
     assert set(_lib._SIGNATURES) <= set(declared), set(_lib._SIGNATURES) - set(declared)
     assert set(declared) <= set(_lib._SIGNATURES), set(declared) - set(_lib._SIGNATURES)
-    assert den_lib.cdll.den_version() == 1
+    assert den_lib.cdll.den_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_is_in_tree_and_sm100a(den_lib):

@@ -21,7 +21,7 @@ def _run(extra_env=None, *flags):
     env.pop("WORLD_SIZE", None)
     env.update(extra_env or {})
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
-                           "--steps", "1", "--warmup", "0", "--cpu-events", "48", *flags],
+                           "--steps", "1", "--warmup", "0", "--cpu-events", "12", *flags],
                           capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
 
 
@@ -36,7 +36,9 @@ def test_reference_arm_prints_one_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["higher_is_better"] is True
     assert line["metric"] == "train rays/s (fwd+bwd)" and line["vs_baseline"] is None
     assert line["value"] > 0 and line["ms_per_step"] > 0 and line["steps"] == 1
-    assert line["config"]["workload"] == "synthetic_pb_off" and line["config"]["bounded_sample"] is True
+    # the default workload is the north-star configuration: pixel-bandwidth model on
+    assert line["config"]["workload"] == "synthetic_pb_on" and line["config"]["bounded_sample"] is True
+    assert line["config"]["pixel_bandwidth"] is True and line["config"]["it_sample_size"] == 30
     base = line["cpu_baseline"]
     assert base["kind"] in ("port", "reference") and base["cores"] >= 1 and base["sample"]
     assert base["value"] == line["value"]

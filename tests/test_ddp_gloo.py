@@ -41,6 +41,31 @@ def _worker(rank, world, port, out_dir):
     nbytes = reducer()
     assert nbytes == sum(p.numel() * p.element_size() for p in model.parameters())
 
+    # the copy-free reducer: .grad tensors are views of one flat buffer, SUM all-reduce, 1/N left to
+    # the optimizer (grad_scale)
+    model2 = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    model2[1].bias.requires_grad_(False)                 # frozen: holds no view, never reduced
+    ddp.broadcast_parameters(model2)
+    red = ddp.GradReducer(model2)
+
+    class _Opt:
+        grad_scale = 1.0
+    opt = red.bind(_Opt())
+    ptrs = [p.grad.data_ptr() for p in model2.parameters() if p.requires_grad]
+    model2(x.float()).pow(2).mean().backward()
+    assert ptrs == [p.grad.data_ptr() for p in model2.parameters() if p.requires_grad]   # accumulated in place
+    local2 = [p.grad.clone() for p in model2.parameters() if p.requires_grad]
+    nbytes2 = red()
+    summed2 = [p.grad.clone() for p in model2.parameters() if p.requires_grad]
+    # dropping the views (zero_grad(set_to_none=True)) is repaired by the next call
+    for p in model2.parameters():
+        p.grad = None
+    model2(x.float()).pow(2).mean().backward()
+    red()
+    again2 = [p.grad.clone() for p in model2.parameters() if p.requires_grad]
+    assert ptrs == [p.grad.data_ptr() for p in model2.parameters() if p.requires_grad]
+    assert model2[1].bias.grad is None
+
     class _R(torch.nn.Module):
         def __init__(self):
             super().__init__()
@@ -53,7 +78,9 @@ def _worker(rank, world, port, out_dir):
     ddp.barrier()
     torch.save({"params": [p.detach().clone() for p in model.parameters()],
                 "local": local, "reduced": [p.grad.clone() for p in model.parameters()],
-                "mean": mean, "max": tmax, "sum": tsum}, os.path.join(out_dir, f"rank{rank}.pt"))
+                "mean": mean, "max": tmax, "sum": tsum, "local2": local2, "summed2": summed2,
+                "again2": again2, "scale2": opt.grad_scale, "nbytes2": nbytes2},
+               os.path.join(out_dir, f"rank{rank}.pt"))
     torch.distributed.destroy_process_group()
 
 
@@ -68,6 +95,12 @@ def test_world_size_2_gloo(tmp_path):
         mean = (res[0]["local"][k] + res[1]["local"][k]) / 2
         assert torch.allclose(res[0]["reduced"][k], mean, rtol=1e-12, atol=0)
         assert torch.equal(res[0]["reduced"][k], res[1]["reduced"][k])
+    for k in range(len(res[0]["local2"])):                       # GradReducer: SUM, mean via grad_scale
+        total = res[0]["local2"][k] + res[1]["local2"][k]
+        assert torch.allclose(res[0]["summed2"][k], total, rtol=1e-6, atol=1e-8)
+        assert torch.equal(res[0]["summed2"][k], res[1]["summed2"][k])
+        assert torch.allclose(res[0]["again2"][k], total, rtol=1e-6, atol=1e-8)
+    assert res[0]["scale2"] == 0.5 and res[0]["nbytes2"] >= (5 * 7 + 7 + 7 * 3) * 4
     assert res[0]["mean"] == res[1]["mean"] == 15.0
     assert res[0]["max"] == res[1]["max"] == 4.0
     assert res[0]["sum"] == res[1]["sum"] == 7.0
