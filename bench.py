@@ -85,6 +85,8 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="--gpus N: split the fixed global batch over the ranks (strong, the north-star "
                          "reading: models/deblur_e_nerf.py:72-75) or give every rank the full batch")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="run every step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -481,22 +483,23 @@ def run_ours(args):
     def updates_in(first, count):
         return sum(1 for i in range(first, first + count) if step_number(i) % 16 == 0)
 
+    # One optimizer step = `acc` micro-batches (training_step + backward), the gradient reduction, Adam.
+    # After two eager steps it is captured in a CUDA graph and replayed (graph_step.GraphedStep): the
+    # sync-free render path has no host read-back, so the whole step is one launch.
+    from deblur_e_nerf_b200.graph_step import GraphedStep
+    stepper = GraphedStep(model, opt, reducer, acc)
+    use_graph = not args.no_graph and w["rays_per_call"] is not None
+    if not use_graph:
+        stepper.warmup_steps = 1 << 60          # never capture: every step eager
+
     def one_step(batches, i):
-        """One optimizer step: `acc` micro-batches, the gradient reduction, Adam."""
-        opt.zero_grad(set_to_none=False)
-        loss = None
-        for m, batch in enumerate(batches):
-            loss = model.training_step(batch, m, step_number(i))
-            (loss / acc if acc > 1 else loss).backward()
-        reducer()
-        opt.step()
-        return loss
+        return stepper(batches, step_number(i))
 
     total = args.warmup + args.steps
     if w["rays_per_call"] is None:
         # reading (R): let the batch controller settle during extra warm-up steps
         for i in range(6):
-            one_step([to_dev(host_batch(100 + i * acc + m, n_events)) for m in range(acc)], 1)
+            one_step([to_dev(host_batch(100 + i * acc + m, n_events)) for m in range(acc)], 1 - step_number(0))
             n_events = max(model.next_train_batch_size or n_events, 1)
     host_batches = [[host_batch(i * acc + m, n_events) for m in range(acc)] for i in range(total)]
     dev_batches = [[to_dev(b) for b in bs] for bs in host_batches]
@@ -507,7 +510,7 @@ def run_ours(args):
     rated_kernels = sorted(set(KERNEL_BYTES_PER_SAMPLE) | set(KERNEL_FLOP_PER_SAMPLE) | {"den_adam_step"})
 
     # ---- device-resident loop (value) ------------------------------------------------
-    samples_seen = 0.0
+    samples_seen = torch.zeros((), dtype=torch.float64, device=dev)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -518,17 +521,21 @@ def run_ours(args):
     t_wall0 = time.time()
     launches0 = ops.launch_count()
     mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
-    ops.enable_kernel_timing(rated_kernels)
+    if not use_graph:
+        ops.enable_kernel_timing(rated_kernels)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for i in range(args.steps):
         one_step(dev_batches[args.warmup + i], args.warmup + i)
         samples_seen += model.logged["train/mean_num_samples_per_ray"] * rays_per_step(n_events)
     end.record()
+    graph_stats = {"enabled": use_graph, "captures": stepper.captures, "replays": stepper.replays,
+                   "overflows": stepper.overflows}
     ddp.barrier()
     torch.cuda.synchronize()
     t_wall1 = time.time()
     ms_total = start.elapsed_time(end)
+    samples_seen = float(samples_seen)
     ms_step = ddp.max_over_ranks(ms_total / args.steps, dev)
     timings = ops.kernel_timings()
     ops.disable_kernel_timing()
@@ -546,13 +553,16 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         for i in range(min(args.warmup, 2)):
-            one_step([to_dev(b) for b in host_batches[i]], i).item()
+            one_step(host_batches[i], i).item()
         ddp.barrier()
         torch.cuda.synchronize()
         start.record()
         d2h = 0
         for i in range(args.steps):
-            loss = one_step([to_dev(b) for b in host_batches[args.warmup + i]], args.warmup + i)
+            # pinned host batches: the copies to the device are part of the step (into the graph's
+            # static input buffers when the step is replayed)
+            loss = one_step(host_batches[args.warmup + i] if use_graph
+                            else [to_dev(b) for b in host_batches[args.warmup + i]], args.warmup + i)
             loss_host = loss.detach().to("cpu", non_blocking=False)
             d2h = loss_host.numel() * loss_host.element_size()
         end.record()
@@ -613,17 +623,30 @@ def run_ours(args):
                      "note": "weak scaling: every rank renders the full single-GPU batch"}
         del full
 
-    # ---- profile pass: every den_b200 entry point bracketed, 2 steps (not part of `value`) -----
+    # ---- kernel pass: every den_b200 entry point bracketed with CUDA events on the launching stream,
+    # EAGER steps over the same batches (a replayed graph has no per-launch host hook to bracket; the
+    # kernels, their arguments and their durations are the ones of the timed region above) ----------
+    stepper.warmup_steps = 1 << 60
+    stepper._graph = None
+    n_profile = min(args.steps, 4)
+    samples_profile = torch.zeros((), dtype=torch.float64, device=dev)
+    one_step(dev_batches[args.warmup], args.warmup + 1)
     ops.enable_kernel_timing(None)
     torch.cuda.synchronize()
     start.record()
-    for i in range(2):
+    for i in range(n_profile):
         one_step(dev_batches[args.warmup + i], args.warmup + 1 + i)      # steps without a grid update
+        samples_profile += model.logged["train/mean_num_samples_per_ray"] * rays_per_step(n_events)
     end.record()
     torch.cuda.synchronize()
     profile_ms = start.elapsed_time(end)
     profile_timings = ops.kernel_timings()
     ops.disable_kernel_timing()
+    if use_graph:           # rooflines from the kernel pass
+        timings = {k: v for k, v in profile_timings.items()}
+        roof_samples, roof_steps = float(samples_profile), n_profile
+    else:
+        roof_samples, roof_steps = samples_seen, args.steps
 
     # ---- occupancy update, also timed on its own (it is INSIDE the timed steps above) ------------
     occ_ms = None
@@ -657,8 +680,8 @@ def run_ours(args):
         n_launch, ms_k = timings[name]
         avg_s = ms_k / n_launch * 1e-3
         # every rated kernel runs once per render launch sequence over all of its samples / rays
-        samples_per_launch = samples_seen / n_launch
-        rays_per_launch = rays_per_step(n_events) * args.steps / n_launch
+        samples_per_launch = roof_samples / n_launch
+        rays_per_launch = rays_per_step(n_events) * roof_steps / n_launch
         traffic = traffic_table.get(name)
         traffic = traffic * samples_per_launch if traffic else None
         if name in KERNEL_FLOP_PER_SAMPLE:
@@ -725,7 +748,8 @@ def run_ours(args):
         "data": "synthetic", "config": config,
         "samples_per_s": global_samples / (ms_step * 1e-3),
         "events_per_s": world * n_events * acc / (ms_step * 1e-3),
-        "mean_samples_per_ray": model.logged["train/mean_num_samples_per_ray"],
+        "mean_samples_per_ray": float(model.logged["train/mean_num_samples_per_ray"]),
+        "cuda_graph": graph_stats,
         "hash_gather_gbs": HASH_GATHER_BYTES * global_samples / (ms_step * 1e-3) / 1e9,
         "e2e": e2e, "device_batches": producer_line, "weak_scaling": weak_line,
         "gpu_launches": launches, "cuda_mallocs_in_timed_region": mallocs,

@@ -82,8 +82,8 @@ _SIGNATURES = {
     "den_version": (_INT, []),
     "den_last_error": (_c.c_char_p, []),
     "den_device_sm_count": (_INT, []),
-    "den_hashgrid_fwd": (_INT, [_c.POINTER(HashGridDesc), _P, _P, _P, _I64, _P]),
-    "den_hashgrid_bwd": (_INT, [_c.POINTER(HashGridDesc), _P, _P, _P, _P, _P, _I64, _P]),
+    "den_hashgrid_fwd": (_INT, [_c.POINTER(HashGridDesc), _P, _P, _P, _I64, _P, _P]),
+    "den_hashgrid_bwd": (_INT, [_c.POINTER(HashGridDesc), _P, _P, _P, _P, _P, _I64, _P, _P]),
     "den_ray_aabb_intersect": (_INT, [_P, _P, _c.POINTER(_F), _P, _P, _I64, _P]),
     "den_clamp_jitter": (_INT, [_P, _P, _P, _INT, _F, _INT, _F, _F, _I64, _P]),
     "den_march_count": (_INT, [_c.POINTER(MarchParams), _P, _P, _P, _P, _P, _P, _I64, _P]),
@@ -102,10 +102,12 @@ _SIGNATURES = {
     "den_rays_from_trajectory": (_INT, [_P, _P, _I64, _P, _P, _P, _I32, _c.POINTER(_F), _P, _P, _I64,
                                         _P]),
     "den_adam_step": (_INT, [_c.POINTER(AdamTensor), _I32, _c.c_double, _c.c_double, _c.c_double, _I64,
-                             _c.c_double, _P]),
-    "den_alpha_from_sigma": (_INT, [_P, _P, _P, _P, _I64, _P]),
+                             _P, _c.c_double, _P]),
+    "den_alpha_from_sigma": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "den_visibility": (_INT, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "den_compact_samples": (_INT, [_P] * 9 + [_I64, _P]),
+    "den_compact_samples_ex": (_INT, [_P] * 9 + [_I64, _P, _P, _I32, _P, _P, _P, _P]),
+    "den_clamp_offsets": (_INT, [_P, _I64, _I32, _P, _P]),
     "den_weight_from_density_fwd": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),
     "den_weight_from_density_bwd": (_INT, [_P, _P, _P, _P, _I64, _P, _P, _P]),
     "den_weight_from_alpha_fwd": (_INT, [_P, _P, _I64, _P, _P]),
@@ -117,12 +119,12 @@ _SIGNATURES = {
                              _I64, _P, _P, _P, _P]),
     "den_field_density_at": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _P, _I64, _P,
                                     _P]),
-    "den_contract_samples": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "den_contract_samples": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "den_mlp_fwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _P, _P, _P, _P, _P, _P,
-                           _I64, _P, _P, _P]),
+                           _I64, _P, _P, _P, _P]),
     "den_mlp_bwd": (_INT, [_c.POINTER(FieldDesc), _c.POINTER(FieldParams), _c.POINTER(FieldGrads),
-                           _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
-    "den_contract_samples_bwd": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _I64, _P,
+                           _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "den_contract_samples_bwd": (_INT, [_c.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _I64, _P, _P,
                                         _P, _P]),
     "den_lpf_fwd": (_INT, [_P, _P, _P, _I32, _I64, _I32, _P, _P]),
     "den_lpf_bwd": (_INT, [_P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P]),

@@ -42,7 +42,15 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 // 16-byte aligned — every torch allocation is)
 __global__ void __launch_bounds__(256)
 adam_kernel(const __grid_constant__ AdamBatch b, float beta1, float beta2, float omb1, float omb2, float eps,
-            float bias1, float inv_sqrt_bias2, float gs) {
+            float bias1, float inv_sqrt_bias2, float gs, const int64_t* __restrict__ step_dev, double beta1_d,
+            double beta2_d) {
+    if (step_dev != nullptr) {
+        // the step number lives on the device (a captured CUDA graph replays this launch with the same
+        // kernel arguments every step): the bias corrections are derived here
+        const double t_d = (double)*step_dev;
+        bias1 = (float)(1.0 - pow(beta1_d, t_d));
+        inv_sqrt_bias2 = (float)(1.0 / sqrt(1.0 - pow(beta2_d, t_d)));
+    }
     const int t = blockIdx.y;
     float* __restrict__ p = b.p[t];
     const float* __restrict__ g = b.g[t];
@@ -81,9 +89,11 @@ adam_kernel(const __grid_constant__ AdamBatch b, float beta1, float beta2, float
 }  // namespace den
 
 extern "C" int den_adam_step(const den_adam_tensor* tensors, int32_t n_tensors, double beta1_d, double beta2_d,
-                             double eps_d, int64_t step, double grad_scale, void* stream) {
+                             double eps_d, int64_t step, const int64_t* step_dev, double grad_scale,
+                             void* stream) {
     using namespace den;
-    DEN_CHECK_ARG(n_tensors >= 0 && step >= 1, "bad tensor count / step");
+    DEN_CHECK_ARG(n_tensors >= 0 && (step >= 1 || step_dev != nullptr), "bad tensor count / step");
+    if (step < 1) step = 1;
     DEN_CHECK_ARG(n_tensors == 0 || tensors != nullptr, "null tensor list");
     const float beta1 = (float)beta1_d, beta2 = (float)beta2_d, eps = (float)eps_d;
     const double bias1 = 1.0 - pow(beta1_d, (double)step);
@@ -100,7 +110,8 @@ extern "C" int den_adam_step(const den_adam_tensor* tensors, int32_t n_tensors, 
             dim3 grid((unsigned)grid_for(blocks > 0 ? blocks : 1, 1, 8), (unsigned)count);
             adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(b, beta1, beta2, (float)(1.0 - (double)beta1_d),
                                                              (float)(1.0 - (double)beta2_d), eps, (float)bias1,
-                                                             inv_sqrt_bias2, (float)grad_scale);
+                                                             inv_sqrt_bias2, (float)grad_scale, step_dev, beta1_d,
+                                                             beta2_d);
             cudaError_t e = cudaGetLastError();
             count = 0;
             largest = 0;

@@ -42,6 +42,15 @@ inline int grid_for(int64_t work_items, int per_cta, int ctas_per_sm) {
 }
 
 // ---- device helpers ----------------------------------------------------------
+// Sample count of a per-sample kernel: the host passes the CAPACITY of the buffers as `n`; when the
+// true count lives on the device (written by the march / the compaction of the same step, so the
+// host never has to read it back) `n_dev` points at it and the kernel works on min(n, *n_dev) rows.
+__device__ __forceinline__ int64_t effective_n(int64_t n, const int32_t* __restrict__ n_dev) {
+    if (n_dev == nullptr) return n;
+    const int64_t m = (int64_t)*n_dev;
+    return m < n ? (m > 0 ? m : 0) : n;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);

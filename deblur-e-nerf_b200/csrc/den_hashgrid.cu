@@ -29,7 +29,9 @@ constexpr int kHashThreads = 256;    // 8 warps
 // ------------------------------------------------------------------ forward --
 __global__ void __launch_bounds__(kHashThreads, 6)
 hashgrid_fwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __restrict__ x,
-                    const float2* __restrict__ table, float* __restrict__ out, int64_t n) {
+                    const float2* __restrict__ table, float* __restrict__ out, int64_t n,
+                    const int32_t* __restrict__ n_dev) {
+    n = effective_n(n, n_dev);
     extern __shared__ float s_tile[];            // kTile x (LF + 1)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -90,7 +92,9 @@ template <bool kInputGrad>
 __global__ void __launch_bounds__(kHashThreads)
 hashgrid_bwd_kernel(const __grid_constant__ den_hashgrid_desc g, const float* __restrict__ x,
                     const float* __restrict__ dout, const float2* __restrict__ table,
-                    float2* __restrict__ dtable, float* __restrict__ dx, int64_t n) {
+                    float2* __restrict__ dtable, float* __restrict__ dx, int64_t n,
+                    const int32_t* __restrict__ n_dev) {
+    n = effective_n(n, n_dev);
     extern __shared__ float s_tile[];            // kTile x (LF + 1)  (+ kTile x 3 for dx)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -223,7 +227,7 @@ static int check_desc(const den_hashgrid_desc* d) {
 extern "C" {
 
 int den_hashgrid_fwd(const den_hashgrid_desc* desc, const float* x, const float* table, float* out,
-                     int64_t n, void* stream) {
+                     int64_t n, const int32_t* n_dev, void* stream) {
     using namespace den;
     int rc = check_desc(desc);
     if (rc) return rc;
@@ -234,13 +238,14 @@ int den_hashgrid_fwd(const den_hashgrid_desc* desc, const float* x, const float*
     const size_t smem = (size_t)kTile * (LF + 1) * sizeof(float);
     const int grid = grid_for((n + kTile - 1) / kTile, 1, 16);
     hashgrid_fwd_kernel<<<grid, kHashThreads, smem, as_stream(stream)>>>(
-        *desc, x, reinterpret_cast<const float2*>(table), out, n);
+        *desc, x, reinterpret_cast<const float2*>(table), out, n, n_dev);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }
 
 int den_hashgrid_bwd(const den_hashgrid_desc* desc, const float* x, const float* dout,
-                     const float* table, float* dtable, float* dx, int64_t n, void* stream) {
+                     const float* table, float* dtable, float* dx, int64_t n, const int32_t* n_dev,
+                     void* stream) {
     using namespace den;
     int rc = check_desc(desc);
     if (rc) return rc;
@@ -254,10 +259,10 @@ int den_hashgrid_bwd(const den_hashgrid_desc* desc, const float* x, const float*
     if (dx) {
         hashgrid_bwd_kernel<true><<<grid, kHashThreads, smem, as_stream(stream)>>>(
             *desc, x, dout, reinterpret_cast<const float2*>(table),
-            reinterpret_cast<float2*>(dtable), dx, n);
+            reinterpret_cast<float2*>(dtable), dx, n, n_dev);
     } else {
         hashgrid_bwd_kernel<false><<<grid, kHashThreads, smem, as_stream(stream)>>>(
-            *desc, x, dout, nullptr, reinterpret_cast<float2*>(dtable), nullptr, n);
+            *desc, x, dout, nullptr, reinterpret_cast<float2*>(dtable), nullptr, n, n_dev);
     }
     DEN_CHECK_LAUNCH();
     return DEN_OK;

@@ -374,7 +374,9 @@ scan_add_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ block_sum
 
 // ------------------------------------------------------------- visibility ----
 __global__ void alpha_kernel(const float* __restrict__ sigmas, const float* __restrict__ t0,
-                             const float* __restrict__ t1, float* __restrict__ alphas, int64_t n) {
+                             const float* __restrict__ t1, float* __restrict__ alphas, int64_t n,
+                             const int32_t* __restrict__ n_dev) {
+    n = effective_n(n, n_dev);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
         alphas[i] = 1.0f - expf(-sigmas[i] * (t1[i] - t0[i]));
@@ -408,7 +410,9 @@ compact_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ off
                const int32_t* __restrict__ off_out, const int32_t* __restrict__ ray_in,
                const float* __restrict__ t0_in, const float* __restrict__ t1_in,
                int32_t* __restrict__ ray_out, float* __restrict__ t0_out,
-               float* __restrict__ t1_out, int64_t n_rays) {
+               float* __restrict__ t1_out, int64_t n_rays, const float* __restrict__ sig_in,
+               const float* __restrict__ rgb_in, int channels, float* __restrict__ sig_out,
+               float* __restrict__ rgb_out, int32_t* __restrict__ src_rows) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -425,8 +429,25 @@ compact_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ off
                 ray_out[k] = ray_in[i];
                 t0_out[k] = t0_in[i];
                 t1_out[k] = t1_in[i];
+                if (sig_out) sig_out[k] = sig_in[i];
+                if (rgb_out)
+                    for (int c = 0; c < channels; ++c) rgb_out[k * (int64_t)channels + c] = rgb_in[i * (int64_t)channels + c];
+                if (src_rows) src_rows[k] = i;
             }
             dst += __popc(ball);
+        }
+    }
+}
+
+// offsets (exclusive prefix of per-ray counts) limited to the capacity of the sample buffers
+__global__ void clamp_offsets_kernel(int32_t* __restrict__ offsets, int64_t n, int32_t capacity,
+                                     int32_t* __restrict__ overflow) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = offsets[i];
+        if (v > capacity) {
+            offsets[i] = capacity;
+            if (i == n - 1 && overflow) *overflow = 1;
         }
     }
 }
@@ -575,12 +596,12 @@ int den_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* wor
 }
 
 int den_alpha_from_sigma(const float* sigmas, const float* t0, const float* t1, float* alphas,
-                         int64_t n, void* stream) {
+                         int64_t n, const int32_t* n_dev, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(n >= 0, "negative sample count");
     if (n == 0) return DEN_OK;
     DEN_CHECK_ARG(sigmas && t0 && t1 && alphas, "null pointer");
-    alpha_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(sigmas, t0, t1, alphas, n);
+    alpha_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(sigmas, t0, t1, alphas, n, n_dev);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }
@@ -601,12 +622,36 @@ int den_compact_samples(const uint8_t* mask, const int32_t* off_in, const int32_
                         const int32_t* ray_in, const float* t0_in, const float* t1_in,
                         int32_t* ray_out, float* t0_out, float* t1_out, int64_t n_rays,
                         void* stream) {
+    return den_compact_samples_ex(mask, off_in, off_out, ray_in, t0_in, t1_in, ray_out, t0_out, t1_out,
+                                  n_rays, nullptr, nullptr, 0, nullptr, nullptr, nullptr, stream);
+}
+
+int den_compact_samples_ex(const uint8_t* mask, const int32_t* off_in, const int32_t* off_out,
+                           const int32_t* ray_in, const float* t0_in, const float* t1_in,
+                           int32_t* ray_out, float* t0_out, float* t1_out, int64_t n_rays,
+                           const float* sig_in, const float* rgb_in, int32_t channels, float* sig_out,
+                           float* rgb_out, int32_t* src_rows, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(n_rays >= 0, "negative ray count");
     if (n_rays == 0) return DEN_OK;
     DEN_CHECK_ARG(off_in && off_out, "null pointer");
+    DEN_CHECK_ARG((sig_out == nullptr || sig_in != nullptr) && (rgb_out == nullptr || rgb_in != nullptr),
+                  "an output row array needs its input");
+    DEN_CHECK_ARG(rgb_out == nullptr || (channels >= 1 && channels <= 4), "1 to 4 channels");
     compact_kernel<<<grid_for(n_rays, 8, 8), 256, 0, as_stream(stream)>>>(
-        mask, off_in, off_out, ray_in, t0_in, t1_in, ray_out, t0_out, t1_out, n_rays);
+        mask, off_in, off_out, ray_in, t0_in, t1_in, ray_out, t0_out, t1_out, n_rays, sig_in, rgb_in,
+        channels, sig_out, rgb_out, src_rows);
+    DEN_CHECK_LAUNCH();
+    return DEN_OK;
+}
+
+int den_clamp_offsets(int32_t* offsets, int64_t n_plus_1, int32_t capacity, int32_t* overflow,
+                      void* stream) {
+    using namespace den;
+    DEN_CHECK_ARG(n_plus_1 >= 1 && capacity >= 0, "bad sizes");
+    DEN_CHECK_ARG(offsets != nullptr, "null pointer");
+    clamp_offsets_kernel<<<grid_for(n_plus_1, 256, 8), 256, 0, as_stream(stream)>>>(offsets, n_plus_1,
+                                                                                   capacity, overflow);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }

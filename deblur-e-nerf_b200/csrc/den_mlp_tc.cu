@@ -72,8 +72,9 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                   const float* __restrict__ enc, const float* __restrict__ rays_o,
                   const float* __restrict__ rays_d, const int32_t* __restrict__ ray_indices,
                   const float* __restrict__ t_starts, const float* __restrict__ t_ends, int64_t n,
-                  float* __restrict__ sigmas, float* __restrict__ rgbs) {
+                  const int32_t* __restrict__ n_dev, float* __restrict__ sigmas, float* __restrict__ rgbs) {
     using namespace fwd;
+    n = effective_n(n, n_dev);
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
@@ -294,7 +295,8 @@ __global__ void contract_samples_kernel(const __grid_constant__ den_field_desc f
                                         const int32_t* __restrict__ ray_indices,
                                         const float* __restrict__ t_starts,
                                         const float* __restrict__ t_ends, int64_t n,
-                                        float* __restrict__ unit_pos) {
+                                        const int32_t* __restrict__ n_dev, float* __restrict__ unit_pos) {
+    n = effective_n(n, n_dev);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = ray_indices[i];
@@ -319,7 +321,9 @@ __global__ void contract_samples_bwd_kernel(const __grid_constant__ den_field_de
                                             const float* __restrict__ t_starts,
                                             const float* __restrict__ t_ends,
                                             const float* __restrict__ d_unit, int64_t n,
-                                            float* __restrict__ d_pos, float* __restrict__ d_pos_t) {
+                                            const int32_t* __restrict__ n_dev, float* __restrict__ d_pos,
+                                            float* __restrict__ d_pos_t) {
+    n = effective_n(n, n_dev);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = ray_indices[i];
@@ -344,8 +348,8 @@ extern "C" {
 
 int den_contract_samples_bwd(const den_field_desc* f, const float* rays_o, const float* rays_d,
                              const int32_t* ray_indices, const float* t_starts, const float* t_ends,
-                             const float* d_unit, int64_t n, float* d_pos, float* d_pos_t,
-                             void* stream) {
+                             const float* d_unit, int64_t n, const int32_t* n_dev, float* d_pos,
+                             float* d_pos_t, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(f != nullptr, "null descriptor");
     DEN_CHECK_ARG(n >= 0, "negative sample count");
@@ -353,29 +357,29 @@ int den_contract_samples_bwd(const den_field_desc* f, const float* rays_o, const
     DEN_CHECK_ARG(rays_o && rays_d && ray_indices && t_starts && t_ends && d_unit && d_pos && d_pos_t,
                   "null pointer");
     contract_samples_bwd_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
-        *f, rays_o, rays_d, ray_indices, t_starts, t_ends, d_unit, n, d_pos, d_pos_t);
+        *f, rays_o, rays_d, ray_indices, t_starts, t_ends, d_unit, n, n_dev, d_pos, d_pos_t);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }
 
 int den_contract_samples(const den_field_desc* f, const float* rays_o, const float* rays_d,
                          const int32_t* ray_indices, const float* t_starts, const float* t_ends,
-                         int64_t n, float* unit_pos, void* stream) {
+                         int64_t n, const int32_t* n_dev, float* unit_pos, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(f != nullptr, "null descriptor");
     DEN_CHECK_ARG(n >= 0, "negative sample count");
     if (n == 0) return DEN_OK;
     DEN_CHECK_ARG(rays_o && rays_d && ray_indices && t_starts && t_ends && unit_pos, "null pointer");
     contract_samples_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
-        *f, rays_o, rays_d, ray_indices, t_starts, t_ends, n, unit_pos);
+        *f, rays_o, rays_d, ray_indices, t_starts, t_ends, n, n_dev, unit_pos);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }
 
 int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float* enc,
                 const float* rays_o, const float* rays_d, const int32_t* ray_indices,
-                const float* t_starts, const float* t_ends, int64_t n, float* sigmas, float* rgbs,
-                void* stream) {
+                const float* t_starts, const float* t_ends, int64_t n, const int32_t* n_dev,
+                float* sigmas, float* rgbs, void* stream) {
     using namespace den;
     const bool full = rgbs != nullptr;
     int rc = check_field(f, p, full);
@@ -393,11 +397,11 @@ int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float*
     if (full) {
         cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         mlp_fwd_tc_kernel<true><<<grid, fwd::kThreads, smem, as_stream(stream)>>>(
-            *f, *p, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, n, sigmas, rgbs);
+            *f, *p, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, n, n_dev, sigmas, rgbs);
     } else {
         cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         mlp_fwd_tc_kernel<false><<<grid, fwd::kThreads, smem, as_stream(stream)>>>(
-            *f, *p, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, n, sigmas, nullptr);
+            *f, *p, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, n, n_dev, sigmas, nullptr);
     }
     DEN_CHECK_LAUNCH();
     return DEN_OK;

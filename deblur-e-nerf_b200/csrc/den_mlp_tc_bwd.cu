@@ -142,8 +142,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                   const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                   const int32_t* __restrict__ ray_indices, const float* __restrict__ t_starts,
                   const float* __restrict__ t_ends, const float* __restrict__ d_sigmas,
-                  const float* __restrict__ d_rgbs, int64_t n, float* __restrict__ d_enc,
+                  const float* __restrict__ d_rgbs, int64_t n, const int32_t* __restrict__ n_dev,
+                  const int32_t* __restrict__ enc_rows, float* __restrict__ d_enc,
                   float* __restrict__ d_dirs) {
+    n = effective_n(n, n_dev);
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);       // done[0..1], dw_done[0..1]
@@ -381,7 +383,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
 #pragma unroll
             for (int k = 0; k < 16; ++k) x[k] = 0.f;
             if (valid) {
-                const float4* src = reinterpret_cast<const float4*>(enc + i * enc_dim + 16 * hf);
+                // enc_rows: sample i's encoding is row enc_rows[i] of `enc` (the survivors of the
+                // visibility filter read the pre-pass encodings in place, no compacted copy)
+                const int64_t src_row = enc_rows ? (int64_t)__ldg(enc_rows + i) : i;
+                const float4* src = reinterpret_cast<const float4*>(enc + src_row * enc_dim + 16 * hf);
 #pragma unroll
                 for (int v4 = 0; v4 < 4; ++v4)
                     if (16 * hf + 4 * v4 < enc_dim) {
@@ -502,7 +507,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             if (k + kSlots < my_tiles) {
                 const int64_t ni = i + (int64_t)kSlots * gridDim.x * kTile;
                 if (ni < n) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(enc + ni * enc_dim + 16 * hf));
+                    if (!enc_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(enc + ni * enc_dim + 16 * hf));
                     if (hf == 0) {
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(ray_indices + ni));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(t_starts + ni));
@@ -684,7 +689,8 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
                            const den_field_grads* g, const float* enc, const float* rays_o,
                            const float* rays_d, const int32_t* ray_indices, const float* t_starts,
                            const float* t_ends, const float* d_sigmas, const float* d_rgbs,
-                           int64_t n, float* d_enc, float* d_dirs, void* stream) {
+                           int64_t n, const int32_t* n_dev, const int32_t* enc_rows, float* d_enc,
+                           float* d_dirs, void* stream) {
     using namespace den;
     int rc = check_field(f, p, true);
     if (rc) return rc;
@@ -704,7 +710,8 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
     cudaFuncSetAttribute(mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)bwd::Smem::total);
     mlp_bwd_tc_kernel<<<grid, bwd::kThreads, bwd::Smem::total, as_stream(stream)>>>(
-        *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, d_enc, d_dirs);
+        *f, *p, *g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas, d_rgbs, n, n_dev, enc_rows,
+        d_enc, d_dirs);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }

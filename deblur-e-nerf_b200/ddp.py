@@ -184,6 +184,10 @@ def attach(renderer):
         return renderer
 
     def reduce_mean(value):
+        if torch.is_tensor(value):            # sync-free steps: the mean stays on the device
+            t = value.detach().clone()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return t / world_size()
         dev = next(renderer.parameters()).device
         t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -108,14 +108,16 @@ class _MlpTcFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, field, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets,
-                precomputed, *weights):
+                precomputed, n_dev, enc_rows, *weights):
         if precomputed is not None:
             # the visibility pre-pass already evaluated these very samples with these weights
             sig, rgb = (t.view_as(t) for t in precomputed)
         else:
+            assert enc_rows is None
             sig, rgb = ops.mlp_fwd(field.field_desc(), field.field_params(), enc, rays_o, rays_d,
-                                   ray_indices, t_starts, t_ends, field.radiance_dim)
+                                   ray_indices, t_starts, t_ends, field.radiance_dim, n_dev)
         ctx.field = field
+        ctx.n_dev, ctx.enc_rows = n_dev, enc_rows
         ctx.save_for_backward(enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets)
         return sig, rgb
 
@@ -131,9 +133,9 @@ class _MlpTcFn(torch.autograd.Function):
             setattr(gs, name, t.data_ptr())
         d_enc, d_dirs = ops.mlp_bwd(field.field_desc(), field.field_params(), gs, enc, rays_o,
                                     rays_d, ray_indices, t_starts, t_ends, d_sig.contiguous(),
-                                    d_rgb.contiguous(), need_d_dirs)
+                                    d_rgb.contiguous(), need_d_dirs, ctx.n_dev, ctx.enc_rows)
         d_rays_d = ops.segment_sum(d_dirs, offsets) if need_d_dirs else None
-        return (None, d_enc, None, d_rays_d, None, None, None, None, None, *grads)
+        return (None, d_enc, None, d_rays_d, None, None, None, None, None, None, None, *grads)
 
 
 class NGPradianceField(torch.nn.Module):
@@ -227,37 +229,42 @@ class NGPradianceField(torch.nn.Module):
                              t_starts, t_ends, self.radiance_dim if full else 0, n_dev)
 
     # ---------------------------------------------- tensor-core path (with autograd) --
-    def encode_samples(self, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets, enc=None):
+    def encode_samples(self, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets, enc=None,
+                       n_dev=None):
         """Hash-grid encoding (M, L*2) of marched samples as an autograd node on the table (and on
         the rays when they require grad); `enc` re-uses an encoding already computed on the same
-        samples."""
+        samples.  `n_dev`: device-side sample count (the tensors are capacity-sized)."""
         if rays_o.requires_grad or rays_d.requires_grad:
             u = ops.contract_samples_autograd(self.field_desc(), rays_o, rays_d, ray_indices,
-                                              t_starts, t_ends, offsets)
+                                              t_starts, t_ends, offsets, n_dev)
         else:
             u = ops.contract_samples(self.field_desc(), rays_o, rays_d, ray_indices, t_starts,
-                                     t_ends)
+                                     t_ends, n_dev)
         if enc is not None:
-            return ops.hashgrid_reuse(u, self.encoding.params, self.encoding.desc, enc)
+            return ops.hashgrid_reuse(u, self.encoding.params, self.encoding.desc, enc, n_dev)
+        assert n_dev is None
         return ops.hashgrid(u, self.encoding.params, self.encoding.desc)
 
     def mlp_samples(self, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets,
-                    precomputed=None):
+                    precomputed=None, n_dev=None, enc_rows=None):
         """(sigma (M,), rgb (M,C)) from encodings on the tensor cores, differentiable in the
         encodings and in every MLP parameter.  `precomputed=(sigma, rgb)` skips the forward
-        launch when the pre-pass has already produced them (the backward recomputes anyway)."""
+        launch when the pre-pass has already produced them (the backward recomputes anyway).
+        `enc_rows` (M) int32: sample i's encoding is row enc_rows[i] of `enc` (survivors of the
+        visibility filter reading the pre-pass encodings in place)."""
         return _MlpTcFn.apply(self, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets,
-                              precomputed, *self.param_tensors()[1:])
+                              precomputed, n_dev, enc_rows, *self.param_tensors()[1:])
 
     @torch.no_grad()
-    def eval_samples_tc(self, rays_o, rays_d, ray_indices, t_starts, t_ends, full=True):
+    def eval_samples_tc(self, rays_o, rays_d, ray_indices, t_starts, t_ends, full=True, n_dev=None):
         """Gather + tensor-core MLP without autograd: (sigma (M,), rgb (M,C) | None, enc (M, L*2)).
         This is the reference's no-grad density pre-pass (external/utils.py:68-81); evaluating
         the colour head in the same launch lets the grad pass re-use every output."""
-        u = ops.contract_samples(self.field_desc(), rays_o, rays_d, ray_indices, t_starts, t_ends)
-        enc = ops.hashgrid_fwd(self.encoding.desc, u, self.encoding.params)
+        u = ops.contract_samples(self.field_desc(), rays_o, rays_d, ray_indices, t_starts, t_ends,
+                                 n_dev)
+        enc = ops.hashgrid_fwd(self.encoding.desc, u, self.encoding.params, n_dev)
         sig, rgb = ops.mlp_fwd(self.field_desc(), self.field_params(), enc, rays_o, rays_d,
-                               ray_indices, t_starts, t_ends, self.radiance_dim if full else 0)
+                               ray_indices, t_starts, t_ends, self.radiance_dim if full else 0, n_dev)
         return sig, rgb, enc
 
     # --------------------------------------------------- reference-signature methods --

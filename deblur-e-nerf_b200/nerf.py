@@ -94,6 +94,7 @@ class NeRF(torch.nn.Module):
             dir_encoding_config=dict(_get(arch_config, "dir_encoding")),
             mlp_base_config=base, mlp_head_config=head)
         self.last_num_samples = None        # device int32 scalar of the latest render call
+        self.last_marched = None            # marched samples of the latest synchronising render call
         # eval mode: the reference renders `test_chunk_size` rays at a time to bound memory
         # (external/utils.py:99-103); rays are independent and the eval march is deterministic, so any
         # chunking gives the same image — on a 180 GB part the chunks are merged up to this many rays
@@ -102,6 +103,16 @@ class NeRF(torch.nn.Module):
         # (~0.4 KB of per-sample buffers each): the first chunk is `test_chunk_size` rays.
         self.eval_chunk_rays = 1 << 20
         self.eval_chunk_samples = 1 << 25
+        # Training without host read-backs: the sample buffers of a render
+        # call are sized from the samples per ray of the previous calls (x `capacity_margin`, whole
+        # allocation quanta), the true counts stay on the device (`n_dev` of every per-sample kernel) and
+        # reach the host one call late through an asynchronous copy.  The first call, and any call after an
+        # overflow, takes the synchronising path (which also teaches the estimate).
+        self.sync_free = True
+        self.capacity_margin = 1.25
+        self._spr_estimate = None            # marched samples per ray, max of the recent calls
+        self._stats = None                   # LaggedReadback of the latest sync-free call
+        self.overflow_count = 0
 
     # ---------------------------------------------------------------- occupancy ------
     def update_occ_grid(self, step, T_wc_position=None):
@@ -133,7 +144,7 @@ class NeRF(torch.nn.Module):
         return T_wc_position, d
 
     # ------------------------------------------------------------------- render ------
-    def _march(self, o, d, jitter, probe=None):
+    def _march(self, o, d, jitter, probe=None, capacity=None, overflow=None):
         grid = self.occupancy_grid
         if self.contraction_type == ContractionType.AABB:
             t_min, t_max = ops.ray_aabb_intersect(o, d, self._aabb_host)
@@ -159,7 +170,77 @@ class NeRF(torch.nn.Module):
             seg_len = ops.march_segment_length(0.0, diag, self._step_host)
         else:
             seg_len = None
+        if overflow is not None:
+            return ops.march(params, o, d, t_min, t_max, grid.binary, capacity=capacity,
+                             seg_len=seg_len, overflow=overflow)
         return ops.march(params, o, d, t_min, t_max, grid.binary, seg_len=seg_len, probe=probe)
+
+    def _segment_bound_known(self):
+        return (self.near_plane is not None and self.far_plane is not None) \
+            or self.contraction_type == ContractionType.AABB
+
+    # ---------------------------------------------------- sync-free bookkeeping ------
+    def _consume_stats(self):
+        """Fold the (lagged) counts of the previous sync-free call into the capacity estimate."""
+        if self._stats is None:
+            return
+        vals = self._stats.pop()
+        self._stats = None
+        if vals is None:
+            return
+        marched, n_rays, overflow = vals[0], vals[1], vals[2]
+        spr = marched / max(n_rays, 1.0)
+        if overflow:
+            self.overflow_count += 1
+            self._spr_estimate = None        # next call: the synchronising path, exact sizes
+        elif self._spr_estimate is not None:
+            self._spr_estimate = max(0.9 * self._spr_estimate, spr)
+
+    def _capacity(self, n_rays):
+        if self._spr_estimate is None:
+            return None
+        need = int(self._spr_estimate * self.capacity_margin * n_rays) + 1
+        q = ops._ROW_QUANTUM
+        return (-(-need // q) + 1) * q
+
+    def render_chunk_sync_free(self, o, d, jitter, groups, capacity):
+        """`render_chunk` for training with NO host read: capacity-sized sample buffers, device-side
+        counts.  Returns colour, opacity, depth and the per-group sample counts as a DEVICE tensor."""
+        field = self.radiance_field
+        n_rays = o.shape[0]
+        dev = o.device
+        overflow = torch.zeros((), dtype=torch.int32, device=dev)
+        ray_idx, t0, t1, offsets = self._march(o, d, jitter, capacity=capacity, overflow=overflow)
+        n_dev = offsets[-1:]
+        marched_total = n_dev
+        sig, rgb, enc = field.eval_samples_tc(o, d, ray_idx, t0, t1, full=True, n_dev=n_dev)
+        enc_rows = None
+        if self.early_stop_eps > 0.0:
+            alphas = ops.alpha_from_sigma(sig, t0, t1, n_dev)
+            mask, counts = ops.visibility(alphas, offsets, self.early_stop_eps, 0.0)
+            offsets_out = ops.exclusive_scan_i32(counts)
+            # survivors keep their order; their pre-pass sigma / rgb travel with them (8 B per sample)
+            # and the 128-byte encodings are read in place through `enc_rows`
+            ray_idx, t0, t1, sig, rgb, enc_rows = ops.compact_ex(
+                mask, offsets, offsets_out, ray_idx, t0, t1, capacity, sig, rgb)
+            offsets = offsets_out
+            n_dev = offsets[-1:]
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in field.parameters())
+        if needs_grad:
+            enc_node = field.encode_samples(o, d, ray_idx, t0, t1, offsets, enc=enc, n_dev=n_dev)
+            sig, rgb = field.mlp_samples(enc_node, o, d, ray_idx, t0, t1, offsets, precomputed=(sig, rgb),
+                                         n_dev=n_dev, enc_rows=enc_rows)
+        colour, opacity, depth = ops.composite(sig, rgb, t0, t1, offsets, self.render_bkgd)
+        per = n_rays // groups
+        counts = offsets[::per].diff()                 # (groups,) samples per render call
+        # the counts reach the host one call late (capacity estimate, overflow check)
+        from .lagged import LaggedReadback
+        stats = torch.stack((marched_total[0].double(),
+                             torch.full((), float(n_rays), device=dev, dtype=torch.float64),
+                             overflow.double()))
+        self._stats = LaggedReadback(stats)
+        return colour, opacity, depth, counts
+
 
     def render_chunk(self, o, d, jitter=None, groups=1):
         """One chunk of rays (R,3),(R,3) -> colour (R,C), opacity (R,), depth (R,), M.
@@ -174,6 +255,7 @@ class NeRF(torch.nn.Module):
             probe = torch.arange(0, groups + 1, device=o.device) * (n_rays // groups)
         marched = self._march(o, d, jitter, probe)
         ray_idx, t0, t1, offsets = marched[:4]
+        self.last_marched = ray_idx.numel()
         bounds = marched[4] if groups > 1 else None
 
         needs_grad = torch.is_grad_enabled() and any(
@@ -230,11 +312,23 @@ class NeRF(torch.nn.Module):
             if jitter is None:
                 # one draw per render call, in call order: the RNG stream of `groups` separate calls
                 jitter = torch.cat([torch.rand(per, device=o.device) for _ in range(groups)])
-            col, opa, dep, counts = self.render_chunk(o, d, jitter.reshape(-1).contiguous(), groups)
+            jitter = jitter.reshape(-1).contiguous()
+            self._consume_stats()
+            capacity = self._capacity(n_rays) if (
+                self.sync_free and o.is_cuda and self.alpha_thre == 0.0
+                and self._segment_bound_known()) else None
+            if capacity is not None:
+                col, opa, dep, counts = self.render_chunk_sync_free(o, d, jitter, groups, capacity)
+                means = list((counts.to(torch.float32) / max(per, 1)).unbind(0))      # device scalars
+            else:
+                col, opa, dep, counts = self.render_chunk(o, d, jitter, groups)
+                means = [c / max(per, 1) for c in counts]
+                if self.last_marched is not None:
+                    self._spr_estimate = self.last_marched / max(n_rays, 1)
             radiance = col.view(*shape[:-1], -1).squeeze(dim=-1)
             opacity = opa.view(*shape[:-1])
             depth = dep.view(*shape[:-1]) / (opacity + self.opacity_eps)
-            return radiance, opacity, depth, [c / max(per, 1) for c in counts]
+            return radiance, opacity, depth, means
         training = self.radiance_field.training
         chunk = n_rays if training else self.test_chunk_size
         cols, opas, deps, total = [], [], [], 0

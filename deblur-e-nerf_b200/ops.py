@@ -162,24 +162,28 @@ def make_hashgrid_desc(n_levels, base_resolution, per_level_scale, log2_hashmap_
     return d, total
 
 
-def hashgrid_fwd(desc, x, table):
+def hashgrid_fwd(desc, x, table, n_dev=None):
+    """`n_dev` (here and in every per-sample wrapper below): optional device int32 with the true row
+    count; the tensors then hold `x.shape[0]` rows of CAPACITY and the kernel works on the first
+    min(capacity, n_dev) of them — no host read-back of the count (see include/den_b200.h)."""
     x = _req(x, torch.float32, "x")
     table = _req(table, torch.float32, "table")
     n = x.shape[0]
     out = _rows(n, (desc.n_levels * desc.n_features,), torch.float32, x.device)
-    _call("den_hashgrid_fwd", ctypes.byref(desc), _ptr(x), _ptr(table), _ptr(out), n, _stream())
+    _call("den_hashgrid_fwd", ctypes.byref(desc), _ptr(x), _ptr(table), _ptr(out), n, _ptr(n_dev),
+          _stream())
     return out
 
 
-def hashgrid_bwd(desc, x, dout, table, need_dx, dtable=None):
+def hashgrid_bwd(desc, x, dout, table, need_dx, dtable=None, n_dev=None):
     x = _req(x, torch.float32, "x")
     dout = _req(dout, torch.float32, "dout")
     n = x.shape[0]
     if dtable is None:
         dtable = torch.zeros_like(table)
-    dx = _rows_like(x) if need_dx else None
+    dx = (torch.zeros_like(x) if n_dev is not None else _rows_like(x)) if need_dx else None
     _call("den_hashgrid_bwd", ctypes.byref(desc), _ptr(x), _ptr(dout), _ptr(table), _ptr(dtable),
-          _ptr(dx), n, _stream())
+          _ptr(dx), n, _ptr(n_dev), _stream())
     return dtable, dx
 
 
@@ -207,20 +211,25 @@ class _HashGridReuseFn(torch.autograd.Function):
     gather on the same positions): forward hands it back, backward is the usual scatter."""
 
     @staticmethod
-    def forward(ctx, x, table, desc, enc):
+    def forward(ctx, x, table, desc, enc, n_dev):
         ctx.desc = desc
+        ctx.n_dev = n_dev
         ctx.save_for_backward(x, table)
         return enc.view_as(enc)
 
     @staticmethod
     def backward(ctx, dout):
         x, table = ctx.saved_tensors
-        dtable, dx = hashgrid_bwd(ctx.desc, x, dout, table, ctx.needs_input_grad[0])
-        return dx, (dtable if ctx.needs_input_grad[1] else None), None, None
+        dtable, dx = hashgrid_bwd(ctx.desc, x, dout, table, ctx.needs_input_grad[0], n_dev=ctx.n_dev)
+        return dx, (dtable if ctx.needs_input_grad[1] else None), None, None, None
 
 
-def hashgrid_reuse(x, table, desc, enc):
-    return _HashGridReuseFn.apply(x, table, desc, enc)
+def hashgrid_reuse(x, table, desc, enc, n_dev=None):
+    """With `enc_rows` (field.mlp_samples) `enc` may be the UN-compacted pre-pass encodings while `x`
+    holds the survivors' positions: the node then stands for the survivors' rows, which only
+    den_mlp_bwd reads (through the row map); both have the same capacity."""
+    assert enc.shape[0] == x.shape[0]
+    return _HashGridReuseFn.apply(x, table, desc, enc, n_dev)
 
 
 # --------------------------------------------------------------------------- #
@@ -293,7 +302,7 @@ def march_segment_length(t_lo, t_hi, step_size):
 
 
 def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=None,
-          single_pass=True, probe=None):
+          single_pass=True, probe=None, overflow=None):
     """Occupancy march.  Returns (ray_indices i32, t_starts, t_ends, offsets (R+1)).
 
     Default: ONE marching pass into an upper-bound arena, then a coalesced pack — the sequential
@@ -309,6 +318,11 @@ def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=N
     ``probe`` (int64 index tensor into ``offsets``): those entries ride along with the host read of
     the total and come back as a fifth return value (a list of ints) — per-group sample counts
     without a second synchronisation.
+
+    ``overflow`` (device int32 scalar) selects the SYNC-FREE single pass: `capacity` rows are
+    allocated from the caller's estimate, the offsets are clamped to it (``overflow`` is set if
+    samples were lost) and NOTHING is read back — the true total stays on the device in
+    ``offsets[-1]`` for the ``n_dev`` argument of the per-sample kernels.  Needs ``seg_len``.
     """
     rays_o = _req(rays_o, torch.float32, "rays_o")
     rays_d = _req(rays_d, torch.float32, "rays_d")
@@ -320,6 +334,28 @@ def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=N
     n = rays_o.shape[0]
     dev = rays_o.device
     counts = torch.empty(n, dtype=torch.int32, device=dev)
+    if overflow is not None:
+        if capacity is None or seg_len is None or n == 0 or n * seg_len > MARCH_ARENA_MAX:
+            raise ValueError("sync-free march needs a capacity and a per-ray segment bound")
+        key = (dev, n, seg_len)
+        seg = _SEG_OFFSETS.get(key)
+        if seg is None:
+            seg = (torch.arange(n + 1, dtype=torch.int64, device=dev) * seg_len).to(torch.int32)
+            if len(_SEG_OFFSETS) > 16:
+                _SEG_OFFSETS.clear()
+            _SEG_OFFSETS[key] = seg
+        arena_t0, arena_t1 = _arena(dev, n * seg_len)
+        _call("den_march_single", ctypes.byref(params), _ptr(rays_o), _ptr(rays_d), _ptr(t_min),
+              _ptr(t_max), _ptr(binary), _ptr(seg), _ptr(counts), _ptr(arena_t0), _ptr(arena_t1), n,
+              _stream())
+        offsets = exclusive_scan_i32(counts)
+        clamp_offsets_(offsets, capacity, overflow)
+        ray_indices = _rows(capacity, (), torch.int32, dev)
+        t_starts = _rows(capacity, (), torch.float32, dev)
+        t_ends = _rows(capacity, (), torch.float32, dev)
+        _call("den_march_pack", _ptr(seg), _ptr(offsets), _ptr(arena_t0), _ptr(arena_t1), n,
+              _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _stream())
+        return ray_indices, t_starts, t_ends, offsets
     if single_pass and capacity is None and n > 0:
         if seg_len is not None and n * seg_len <= MARCH_ARENA_MAX:
             key = (dev, n, seg_len)
@@ -372,11 +408,11 @@ def march(params, rays_o, rays_d, t_min, t_max, binary, capacity=None, seg_len=N
     return out if probe is None else out + ([int(v) for v in offsets[probe].tolist()],)
 
 
-def alpha_from_sigma(sigmas, t_starts, t_ends):
+def alpha_from_sigma(sigmas, t_starts, t_ends, n_dev=None):
     sigmas = _req(sigmas.reshape(-1), torch.float32, "sigmas")
     out = _rows_like(sigmas)
     _call("den_alpha_from_sigma", _ptr(sigmas), _ptr(t_starts), _ptr(t_ends), _ptr(out),
-          sigmas.numel(), _stream())
+          sigmas.numel(), _ptr(n_dev), _stream())
     return out
 
 
@@ -401,6 +437,31 @@ def compact(mask, offsets_in, offsets_out, ray_indices, t_starts, t_ends, capaci
           _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _ptr(ro), _ptr(t0), _ptr(t1), n_rays,
           _stream())
     return ro, t0, t1
+
+
+def compact_ex(mask, offsets_in, offsets_out, ray_indices, t_starts, t_ends, capacity, sigmas, rgbs):
+    """Compaction that also carries the survivors' pre-pass sigma / rgb along and records, per
+    survivor, its row in the un-compacted arrays.  Capacity-sized outputs; no host read."""
+    dev = mask.device
+    n_rays = offsets_in.numel() - 1
+    ro = _rows(capacity, (), torch.int32, dev)
+    t0 = _rows(capacity, (), torch.float32, dev)
+    t1 = _rows(capacity, (), torch.float32, dev)
+    sig = _rows(capacity, (), torch.float32, dev)
+    channels = rgbs.shape[-1]
+    rgb = _rows(capacity, (channels,), torch.float32, dev)
+    rows = _rows(capacity, (), torch.int32, dev)
+    _call("den_compact_samples_ex", _ptr(mask), _ptr(offsets_in), _ptr(offsets_out),
+          _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _ptr(ro), _ptr(t0), _ptr(t1), n_rays,
+          _ptr(sigmas), _ptr(rgbs), channels, _ptr(sig), _ptr(rgb), _ptr(rows), _stream())
+    return ro, t0, t1, sig, rgb, rows
+
+
+def clamp_offsets_(offsets, capacity, overflow):
+    """offsets <- min(offsets, capacity) in place; `overflow` (device int32) is set when the total
+    exceeded the capacity."""
+    _call("den_clamp_offsets", _ptr(offsets), offsets.numel(), int(capacity), _ptr(overflow), _stream())
+    return offsets
 
 
 def offsets_from_ray_indices(ray_indices, n_rays):
@@ -654,38 +715,39 @@ def field_fwd(desc, params, rays_o, rays_d, ray_indices, t_starts, t_ends, chann
 # --------------------------------------------------------------------------- #
 # tensor-core MLP on pre-encoded samples
 # --------------------------------------------------------------------------- #
-def contract_samples(desc, rays_o, rays_d, ray_indices, t_starts, t_ends):
+def contract_samples(desc, rays_o, rays_d, ray_indices, t_starts, t_ends, n_dev=None):
     n = ray_indices.numel()
     out = _rows(n, (3,), torch.float32, rays_o.device)
     _call("den_contract_samples", ctypes.byref(desc), _ptr(rays_o), _ptr(rays_d),
-          _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(out), _stream())
+          _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(n_dev), _ptr(out), _stream())
     return out
 
 
-def mlp_fwd(desc, params, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, channels):
+def mlp_fwd(desc, params, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, channels, n_dev=None):
     enc = _req(enc, torch.float32, "enc")
     n = ray_indices.numel()
     dev = enc.device
     sig = _rows(n, (), torch.float32, dev)
     rgb = _rows(n, (channels,), torch.float32, dev) if channels else None
     _call("den_mlp_fwd", ctypes.byref(desc), ctypes.byref(params), _ptr(enc), _ptr(rays_o),
-          _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(sig), _ptr(rgb),
-          _stream())
+          _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), n, _ptr(n_dev), _ptr(sig),
+          _ptr(rgb), _stream())
     return sig, rgb
 
 
 def mlp_bwd(desc, params, grads_struct, enc, rays_o, rays_d, ray_indices, t_starts, t_ends,
-            d_sigmas, d_rgbs, need_d_dirs=False):
+            d_sigmas, d_rgbs, need_d_dirs=False, n_dev=None, enc_rows=None):
     """dL/denc (M, L*2) [and dL/d(view dir) (M,3)]; weight gradients are accumulated into the
-    buffers of `grads_struct`."""
+    buffers of `grads_struct`.  `enc_rows` (M) int32: sample i reads row enc_rows[i] of `enc`."""
     n = ray_indices.numel()
-    d_enc = _rows_like(enc)
+    d_enc = _rows(n, (enc.shape[1],), torch.float32, enc.device)
     d_dirs = torch.zeros((n, 3), dtype=torch.float32, device=enc.device) if need_d_dirs else None
     d_sigmas = _req(d_sigmas.reshape(-1), torch.float32, "d_sigmas")
     d_rgbs = _req(d_rgbs, torch.float32, "d_rgbs")
     _call("den_mlp_bwd", ctypes.byref(desc), ctypes.byref(params), ctypes.byref(grads_struct),
           _ptr(enc), _ptr(rays_o), _ptr(rays_d), _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends),
-          _ptr(d_sigmas), _ptr(d_rgbs), n, _ptr(d_enc), _ptr(d_dirs), _stream())
+          _ptr(d_sigmas), _ptr(d_rgbs), n, _ptr(n_dev), _ptr(enc_rows), _ptr(d_enc), _ptr(d_dirs),
+          _stream())
     return d_enc, d_dirs
 
 
@@ -704,10 +766,11 @@ class _ContractSamplesFn(torch.autograd.Function):
     the refractory-period gradient path)."""
 
     @staticmethod
-    def forward(ctx, desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets):
+    def forward(ctx, desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets, n_dev):
         ctx.desc = desc
+        ctx.n_dev = n_dev
         ctx.save_for_backward(rays_o, rays_d, ray_indices, t_starts, t_ends, offsets)
-        return contract_samples(desc, rays_o, rays_d, ray_indices, t_starts, t_ends)
+        return contract_samples(desc, rays_o, rays_d, ray_indices, t_starts, t_ends, n_dev)
 
     @staticmethod
     def backward(ctx, d_unit):
@@ -717,22 +780,24 @@ class _ContractSamplesFn(torch.autograd.Function):
         d_pos = _rows_like(d_unit)
         d_pos_t = _rows_like(d_unit)
         _call("den_contract_samples_bwd", ctypes.byref(ctx.desc), _ptr(rays_o), _ptr(rays_d),
-              _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _ptr(d_unit), n, _ptr(d_pos),
-              _ptr(d_pos_t), _stream())
-        return None, segment_sum(d_pos, offsets), segment_sum(d_pos_t, offsets), None, None, None, None
+              _ptr(ray_indices), _ptr(t_starts), _ptr(t_ends), _ptr(d_unit), n, _ptr(ctx.n_dev),
+              _ptr(d_pos), _ptr(d_pos_t), _stream())
+        return (None, segment_sum(d_pos, offsets), segment_sum(d_pos_t, offsets), None, None, None, None,
+                None)
 
 
-def contract_samples_autograd(desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets):
-    return _ContractSamplesFn.apply(desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets)
+def contract_samples_autograd(desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets, n_dev=None):
+    return _ContractSamplesFn.apply(desc, rays_o, rays_d, ray_indices, t_starts, t_ends, offsets, n_dev)
 
 
 # --------------------------------------------------------------------------- #
 # optimiser
 # --------------------------------------------------------------------------- #
-def adam_step(tensor_array, n_tensors, beta1, beta2, eps, step, grad_scale=1.0):
-    """One Adam step over a ctypes array of ``AdamTensor`` descriptors (see optim.FusedAdam)."""
+def adam_step(tensor_array, n_tensors, beta1, beta2, eps, step, grad_scale=1.0, step_dev=None):
+    """One Adam step over a ctypes array of ``AdamTensor`` descriptors (see optim.FusedAdam).
+    `step_dev`: device int64 step counter (CUDA-graph capture) instead of the host `step`."""
     _call("den_adam_step", tensor_array, int(n_tensors), float(beta1), float(beta2), float(eps),
-          int(step), float(grad_scale), _stream(), launches=2)
+          int(step), _ptr(step_dev), float(grad_scale), _stream(), launches=2)
 
 
 # --------------------------------------------------------------------------- #

@@ -6,7 +6,11 @@ step (the 12.6 M-entry hash table on its own, the small MLP / background / event
 together) instead of torch's per-dtype multi-tensor passes.  The float64 refractory-period scalar is
 updated with the same formula in torch (one element).  ``state_dict`` keys (``step``, ``exp_avg``,
 ``exp_avg_sq``) follow ``torch.optim.Adam``, so a learning-rate scheduler (MultiStepLR, :1096-1101)
-and checkpoints work unchanged."""
+and checkpoints work unchanged.
+
+``capturable=True`` keeps the step number in a device tensor that is incremented on the device, so a
+step captured in a CUDA graph (graph_step.GraphedStep) applies the right bias correction on every
+replay; ``state[p]["step"]`` is then refreshed from the host-side replay count."""
 
 import ctypes
 import math
@@ -25,6 +29,24 @@ class FusedAdam(torch.optim.Optimizer):
         # gradients are multiplied by this inside the update: ddp.GradReducer sets 1 / world_size so the
         # SUM all-reduce needs no separate division pass
         self.grad_scale = 1.0
+        self.capturable = False
+        self._step_dev = None           # device int64 step counter (capturable mode)
+
+    def enable_capture(self, device):
+        """Switch to the device-side step counter (call once, before capturing a step)."""
+        steps = {int(s["step"]) for s in self.state.values() if "step" in s}
+        if len(steps) > 1:
+            raise RuntimeError("capturable FusedAdam needs every parameter at the same step")
+        start = steps.pop() if steps else 0
+        self._step_dev = torch.full((), start, dtype=torch.int64, device=device)
+        self.capturable = True
+
+    def note_replayed_steps(self, n=1):
+        """A captured step was replayed `n` times: keep the host-side step numbers (checkpoints,
+        state_dict) in line with the device counter."""
+        for s in self.state.values():
+            if "step" in s:
+                s["step"] += n
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -32,6 +54,8 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if self.capturable:
+            self._step_dev += 1
         launches = {}                  # (beta1, beta2, eps, step) -> [AdamTensor, ...]
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
@@ -52,7 +76,8 @@ class FusedAdam(torch.optim.Optimizer):
                     g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                     entry = AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
                                        p.numel(), float(group["lr"]), float(group["weight_decay"]))
-                    launches.setdefault((beta1, beta2, group["eps"], t), []).append((entry, g))
+                    key = (beta1, beta2, group["eps"], 0 if self.capturable else t)
+                    launches.setdefault(key, []).append((entry, g))
                 elif not p.is_cuda:
                     raise NotImplementedError("FusedAdam: only CUDA parameters are supported (no CPU fallback)")
                 else:
@@ -61,9 +86,15 @@ class FusedAdam(torch.optim.Optimizer):
                     g = g.add(p, alpha=group["weight_decay"]) if group["weight_decay"] else g
                     m.mul_(beta1).add_(g, alpha=1 - beta1)
                     v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
-                    denom = (v.sqrt() / math.sqrt(1 - beta2 ** t)).add_(group["eps"])
-                    p.addcdiv_(m, denom, value=-group["lr"] / (1 - beta1 ** t))
+                    if self.capturable:
+                        td = self._step_dev.to(v.dtype)
+                        denom = (v.sqrt() / torch.sqrt(1 - beta2 ** td)).add_(group["eps"])
+                        p.sub_(group["lr"] * m / denom / (1 - beta1 ** td))
+                    else:
+                        denom = (v.sqrt() / math.sqrt(1 - beta2 ** t)).add_(group["eps"])
+                        p.addcdiv_(m, denom, value=-group["lr"] / (1 - beta1 ** t))
         for (beta1, beta2, eps, t), entries in launches.items():
             arr = (AdamTensor * len(entries))(*[e for e, _ in entries])
-            ops.adam_step(arr, len(entries), beta1, beta2, eps, t, self.grad_scale)
+            ops.adam_step(arr, len(entries), beta1, beta2, eps, t, self.grad_scale,
+                          self._step_dev if self.capturable else None)
         return loss

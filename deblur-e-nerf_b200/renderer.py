@@ -289,8 +289,21 @@ class EventRenderer(torch.nn.Module):
         return self._finish_step(terms, mean_samples, occ_rates, weight, size, batch_index)
 
     def _finish_step(self, terms, mean_samples, occ_rates, weight, size, batch_index):
-        self._last_mean_samples = max(mean_samples) if mean_samples else None
-        mean_samples = self.update_train_batch_size(mean_samples, batch_index)
+        if mean_samples and torch.is_tensor(mean_samples[0]):
+            # sync-free render calls: the sample counts are device scalars.  The batch controller and the
+            # memory guard consume them one step late (an asynchronous copy started now, read when the
+            # next step reaches this point), so the step never waits for the device.
+            from .lagged import LaggedReadback
+            self._apply_lagged_controller()
+            stacked = torch.stack(mean_samples).double()
+            mean_dev = stacked.mean()
+            if self.mean_samples_reduce_fn is not None:
+                mean_dev = self.mean_samples_reduce_fn(mean_dev)
+            self._pending_controller = (LaggedReadback(torch.stack((mean_dev, stacked.max()))), batch_index)
+            mean_samples = mean_dev
+        else:
+            self._last_mean_samples = max(mean_samples) if mean_samples else None
+            mean_samples = self.update_train_batch_size(mean_samples, batch_index)
         loss = sum(v * _get(weight, k) for k, v in terms.items())
 
         self.logged = {"train/loss": loss.detach(), "train/batch_size": size,
@@ -299,6 +312,19 @@ class EventRenderer(torch.nn.Module):
             self.logged[f"train/{key}"] = value.detach()
         self.logged["train/mean_ray_occ_rate"] = sum(occ_rates) / len(occ_rates)
         return loss
+
+    def _apply_lagged_controller(self):
+        pending = getattr(self, "_pending_controller", None)
+        if pending is None:
+            return
+        readback, batch_index = pending
+        self._pending_controller = None
+        mean, largest = readback.pop()
+        self._last_mean_samples = largest
+        acc = self.accumulate_grad_batches
+        if acc > 1 and (batch_index % acc) != (acc - 2):
+            return
+        self.next_train_batch_size = int(self.train_ray_sample_batch_size / max(mean, 1e-9))
 
     def _batch_fits(self, n_render_rays, gen):
         """Memory guard of the batched render calls: estimated per-sample buffers (from the samples

@@ -74,15 +74,21 @@ typedef struct den_hashgrid_desc {
     uint32_t offset[DEN_MAX_LEVELS];    /* entry offset of the level */
 } den_hashgrid_desc;
 
+/* Device-side sample counts.  Every per-sample entry point takes `n_samples` (the number of rows
+ * the host KNOWS the buffers hold — their capacity) and `n_samples_dev`: NULL, or a device int32 with
+ * the true count written earlier in the stream (the march total, the survivor total of the
+ * visibility filter); the kernel then works on min(n_samples, *n_samples_dev) rows.  With it a
+ * training step has no host read-back (upstream reads both totals back: SURVEY.md App. C rows 1, 3,
+ * 4) and can be captured in a CUDA graph. */
 /* x (M,3) in unit-cube coordinates -> out (M, L*2).  tcnn kernel_grid. */
 int den_hashgrid_fwd(const den_hashgrid_desc* desc, const float* x, const float* table,
-                     float* out, int64_t n_samples, void* stream);
+                     float* out, int64_t n_samples, const int32_t* n_samples_dev, void* stream);
 /* dtable (n_entries*2, pre-zeroed or accumulating) += scatter of dout (M, L*2).
  * tcnn kernel_grid_backward.  If dx != NULL also writes dL/dx (M,3)
  * (kernel_grid_backward_input; needs `table`). */
 int den_hashgrid_bwd(const den_hashgrid_desc* desc, const float* x, const float* dout,
                      const float* table, float* dtable, float* dx, int64_t n_samples,
-                     void* stream);
+                     const int32_t* n_samples_dev, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Ray marching — replaces nerfacc.ray_marching (external/utils.py:106-119)
@@ -180,7 +186,7 @@ int den_rays_from_trajectory(const double* timestamps, const float* pixels, int6
  * three boolean-mask compactions inside nerfacc.ray_marching. */
 /* alpha = 1 - exp(-sigma * (t1 - t0)) */
 int den_alpha_from_sigma(const float* sigmas, const float* t_starts, const float* t_ends,
-                         float* alphas, int64_t n_samples, void* stream);
+                         float* alphas, int64_t n_samples, const int32_t* n_samples_dev, void* stream);
 /* mask[i] = (T_i >= eps) && (alpha_thre <= 0 || alpha_i >= alpha_thre), T sequential fp32 per ray;
  * vis_count[r] = number of visible samples of ray r */
 int den_visibility(const float* alphas, const int32_t* offsets, int64_t n_rays, float early_stop_eps,
@@ -189,6 +195,22 @@ int den_compact_samples(const uint8_t* mask, const int32_t* offsets_in, const in
                         const int32_t* ray_indices_in, const float* t_starts_in, const float* t_ends_in,
                         int32_t* ray_indices_out, float* t_starts_out, float* t_ends_out,
                         int64_t n_rays, void* stream);
+/* The same compaction, also carrying the pre-pass outputs of the survivors along: sigmas (M) and
+ * rgbs (M, channels) are copied (8 B per sample), and src_rows[k] = index of survivor k in the
+ * un-compacted arrays, which lets den_mlp_bwd read the 128-byte encodings of the pre-pass IN PLACE
+ * instead of from a compacted copy.  Any of sig / rgb / src_rows may be NULL. */
+int den_compact_samples_ex(const uint8_t* mask, const int32_t* offsets_in, const int32_t* offsets_out,
+                           const int32_t* ray_indices_in, const float* t_starts_in,
+                           const float* t_ends_in, int32_t* ray_indices_out, float* t_starts_out,
+                           float* t_ends_out, int64_t n_rays, const float* sigmas_in,
+                           const float* rgbs_in, int32_t channels, float* sigmas_out, float* rgbs_out,
+                           int32_t* src_rows, void* stream);
+/* offsets[i] = min(offsets[i], capacity) for the n_rays + 1 entries; *overflow = 1 (device int32,
+ * may be NULL) when the total exceeded the capacity.  Run after the scan of a march whose sample
+ * buffers were sized WITHOUT reading the total back: every per-ray consumer then stays inside the
+ * buffers, and the step that lost samples is flagged instead of synchronised on. */
+int den_clamp_offsets(int32_t* offsets, int64_t n_rays_plus_1, int32_t capacity, int32_t* overflow,
+                      void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Transmittance / weights / accumulation — replaces
@@ -287,12 +309,12 @@ int den_field_density_at(const den_field_desc* f, const den_field_params* p, con
  * (external/utils.py:68-96 + external/ngp.py:231-237) */
 int den_contract_samples(const den_field_desc* f, const float* rays_o, const float* rays_d,
                          const int32_t* ray_indices, const float* t_starts, const float* t_ends,
-                         int64_t n_samples, float* unit_pos, void* stream);
+                         int64_t n_samples, const int32_t* n_samples_dev, float* unit_pos, void* stream);
 /* sigmas (M); rgbs (M,C) or NULL (density only) */
 int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float* enc,
                 const float* rays_o, const float* rays_d, const int32_t* ray_indices,
-                const float* t_starts, const float* t_ends, int64_t n_samples, float* sigmas,
-                float* rgbs, void* stream);
+                const float* t_starts, const float* t_ends, int64_t n_samples,
+                const int32_t* n_samples_dev, float* sigmas, float* rgbs, void* stream);
 
 /* fp32 gradient accumulators of the MLP parameters (same shapes as den_field_params; the
  * kernel ADDS into them with atomics, so the caller zeroes them or passes .grad buffers) */
@@ -303,20 +325,22 @@ typedef struct den_field_grads {
 
 /* Backward of den_mlp_fwd with forward recompute: d_enc (M, L*2) is written, the weight /
  * bias gradients are accumulated into `g`.  d_sigmas (M), d_rgbs (M,C).  d_dirs (M,3) or NULL:
- * dL/d(view direction) through the SH encoding. */
+ * dL/d(view direction) through the SH encoding.  enc_rows (M) int32 or NULL: sample i reads row
+ * enc_rows[i] of `enc` (den_compact_samples_ex's src_rows: the pre-pass encodings in place). */
 int den_mlp_bwd(const den_field_desc* f, const den_field_params* p, const den_field_grads* g,
                 const float* enc, const float* rays_o, const float* rays_d,
                 const int32_t* ray_indices, const float* t_starts, const float* t_ends,
-                const float* d_sigmas, const float* d_rgbs, int64_t n_samples, float* d_enc,
-                float* d_dirs, void* stream);
+                const float* d_sigmas, const float* d_rgbs, int64_t n_samples,
+                const int32_t* n_samples_dev, const int32_t* enc_rows, float* d_enc, float* d_dirs,
+                void* stream);
 /* Reverse mode of den_contract_samples w.r.t. the rays (the refractory-period gradient path,
  * models/trajectories.py -> models/nerf.py:206-228 -> external/utils.py:83-96): per sample
  * d_pos = J^T d_unit and d_pos_t = d_pos * (t0+t1)/2; den_accumulate_fwd sums them per ray
  * into dL/d rays_o and dL/d rays_d. */
 int den_contract_samples_bwd(const den_field_desc* f, const float* rays_o, const float* rays_d,
                              const int32_t* ray_indices, const float* t_starts, const float* t_ends,
-                             const float* d_unit, int64_t n_samples, float* d_pos, float* d_pos_t,
-                             void* stream);
+                             const float* d_unit, int64_t n_samples, const int32_t* n_samples_dev,
+                             float* d_pos, float* d_pos_t, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Pixel-bandwidth low-pass filter — replaces PixelBandwidth.intensity_sample_to_weight,
@@ -393,8 +417,10 @@ typedef struct den_adam_tensor {
 
 /* grad_scale: 1 for a single process; 1 / world_size when the gradients were SUM all-reduced
  * (the mean of Lightning's DDP, scripts/run.py:84-89, folded into the update). */
+/* step_dev: NULL, or a device int64 holding the step number t (then `step` is ignored): a step
+ * captured in a CUDA graph keeps its step counter on the device and increments it inside the graph. */
 int den_adam_step(const den_adam_tensor* tensors_host, int32_t n_tensors, double beta1, double beta2,
-                  double eps, int64_t step, double grad_scale, void* stream);
+                  double eps, int64_t step, const int64_t* step_dev, double grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

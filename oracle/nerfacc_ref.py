@@ -54,6 +54,13 @@ def _roi_split(roi):
 SPHERE_INV_EPS = 1e-10      # helpers_contraction.h: fmaxf(2n - n^2, 1e-10f) in the sphere inverse
 
 
+def _sqrt(x):
+    """Correctly rounded square root, like CUDA's `sqrtf` in the upstream kernels.  torch's CPU
+    float32 sqrt (vectorised math library) is off by one ulp for ~0.6 % of inputs on this build,
+    which is enough to move an un-contracted point; going through float64 rounds correctly."""
+    return torch.sqrt(x.double()).to(x.dtype) if x.dtype == torch.float32 else torch.sqrt(x)
+
+
 def _dot3(u):
     return (u[..., 0] * u[..., 0] + u[..., 1] * u[..., 1]) + u[..., 2] * u[..., 2]
 
@@ -68,7 +75,7 @@ def contract(x, roi, type=ContractionType.AABB):
         return torch.tanh(u - 0.5) * 0.5 + 0.5
     if type == ContractionType.UN_BOUNDED_SPHERE:
         u = u * 2.0 - 1.0
-        norm = torch.sqrt(_dot3(u))
+        norm = _sqrt(_dot3(u))
         outside = norm > 1.0
         safe = torch.where(outside, norm, torch.ones_like(norm))
         warped = (2.0 - 1.0 / safe)[..., None] * (u / safe[..., None])
@@ -88,7 +95,7 @@ def contract_inv(x, roi, type=ContractionType.AABB):
         # helpers_contraction.h `unit_sphere_to_inf`: v / max(2n - n^2, eps)
         u = (x - 0.5) * 4.0
         norm_sq = _dot3(u)
-        norm = torch.sqrt(norm_sq)
+        norm = _sqrt(norm_sq)
         denom = torch.clamp(2.0 * norm - norm_sq, min=SPHERE_INV_EPS)
         u = torch.where((norm > 1.0)[..., None], u / denom[..., None], u)
         u = u * 0.5 + 0.5

@@ -29,7 +29,7 @@ def test_argument_validation_needs_no_gpu(den_lib):
     desc = HashGridDesc()
     desc.n_levels = 4
     desc.n_features = 3            # unsupported
-    rc = den_lib.cdll.den_hashgrid_fwd(ctypes.byref(desc), None, None, None, 8, None)
+    rc = den_lib.cdll.den_hashgrid_fwd(ctypes.byref(desc), None, None, None, 8, None, None)
     assert rc < 0
     assert b"n_features" in den_lib.cdll.den_last_error()
     rc = den_lib.cdll.den_composite_fwd(None, None, None, None, None, 4, 2, None, None, None, None,

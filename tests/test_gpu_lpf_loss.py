@@ -21,8 +21,10 @@ def _rel(a, b):
 def _inputs(S, n, seed, invalid_fraction):
     g = torch.Generator().manual_seed(seed)
     base = 40e6 + torch.rand(n, generator=g, dtype=torch.float64) * 100e6
-    # four output timestamps per event: diff (start, end), subdiff (start, end) inside it
-    span = 2e6 + torch.rand(n, generator=g, dtype=torch.float64) * 6e6
+    # four output timestamps per event: diff (start, end), subdiff (start, end) inside it; a few
+    # microseconds apart so that the reset decay exp(-omega_diff dt) (1 / omega_diff = 1.9 us) is
+    # neither 1 nor 0 and its gradient w.r.t. the timestamps is a real number
+    span = 2e3 + torch.rand(n, generator=g, dtype=torch.float64) * 8e3
     out_ts = torch.stack([base, base + span, base + 0.2 * span, base + 0.7 * span])
     gen = torch.rand(S - 1, n, generator=g, dtype=torch.float64)
     intensity = torch.exp(torch.randn(4, S, n, generator=g) * 1.2 - 2.0).clamp(1e-3, 5.0)
