@@ -87,6 +87,9 @@ def parse_args():
                          "reading: models/deblur_e_nerf.py:72-75) or give every rank the full batch")
     ap.add_argument("--no-graph", action="store_true",
                     help="run every step eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--emulate-ranks", type=int, default=1,
+                    help="diagnostic: run ONE rank's share of an N-rank strong-scaling step on this GPU "
+                         "(no collective); reported in config, never a scaling result")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -455,6 +458,7 @@ def run_ours(args):
     if w["rays_per_call"] is not None:
         n_global = w["rays_per_call"] // w["S"]
         n_events = max(n_global // world, 1) if strong else n_global
+        n_events = max(n_events // max(args.emulate_ranks, 1), 1)
     else:
         n_events = 256          # the controller's start (synthetic.yaml:18); adapts below
     rays_per_step = lambda n: 4 * w["S"] * n * acc        # noqa: E731
@@ -520,6 +524,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_wall0 = time.time()
     launches0 = ops.launch_count()
+    replays0 = stepper.replays
     mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     if not use_graph:
         ops.enable_kernel_timing(rated_kernels)
@@ -539,7 +544,9 @@ def run_ours(args):
     ms_step = ddp.max_over_ranks(ms_total / args.steps, dev)
     timings = ops.kernel_timings()
     ops.disable_kernel_timing()
-    launches = (ops.launch_count() - launches0)
+    # kernels launched in the timed region: the eager ones plus, per replay, those recorded in the graph
+    launches = (ops.launch_count() - launches0) + stepper.launches_per_replay * (
+        stepper.replays - replays0)
     mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
     if rank == 0:
         time.sleep(0.15)                    # let the last in-window sample arrive
@@ -553,7 +560,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         for i in range(min(args.warmup, 2)):
-            one_step(host_batches[i], i).item()
+            one_step(host_batches[i] if use_graph else [to_dev(b) for b in host_batches[i]], i).item()
         ddp.barrier()
         torch.cuda.synchronize()
         start.record()
@@ -734,6 +741,7 @@ def run_ours(args):
     config = workload_config(args.workload, w, n_events)
     config.update({
         "events_per_step_global": n_events * world, "accumulate_grad_batches": acc,
+        "emulated_share_of_ranks": args.emulate_ranks,
         "trainable": "NeRF + C_p + tau + Omega" if w.get("unfrozen") else "NeRF (synthetic.yaml freezes C_p, tau, Omega)",
         "parallelism": f"dp{world}" + (" (batch sharded over the ranks)" if strong else ""),
         "occupancy": "controlled solid sphere r=0.75 as the start state (SURVEY 8(d)(ii)); the grid update "

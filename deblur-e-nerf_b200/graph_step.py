@@ -43,13 +43,19 @@ class GraphedStep:
         self.captures = 0
         self.replays = 0
         self.overflows = 0
+        self.launches_per_replay = 0            # den_b200 kernels recorded in the captured step
+        self._side = None                       # every step of this object runs on one side stream
 
     # ----------------------------------------------------------------- pieces --------
     def _eager(self, batches, global_step):
         opt, acc = self.optimizer, self.acc
         opt.zero_grad(set_to_none=False)
         loss = None
+        dev = next(self.model.parameters()).device
         for m, batch in enumerate(batches):
+            if not next(iter(batch["event"].values())).is_cuda:        # a (pinned) host batch
+                batch = {k: {kk: v.to(dev, non_blocking=True) for kk, v in d.items()}
+                         for k, d in batch.items()}
             loss = self.model.training_step(batch, m, global_step)
             (loss / acc if acc > 1 else loss).backward()
         self.reducer()
@@ -70,11 +76,14 @@ class GraphedStep:
         nerf.update_occ_grid = lambda *a, **k: None         # host-gated: runs outside the graph
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
+        from . import ops
+        launches0 = ops.launch_count()
         try:
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._stream()):
                 self._loss = self._eager(self._static, global_step)
         finally:
             nerf.update_occ_grid = update
+        self.launches_per_replay = ops.launch_count() - launches0
         if nerf._stats is None:
             raise RuntimeError("the captured step took the synchronising render path: no capture")
         self._graph = graph
@@ -84,6 +93,13 @@ class GraphedStep:
         self._controller_host = pending[0]._host if pending else None
         self.model._pending_controller = None
         self.captures += 1
+
+    def _stream(self):
+        # eager warm-up steps and the capture share one side stream, so the autograd nodes the capture
+        # meets (AccumulateGrad of every parameter) were created on the stream that is being captured
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
 
     def _copy_in(self, batches):
         for dst, src in zip(self._static, batches):
@@ -145,7 +161,12 @@ class GraphedStep:
         nerf = self.model.nerf
         update = nerf.update_occ_grid
         nerf.update_occ_grid = lambda *a, **k: None         # already done above for this step
+        side, cur = self._stream(), torch.cuda.current_stream()
+        side.wait_stream(cur)
         try:
-            return self._eager(batches, global_step)
+            with torch.cuda.stream(side):
+                loss = self._eager(batches, global_step)
         finally:
             nerf.update_occ_grid = update
+        cur.wait_stream(side)
+        return loss

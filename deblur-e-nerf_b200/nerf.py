@@ -319,7 +319,7 @@ class NeRF(torch.nn.Module):
                 and self._segment_bound_known()) else None
             if capacity is not None:
                 col, opa, dep, counts = self.render_chunk_sync_free(o, d, jitter, groups, capacity)
-                means = list((counts.to(torch.float32) / max(per, 1)).unbind(0))      # device scalars
+                means = list((counts.to(torch.float64) / max(per, 1)).unbind(0))      # device scalars
             else:
                 col, opa, dep, counts = self.render_chunk(o, d, jitter, groups)
                 means = [c / max(per, 1) for c in counts]
