@@ -43,7 +43,10 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 __global__ void __launch_bounds__(256)
 adam_kernel(const __grid_constant__ AdamBatch b, float beta1, float beta2, float omb1, float omb2, float eps,
             float bias1, float inv_sqrt_bias2, float gs, const int64_t* __restrict__ step_dev, double beta1_d,
-            double beta2_d) {
+            double beta2_d, const int32_t* __restrict__ skip_flag) {
+    // a step whose sample buffers overflowed (den_clamp_offsets set the flag) lost samples: its
+    // gradients are not applied — the update is skipped on the device, nobody waits for the flag
+    if (skip_flag != nullptr && *skip_flag != 0) return;
     if (step_dev != nullptr) {
         // the step number lives on the device (a captured CUDA graph replays this launch with the same
         // kernel arguments every step): the bias corrections are derived here
@@ -90,7 +93,7 @@ adam_kernel(const __grid_constant__ AdamBatch b, float beta1, float beta2, float
 
 extern "C" int den_adam_step(const den_adam_tensor* tensors, int32_t n_tensors, double beta1_d, double beta2_d,
                              double eps_d, int64_t step, const int64_t* step_dev, double grad_scale,
-                             void* stream) {
+                             const int32_t* skip_flag, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(n_tensors >= 0 && (step >= 1 || step_dev != nullptr), "bad tensor count / step");
     if (step < 1) step = 1;
@@ -111,7 +114,7 @@ extern "C" int den_adam_step(const den_adam_tensor* tensors, int32_t n_tensors, 
             adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(b, beta1, beta2, (float)(1.0 - (double)beta1_d),
                                                              (float)(1.0 - (double)beta2_d), eps, (float)bias1,
                                                              inv_sqrt_bias2, (float)grad_scale, step_dev, beta1_d,
-                                                             beta2_d);
+                                                             beta2_d, skip_flag);
             cudaError_t e = cudaGetLastError();
             count = 0;
             largest = 0;

@@ -110,5 +110,8 @@ def configure_optimizer(model, lr=0.01, weight_decay=1e-6, refractory_relative_l
         fused = all(p.is_cuda for p in model.parameters())
     if fused:
         from .optim import FusedAdam          # den_adam_step: two launches per step
-        return FusedAdam(groups, lr=lr)
+        opt = FusedAdam(groups, lr=lr)
+        # a sync-free step that ran out of sample capacity lost samples: its update is skipped on the device
+        opt.skip_flag = getattr(model.nerf, "overflow_flag", None)
+        return opt
     return torch.optim.Adam(groups, lr=lr)

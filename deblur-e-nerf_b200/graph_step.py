@@ -115,6 +115,10 @@ class GraphedStep:
         marched, n_rays, overflow = self._stats_host.tolist()
         nerf = self.model.nerf
         if overflow:
+            import sys
+            print(f"den_b200: sample capacity overflow in a replayed step (marched {marched:.0f} samples for "
+                  f"{n_rays:.0f} rays, estimate {nerf._spr_estimate} samples/ray): re-capturing",
+                  file=sys.stderr)
             self.overflows += 1
             nerf.overflow_count += 1
             nerf._spr_estimate = 1.5 * max(nerf._spr_estimate or 0.0, marched / max(n_rays, 1.0))

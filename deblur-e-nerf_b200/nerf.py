@@ -109,7 +109,10 @@ class NeRF(torch.nn.Module):
         # reach the host one call late through an asynchronous copy.  The first call, and any call after an
         # overflow, takes the synchronising path (which also teaches the estimate).
         self.sync_free = True
-        self.capacity_margin = 1.25
+        self.capacity_margin = 1.1           # + a term for the batch-to-batch spread, see _capacity
+        # set by den_clamp_offsets when a sync-free render call ran out of capacity; cleared by the
+        # renderer at the start of every optimizer step; FusedAdam skips the update while it is set
+        self.register_buffer("overflow_flag", torch.zeros((), dtype=torch.int32), persistent=False)
         self._spr_estimate = None            # marched samples per ray, max of the recent calls
         self._stats = None                   # LaggedReadback of the latest sync-free call
         self.overflow_count = 0
@@ -194,12 +197,16 @@ class NeRF(torch.nn.Module):
             self.overflow_count += 1
             self._spr_estimate = None        # next call: the synchronising path, exact sizes
         elif self._spr_estimate is not None:
-            self._spr_estimate = max(0.9 * self._spr_estimate, spr)
+            self._spr_estimate = max(0.98 * self._spr_estimate, spr)
 
     def _capacity(self, n_rays):
         if self._spr_estimate is None:
             return None
-        need = int(self._spr_estimate * self.capacity_margin * n_rays) + 1
+        # samples per ray vary from batch to batch like the share of rays that hit the scene: rays of one
+        # event (4 render calls x S pixel-bandwidth samples) move together, so a batch holds roughly
+        # n_rays / 120 independent draws; five standard deviations of a ~170 % per-event spread on top
+        margin = self.capacity_margin + 8.5 / max(n_rays / 120.0, 1.0) ** 0.5
+        need = int(self._spr_estimate * margin * n_rays) + 1
         q = ops._ROW_QUANTUM
         return (-(-need // q) + 1) * q
 
@@ -209,7 +216,7 @@ class NeRF(torch.nn.Module):
         field = self.radiance_field
         n_rays = o.shape[0]
         dev = o.device
-        overflow = torch.zeros((), dtype=torch.int32, device=dev)
+        overflow = self.overflow_flag
         ray_idx, t0, t1, offsets = self._march(o, d, jitter, capacity=capacity, overflow=overflow)
         n_dev = offsets[-1:]
         marched_total = n_dev

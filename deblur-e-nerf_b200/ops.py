@@ -793,11 +793,13 @@ def contract_samples_autograd(desc, rays_o, rays_d, ray_indices, t_starts, t_end
 # --------------------------------------------------------------------------- #
 # optimiser
 # --------------------------------------------------------------------------- #
-def adam_step(tensor_array, n_tensors, beta1, beta2, eps, step, grad_scale=1.0, step_dev=None):
+def adam_step(tensor_array, n_tensors, beta1, beta2, eps, step, grad_scale=1.0, step_dev=None,
+              skip_flag=None):
     """One Adam step over a ctypes array of ``AdamTensor`` descriptors (see optim.FusedAdam).
-    `step_dev`: device int64 step counter (CUDA-graph capture) instead of the host `step`."""
+    `step_dev`: device int64 step counter (CUDA-graph capture) instead of the host `step`;
+    `skip_flag`: device int32, non-zero -> the update is skipped."""
     _call("den_adam_step", tensor_array, int(n_tensors), float(beta1), float(beta2), float(eps),
-          int(step), _ptr(step_dev), float(grad_scale), _stream(), launches=2)
+          int(step), _ptr(step_dev), float(grad_scale), _ptr(skip_flag), _stream(), launches=2)
 
 
 # --------------------------------------------------------------------------- #

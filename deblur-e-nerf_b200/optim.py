@@ -31,6 +31,9 @@ class FusedAdam(torch.optim.Optimizer):
         self.grad_scale = 1.0
         self.capturable = False
         self._step_dev = None           # device int64 step counter (capturable mode)
+        # device int32: non-zero -> this step's update is skipped on the device (NeRF.overflow_flag: a
+        # sync-free step whose sample buffers overflowed lost samples and must not be applied)
+        self.skip_flag = None
 
     def enable_capture(self, device):
         """Switch to the device-side step counter (call once, before capturing a step)."""
@@ -54,8 +57,9 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        skip = self.skip_flag
         if self.capturable:
-            self._step_dev += 1
+            self._step_dev += 1 if skip is None else (skip == 0).to(torch.int64)
         launches = {}                  # (beta1, beta2, eps, step) -> [AdamTensor, ...]
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
@@ -84,6 +88,18 @@ class FusedAdam(torch.optim.Optimizer):
                     # e.g. the float64 refractory-period scalar: the same formula in torch
                     g = p.grad * self.grad_scale if self.grad_scale != 1.0 else p.grad
                     g = g.add(p, alpha=group["weight_decay"]) if group["weight_decay"] else g
+                    if skip is not None:            # same rule as the kernel, elementwise on the scalar
+                        keep = (skip == 0)
+                        m_new = m * beta1 + g * (1 - beta1)
+                        v_new = v * beta2 + g * g * (1 - beta2)
+                        td = self._step_dev.to(v.dtype) if self.capturable else torch.tensor(
+                            float(t), dtype=v.dtype, device=v.device)
+                        denom = v_new.sqrt() / torch.sqrt(1 - beta2 ** td) + group["eps"]
+                        p_new = p - group["lr"] * m_new / denom / (1 - beta1 ** td)
+                        m.copy_(torch.where(keep, m_new, m))
+                        v.copy_(torch.where(keep, v_new, v))
+                        p.copy_(torch.where(keep, p_new, p))
+                        continue
                     m.mul_(beta1).add_(g, alpha=1 - beta1)
                     v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
                     if self.capturable:
@@ -96,5 +112,5 @@ class FusedAdam(torch.optim.Optimizer):
         for (beta1, beta2, eps, t), entries in launches.items():
             arr = (AdamTensor * len(entries))(*[e for e, _ in entries])
             ops.adam_step(arr, len(entries), beta1, beta2, eps, t, self.grad_scale,
-                          self._step_dev if self.capturable else None)
+                          self._step_dev if self.capturable else None, skip)
         return loss

@@ -250,6 +250,8 @@ class EventRenderer(torch.nn.Module):
         gen = normalized.get("interval_gen")
 
         if batch_index % self.accumulate_grad_batches == 0:
+            if self.nerf.overflow_flag.is_cuda:
+                self.nerf.overflow_flag.zero_()         # a new optimizer step: nothing has overflowed yet
             self.nerf.update_occ_grid(step=global_step,
                                       T_wc_position=self.trajectory.T_wc_position)
 

@@ -419,8 +419,11 @@ typedef struct den_adam_tensor {
  * (the mean of Lightning's DDP, scripts/run.py:84-89, folded into the update). */
 /* step_dev: NULL, or a device int64 holding the step number t (then `step` is ignored): a step
  * captured in a CUDA graph keeps its step counter on the device and increments it inside the graph. */
+/* skip_flag: NULL, or a device int32; when it is non-zero the launch changes nothing (the overflow
+ * flag of den_clamp_offsets: a step that lost samples applies no update). */
 int den_adam_step(const den_adam_tensor* tensors_host, int32_t n_tensors, double beta1, double beta2,
-                  double eps, int64_t step, const int64_t* step_dev, double grad_scale, void* stream);
+                  double eps, int64_t step, const int64_t* step_dev, double grad_scale,
+                  const int32_t* skip_flag, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,15 +67,25 @@ def test_sync_free_step_equals_synchronising_step(den_lib, cuda, scene, pb_on, d
 def test_sync_free_overflow_is_flagged_and_recovers(den_lib, cuda):
     """A capacity that is too small loses samples: the step is flagged (one call late), the estimate is
     dropped, and the next call synchronises again."""
+    from deblur_e_nerf_b200 import factory
     model, batch, jitters = _setup(cuda, "synthetic", True)
     nerf = model.nerf
+    opt = factory.configure_optimizer(model)
+    assert opt.skip_flag is nerf.overflow_flag
     model.training_step(batch, 0, 0, jitters=jitters)
     nerf._spr_estimate *= 0.001                   # pretend the scene was almost empty so far
+    nerf.capacity_margin = 0.0
     import deblur_e_nerf_b200.ops as ops
     quantum, ops._ROW_QUANTUM = ops._ROW_QUANTUM, 1024
     try:
-        model.training_step(batch, 0, 0, jitters=jitters)             # sync-free with a tiny capacity
+        before = {n: p.detach().clone() for n, p in model.named_parameters()}
+        model.zero_grad()
+        model.training_step(batch, 0, 0, jitters=jitters).backward()  # sync-free with a tiny capacity
         assert nerf._stats is not None
+        opt.step()                                                    # ... its update is skipped on the device
+        assert int(nerf.overflow_flag) == 1
+        for n, p in model.named_parameters():
+            assert torch.equal(p.detach(), before[n]), n
         ref_mean = None
         loss = model.training_step(batch, 0, 0, jitters=jitters)      # consumes the stats: overflow seen
         assert nerf.overflow_count == 1 and nerf._stats is None       # -> this call synchronised
