@@ -60,8 +60,14 @@ def test_sync_free_step_equals_synchronising_step(den_lib, cuda, scene, pb_on, d
     if dense:
         assert float(ga["train/mean_num_samples_per_ray"]) < 60      # most samples were culled
     assert set(gra) == set(grb)
+    # fp32 atomics: only the summation order differs.  2e-4, or — for the sums that cancel almost
+    # completely — twice what one-ulp perturbations do to the reference's own gradient
+    # (tests/golden/gradient_conditioning.npz)
+    cond = _scene.load_golden("gradient_conditioning")
+    name = {"synthetic": "pb_on" if pb_on else "pb_off", "eds": "eds"}[scene]
     for key in gra:
-        assert _rel(grb[key], gra[key]) < 2e-4, key             # fp32 atomics: summation order only
+        bound = max(2e-4, 2 * float(cond.get(f"{name}/{key}", 0.0)))
+        assert _rel(grb[key], gra[key]) < bound, (key, bound)
 
 
 def test_sync_free_overflow_is_flagged_and_recovers(den_lib, cuda):
