@@ -152,3 +152,40 @@ def test_checkpoint_restores_the_training_state(den_lib, cuda, tmp_path):
     assert model_b.next_train_batch_size == model.next_train_batch_size
     tr_b.fit(model_b, producer_b, opt_b)
     assert tr_b.global_step == 12
+
+
+def test_event_batch_producer_graph_replay(den_lib, cuda):
+    """On the device a draw is replayed from a CUDA graph (captured the second time a batch size is
+    asked for): batches keep the layout and value ranges of the eager draw, differ from call to call
+    (the generator advances on every replay), and the previously returned batch stays intact while
+    the next one is drawn (two alternating buffers — the trainer prefetches one batch)."""
+    from deblur_e_nerf_b200 import synthetic
+    from deblur_e_nerf_b200.data import EventBatchProducer
+    cfg = synthetic.CONFIGS["synthetic"]
+    poses = synthetic.camera_poses(cfg, n_poses=50)
+    pool = synthetic.event_batch(5000, cfg, poses[2], torch.Generator().manual_seed(0))
+    prod = EventBatchProducer(pool, 257, it_sample_size=8, device=cuda, seed=3)
+    eager = prod.next_batch()                      # first call: eager
+    seen = []
+    prev = prev_copy = None
+    for i in range(6):
+        b = prod.next_batch()
+        if prev is not None:
+            for k in prev["event"]:
+                assert torch.equal(prev["event"][k], prev_copy[k]), k      # untouched by the new draw
+        for k, v in eager["event"].items():
+            assert b["event"][k].shape == v.shape and b["event"][k].dtype == v.dtype
+        for k, v in eager["normalized"].items():
+            assert b["normalized"][k].shape == v.shape and b["normalized"][k].dtype == v.dtype
+        u = b["normalized"]["diff_start_ts"]
+        assert float(u.min()) >= 0 and float(u.max()) < 1
+        assert bool((b["event"]["end_ts"] > b["event"]["start_ts"]).all())
+        # every row is a row of the pool
+        idx = (b["event"]["end_ts"][:, None] == pool["end_ts"].to(cuda)[None, :]).float().argmax(dim=1)
+        assert torch.equal(pool["position"].to(cuda)[idx], b["event"]["position"])
+        seen.append(b["event"]["end_ts"].clone())
+        prev, prev_copy = b, {k: v.clone() for k, v in b["event"].items()}
+    assert len(prod._graphs[257][1]) == 2
+    for a in range(len(seen)):
+        for c in range(a + 1, len(seen)):
+            assert not torch.equal(seen[a], seen[c])
