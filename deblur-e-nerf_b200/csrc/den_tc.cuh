@@ -30,10 +30,16 @@ __device__ __forceinline__ void fence_barrier_init() {
 // is kept ROLLED (nvcc unrolled it into ~50 try_wait copies per call site: 190 KB of SASS for the
 // backward kernel, instruction-cache misses on every epilogue phase) and the time-out report is
 // out of line.
+constexpr uint32_t kMbarSuspendNs = 20000;      // upper bound of one parked wait (the MMA rounds take ~1 us)
 static __device__ __noinline__ void mbar_timeout() {
     printf("den_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
     __trap();
 }
+// The wait blocks INSIDE the instruction: `suspendTimeHint` lets the hardware park the thread until the
+// phase completes (or the hint expires) instead of returning after its short default period.  ncu on the
+// round-1 kernels showed the poll loop itself (try_wait, predicate, branch, spin counter, convergence
+// barrier) issuing ~25 % of all warp instructions of den_mlp_bwd while the other tiles' warps competed
+// for the same issue slots; with the hint a wait is a handful of instructions.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t spin = 0;
@@ -42,13 +48,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(kMbarSuspendNs)
             : "memory");
         if (done) return;
-        if (++spin == (1u << 28)) mbar_timeout();
+        if (++spin == (1u << 22)) mbar_timeout();
     }
 }
 
