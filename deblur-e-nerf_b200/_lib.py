@@ -133,6 +133,9 @@ _SIGNATURES = {
                                 _P]),
     "den_lpf_loss_bwd": (_INT, [_c.POINTER(LpfLossDesc), _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P,
                                 _P, _P, _P, _P]),
+    "den_eval_affine_moments": (_INT, [_P, _P, _P, _I32, _I32, _I64, _P, _P]),
+    "den_eval_lm_moments": (_INT, [_P, _P, _P, _P, _I32, _I32, _I64, _P, _P]),
+    "den_eval_apply": (_INT, [_P, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P]),
     "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
 }

@@ -1,0 +1,142 @@
+"""Evaluation post-processing on the device: what
+``DeblurENeRF.evaluation_epoch_end`` (models/deblur_e_nerf.py:705-969) does on the host after moving
+every image there — the gain-exposure normalisation (:707-712), the float64 affine least squares in log
+space that removes the affine ambiguity of the predicted log-intensity (:733-797), the Levenberg-
+Marquardt refinement of the offset-gamma correction when ``correction.black_level_offset`` is set
+(:846-937 with models/offset_gamma_correction.py and external/optimizer.py:60-111) and the L1 / PSNR
+terms of ``Metric.compute`` (loss_metric/metric.py:57-72).
+
+Each of them is a sum over pixels: one ``den_eval_*`` kernel pass with fp64 accumulation produces the
+moments, the 2x2 / 3x3 systems are solved on the device, and the images never leave HBM.  SSIM and
+LPIPS (torchmetrics / lpips, absent from this image) are not part of this module; the shared-scale
+Bayer variant (``per_channel_log_it_scale: false`` with a colour sensor, :756-766) is not built — mono
+sensors and per-channel scales are."""
+
+import ctypes
+
+import torch
+
+from . import ops
+
+# pypose.optim.LevenbergMarquardt / strategy.TrustRegion defaults as the reference instantiates them
+# (models/deblur_e_nerf.py:859-866, configs/*: `lm.radius: 1.0e+6`)
+LM_DEFAULTS = dict(min=1e-6, max=1e32, high=0.5, low=1e-3, up=2.0, down=0.5, factor=3.0, reject=16)
+
+
+def _moments(kind, pred, target, gain_vec, params, n_out):
+    B, C, H, W = pred.shape
+    out = torch.zeros((C, n_out), dtype=torch.float64, device=pred.device)
+    args = [ops._ptr(pred), ops._ptr(target), ops._ptr(gain_vec)]
+    if params is not None:
+        args.append(ops._ptr(params))
+    ops._call(kind, *args, B, C, H * W, ops._ptr(out), ops._stream())
+    return out
+
+
+def affine_log_fit(pred, target, norm_gain):
+    """(C, 2) float64 (scale, offset) of the least squares  scale * log pred + offset ~ log target - log g."""
+    log_gain = norm_gain.log().double().contiguous()      # the reference takes this log in fp32 (:745)
+    m = _moments("den_eval_affine_moments", pred, target, log_gain, None, 5)
+    n, sx, sy, sxx, sxy = m.unbind(-1)
+    det = n * sxx - sx * sx
+    scale = (n * sxy - sx * sy) / det
+    offset = (sy - scale * sx) / n
+    return torch.stack((scale, offset), dim=-1)
+
+
+def _apply(pred, target, gain, params):
+    B, C, H, W = pred.shape
+    out = torch.empty_like(pred)
+    sums = torch.zeros((B, 2), dtype=torch.float64, device=pred.device)
+    ops._call("den_eval_apply", ops._ptr(pred), ops._ptr(target), ops._ptr(gain), ops._ptr(params), B, C,
+              H * W, ops._ptr(out), ops._ptr(sums), ops._stream())
+    return out, sums
+
+
+def lm_refine(pred, target, gain, affine, init, max_steps=10, radius=1e6):
+    """Levenberg-Marquardt on (scale, gamma, offset) per channel, external/optimizer.py:60-111 step for
+    step; every J^T J / J^T r / loss evaluation is one den_eval_lm_moments pass.  Returns (C, 3) f64."""
+    C = pred.shape[1]
+    cfg = LM_DEFAULTS
+    p = torch.cat((affine, torch.stack(init, dim=-1).double().to(pred.device)), dim=-1).contiguous()   # (C, 5)
+    damping, down = 1.0 / radius, cfg["down"]
+    n = float(target.numel())
+
+    def moments(params):
+        return _moments("den_eval_lm_moments", pred, target, gain, params.contiguous(), 10)
+
+    m = moments(p)
+    loss = float(m[:, 9].sum())
+    errors = [loss / n]
+    for _ in range(max_steps):
+        prev = p[:, 2:].clone()
+        last = loss
+        idx = torch.tensor([[0, 1, 2], [1, 3, 4], [2, 4, 5]], device=pred.device)
+        A = m[:, :6][:, idx].clone()                                   # (C, 3, 3)
+        g = m[:, 6:9].clone()                                          # J^T r
+        A.diagonal(dim1=1, dim2=2).clamp_(cfg["min"], cfg["max"])
+        rejects = 0
+        while last <= loss:
+            d = A.diagonal(dim1=1, dim2=2)
+            d.add_(d * damping)
+            D = torch.linalg.solve(A, -g.unsqueeze(-1))[:, :, 0]       # (C, 3)
+            trial = p.clone()
+            trial[:, 2:] += D
+            m_trial = moments(trial)
+            loss = float(m_trial[:, 9].sum())
+            # predicted decrease -(J D)^T (2 R + J D) from the moments of the CURRENT point
+            Aund = m[:, :6][:, idx]
+            pred_dec = -float((D.unsqueeze(1) @ Aund @ D.unsqueeze(-1)).sum() + 2 * (D * m[:, 6:9]).sum())
+            quality = (last - loss) / pred_dec if pred_dec != 0 else 0.0
+            rad = 1.0 / damping
+            if quality > cfg["high"]:
+                rad, down = rad * cfg["up"], cfg["down"]
+            elif quality > cfg["low"]:
+                rad, down = rad * (1 - (2 * quality - 1) ** cfg["factor"]), cfg["down"]
+            else:
+                rad, down = rad * down, down * cfg["down"]
+            down = max(cfg["min"], min(down, cfg["max"]))
+            rad = max(cfg["min"], min(rad, cfg["max"]))
+            damping = 1.0 / rad
+            if last < loss and rejects < cfg["reject"]:
+                loss, rejects = last, rejects + 1                       # rejected: stay, more damping
+            else:
+                p, m = trial, m_trial
+                break
+        errors.append(loss / n)
+        if abs(errors[-1] - errors[-2]) <= 1e-8 + 1e-5 * abs(errors[-2]) and torch.allclose(p[:, 2:], prev):
+            break
+    return p[:, 2:].clone(), errors
+
+
+@torch.no_grad()
+def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_offset=True, init=None,
+             max_steps=10, radius=1e6):
+    """pred, target (B, C, H, W) or (B, H, W) fp32 CUDA tensors (C = 1: mono); exposure_time, gain (B,).
+    Returns dict(l1, psnr (device scalars), pred (corrected, fp32), affine (C, 2), correction (C, 3) |
+    None, correction_errors)."""
+    if not pred.is_cuda:
+        raise NotImplementedError("eval_post: only CUDA tensors are supported (no CPU fallback)")
+    if pred.dim() == 3:
+        pred, target = pred.unsqueeze(1), target.unsqueeze(1)
+    pred = ops._req(pred, torch.float32, "pred")
+    target = ops._req(target, torch.float32, "target")
+    B, C, H, W = target.shape
+    prod = gain.to(torch.float32) * exposure_time                           # :707
+    norm = (prod / prod.mean()).to(pred.device)                             # :709-712
+    gain64 = norm.double().contiguous()
+    affine = affine_log_fit(pred, target, norm)
+    errors = None
+    if black_level_offset:
+        if init is None:
+            init = (torch.ones(C), torch.ones(C), torch.zeros(C))
+        corr, errors = lm_refine(pred, target, gain64, affine, init, max_steps, radius)
+    else:
+        corr = torch.tensor([[1.0, 1.0, 0.0]], dtype=torch.float64, device=pred.device).repeat(C, 1)
+    params = torch.cat((affine, corr), dim=-1).contiguous()
+    out, sums = _apply(pred, target, gain64, params)
+    n_img = float(C * H * W)
+    l1 = (sums[:, 0] / n_img).mean()
+    psnr = (10 * torch.log10((max_val - min_val) ** 2 / (sums[:, 1] / n_img))).mean()
+    return {"l1": l1, "psnr": psnr, "pred": out, "affine": affine,
+            "correction": corr if black_level_offset else None, "correction_errors": errors}

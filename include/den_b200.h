@@ -425,6 +425,27 @@ int den_adam_step(const den_adam_tensor* tensors_host, int32_t n_tensors, double
                   double eps, int64_t step, const int64_t* step_dev, double grad_scale,
                   const int32_t* skip_flag, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Evaluation post-processing on the device — replaces the host part of
+ * DeblurENeRF.evaluation_epoch_end (models/deblur_e_nerf.py:705-969): images (B, C, HW) fp32;
+ * every entry point is one pass over the images with fp64 accumulation (atomics into pre-zeroed
+ * outputs).  params (C, 5) fp64 on the device: a, b (the log-space affine correction of :789-797),
+ * s, gamma, o (OffsetGammaCorrection, models/offset_gamma_correction.py:37-40); gain (B) fp64: the
+ * mean-normalised gain-exposure products (:707-712); log_gain their logs.
+ *   affine moments (C, 5): n, sum x, sum y, sum xx, sum xy, x = log pred, y = log target - log_gain_b
+ *   lm moments (C, 10): J^T J (ss, sg, so, gg, go, oo), J^T r (s, g, o), sum r^2 for
+ *       f = gain_b (s x^gamma - o), x = exp(a log pred + b), r = f - target
+ *       (external/optimizer.py:86-92 builds exactly these normal equations from a B*HW x 3 Jacobian)
+ *   apply: out = f (fp32) and image_sums (B, 2): sum |out - target|, sum (out - target)^2
+ *       (the L1 and PSNR terms of loss_metric/metric.py:57-72)
+ * ------------------------------------------------------------------------- */
+int den_eval_affine_moments(const float* pred, const float* target, const double* log_gain, int32_t B,
+                            int32_t C, int64_t HW, double* moments, void* stream);
+int den_eval_lm_moments(const float* pred, const float* target, const double* gain, const double* params,
+                        int32_t B, int32_t C, int64_t HW, double* moments, void* stream);
+int den_eval_apply(const float* pred, const float* target, const double* gain, const double* params,
+                   int32_t B, int32_t C, int64_t HW, float* out, double* image_sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,149 @@
+"""CPU restatement of the evaluation post-processing (TEST INFRASTRUCTURE — never imported by the
+product path): ``DeblurENeRF.evaluation_epoch_end`` (models/deblur_e_nerf.py:705-969) up to the L1 /
+PSNR terms of ``Metric.compute`` (loss_metric/metric.py:57-72).
+
+Pinned parts: the gain-exposure normalisation, the float64 log-space affine least squares and the
+metrics are checked against the reference's OWN method run under ``oracle/ref_shim``
+(tests/test_oracle_vs_reference.py::test_eval_post_processing_matches_reference, correction without the
+black-level offset).  The Levenberg-Marquardt refinement follows the reference's
+``external/optimizer.py:60-111`` line by line, but the trust-region rule it calls
+(``pypose.optim.strategy.TrustRegion.update``) lives in pypose, which is absent here: its constants are
+RECALLED (radius 1e6, high 0.5, low 1e-3, up 2, down 0.5, factor 3, reject 16, min 1e-6, max 1e32) —
+parity of the refinement is UNPINNED.  They only steer the damping (~1e-6 relative); the converged
+parameters are the least-squares minimiser either way."""
+
+import math
+
+import torch
+
+
+def normalized_gain(gain, exposure_time):
+    prod = gain * exposure_time                                   # :707
+    return prod / prod.mean()                                     # :709-712 (fp32 like the reference)
+
+
+def affine_log_correction(pred, target, norm_gain):
+    """:733-797, mono / per-channel scale.  pred, target (B,C,H,W) fp32; norm_gain (B,) fp32.
+    Returns (scale_offset (C,2) f64, corrected log prediction (B,C,H,W) f64, log_gain (B,1,1,1) f32)."""
+    B, C, H, W = target.shape
+    log_gain = norm_gain.view(-1, 1, 1, 1).log()
+    x = pred.log()
+    y = target.log() - log_gain
+    A = torch.stack((x, torch.ones_like(x)), dim=-1).transpose(0, 1).flatten(1, 3).double()   # (C, BHW, 2)
+    rhs = y.unsqueeze(-1).transpose(0, 1).flatten(1, 3).double()                               # (C, BHW, 1)
+    sol = torch.linalg.lstsq(A, rhs).solution                                                  # (C, 2, 1)
+    fitted = (A @ sol).view(C, B, H, W).transpose(0, 1)
+    return sol[:, :, 0], fitted, log_gain
+
+
+class _Correction:
+    """models/offset_gamma_correction.py: f(x) = const_scale (scale x^gamma - offset), parameters (C,)."""
+
+    def __init__(self, const_scale, scale, gamma, offset):
+        self.g = const_scale.double().view(-1, 1, 1, 1)
+        self.p = torch.stack((scale.double(), gamma.double(), offset.double()), dim=-1)       # (C, 3)
+
+    def forward(self, x):
+        s, gm, o = (self.p[:, k].view(1, -1, 1, 1) for k in range(3))
+        return self.g * (s * x.pow(gm) - o)
+
+    def jacobian(self, x):
+        s, gm, _ = (self.p[:, k].view(1, -1, 1, 1) for k in range(3))
+        js = self.g * x.pow(gm)
+        jg = s * x.log() * js
+        jo = (-self.g).expand_as(x)
+        return torch.stack((js, jg, jo), dim=-1)                                               # (B,C,H,W,3)
+
+
+def lm_refine(x, target, norm_gain, init, max_steps=10, radius=1e6):
+    """:846-895 with external/optimizer.py:60-111.  x: affinely corrected prediction (B,C,H,W) f64;
+    target (B,C,H,W) fp32.  Returns (params (C,3), errors list)."""
+    C = x.shape[1]
+    model = _Correction(norm_gain, *init)
+    t = target.double()
+    pg = dict(min=1e-6, max=1e32, radius=radius, high=0.5, low=1e-3, up=2.0, down=0.5, damping=1.0 / radius)
+    reject, factor, down0 = 16, 3.0, 0.5
+
+    def loss():
+        return float(((model.forward(x) - t) ** 2).sum())
+
+    state = {"loss": None}
+
+    def step():
+        R = (model.forward(x) - t).transpose(0, 1).reshape(C, -1)                              # (C, N)
+        J = model.jacobian(x).transpose(0, 1).reshape(C, -1, 3)                                # (C, N, 3)
+        last = cur = state["loss"] if state["loss"] is not None else loss()
+        A = J.transpose(1, 2) @ J                                                              # (C, 3, 3)
+        g = J.transpose(1, 2) @ R.unsqueeze(-1)
+        A.diagonal(dim1=1, dim2=2).clamp_(pg["min"], pg["max"])
+        rejects = 0
+        while last <= cur:
+            d = A.diagonal(dim1=1, dim2=2)
+            d.add_(d * pg["damping"])
+            D = torch.linalg.solve(A, -g)[:, :, 0]                                             # (C, 3)
+            model.p += D
+            cur = loss()
+            JD = (J @ D.unsqueeze(-1))[:, :, 0]
+            quality = (last - cur) / -float((JD * (2 * R + JD)).sum())
+            pg["radius"] = 1.0 / pg["damping"]
+            if quality > pg["high"]:
+                pg["radius"] *= pg["up"]
+                pg["down"] = down0
+            elif quality > pg["low"]:
+                pg["radius"] *= 1 - (2 * quality - 1) ** factor
+                pg["down"] = down0
+            else:
+                pg["radius"] *= pg["down"]
+                pg["down"] *= down0
+            pg["down"] = max(pg["min"], min(pg["down"], pg["max"]))
+            pg["radius"] = max(pg["min"], min(pg["radius"], pg["max"]))
+            pg["damping"] = 1.0 / pg["radius"]
+            if last < cur and rejects < reject:
+                model.p -= D
+                cur, rejects = last, rejects + 1
+            else:
+                break
+        state["loss"] = cur
+        return cur
+
+    n = t.numel()
+    errors = [loss() / n]
+    for _ in range(max_steps):
+        prev = model.p.clone()
+        errors.append(step() / n)
+        if math.isclose(errors[-1], errors[-2], rel_tol=1e-5, abs_tol=1e-8) and torch.allclose(model.p, prev):
+            break
+    return model.p.clone(), errors
+
+
+def metrics(pred, target, min_val, max_val):
+    """Mean over the images of Metric.compute's L1 and PSNR (loss_metric/metric.py:57-72)."""
+    pred = pred.to(target.dtype)
+    l1, psnr = [], []
+    for p, t in zip(pred, target):
+        l1.append(torch.nn.functional.l1_loss(p, t))
+        mse = ((p - t) ** 2).mean()
+        psnr.append(10 * torch.log10((max_val - min_val) ** 2 / mse))
+    return {"l1": float(sum(l1) / len(l1)), "psnr": float(sum(psnr) / len(psnr))}
+
+
+def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_offset=True, init=None,
+             max_steps=10):
+    """pred, target (B,C,H,W) fp32 (C = 1: mono).  Returns dict(l1, psnr, pred (B,C,H,W) fp32, affine
+    (C,2), correction (C,3) | None)."""
+    norm = normalized_gain(gain, exposure_time)
+    sol, fitted, log_gain = affine_log_correction(pred, target, norm)
+    C = target.shape[1]
+    if not black_level_offset:
+        out = (fitted + log_gain).exp()                                                        # :822-829
+        params = None
+    else:
+        x = fitted.exp()
+        if init is None:
+            init = (torch.ones(C), torch.ones(C), torch.zeros(C))
+        params, _ = lm_refine(x, target, norm, init, max_steps)
+        out = _Correction(norm, params[:, 0], params[:, 1], params[:, 2]).forward(x)
+    out = out.to(target.dtype)
+    res = metrics(out, target, min_val, max_val)
+    res.update(pred=out, affine=sol, correction=params)
+    return res
