@@ -1,0 +1,48 @@
+"""GPU parity of the evaluation post-processing (`eval_post.evaluate`, `den_eval_*` kernels, SURVEY.md
+§8(f) N4) against oracle/eval_ref.py — which is pinned against the reference's own
+`evaluation_epoch_end` for the affine path (tests/test_oracle_vs_reference.py) — on mono image batches
+with varying exposure / gain, with and without the black-level-offset refinement."""
+
+import pytest
+import torch
+
+from oracle import eval_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _images(seed, B, H, W, offset=0.0):
+    g = torch.Generator().manual_seed(seed)
+    target = torch.rand(B, H, W, generator=g) * 0.9 + 0.05
+    exposure = torch.randint(1, 5, (B,), generator=g)
+    gain = torch.rand(B, generator=g) + 0.5
+    norm = gain * exposure / (gain * exposure).mean()
+    scene = target / norm.view(-1, 1, 1)
+    pred = (0.7 * scene.pow(1.3)) * torch.exp(0.02 * torch.randn(B, H, W, generator=g))
+    return pred.float(), (target + offset).float(), exposure, gain
+
+
+@pytest.mark.parametrize("black_level_offset", [False, True])
+@pytest.mark.parametrize("shape", [(1, 8, 8), (3, 37, 53), (2, 260, 346)])
+def test_eval_post_matches_oracle(den_lib, cuda, shape, black_level_offset):
+    from deblur_e_nerf_b200 import eval_post
+    pred, target, exposure, gain = _images(sum(shape), *shape, offset=0.03 if black_level_offset else 0.0)
+    want = eval_ref.evaluate(pred[:, None], target[:, None], exposure, gain, 0.0, 1.1,
+                             black_level_offset=black_level_offset)
+    got = eval_post.evaluate(pred.to(cuda), target.to(cuda), exposure.to(cuda), gain.to(cuda), 0.0, 1.1,
+                             black_level_offset=black_level_offset)
+    assert torch.allclose(got["affine"].cpu(), want["affine"], rtol=1e-9, atol=1e-11)
+    if black_level_offset:
+        assert torch.allclose(got["correction"].cpu(), want["correction"], rtol=1e-5, atol=1e-7), \
+            (got["correction"], want["correction"])
+    assert (got["pred"].cpu() - want["pred"]).abs().max().item() <= 2e-6 * want["pred"].abs().max().item()
+    assert abs(float(got["l1"]) - want["l1"]) <= 1e-5 * want["l1"]
+    assert abs(float(got["psnr"]) - want["psnr"]) <= 1e-5 * abs(want["psnr"])
+    assert got["pred"].is_cuda and got["l1"].is_cuda          # nothing went through the host
+
+
+def test_eval_post_refuses_cpu_tensors(den_lib):
+    from deblur_e_nerf_b200 import eval_post
+    pred, target, exposure, gain = _images(0, 1, 4, 4)
+    with pytest.raises(NotImplementedError):
+        eval_post.evaluate(pred, target, exposure, gain, 0.0, 1.0)

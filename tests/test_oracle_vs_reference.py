@@ -225,3 +225,89 @@ def test_event_batch_producer_reproduces_the_reference_samplers():
             assert out["event"][k].dtype == ev[k].dtype and torch.equal(out["event"][k], ev[k]), k
         for k in nm:
             assert out["normalized"][k].dtype == nm[k].dtype and torch.equal(out["normalized"][k], nm[k]), k
+
+
+def _eval_images(seed, B=3, H=24, W=32):
+    g = torch.Generator().manual_seed(seed)
+    target = (torch.rand(B, H, W, generator=g) * 0.9 + 0.05)
+    exposure = torch.tensor([1, 2, 4][:B], dtype=torch.int64)
+    gain = torch.tensor([1.0, 1.5, 0.75][:B])
+    norm = gain * exposure / (gain * exposure).mean()
+    # an affinely ambiguous (in log space) prediction of the exposure-normalised scene + a little noise
+    scene = target / norm.view(-1, 1, 1)
+    pred = (0.7 * scene.pow(1.3)) * torch.exp(0.02 * torch.randn(B, H, W, generator=g))
+    return pred.float(), target.float(), exposure, gain
+
+
+def test_eval_post_processing_matches_reference(pair):
+    """oracle/eval_ref.py (gain-exposure normalisation, float64 log-space affine least squares, L1 /
+    PSNR) against the reference's OWN evaluation_epoch_end (models/deblur_e_nerf.py:661-969) run under
+    the shim with `correction.black_level_offset: false` (the refinement needs pypose, absent here)."""
+    import easydict
+    from oracle import eval_ref
+    _, ref, _, _ = pair
+    pred, target, exposure, gain = _eval_images(0)
+    recorded = {}
+
+    class _Metric:
+        def init_batch_metric(self):
+            return easydict.EasyDict(l1=[], psnr=[])
+
+        def compute(self, p, t, min_target_val, max_target_val):
+            recorded.setdefault("pred", []).append(p.clone())
+            mse = ((p - t) ** 2).mean()
+            return easydict.EasyDict(l1=torch.nn.functional.l1_loss(p, t),
+                                     psnr=10 * torch.log10((max_target_val - min_target_val) ** 2 / mse))
+
+    class _Trainer:
+        log_dir = "/tmp"
+        is_global_zero = True
+        sanity_checking = False
+
+    object.__setattr__(ref, "trainer", _Trainer())
+    ref.correction = easydict.EasyDict(per_channel_log_it_scale=False, black_level_offset=False)
+    ref.has_bayer_filter = False
+    ref.metric = _Metric()
+    ref.logger = None
+    type(ref).current_epoch = 0
+    type(ref).device = torch.device("cpu")
+    ref.eval_save_pred_intensity_img = False
+    ref.all_gather = lambda outs: [{k: v[None] for k, v in o.items()} for o in outs]
+    logged = {}
+    ref.log = lambda name, value, **kw: logged.__setitem__(name, value)
+    outputs = [{"sample_id": torch.tensor([ord(c) for c in f"{i:04d}    "]),
+                "pred_intensity_img": pred[i], "target_intensity_img": target[i],
+                "exposure_time": exposure[i], "gain": gain[i]} for i in range(len(pred))]
+    stage = easydict.EasyDict(name="val", min_normalized_pixel_value=0.0, max_normalized_pixel_value=1.0)
+    ref.evaluation_epoch_end(outputs, stage)
+
+    res = eval_ref.evaluate(pred[:, None], target[:, None], exposure, gain, 0.0, 1.0,
+                            black_level_offset=False)
+    ref_pred = torch.stack(recorded["pred"])
+    _close(res["pred"], ref_pred, 1e-6)
+    assert abs(res["l1"] - float(logged["val/l1"])) <= 1e-6 * abs(float(logged["val/l1"]))
+    assert abs(res["psnr"] - float(logged["val/psnr"])) <= 1e-5 * abs(float(logged["val/psnr"]))
+    # the fit recovers the construction: gamma 1 / 1.3 in log space
+    assert abs(float(res["affine"][0, 0]) - 1 / 1.3) < 0.02
+
+
+def test_eval_lm_refinement_reaches_the_least_squares_minimum():
+    """The offset-gamma refinement (black_level_offset: true) — unpinned against pypose, so checked
+    against what it must compute: at convergence the gradient J^T r vanishes and the error is no larger
+    than that of an independent float64 optimisation."""
+    from oracle import eval_ref
+    pred, target, exposure, gain = _eval_images(1)
+    target = target + 0.03                                   # a black-level offset the affine fit cannot absorb
+    res = eval_ref.evaluate(pred[:, None], target[:, None], exposure, gain, 0.0, 1.1, black_level_offset=True)
+    norm = eval_ref.normalized_gain(gain, exposure)
+    _, fitted, _ = eval_ref.affine_log_correction(pred[:, None], target[:, None], norm)
+    x = fitted.exp()
+    p = res["correction"].clone().requires_grad_(True)
+    g = norm.double().view(-1, 1, 1, 1)
+    f = g * (p[:, 0].view(1, -1, 1, 1) * x.pow(p[:, 1].view(1, -1, 1, 1)) - p[:, 2].view(1, -1, 1, 1))
+    loss = ((f - target[:, None].double()) ** 2).sum()
+    loss.backward()
+    assert float(p.grad.abs().max()) < 1e-6 * float(loss) + 1e-9
+    no_refine = eval_ref.evaluate(pred[:, None], target[:, None], exposure, gain, 0.0, 1.1,
+                                  black_level_offset=False)
+    assert res["l1"] < no_refine["l1"]
