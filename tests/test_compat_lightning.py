@@ -1,0 +1,189 @@
+"""CPU: the `pytorch_lightning`-shaped façade (deblur_e_nerf_b200.compat).
+
+1. Loop semantics on a toy module: optimizer-step counting under accumulation, the one-batch prefetch lag
+   of a batch-size change, per-epoch scheduler stepping, checkpoint naming / keys, `save_hyperparameters`.
+2. Where `/root/reference` exists: the reference's OWN `scripts/run.py train <cfg>` runs UNCHANGED through
+   `deblur_e_nerf_b200.run_reference` on a tiny on-disk dataset (the YAML is the reference's synthetic.yaml
+   with paths, sizes and `limit_val_batches: 0` edited) — three optimizer steps, TensorBoard events, the
+   copied config and a Lightning-named checkpoint.  This container has no GPU, so the CUDA-only drop-ins are
+   replaced by the oracle's operators for this run (and `torch.cuda.device`, which the reference enters
+   while building tcnn, is a no-op): what is tested is the façade and the unchanged script, not kernels."""
+
+import contextlib
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import yaml
+
+from deblur_e_nerf_b200.compat import easydict as ed
+from deblur_e_nerf_b200.compat import pytorch_lightning as pl
+from deblur_e_nerf_b200.compat import roma
+
+
+class _Stream(torch.utils.data.IterableDataset):
+    def __init__(self):
+        self.batch_size = 2
+
+    def __iter__(self):
+        while True:
+            yield torch.ones(self.batch_size, 1)
+
+
+class _Toy(pl.LightningModule):
+    def __init__(self, lr, width=3):
+        super().__init__()
+        self.save_hyperparameters("lr")
+        self.lin = torch.nn.Linear(1, 1)
+        self.sizes, self.epochs_started = [], 0
+
+    def on_train_epoch_start(self):
+        self.epochs_started += 1
+
+    def training_step(self, batch, batch_index):
+        x = batch["a"].squeeze(0)
+        self.sizes.append(x.shape[0])
+        # like update_train_batch_size: the step writes a new batch size into the dataset
+        self.trainer.datamodule.ds.batch_size = x.shape[0] + 1
+        loss = self.lin(x).pow(2).mean()
+        self.log("train/loss", loss)
+        return loss
+
+    def configure_optimizers(self):
+        opt = torch.optim.SGD(self.parameters(), lr=self.hparams.lr)
+        sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1], gamma=0.5)
+        return {"optimizer": opt, "lr_scheduler": {"scheduler": sched, "interval": "epoch"}}
+
+
+class _Data(pl.LightningDataModule):
+    def setup(self, stage=None):
+        self.ds = _Stream()
+
+    def train_dataloader(self):
+        return {"a": torch.utils.data.DataLoader(self.ds, batch_size=1),
+                "b": torch.utils.data.DataLoader(_Stream(), batch_size=1)}
+
+
+def test_trainer_loop_semantics(tmp_path):
+    logger = pl.loggers.tensorboard.TensorBoardLogger(save_dir=str(tmp_path), name="run", version=None)
+    ckpt = pl.callbacks.ModelCheckpoint(dirpath=None, monitor=None, save_top_k=1, every_n_epochs=1)
+    trainer = pl.Trainer(callbacks=[ckpt], logger=logger, plugins=None, replace_sampler_ddp=True,
+                         sync_batchnorm=True, terminate_on_nan=True, multiple_trainloader_mode="min_size",
+                         num_nodes=1, gpus=None, accelerator=None, max_epochs=2, log_every_n_steps=1,
+                         check_val_every_n_epoch=1, flush_logs_every_n_steps=500, val_check_interval=1.0,
+                         limit_train_batches=4, limit_val_batches=0, accumulate_grad_batches=2)
+    model, data = _Toy(lr=0.1), _Data()
+    assert model.hparams.lr == 0.1 and "width" not in model.hparams
+    trainer.fit(model, data)
+    assert trainer.global_step == 4                       # 2 epochs x 4 batches / 2 accumulated
+    assert model.epochs_started == 2
+    # batch k + 1 was fetched before step k wrote (its own size + 1) into the dataset: the change of step
+    # k shows up in batch k + 2
+    assert model.sizes[:4] == [2, 2, 3, 3]
+    assert all(model.sizes[k + 2] == model.sizes[k] + 1 for k in range(2))
+    assert trainer.optimizers[0].param_groups[0]["lr"] == pytest.approx(0.05)      # milestone after epoch 1
+    folder = os.path.join(logger.log_dir, "checkpoints")
+    assert os.listdir(folder) == ["epoch=1-step=3.ckpt"]                           # top-1 = the latest
+    saved = torch.load(os.path.join(folder, "epoch=1-step=3.ckpt"), weights_only=False)
+    assert {"epoch", "global_step", "state_dict", "optimizer_states", "lr_schedulers",
+            "pytorch-lightning_version", "hyper_parameters"} <= set(saved)
+    assert saved["global_step"] == 4 and saved["epoch"] == 2
+    assert any(f.startswith("events.out.tfevents") for f in os.listdir(logger.log_dir))
+    assert model.all_gather({"x": torch.zeros(3)})["x"].shape == (1, 3)
+
+
+def test_easydict_and_roma_stand_ins():
+    cfg = ed.EasyDict({"a": {"b": 1}, "l": [{"c": 2}]})
+    assert cfg.a.b == 1 and cfg["a"]["b"] == 1 and cfg.l[0].c == 2
+    cfg.d = {}
+    cfg.d.e = 5
+    assert cfg["d"]["e"] == 5 and cfg.pop("d") == {"e": 5} and not hasattr(cfg, "d")
+    assert dict(**cfg) == {"a": {"b": 1}, "l": [{"c": 2}]}
+    g = torch.Generator().manual_seed(0)
+    q = torch.nn.functional.normalize(torch.randn(50, 4, generator=g, dtype=torch.float64), dim=-1)
+    R = roma.unitquat_to_rotmat(q)
+    assert torch.allclose(R @ R.transpose(-1, -2), torch.eye(3, dtype=torch.float64).expand(50, 3, 3), atol=1e-12)
+    assert torch.allclose(torch.linalg.det(R), torch.ones(50, dtype=torch.float64))
+    rv = roma.unitquat_to_rotvec(q)
+    q2 = roma.rotvec_to_unitquat(rv)
+    q_pos = torch.where(q[:, 3:] < 0, -q, q)
+    assert torch.allclose(q2, q_pos, atol=1e-10)
+    ident = roma.quat_product(q, roma.quat_conjugation(q))
+    assert torch.allclose(ident, torch.tensor([0.0, 0, 0, 1], dtype=torch.float64).expand(50, 4), atol=1e-12)
+    mid = roma.unitquat_slerp(q[:5], q[5:10], torch.tensor([0.0, 1.0], dtype=torch.float64), shortest_path=True)
+    assert torch.allclose(mid[0], q[:5], atol=1e-10)
+    assert torch.allclose(mid[1].abs(), q[5:10].abs(), atol=1e-10)
+    flat, lead = roma.internal.flatten_batch_dims(torch.zeros(2, 3, 4), end_dim=-2)
+    assert flat.shape == (6, 4) and roma.internal.unflatten_batch_dims(flat, lead).shape == (2, 3, 4)
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.reference
+@pytest.mark.timeout(1500)
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "deblur_e_nerf")), reason="needs /root/reference")
+def test_reference_run_py_trains_unchanged(tmp_path, monkeypatch):
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _dataset
+    from deblur_e_nerf_b200 import run_reference, synthetic
+    from oracle import nerfacc_ref, tcnn_ref
+    data_dir = str(tmp_path / "data")
+    _dataset.write(data_dir, dict(synthetic.CONFIGS["synthetic"]))
+    with open(os.path.join(REFERENCE, "configs", "train", "synthetic.yaml")) as fh:
+        conf = yaml.full_load(fh)
+    conf["seed"] = 3
+    conf["data"].update(dataset_directory=data_dir, train_init_eff_batch_size=16,
+                        train_eff_ray_sample_batch_size=4096)
+    conf["logger"]["save_dir"] = str(tmp_path / "logs")
+    conf["trainer"].update(max_epochs=1, limit_train_batches=3, log_every_n_steps=1, limit_val_batches=0,
+                           num_sanity_val_steps=0)
+    conf["model"]["nerf"]["occ_grid"]["resolution"] = 16
+    conf["model"]["nerf"]["ngp"]["pos_encoding"].update(n_levels=4, log2_hashmap_size=12)
+    conf["model"]["pixel_bandwidth"]["it_sample_size"] = 4
+    cfg_path = str(tmp_path / "cfg.yaml")
+    with open(cfg_path, "w") as fh:
+        yaml.safe_dump(conf, fh)
+    # run.py asks git for HEAD (scripts/run.py:27-29): a work tree whose files are links to the reference
+    ref = tmp_path / "ref"
+    (ref / "scripts").mkdir(parents=True)
+    os.symlink(os.path.join(REFERENCE, "scripts", "run.py"), ref / "scripts" / "run.py")
+    os.symlink(os.path.join(REFERENCE, "deblur_e_nerf"), ref / "deblur_e_nerf")
+    subprocess.run(["git", "init", "-q"], cwd=ref, check=True)
+    subprocess.run(["git", "-c", "user.name=t", "-c", "user.email=t@t", "commit", "-q", "--allow-empty",
+                    "-m", "x"], cwd=ref, check=True)
+    for name in [m for m in sys.modules if m == "deblur_e_nerf" or m.startswith("deblur_e_nerf.")]:
+        monkeypatch.delitem(sys.modules, name)
+    for name in ("easydict", "roma", "pytorch_lightning", "pypose", "torchmetrics", "lpips"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    monkeypatch.setitem(sys.modules, "nerfacc", nerfacc_ref)
+    monkeypatch.setitem(sys.modules, "tinycudann", tcnn_ref)
+    monkeypatch.setattr(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    before = set(sys.modules)
+    try:
+        run_reference.main([str(ref / "scripts" / "run.py"), "train", cfg_path], operators=False)
+    finally:
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in ("deblur_e_nerf", "easydict", "roma", "pytorch_lightning", "pypose",
+                                      "torchmetrics", "lpips"):
+                sys.modules.pop(name, None)
+    log_dir = tmp_path / "logs" / conf["logger"]["name"] / "version_0"
+    files = os.listdir(log_dir)
+    assert "cfg.yaml" in files and "hparams.yaml" in files
+    assert any(f.startswith("events.out.tfevents") for f in files)
+    assert os.listdir(log_dir / "checkpoints") == ["epoch=0-step=2.ckpt"]
+    ckpt = torch.load(log_dir / "checkpoints" / "epoch=0-step=2.ckpt", weights_only=False)
+    assert ckpt["global_step"] == 3
+    assert "nerf.radiance_field.mlp_base.0.params" in ckpt["state_dict"]
+    assert len(ckpt["optimizer_states"][0]["param_groups"]) == 11      # tau, mlp, 2 C_p, 6 Omega, rest
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(str(log_dir))
+    acc.Reload()
+    tags = set(acc.Tags()["scalars"])
+    assert {"train/loss", "train/log_intensity_diff", "train/log_intensity_tv", "train/batch_size",
+            "train/mean_num_samples_per_ray"} <= tags
+    losses = [e.value for e in acc.Scalars("train/loss")]
+    assert len(losses) == 3 and all(l == l and l > 0 for l in losses)
