@@ -117,6 +117,53 @@ __device__ __forceinline__ void tmem_ld16_words(uint32_t taddr, uint32_t (&r)[16
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- activations as the A operand IN TENSOR MEMORY (ts-form tcgen05.mma) ------------------------------
+// An M = 128 A operand of K bf16 columns occupies K / 2 TMEM columns: lane = row, column c = the pair
+// (a[2c], a[2c+1]), low half first (pinned by tests/test_gpu_mlp_tc.py, probe mode 3).  The epilogue
+// thread of a row writes its packed hi / lo words with tcgen05.st; no shared-memory store, no
+// generic->async proxy fence, and the MMA fetches only B from shared memory.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// 16 values of this thread's row, K columns [8 chunk0, 8 chunk0 + 16) -> hi / lo operand columns
+__device__ __forceinline__ void tstore16(uint32_t t_hi, uint32_t t_lo, int chunk0, const float (&v)[16]) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint4 h, l;
+        split8(&v[8 * c], h, l);
+        hi[4 * c] = h.x; hi[4 * c + 1] = h.y; hi[4 * c + 2] = h.z; hi[4 * c + 3] = h.w;
+        lo[4 * c] = l.x; lo[4 * c + 1] = l.y; lo[4 * c + 2] = l.z; lo[4 * c + 3] = l.w;
+    }
+    tmem_st8(t_hi + 4 * chunk0, hi);
+    tmem_st8(t_lo + 4 * chunk0, lo);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mma1_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D (+)= A * B, A = (hi, lo) columns in TMEM, B = hi / lo tiles in shared memory, 3-product split
+template <int KSTEPS>
+__device__ __forceinline__ void gemm3_ts(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, const OpDesc& b,
+                                         uint32_t idesc, bool accumulate) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+        mma1_ts(tmem_d, a_hi + 8 * ks, b.hi.at(ks * b.kstep), idesc, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) mma1_ts(tmem_d, a_lo + 8 * ks, b.hi.at(ks * b.kstep), idesc, 1u);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) mma1_ts(tmem_d, a_hi + 8 * ks, b.lo.at(ks * b.kstep), idesc, 1u);
+}
+
 template <class T>
 __device__ __forceinline__ void load16(const uint8_t* tile, int r, int chunk0, float (&v)[16]) {
 #pragma unroll

@@ -15,6 +15,8 @@
 // measured 2e-3 on the head-weight gradients, outside the 1e-3 parity bound).
 //
 // Thread layout and pipeline: see namespace fwd below (three tiles in flight per CTA).
+#include <stdlib.h>
+
 #include "den_mlp_ops.cuh"
 
 namespace den {
@@ -37,6 +39,10 @@ constexpr int kGroupThreads = 256;
 constexpr int kEpiThreads = kSlots * kGroupThreads;
 constexpr int kThreads = kEpiThreads;              // no dedicated MMA warp: each group issues its own GEMMs
 constexpr uint32_t kTmemCols = 256;
+// TMEM-A variant: per slot 64 accumulator columns + the A operands (K = 64: 32 hi + 32 lo, K = 32: 16 + 16)
+constexpr uint32_t kTmemColsA = 512;
+constexpr uint32_t kSlotColsA = 160;
+constexpr uint32_t kColA64 = 64, kColA32 = 128;
 
 using TA32 = OpTile<kTile, 4>;
 using TA64 = OpTile<kTile, 8>;
@@ -66,7 +72,7 @@ static_assert(Smem::total <= 227 * 1024, "shared-memory plan exceeds 227 KB");
 
 }  // namespace fwd
 
-template <bool kFull>
+template <bool kFull, bool kTmemA>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constant__ den_field_params p,
                   const float* __restrict__ enc, const float* __restrict__ rays_o,
@@ -110,7 +116,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         for (int b = 0; b < kSlots; ++b) tc::mbar_init(&bars[b], 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemA ? kTmemColsA : kTmemCols);
     tc::fence_smem_to_async_proxy();
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -130,26 +136,54 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
         uint8_t* A64 = slot + Smem::a64;
         uint64_t* done = &bars[slot_id];
         float* zx = reinterpret_cast<float*>(smem + Smem::zx) + slot_id * (kTile * 2 * 4);
-        const uint32_t Z = tmem_base + ((uint32_t)(q * 32) << 16) + 64u * slot_id;
+        const uint32_t slot_cols = kTmemA ? kSlotColsA * slot_id : 64u * slot_id;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + slot_cols;
+        const uint32_t Z = lane_base;
+        // TMEM-A: this thread's row of the A operands (hi | lo columns), and their lane-0 addresses
+        const uint32_t T64 = lane_base + kColA64, T32 = lane_base + kColA32;
+        const uint32_t M64 = tmem_base + slot_cols + kColA64, M32 = tmem_base + slot_cols + kColA32;
+        auto put32 = [&](int chunk0, const float (&x)[16]) {
+            if constexpr (kTmemA) tstore16(T32, T32 + 16, chunk0, x);
+            else store16<TA32>(A32, row, chunk0, x);
+        };
+        auto put64 = [&](int chunk0, const float (&x)[16]) {
+            if constexpr (kTmemA) tstore16(T64, T64 + 32, chunk0, x);
+            else store16<TA64>(A64, row, chunk0, x);
+        };
         const int hact = f.hidden_act;
         uint32_t phase = 0;
         const uint8_t* wb1 = smem + Smem::wb1;
         const uint8_t* wb2 = smem + Smem::wb2;
         const uint8_t* w1 = smem + Smem::w1;
         const uint8_t* w2 = smem + Smem::w2;
-        const uint32_t Zd = tmem_base + 64u * slot_id;            // accumulator address (lane 0) for the MMAs
+        const uint32_t Zd = tmem_base + slot_cols;                // accumulator address (lane 0) for the MMAs
         // Hand the operand tiles to the tensor core: every thread makes its shared-memory writes
         // visible to the async proxy, the 8 warps of the group meet at a hardware named barrier, then
         // ONE elected lane of the group's first warp issues the round's GEMM and its commit — the
         // slots own disjoint accumulators, so the three issuing threads never touch the same TMEM
         // columns and no dedicated MMA warp (and no second hand-off hop) is needed.
         auto launch_round = [&](int round) {
-            tc::fence_smem_to_async_proxy();
+            if constexpr (kTmemA) tmem_wait_st();
+            else tc::fence_smem_to_async_proxy();
             tc::tc_fence_before_sync();
             named_sync(4 + slot_id, kGroupThreads);
             if ((warp & 7) == 0) {
                 tc::tc_fence_after_sync();
                 if (elect_one()) {
+                    if constexpr (kTmemA) {
+                        if (round == 0)
+                            gemm3_ts<kEncDim / 16>(Zd, M32, M32 + 16, kmajor<TWb1>(wb1),
+                                                   tc::instr_desc_bf16(128, kWidth, false, false), false);
+                        else if (round == 1)
+                            gemm3_ts<kWidth / 16>(Zd, M64, M64 + 32, kmajor<TWb2>(wb2),
+                                                  tc::instr_desc_bf16(128, kBaseOut, false, false), false);
+                        else if (round == 2)
+                            gemm3_ts<kHeadIn / 16>(Zd, M32, M32 + 16, kmajor<TW1>(w1),
+                                                   tc::instr_desc_bf16(128, kWidth, false, false), false);
+                        else
+                            gemm3_ts<kWidth / 16>(Zd, M64, M64 + 32, kmajor<TW2>(w2),
+                                                  tc::instr_desc_bf16(128, kWidth, false, false), false);
+                    } else
                     if (round == 0)        // z_b1 = enc Wb1^T
                         gemm3<kEncDim / 16>(Zd, kmajor<TA32>(A32), kmajor<TWb1>(wb1),
                                             tc::instr_desc_bf16(128, kWidth, false, false), false);
@@ -198,7 +232,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                     }
                     if (hf == 0) inside = contract_position(f, pos, u);
                 }
-                store16<TA32>(A32, row, 2 * hf, x);
+                put32(2 * hf, x);
             }
             launch_round(0);
 
@@ -209,7 +243,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 float h[16];
                 tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
                 bias_hidden_act<16>(hact, h, s_bb1 + 32 * hf + 16 * c);
-                store16<TA64>(A64, row, 4 * hf + 2 * c, h);
+                put64(4 * hf + 2 * c, h);
             }
             launch_round(1);
 
@@ -226,12 +260,12 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < kGeo; ++j) x[j] = y[1 + j];
                     x[15] = 0.f;
-                    store16<TA32>(A32, row, 2, x);
+                    put32(2, x);
                 }
             } else if (kFull) {
                 float x[16];
                 sh_degree4(dir, x);
-                store16<TA32>(A32, row, 0, x);
+                put32(0, x);
             }
             if (!kFull) {
                 tc::tc_fence_before_sync();
@@ -246,7 +280,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 float h[16];
                 tmem_ld_cols<16>(Z + 32 * hf + 16 * c, h);
                 bias_hidden_act<16>(hact, h, s_b1 + 32 * hf + 16 * c);
-                store16<TA64>(A64, row, 4 * hf + 2 * c, h);
+                put64(4 * hf + 2 * c, h);
             }
             launch_round(3);
 
@@ -285,7 +319,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
 
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, fwd::kTmemCols);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemA ? fwd::kTmemColsA : fwd::kTmemCols);
 }
 
 // positions of marched samples in the field's unit cube (input of the hash-grid kernels)
@@ -393,15 +427,24 @@ int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float*
     // three tiles in flight per CTA: one persistent CTA per SM, at least three tiles each when there are enough
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int grid = grid_for((n_tiles + fwd::kSlots - 1) / fwd::kSlots, 1, 1);
-    const size_t smem = fwd::Smem::total;
+    // DEN_MLP_FWD_TMEM_A=1 selects the variant whose activations reach the tensor core as the TMEM A
+    // operand (no operand tiles in shared memory); read once per process
+    static const bool tmem_a = [] {
+        const char* e = getenv("DEN_MLP_FWD_TMEM_A");
+        return e != nullptr && e[0] == '1';
+    }();
+    const size_t smem = tmem_a ? (size_t)fwd::Smem::slot0 : (size_t)fwd::Smem::total;
+    auto launch = [&](auto kernel, float* rgb_out) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kernel<<<grid, fwd::kThreads, smem, as_stream(stream)>>>(*f, *p, enc, rays_o, rays_d, ray_indices,
+                                                                 t_starts, t_ends, n, n_dev, sigmas, rgb_out);
+    };
     if (full) {
-        cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mlp_fwd_tc_kernel<true><<<grid, fwd::kThreads, smem, as_stream(stream)>>>(
-            *f, *p, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, n, n_dev, sigmas, rgbs);
+        if (tmem_a) launch(mlp_fwd_tc_kernel<true, true>, rgbs);
+        else launch(mlp_fwd_tc_kernel<true, false>, rgbs);
     } else {
-        cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mlp_fwd_tc_kernel<false><<<grid, fwd::kThreads, smem, as_stream(stream)>>>(
-            *f, *p, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, n, n_dev, sigmas, nullptr);
+        if (tmem_a) launch(mlp_fwd_tc_kernel<false, true>, nullptr);
+        else launch(mlp_fwd_tc_kernel<false, false>, nullptr);
     }
     DEN_CHECK_LAUNCH();
     return DEN_OK;

@@ -310,8 +310,23 @@ class NGPradianceField(torch.nn.Module):
         return z.reshape(*embedding.shape[:-1], self.radiance_dim)
 
     def forward(self, positions, directions=None):
+        """external/ngp.py:269-280: (rgb (..., C), density (..., 1)).  On CUDA tensors this is the
+        hash-grid kernel pair + the tensor-core MLP pair (each position is a "ray" with t = 0), so callers
+        of the reference-signature method stay on the fused path, with autograd to the table, the MLP
+        parameters and the positions; the torch evaluation below remains for CPU tensors."""
         if directions is not None:
             assert positions.shape == directions.shape, \
                 f"{positions.shape} v.s. {directions.shape}"
+        if positions.is_cuda and directions is not None and positions.numel() > 0:
+            x = positions.reshape(-1, 3).float().contiguous()
+            d = directions.reshape(-1, 3).float().contiguous()
+            n = x.shape[0]
+            ray_idx = torch.arange(n, dtype=torch.int32, device=x.device)
+            t0 = torch.zeros(n, dtype=torch.float32, device=x.device)
+            offsets = torch.arange(n + 1, dtype=torch.int32, device=x.device)
+            enc = self.encode_samples(x, d, ray_idx, t0, t0, offsets)
+            sig, rgb = self.mlp_samples(enc, x, d, ray_idx, t0, t0, offsets)
+            return (rgb.reshape(*positions.shape[:-1], self.radiance_dim),
+                    sig.reshape(*positions.shape[:-1], 1))
         density, embedding = self.query_density(positions, return_feat=True)
         return self._query_rgb(directions, embedding), density

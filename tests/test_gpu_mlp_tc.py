@@ -52,13 +52,14 @@ def test_mlp_fwd_tc_matches_fp32(den_lib, cuda, small, n):
 
 
 @pytest.mark.parametrize("mode,n,k", [(0, 64, 32), (0, 16, 64), (1, 64, 64), (1, 32, 64),
-                                      (1, 64, 16), (2, 64, 128), (2, 32, 128), (2, 16, 128)])
+                                      (1, 64, 16), (2, 64, 128), (2, 32, 128), (2, 16, 128),
+                                      (3, 64, 32), (3, 64, 64), (3, 16, 64)])
 def test_tc_probe_gemm_flavours(den_lib, cuda, mode, n, k):
     """K-major / MN-major operand reuse and the M=64 accumulator lane mapping."""
     import ctypes
     g = torch.Generator().manual_seed(mode * 100 + n + k)
     bf = lambda t: t.to(torch.bfloat16).float()          # noqa: E731  (exact bf16 inputs)
-    if mode == 0:
+    if mode in (0, 3):          # 3: the A operand lives in tensor memory (tcgen05.st + ts-form MMA)
         x, w = bf(torch.randn(128, k, generator=g)), bf(torch.randn(n, k, generator=g))
         ref = x @ w.t()
         rows = 128
