@@ -322,6 +322,236 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
     if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemA ? fwd::kTmemColsA : fwd::kTmemCols);
 }
 
+// ---- v5: FOUR tiles in flight, one warp per TMEM lane quadrant (4 warps per slot), TMEM-A only -------
+// With the activations in tensor memory a slot needs no shared-memory tile at all, and the A operands of
+// consecutive rounds are never live together (enc -> hb -> [SH | geo] -> h1), so they share 64 columns:
+// 64 (accumulator) + 64 (A hi | lo) = 128 columns per slot, four slots fill the 512 columns.  Each thread
+// owns a whole row (64 columns per round, 16 at a time), which also removes the cross-half exchange of the
+// output layer; 16 warps instead of 24 leave 128 registers per thread.
+namespace fwd4 {
+constexpr int kSlots = 4;
+constexpr int kGroupThreads = 128;
+constexpr int kThreads = kSlots * kGroupThreads;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kSlotCols = 128, kColA = 64;
+}  // namespace fwd4
+
+template <bool kFull>
+__global__ void __launch_bounds__(fwd4::kThreads, 1)
+mlp_fwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_constant__ den_field_params p,
+                   const float* __restrict__ enc, const float* __restrict__ rays_o,
+                   const float* __restrict__ rays_d, const int32_t* __restrict__ ray_indices,
+                   const float* __restrict__ t_starts, const float* __restrict__ t_ends, int64_t n,
+                   const int32_t* __restrict__ n_dev, float* __restrict__ sigmas, float* __restrict__ rgbs) {
+    using namespace fwd4;
+    using fwd::Smem;
+    using fwd::TWb1; using fwd::TWb2; using fwd::TW1; using fwd::TW2;
+    n = effective_n(n, n_dev);
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::tmem_ptr);
+    const float* s_bb1 = reinterpret_cast<const float*>(smem + Smem::bias);
+    const float* s_bb2 = s_bb1 + kWidth;
+    const float* s_b1 = s_bb2 + kBaseOut;
+    const float* s_b2 = s_b1 + kWidth;
+    const float* s_b3 = s_b2 + kWidth;
+    float* s_w3f = reinterpret_cast<float*>(smem + Smem::w3f);
+    const int enc_dim = f.grid.n_levels * 2;
+    const int C = f.channels;
+
+    tc::load_weight_split(smem + Smem::wb1, smem + Smem::wb1 + TWb1::half, p.wb1, kWidth, enc_dim, kWidth, kEncDim);
+    tc::load_weight_split(smem + Smem::wb2, smem + Smem::wb2 + TWb2::half, p.wb2, kBaseOut, kWidth, kBaseOut, kWidth);
+    {
+        float* b = reinterpret_cast<float*>(smem + Smem::bias);
+        load_padded(b, p.bb1, kWidth, kWidth);
+        load_padded(b + kWidth, p.bb2, kBaseOut, kBaseOut);
+        if (kFull) {
+            load_padded(b + kWidth + kBaseOut, p.b1, kWidth, kWidth);
+            load_padded(b + 2 * kWidth + kBaseOut, p.b2, kWidth, kWidth);
+            load_padded(b + 3 * kWidth + kBaseOut, p.b3, C, 16);
+        }
+    }
+    if (kFull) {
+        tc::load_weight_split(smem + Smem::w1, smem + Smem::w1 + TW1::half, p.w1, kWidth, kShDim + kGeo, kWidth, kHeadIn);
+        tc::load_weight_split(smem + Smem::w2, smem + Smem::w2 + TW2::half, p.w2, kWidth, kWidth, kWidth, kWidth);
+        for (int i = tid; i < 3 * kWidth; i += kThreads) s_w3f[i] = (i / kWidth) < C ? __ldg(p.w3 + i) : 0.f;
+    }
+    if (tid == 0) {
+        for (int b = 0; b < kSlots; ++b) tc::mbar_init(&bars[b], 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
+    tc::fence_smem_to_async_proxy();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+    const int slot_id = warp >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint64_t* done = &bars[slot_id];
+    const uint32_t slot_cols = kSlotCols * slot_id;
+    const uint32_t Z = tmem_base + ((uint32_t)(q * 32) << 16) + slot_cols;      // this thread's accumulator row
+    const uint32_t TA = Z + kColA;                                               // ... and A operand row
+    const uint32_t Zd = tmem_base + slot_cols, MA = Zd + kColA;                 // lane-0 addresses for the MMAs
+    const int hact = f.hidden_act;
+    uint32_t phase = 0;
+    const uint8_t* wb1 = smem + Smem::wb1;
+    const uint8_t* wb2 = smem + Smem::wb2;
+    const uint8_t* w1 = smem + Smem::w1;
+    const uint8_t* w2 = smem + Smem::w2;
+
+    // K = 32 operands: hi columns [0, 16), lo [16, 32); K = 64: hi [0, 32), lo [32, 64) of the A region
+    auto launch_round = [&](int round) {
+        tmem_wait_st();
+        tc::tc_fence_before_sync();
+        named_sync(4 + slot_id, kGroupThreads);
+        if (q == 0) {
+            tc::tc_fence_after_sync();
+            if (elect_one()) {
+                if (round == 0)
+                    gemm3_ts<kEncDim / 16>(Zd, MA, MA + 16, kmajor<TWb1>(wb1),
+                                           tc::instr_desc_bf16(128, kWidth, false, false), false);
+                else if (round == 1)
+                    gemm3_ts<kWidth / 16>(Zd, MA, MA + 32, kmajor<TWb2>(wb2),
+                                          tc::instr_desc_bf16(128, kBaseOut, false, false), false);
+                else if (round == 2)
+                    gemm3_ts<kHeadIn / 16>(Zd, MA, MA + 16, kmajor<TW1>(w1),
+                                           tc::instr_desc_bf16(128, kWidth, false, false), false);
+                else
+                    gemm3_ts<kWidth / 16>(Zd, MA, MA + 32, kmajor<TW2>(w2),
+                                          tc::instr_desc_bf16(128, kWidth, false, false), false);
+                tc::mma_commit_1t(done);
+            }
+            __syncwarp();
+        }
+    };
+    // a 64-wide hidden layer: accumulator -> bias + activation -> A operand (K = 64); the TMEM load of
+    // the next 16 columns is in flight while the current 16 are processed
+    auto hidden_to_operand = [&](const float* bias) {
+        uint32_t raw[2][16];
+        tmem_ld16_nowait(Z, raw[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c < 3) tmem_ld16_nowait(Z + 16 * (c + 1), raw[(c + 1) & 1]);
+            float h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h[j] = __uint_as_float(raw[c & 1][j]);
+            bias_hidden_act<16>(hact, h, bias + 16 * c);
+            tstore16(TA, TA + 32, 2 * c, h);
+        }
+    };
+
+    for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
+        const int64_t tile = blockIdx.x + k * gridDim.x;
+        const int64_t i = tile * kTile + row;
+        const bool valid = i < n;
+        float dir[3] = {0.f, 0.f, 1.f};
+        bool inside = false;
+        // ---- round 0 operand: the 32 encoding features of this row ------------------------------
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            float x[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) x[c] = 0.f;
+            if (valid) {
+                const float4* src = reinterpret_cast<const float4*>(enc + i * enc_dim + 16 * hf);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4)
+                    if (16 * hf + 4 * v4 < enc_dim) {
+                        const float4 v = __ldg(src + v4);
+                        x[4 * v4] = v.x; x[4 * v4 + 1] = v.y; x[4 * v4 + 2] = v.z; x[4 * v4 + 3] = v.w;
+                    }
+            }
+            tstore16(TA, TA + 16, 2 * hf, x);
+        }
+        if (valid) {
+            const int64_t r = ray_indices[i];
+            const float tm = t_starts[i] + t_ends[i];
+            float pos[3], u[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                dir[d] = __ldg(rays_d + 3 * r + d);
+                pos[d] = __ldg(rays_o + 3 * r + d) + (dir[d] * tm) * 0.5f;
+            }
+            inside = contract_position(f, pos, u);
+        }
+        launch_round(0);
+
+        // ---- round 0 done: hb -> A (K = 64) -------------------------------------------------------
+        tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
+        hidden_to_operand(s_bb1);
+        launch_round(1);
+
+        // ---- round 1 done: density; [SH | geo | 0] -> A (K = 32) -------------------------------------
+        tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
+        {
+            float y[16];
+            tmem_ld_cols<16>(Z, y);
+#pragma unroll
+            for (int j = 0; j < kBaseOut; ++j) y[j] += s_bb2[j];
+            if (valid) sigmas[i] = inside ? density_act(f.density_act, y[0]) : 0.f;
+            if (kFull) {
+                float x[16];
+                sh_degree4(dir, x);
+                tstore16(TA, TA + 16, 0, x);
+#pragma unroll
+                for (int j = 0; j < kGeo; ++j) x[j] = y[1 + j];
+                x[15] = 0.f;
+                tstore16(TA, TA + 16, 2, x);
+            }
+        }
+        if (!kFull) {
+            tc::tc_fence_before_sync();
+            continue;
+        }
+        launch_round(2);
+
+        // ---- round 2 done: h1 -> A (K = 64) ------------------------------------------------------------
+        tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
+        hidden_to_operand(s_b1);
+        launch_round(3);
+
+        // ---- round 3 done: h2 in registers, output layer = dot with the fp32 W3 rows ---------------------
+        tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
+        {
+            float z3[3] = {0.f, 0.f, 0.f};
+            uint32_t raw[2][16];
+            tmem_ld16_nowait(Z, raw[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c < 3) tmem_ld16_nowait(Z + 16 * (c + 1), raw[(c + 1) & 1]);
+                float h[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) h[j] = __uint_as_float(raw[c & 1][j]);
+                bias_hidden_act<16>(hact, h, s_b2 + 16 * c);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    if (ch < C) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) z3[ch] = fmaf(h[j], s_w3f[ch * kWidth + 16 * c + j], z3[ch]);
+                    }
+            }
+            tc::tc_fence_before_sync();
+            if (valid) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    if (ch < C) rgbs[i * C + ch] = radiance_act(f.radiance_act, z3[ch] + s_b3[ch]);
+            }
+        }
+    }
+
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // positions of marched samples in the field's unit cube (input of the hash-grid kernels)
 __global__ void contract_samples_kernel(const __grid_constant__ den_field_desc f,
                                         const float* __restrict__ rays_o,
@@ -427,12 +657,27 @@ int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float*
     // three tiles in flight per CTA: one persistent CTA per SM, at least three tiles each when there are enough
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int grid = grid_for((n_tiles + fwd::kSlots - 1) / fwd::kSlots, 1, 1);
-    // DEN_MLP_FWD_TMEM_A=1 selects the variant whose activations reach the tensor core as the TMEM A
-    // operand (no operand tiles in shared memory); read once per process
-    static const bool tmem_a = [] {
+    // The activations reach the tensor core as the TMEM A operand (no operand tiles in shared memory).
+    // DEN_MLP_FWD_TMEM_A=0 selects the round-1 kernel with shared-memory operand tiles (kept for
+    // comparison), =2 the four-slot variant; read once per process
+    static const int variant = [] {              // 0: SS operands, 1: TMEM-A 3 x 8 warps, 2: TMEM-A 4 x 4 warps
         const char* e = getenv("DEN_MLP_FWD_TMEM_A");
-        return e != nullptr && e[0] == '1';
+        return e != nullptr ? (int)(e[0] - '0') : 1;
     }();
+    const bool tmem_a = variant >= 1;
+    if (variant == 2) {
+        const int grid4 = grid_for((n_tiles + fwd4::kSlots - 1) / fwd4::kSlots, 1, 1);
+        const size_t smem4 = (size_t)fwd::Smem::slot0;
+        auto launch4 = [&](auto kernel, float* rgb_out) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+            kernel<<<grid4, fwd4::kThreads, smem4, as_stream(stream)>>>(*f, *p, enc, rays_o, rays_d, ray_indices,
+                                                                       t_starts, t_ends, n, n_dev, sigmas, rgb_out);
+        };
+        if (full) launch4(mlp_fwd_tc4_kernel<true>, rgbs);
+        else launch4(mlp_fwd_tc4_kernel<false>, nullptr);
+        DEN_CHECK_LAUNCH();
+        return DEN_OK;
+    }
     const size_t smem = tmem_a ? (size_t)fwd::Smem::slot0 : (size_t)fwd::Smem::total;
     auto launch = [&](auto kernel, float* rgb_out) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
