@@ -658,12 +658,16 @@ int den_mlp_fwd(const den_field_desc* f, const den_field_params* p, const float*
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int grid = grid_for((n_tiles + fwd::kSlots - 1) / fwd::kSlots, 1, 1);
     // The activations reach the tensor core as the TMEM A operand (no operand tiles in shared memory).
-    // DEN_MLP_FWD_TMEM_A=0 selects the round-1 kernel with shared-memory operand tiles (kept for
-    // comparison), =2 the four-slot variant; read once per process
-    static const int variant = [] {              // 0: SS operands, 1: TMEM-A 3 x 8 warps, 2: TMEM-A 4 x 4 warps
+    // DEN_MLP_FWD_TMEM_A=0 forces the round-1 kernel with shared-memory operand tiles (kept for
+    // comparison), =1 / =2 one of the two TMEM-A kernels; read once per process
+    // measured at 40.8 M samples (profiles/r02_time_mlp_variants.md): full evaluation 7.01 ms (SS operand
+    // tiles) / 5.77 (TMEM-A, 3 slots x 8 warps) / 6.22 (TMEM-A, 4 slots x 4 warps); density only 4.13 / 3.38 /
+    // 3.14 — so the default is the 3 x 8 kernel for the full evaluation and the 4 x 4 one for density only
+    static const int forced = [] {               // 0: SS operands, 1: TMEM-A 3 x 8 warps, 2: TMEM-A 4 x 4 warps
         const char* e = getenv("DEN_MLP_FWD_TMEM_A");
-        return e != nullptr ? (int)(e[0] - '0') : 1;
+        return e != nullptr ? (int)(e[0] - '0') : -1;
     }();
+    const int variant = forced >= 0 ? forced : (full ? 1 : 2);
     const bool tmem_a = variant >= 1;
     if (variant == 2) {
         const int grid4 = grid_for((n_tiles + fwd4::kSlots - 1) / fwd4::kSlots, 1, 1);
