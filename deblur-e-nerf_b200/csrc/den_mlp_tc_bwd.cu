@@ -48,6 +48,8 @@
 // dL/dz tile) = 88 KB; 2 slots + 36 KB of weight tiles = 223 KB.  The price of fitting two
 // slots: the split hb and enc tiles are parked in TMEM (64 + 32 columns of packed bf16 words per
 // slot) while h1 / [SH | geo] / dy occupy H / E, and copied back afterwards.
+#include <stdlib.h>
+
 #include "den_mlp_ops.cuh"
 
 namespace den {
@@ -683,6 +685,13 @@ mlp_bwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
     if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// pipeline v4 (den_mlp_tc_bwd4.cu): slot-issued GEMMs, private accumulators, tensor-memory A operands
+int launch_mlp_bwd4(const den_field_desc* f, const den_field_params* p, const den_field_grads* g,
+                    const float* enc, const float* rays_o, const float* rays_d, const int32_t* ray_indices,
+                    const float* t_starts, const float* t_ends, const float* d_sigmas, const float* d_rgbs,
+                    int64_t n, const int32_t* n_dev, const int32_t* enc_rows, float* d_enc, float* d_dirs,
+                    cudaStream_t stream);
+
 }  // namespace den
 
 extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
@@ -704,6 +713,16 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
                   "null pointer");
     DEN_CHECK_ARG((f->grid.n_levels * 2) % 4 == 0, "encoding width must be a multiple of 4");
     DEN_CHECK_ARG(f->channels >= 1 && f->channels <= 3, "1 to 3 radiance channels");
+    // DEN_MLP_BWD_VARIANT: 0 = pipeline v3 (this file: 2 x 8 epilogue warps + MMA warp), 4 = pipeline v4
+    // (den_mlp_tc_bwd4.cu); read once per process
+    static const int forced = [] {
+        const char* e = getenv("DEN_MLP_BWD_VARIANT");
+        return e != nullptr ? (int)(e[0] - '0') : -1;
+    }();
+    const int variant = forced >= 0 ? forced : 0;
+    if (variant == 4)
+        return launch_mlp_bwd4(f, p, g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas,
+                               d_rgbs, n, n_dev, enc_rows, d_enc, d_dirs, as_stream(stream));
     // two tiles in flight per CTA: at least two tiles per CTA whenever there are enough of them
     const int64_t n_tiles = (n + kTile - 1) / kTile;
     const int grid = grid_for((n_tiles + 1) / 2, 1, 1);
