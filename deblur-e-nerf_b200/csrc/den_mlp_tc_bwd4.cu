@@ -285,7 +285,6 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
     // ===================== every warp is an epilogue warp: one group of 8 per slot =====================
     const int slot_id = warp / kGroupWarps;
     const int wslot = warp - slot_id * kGroupWarps;
-    const bool issuer = wslot == 0;                        // the slot's first warp issues the slot's GEMMs
     const int q = warp & 3, hf = wslot >> 2;               // TMEM quadrant (rows), column half
     const int row = q * 32 + lane;
     uint8_t* slot = smem + S::slot0 + slot_id * S::slot_bytes;
@@ -307,6 +306,11 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
     uint32_t phase = 0, dw_phase = 0;
     bool dw_pending = false;         // the slot's previous tile left its last dW GEMM un-awaited
     bool acc_live = false;           // the slot's weight-gradient accumulators hold earlier tiles of the period
+    // SIMT-side sums kept in registers across the tiles of this thread and added to shared memory once:
+    // lane l of a warp owns column 32 hf + l of dW3 (per channel), lanes < 16 of the hf = 0 warps own dbb2,
+    // lane 0 of the hf = 0 warps db3  (shared-memory float atomics are CAS loops: 16 warps contending on
+    // the same 32 words every tile)
+    float r_dw3[3] = {0.f, 0.f, 0.f}, r_db3[3] = {0.f, 0.f, 0.f}, r_dbb2 = 0.f;
     auto await_mma = [&]() {
         tc::mbar_wait(done, phase);
         phase ^= 1;
@@ -324,11 +328,15 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
 
     // hand-off: this thread's part of the operands is written (shared memory: generic -> async proxy
     // fence; tensor memory: tcgen05.wait::st by the writer); the slot's first warp waits for the whole
-    // group and one elected thread issues round `rnd`; the other warps arrive and move on
+    // group and one elected thread issues round `rnd`; the other warps arrive and move on.  Round r is
+    // issued by warp r of the slot: issuing costs ~5 instructions per MMA (171 MMAs per tile, a third of
+    // a warp's epilogue work), and a fixed issuing warp would be the straggler of every hand-off.  The
+    // accumulating GEMMs of a given accumulator always come from the same thread (same round, same
+    // warp), and successive rounds are ordered through the mbarrier they wait on.
     auto launch = [&](int rnd) {
         tc::fence_smem_to_async_proxy();
         tc::tc_fence_before_sync();
-        if (!issuer) {
+        if (wslot != rnd) {
             asm volatile("bar.arrive %0, %1;" ::"r"(3 + slot_id), "r"(kGroupThreads) : "memory");
             return;
         }
@@ -452,26 +460,36 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
     float xe[16];
     int64_t i = ((int64_t)blockIdx.x + (int64_t)slot_id * gridDim.x) * kTile + row;
     bool valid = slot_id < my_tiles && i < n;
-    int64_t ray = 0;
     float tmid2 = 0.f;                       // t_start + t_end
+    // the ray of a sample is a dependent chain (sample -> ray index -> origin / direction): the index of the
+    // slot's NEXT tile is fetched in the middle of the current one, origin / direction before its last
+    // wait, so that no tile starts on that chain (ncu: 7 % of the warp samples sat there)
+    float dn[3] = {0.f, 0.f, 1.f}, on[3] = {0.f, 0.f, 0.f};
+    auto load_ray = [&](int64_t r) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            dn[d] = __ldg(rays_d + 3 * r + d);
+            if (hf == 0) on[d] = __ldg(rays_o + 3 * r + d);
+        }
+    };
     load_enc(i, valid, xe);
-    if (valid) { ray = ray_indices[i]; tmid2 = t_starts[i] + t_ends[i]; }
+    if (valid) {
+        tmid2 = t_starts[i] + t_ends[i];
+        load_ray(ray_indices[i]);
+    }
 
     for (int64_t c0 = 0; c0 < my_tiles; c0 += kFlushTiles) {
         const int64_t c1 = min(c0 + (int64_t)kFlushTiles, my_tiles);
         acc_live = false;
         for (int64_t k = c0 + slot_id; k < c1; k += kSlots) {
             // ---- operands of round 0: enc -------------------------------------------------------
-            float dir[3] = {0.f, 0.f, 1.f};
+            const float dir[3] = {dn[0], dn[1], dn[2]};
             bool inside = false;
-            if (valid) {
+            if (valid && hf == 0) {
                 float pos[3], u[3];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    dir[d] = __ldg(rays_d + 3 * ray + d);
-                    pos[d] = __ldg(rays_o + 3 * ray + d) + (dir[d] * tmid2) * 0.5f;
-                }
-                if (hf == 0) inside = contract_position(f, pos, u);
+                for (int d = 0; d < 3; ++d) pos[d] = on[d] + (dir[d] * tmid2) * 0.5f;
+                inside = contract_position(f, pos, u);
             }
             stage_enc(xe);
             launch(0);
@@ -518,19 +536,17 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
             }
             launch(3);
 
-            // next tile of this slot: pull its rows towards L2 while this one is in flight
-            if (k + kSlots < my_tiles) {
-                const int64_t ni = i + (int64_t)kSlots * gridDim.x * kTile;
-                if (ni < n) {
-                    if (!enc_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(enc + ni * enc_dim + 16 * hf));
-                    if (hf == 0) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ray_indices + ni));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(t_starts + ni));
-                    } else {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(t_ends + ni));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(d_rgbs + ni * C));
-                    }
-                }
+            // next tile of this slot: its ray index and interval now (consumed before the tile's last wait),
+            // its other rows pulled towards L2 while this one is in flight
+            const int64_t ni = i + (int64_t)kSlots * gridDim.x * kTile;
+            const bool valid_n = k + kSlots < my_tiles && ni < n;
+            int32_t ray_n = 0;
+            float tmid2_n = 0.f;
+            if (valid_n) {
+                ray_n = __ldg(ray_indices + ni);
+                tmid2_n = __ldg(t_starts + ni) + __ldg(t_ends + ni);
+                if (!enc_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(enc + ni * enc_dim + 16 * hf));
+                if (hf == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(d_rgbs + ni * C));
             }
 
             // ---- round 3 done: h2 (registers), output layer forward + backward on the SIMT side ---
@@ -588,16 +604,14 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
                 }
                 launch(4);
                 // dW3 += d3^T h2, db3 += sum d3  (off the critical path: the MMA round is running)
-                for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (c >= C) break;
                     float t[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) t[j] = d3[c] * h2[j];
-                    const float s = warp_transpose_sum<32>(t, lane);
-                    atomicAdd(&s_dw3[c * kWidth + 32 * hf + lane], s);
-                    if (hf == 0) {
-                        const float sb = warp_sum(d3[c]);
-                        if (lane == 0) atomicAdd(&s_db3[c], sb);
-                    }
+                    r_dw3[c] += warp_transpose_sum<32>(t, lane);
+                    if (hf == 0) r_db3[c] += warp_sum(d3[c]);
                 }
             }
 
@@ -632,8 +646,7 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
                 launch(6);
                 const float s = warp_transpose_sum<16>(dy, lane & 15);
                 // lanes l and l + 16 hold the two half-warp sums of column l
-                const float tot = s + __shfl_xor_sync(0xffffffffu, s, 16);
-                if (lane < 16) atomicAdd(&s_dbb2[lane], tot);
+                r_dbb2 += s + __shfl_xor_sync(0xffffffffu, s, 16);
             } else {
                 if (d_dirs != nullptr) {
                     // dL/d(view direction) through the SH encoding (only the tau path needs it)
@@ -672,11 +685,12 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
             // ---- round 7 done: denc -> HBM ---------------------------------------------------------------
             const int64_t i_cur = i;
             const bool valid_cur = valid;
-            i += (int64_t)kSlots * gridDim.x * kTile;     // this slot's next tile: loads in flight across the wait
-            valid = k + kSlots < my_tiles && i < n;
+            i = ni;                                       // this slot's next tile: loads in flight across the wait
+            valid = valid_n;
             load_enc(i, valid, xe);
-            ray = 0; tmid2 = 0.f;
-            if (valid) { ray = ray_indices[i]; tmid2 = t_starts[i] + t_ends[i]; }
+            tmid2 = tmid2_n;
+            dn[0] = 0.f; dn[1] = 0.f; dn[2] = 1.f;
+            if (valid) load_ray(ray_n);
             await_mma();
             {
                 float de[16];
@@ -702,7 +716,14 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
         tc::tc_fence_after_sync();
     }
 
-    // ---- the SIMT-side accumulators (dW3, dbb2, db3: fp32 shared-memory atomics) go out once ----------
+    // ---- the SIMT-side accumulators (dW3, dbb2, db3) go out once: registers -> shared -> global ------
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c >= C) break;
+        atomicAdd(&s_dw3[c * kWidth + 32 * hf + lane], r_dw3[c]);
+        if (hf == 0 && lane == 0) atomicAdd(&s_db3[c], r_db3[c]);
+    }
+    if (hf == 0 && lane < 16) atomicAdd(&s_dbb2[lane], r_dbb2);
     tc::tc_fence_before_sync();
     __syncthreads();
     if (my_tiles > 0 && warp < 4) {
