@@ -243,7 +243,7 @@ template <int N>
 __device__ __forceinline__ void mul_hidden_act_grad(int id, float (&d)[N], const float (&h)[N]) {
     if (id == kActSoftplus100) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) d[j] *= 1.f - ex2_approx(-144.26950408889634f * h[j]);
+        for (int j = 0; j < N; ++j) d[j] = fmaf(-d[j], ex2_approx(-144.26950408889634f * h[j]), d[j]);   // d (1 - e)
     } else {
 #pragma unroll
         for (int j = 0; j < N; ++j) d[j] = h[j] > 0.f ? d[j] : 0.f;

@@ -202,38 +202,70 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
             }
         };
 
-        for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
-            const int64_t tile = blockIdx.x + k * gridDim.x;
-            const int64_t i = tile * kTile + row;
-            const bool valid = i < n;
-
-            // ---- operands of round 0: this thread's 16 encoding features -------------------------
-            float dir[3] = {0.f, 0.f, 1.f};
-            bool inside = false;
-            {
-                float x[16];
+        // Software pipeline over this slot's tiles.  A sample's ray is a dependent chain (sample -> ray
+        // index -> origin / direction) and its encoding row a 64-byte gather: the NEXT tile's ray index is
+        // fetched at the start of the current tile, its origin / direction and encoding before the current
+        // tile's last wait, so that no tile starts on HBM / L2 latency (ncu, profiles/r02_ncu_mlp.md: 8 % of
+        // the warp samples of the un-pipelined kernel sat on the t_starts line alone).
+        float xe[16], dn[3] = {0.f, 0.f, 1.f}, on[3] = {0.f, 0.f, 0.f}, tm = 0.f;
+        auto load_enc = [&](int64_t i, bool valid) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) x[c] = 0.f;
-                if (valid) {
-                    const float4* src = reinterpret_cast<const float4*>(enc + i * enc_dim + 16 * hf);
+            for (int c = 0; c < 16; ++c) xe[c] = 0.f;
+            if (valid) {
+                const float4* src = reinterpret_cast<const float4*>(enc + i * enc_dim + 16 * hf);
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4)
-                        if (16 * hf + 4 * v4 < enc_dim) {
-                            const float4 v = __ldg(src + v4);
-                            x[4 * v4] = v.x; x[4 * v4 + 1] = v.y; x[4 * v4 + 2] = v.z; x[4 * v4 + 3] = v.w;
-                        }
-                    const int64_t r = ray_indices[i];
-                    const float tm = t_starts[i] + t_ends[i];
-                    float pos[3], u[3];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        dir[d] = __ldg(rays_d + 3 * r + d);
-                        pos[d] = __ldg(rays_o + 3 * r + d) + (dir[d] * tm) * 0.5f;
+                for (int v4 = 0; v4 < 4; ++v4)
+                    if (16 * hf + 4 * v4 < enc_dim) {
+                        const float4 v = __ldg(src + v4);
+                        xe[4 * v4] = v.x; xe[4 * v4 + 1] = v.y; xe[4 * v4 + 2] = v.z; xe[4 * v4 + 3] = v.w;
                     }
-                    if (hf == 0) inside = contract_position(f, pos, u);
-                }
-                put32(2 * hf, x);
             }
+        };
+        auto load_ray = [&](int64_t r) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                dn[d] = __ldg(rays_d + 3 * r + d);
+                if (hf == 0) on[d] = __ldg(rays_o + 3 * r + d);
+            }
+        };
+        const int64_t tile_stride = (int64_t)kSlots * gridDim.x * kTile;
+        int64_t i = ((int64_t)blockIdx.x + (int64_t)slot_id * gridDim.x) * kTile + row;
+        bool valid = slot_id < my_tiles && i < n;
+        load_enc(i, valid);
+        if (valid) {
+            tm = t_starts[i] + t_ends[i];
+            load_ray(ray_indices[i]);
+        }
+        for (int64_t k = slot_id; k < my_tiles; k += kSlots) {
+            // ---- operands of round 0: this thread's 16 encoding features -------------------------
+            const float dir[3] = {dn[0], dn[1], dn[2]};
+            bool inside = false;
+            if (valid && hf == 0) {
+                float pos[3], u[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pos[d] = on[d] + (dir[d] * tm) * 0.5f;
+                inside = contract_position(f, pos, u);
+            }
+            put32(2 * hf, xe);
+            // the slot's next tile: ray index and interval now, the rest before this tile's last wait
+            const int64_t i_cur = i;
+            const bool valid_cur = valid;
+            const int64_t ni = i + tile_stride;
+            const bool valid_n = k + kSlots < my_tiles && ni < n;
+            int32_t ray_n = 0;
+            float tm_n = 0.f;
+            if (valid_n) {
+                ray_n = __ldg(ray_indices + ni);
+                tm_n = __ldg(t_starts + ni) + __ldg(t_ends + ni);
+            }
+            auto fetch_next = [&]() {
+                i = ni;
+                valid = valid_n;
+                tm = tm_n;
+                load_enc(ni, valid_n);
+                dn[0] = 0.f; dn[1] = 0.f; dn[2] = 1.f;
+                if (valid_n) load_ray(ray_n);
+            };
             launch_round(0);
 
             // ---- round 0 done: hb -> A64 ---------------------------------------------------------------
@@ -254,7 +286,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 tmem_ld_cols<16>(Z, y);
 #pragma unroll
                 for (int j = 0; j < kBaseOut; ++j) y[j] += s_bb2[j];
-                if (valid) sigmas[i] = inside ? density_act(f.density_act, y[0]) : 0.f;
+                if (valid_cur) sigmas[i_cur] = inside ? density_act(f.density_act, y[0]) : 0.f;
                 if (kFull) {
                     float x[16];
 #pragma unroll
@@ -268,6 +300,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 put32(0, x);
             }
             if (!kFull) {
+                fetch_next();
                 tc::tc_fence_before_sync();
                 continue;
             }
@@ -283,6 +316,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 put64(4 * hf + 2 * c, h);
             }
             launch_round(3);
+            fetch_next();
 
             // ---- round 3 done: h2 stays in registers; output layer = dot with the fp32 W3 rows ----------------
             tc::mbar_wait(done, phase); phase ^= 1; tc::tc_fence_after_sync();
@@ -307,10 +341,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ den_field_desc f, const __grid_constan
                 if (hf == 0) {
                     const float4 other = *reinterpret_cast<const float4*>(zx + row * 4);
                     z3[0] += other.x; z3[1] += other.y; z3[2] += other.z;
-                    if (valid) {
+                    if (valid_cur) {
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch)
-                            if (ch < C) rgbs[i * C + ch] = radiance_act(f.radiance_act, z3[ch] + s_b3[ch]);
+                            if (ch < C) rgbs[i_cur * C + ch] = radiance_act(f.radiance_act, z3[ch] + s_b3[ch]);
                     }
                 }
             }

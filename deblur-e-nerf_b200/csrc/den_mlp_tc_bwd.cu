@@ -719,7 +719,7 @@ extern "C" int den_mlp_bwd(const den_field_desc* f, const den_field_params* p,
         const char* e = getenv("DEN_MLP_BWD_VARIANT");
         return e != nullptr ? (int)(e[0] - '0') : -1;
     }();
-    const int variant = forced >= 0 ? forced : 0;
+    const int variant = forced >= 0 ? forced : 4;       // v4 measured 17.0 ms against 19.6 ms at 40.8 M samples
     if (variant == 4)
         return launch_mlp_bwd4(f, p, g, enc, rays_o, rays_d, ray_indices, t_starts, t_ends, d_sigmas,
                                d_rgbs, n, n_dev, enc_rows, d_enc, d_dirs, as_stream(stream));

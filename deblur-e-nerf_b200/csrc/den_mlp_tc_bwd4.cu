@@ -598,8 +598,12 @@ mlp_bwd_tc4_kernel(const __grid_constant__ den_field_desc f, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 16; ++j) dl[j] = fmaf(d3[2], s_w3f[2 * kWidth + 32 * hf + 16 * c2 + j], dl[j]);
                     }
+                    {
+                        float hh[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dl[j] *= hidden_act_grad_from_out(hact, h2[16 * c2 + j]);
+                        for (int j = 0; j < 16; ++j) hh[j] = h2[16 * c2 + j];
+                        mul_hidden_act_grad<16>(hact, dl, hh);
+                    }
                     store16<TD>(D, row, 4 * hf + 2 * c2, dl);
                 }
                 launch(4);
