@@ -101,6 +101,7 @@ _SIGNATURES = {
     "den_occgrid_ema_update": (_INT, [_P, _P, _P, _I64, _F, _F, _P, _I64, _P, _P, _P, _P]),
     "den_rays_from_trajectory": (_INT, [_P, _P, _I64, _P, _P, _P, _I32, _c.POINTER(_F), _P, _P, _I64,
                                         _P]),
+    "den_rays_from_trajectory_bwd": (_INT, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _I64, _P]),
     "den_adam_step": (_INT, [_c.POINTER(AdamTensor), _I32, _c.c_double, _c.c_double, _c.c_double, _I64,
                              _P, _c.c_double, _P, _P]),
     "den_alpha_from_sigma": (_INT, [_P, _P, _P, _P, _I64, _P, _P]),

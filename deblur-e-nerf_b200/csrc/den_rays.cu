@@ -8,8 +8,17 @@
 // NeRF.pixel_params_to_ray (models/nerf.py:206-228: d = R K^-1 [u, v, 1], normalised; o = position).
 // One thread per ray; the pose table (C ~ 1 000 poses, 36 KB) stays L1/L2 resident.  The formulas are
 // the torch host path's, term by term (deblur_e_nerf_b200/trajectories.py), so both paths agree to
-// fp32 rounding; the refractory-period gradient path (timestamps with requires_grad) keeps the torch
-// autograd form.
+// fp32 rounding.
+//
+// Reverse mode (the refractory-period path: timestamps = event time - tau carry a gradient, config 4,
+// models/deblur_e_nerf.py:465-469): poses are buffers, so the only gradient is dL/dt per ray, and inside a
+// pose interval it has a closed form.  With w = (t - t_left) / width: position = lerp(p0, p1, w) gives
+// d o / d w = p1 - p0; orientation R(w) = R0 Exp(w r), r = rotation vector of q0^-1 q1 (body frame),
+// gives d R / d w = R(w) [r]x, and since the direction is d = R(w) c / |c| with a fixed camera-frame c,
+// d d / d w = (R(w) r) x d = (R0 r) x d  (Exp(w r) leaves r in place).  Hence
+//     dL/dt = (dL/do . (p1 - p0) + dL/dd . ((R0 r) x d)) / width
+// — one thread per ray, no saved intermediates but the forward direction.  The torch autograd form
+// (trajectories.py) differentiates the same functions term by term; tests compare the two.
 #include "den_common.cuh"
 
 namespace den {
@@ -103,7 +112,81 @@ rays_from_trajectory_kernel(const double* __restrict__ ts, const float* __restri
     }
 }
 
+__global__ void __launch_bounds__(256)
+rays_from_trajectory_bwd_kernel(const double* __restrict__ ts, const int64_t* __restrict__ pose_ts,
+                                const float* __restrict__ pose_pos, const float* __restrict__ pose_quat,
+                                int32_t n_poses, const float* __restrict__ rays_d,
+                                const float* __restrict__ d_rays_o, const float* __restrict__ d_rays_d,
+                                double* __restrict__ d_ts, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = ts[i];
+        int lo = 0, hi = n_poses;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((double)pose_ts[mid] < t) lo = mid + 1; else hi = mid;
+        }
+        int right = lo;
+        int left = (t == (double)pose_ts[0]) ? right : right - 1;
+        left = min(max(left, 0), n_poses - 2);
+        right = min(max(right, 1), n_poses - 1);
+        const double width = (double)(pose_ts[left + 1] - pose_ts[left]);
+        float g = 0.f;                                   // dL/dw
+        if (d_rays_o != nullptr) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                g = fmaf(d_rays_o[3 * i + d], pose_pos[3 * right + d] - pose_pos[3 * left + d], g);
+        }
+        if (d_rays_d != nullptr) {
+            float q0[4], q1[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) { q0[d] = pose_quat[4 * left + d]; q1[d] = pose_quat[4 * right + d]; }
+            const float dot = q0[0] * q1[0] + q0[1] * q1[1] + q0[2] * q1[2] + q0[3] * q1[3];
+            if (dot < 0.f) {
+#pragma unroll
+                for (int d = 0; d < 4; ++d) q1[d] = -q1[d];
+            }
+            const float q0c[4] = {-q0[0], -q0[1], -q0[2], q0[3]};
+            float rel[4];
+            quat_mul(q0c, q1, rel);
+            const float vnorm = sqrtf(rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2]);
+            const float angle = 2.f * atan2f(vnorm, rel[3]);
+            const bool small_a = fabsf(angle) <= 1e-3f;
+            const float a2 = angle * angle;
+            const float scale_v = small_a ? 2.f + a2 / 12.f + 7.f * a2 * a2 / 2880.f : angle / sinf(angle * 0.5f);
+            // body-frame rotation vector r, turned into the world frame by q0: q0 (r, 0) q0^-1
+            const float r[4] = {scale_v * rel[0], scale_v * rel[1], scale_v * rel[2], 0.f};
+            float tmp[4], om[4];
+            quat_mul(q0, r, tmp);
+            quat_mul(tmp, q0c, om);
+            const float inv_n2 = 1.f / (q0[0] * q0[0] + q0[1] * q0[1] + q0[2] * q0[2] + q0[3] * q0[3]);
+            const float ox = om[0] * inv_n2, oy = om[1] * inv_n2, oz = om[2] * inv_n2;
+            const float dx = rays_d[3 * i], dy = rays_d[3 * i + 1], dz = rays_d[3 * i + 2];
+            g = fmaf(d_rays_d[3 * i], oy * dz - oz * dy, g);
+            g = fmaf(d_rays_d[3 * i + 1], oz * dx - ox * dz, g);
+            g = fmaf(d_rays_d[3 * i + 2], ox * dy - oy * dx, g);
+        }
+        d_ts[i] = (double)g / width;
+    }
+}
+
 }  // namespace den
+
+extern "C" int den_rays_from_trajectory_bwd(const double* timestamps, const int64_t* pose_ts,
+                                            const float* pose_pos, const float* pose_quat, int32_t n_poses,
+                                            const float* rays_d, const float* d_rays_o, const float* d_rays_d,
+                                            double* d_timestamps, int64_t n_rays, void* stream) {
+    using namespace den;
+    DEN_CHECK_ARG(n_rays >= 0, "bad sizes");
+    DEN_CHECK_ARG(n_poses >= 2, "at least two poses");
+    if (n_rays == 0) return DEN_OK;
+    DEN_CHECK_ARG(timestamps && pose_ts && pose_pos && pose_quat && d_timestamps, "null pointer");
+    DEN_CHECK_ARG(d_rays_d == nullptr || rays_d != nullptr, "the direction gradient needs the forward directions");
+    rays_from_trajectory_bwd_kernel<<<grid_for(n_rays, 256, 8), 256, 0, as_stream(stream)>>>(
+        timestamps, pose_ts, pose_pos, pose_quat, n_poses, rays_d, d_rays_o, d_rays_d, d_timestamps, n_rays);
+    DEN_CHECK_LAUNCH();
+    return DEN_OK;
+}
 
 extern "C" int den_rays_from_trajectory(const double* timestamps, const float* pixels, int64_t n_pixels,
                                         const int64_t* pose_ts, const float* pose_pos,

@@ -805,9 +805,37 @@ def adam_step(tensor_array, n_tensors, beta1, beta2, eps, step, grad_scale=1.0, 
 # --------------------------------------------------------------------------- #
 # trajectory + camera model -> rays
 # --------------------------------------------------------------------------- #
+class _RaysFn(torch.autograd.Function):
+    """den_rays_from_trajectory with its reverse mode w.r.t. the timestamps (den_rays_from_trajectory_bwd)."""
+
+    @staticmethod
+    def forward(ctx, timestamps, pixels, pose_ts, pose_pos, pose_quat, kinv_host):
+        o, d = rays_from_trajectory(timestamps.detach(), pixels, pose_ts, pose_pos, pose_quat, kinv_host)
+        ctx.save_for_backward(timestamps.detach(), pose_ts, pose_pos, pose_quat, d)
+        return o, d
+
+    @staticmethod
+    def backward(ctx, d_o, d_d):
+        timestamps, pose_ts, pose_pos, pose_quat, d = ctx.saved_tensors
+        ts = _req(timestamps.reshape(-1), torch.float64, "timestamps")
+        n = ts.numel()
+        g_o = None if d_o is None else _req(d_o.reshape(-1, 3), torch.float32, "d_rays_o")
+        g_d = None if d_d is None else _req(d_d.reshape(-1, 3), torch.float32, "d_rays_d")
+        out = torch.empty(n, dtype=torch.float64, device=ts.device)
+        _call("den_rays_from_trajectory_bwd", _ptr(ts), _ptr(_req(pose_ts, torch.int64, "pose_ts")),
+              _ptr(_req(pose_pos, torch.float32, "pose_pos")), _ptr(_req(pose_quat, torch.float32, "pose_quat")),
+              pose_ts.numel(), _ptr(d.reshape(-1, 3)), _ptr(g_o), _ptr(g_d), _ptr(out), n, _stream())
+        return out.view(timestamps.shape).to(timestamps.dtype), None, None, None, None, None
+
+
+def rays_from_trajectory_grad(timestamps, pixels, pose_ts, pose_pos, pose_quat, kinv_host):
+    """rays_from_trajectory for timestamps that carry a gradient (the refractory-period path)."""
+    return _RaysFn.apply(timestamps, pixels, pose_ts, pose_pos, pose_quat, kinv_host)
+
+
 def rays_from_trajectory(timestamps, pixels, pose_ts, pose_pos, pose_quat, kinv_host):
     """timestamps (..., N) f64 ns, pixels (N, 2) f32 -> rays_o, rays_d (..., N, 3) in one launch
-    (no gradient: callers keep the torch autograd path when the timestamps require grad).
+    (no gradient; `rays_from_trajectory_grad` is the differentiable form).
     `kinv_host`: the 9 floats of K^-1, row-major, on the host."""
     shape = tuple(timestamps.shape)
     ts = _req(timestamps.detach().reshape(-1), torch.float64, "timestamps")

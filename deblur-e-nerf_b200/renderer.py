@@ -49,6 +49,9 @@ class EventRenderer(torch.nn.Module):
         # with the pixel-bandwidth model on, filter + reset + loss of all requests run as ONE kernel per
         # direction (den_lpf_loss_fwd / _bwd) instead of a filter launch per request + eager loss ops
         self.fuse_lpf_loss = True
+        # reverse mode of the ray generation w.r.t. the timestamps (the tau path): "kernel" = closed form
+        # per pose interval (den_rays_from_trajectory_bwd), "autograd" = the reference's torch form
+        self.rays_reverse_mode = "kernel"
         self.batch_bytes_per_sample = 448        # encodings + their gradient + the per-sample scalars
         self._last_mean_samples = None           # samples per ray of the previous step (memory guard)
 
@@ -61,15 +64,19 @@ class EventRenderer(torch.nn.Module):
 
     def rays(self, timestamp, pixel_position):
         """Camera rays of `pixel_position` (N,2) at `timestamp` (..., N): one fused kernel
-        (trajectory interpolation + pinhole model) unless the timestamps carry a gradient (the
-        refractory-period path), which keeps the torch autograd form."""
-        if timestamp.requires_grad or pixel_position.requires_grad or not timestamp.is_cuda:
+        (trajectory interpolation + pinhole model); when the timestamps carry a gradient (the
+        refractory-period path) its reverse mode is one kernel too (dL/dt in closed form).
+        `rays_reverse_mode = "autograd"` keeps the term-by-term torch form of the reference for that
+        path (its fp32 rounding differs from the closed form's: tests/test_gpu_b2_renderer.py)."""
+        if pixel_position.requires_grad or not timestamp.is_cuda or (
+                timestamp.requires_grad and self.rays_reverse_mode == "autograd"):
             pos, rot = self.trajectory(timestamp)
             return self.nerf.pixel_params_to_ray(self.train_intrinsics_inv, pixel_position, pos, rot)
         from . import ops
         tr = self.trajectory
-        return ops.rays_from_trajectory(timestamp, pixel_position, tr.T_wc_timestamp, tr.T_wc_position,
-                                        tr.T_wc_orientation_quat, self._kinv_host())
+        fn = ops.rays_from_trajectory_grad if timestamp.requires_grad else ops.rays_from_trajectory
+        return fn(timestamp, pixel_position, tr.T_wc_timestamp, tr.T_wc_position,
+                  tr.T_wc_orientation_quat, self._kinv_host())
 
     def render_pixels(self, intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation):
         o, d = self.nerf.pixel_params_to_ray(intrinsics_inverse, pixel_position, T_wc_position,

@@ -176,11 +176,21 @@ int den_occgrid_ema_update(const int64_t* indices, const uint8_t* keep, const fl
  * f64 weight, LERP, shortest-path SLERP via utils/tensor_ops.py:118-184, quaternion -> R) fused with
  * NeRF.pixel_params_to_ray (models/nerf.py:206-228).  timestamps (n_rays) f64 ns; ray i looks through
  * pixel i % n_pixels of pixels (n_pixels, 2); pose_ts (C) int64 ascending, pose_pos (C,3), pose_quat
- * (C,4) xyzw; kinv9_host: row-major K^-1 on the HOST.  No gradient (the tau path stays in autograd). */
+ * (C,4) xyzw; kinv9_host: row-major K^-1 on the HOST. */
 int den_rays_from_trajectory(const double* timestamps, const float* pixels, int64_t n_pixels,
                              const int64_t* pose_ts, const float* pose_pos, const float* pose_quat,
                              int32_t n_poses, const float* kinv9_host, float* rays_o, float* rays_d,
                              int64_t n_rays, void* stream);
+/* Reverse mode of the above with respect to the timestamps (the refractory-period path,
+ * models/deblur_e_nerf.py:465-469: timestamps = event time - tau; the autograd of trajectories.py:30-90 +
+ * utils/tensor_ops.py:118-184 + nerf.py:206-228, ~80 launches): d_timestamps[i] (f64, per ns) =
+ * (d_rays_o[i] . (p_right - p_left) + d_rays_d[i] . ((R_left r) x rays_d[i])) / interval width, r = the
+ * rotation vector of q_left^-1 q_right.  rays_d = the forward output; d_rays_o / d_rays_d may be NULL
+ * (no gradient through that output). */
+int den_rays_from_trajectory_bwd(const double* timestamps, const int64_t* pose_ts, const float* pose_pos,
+                                 const float* pose_quat, int32_t n_poses, const float* rays_d,
+                                 const float* d_rays_o, const float* d_rays_d, double* d_timestamps,
+                                 int64_t n_rays, void* stream);
 
 /* Visibility filter + compaction — replaces nerfacc.render_visibility and the
  * three boolean-mask compactions inside nerfacc.ray_marching. */

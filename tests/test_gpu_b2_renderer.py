@@ -168,42 +168,60 @@ def test_cell_densities_match_oracle_field(den_lib, cuda):
     assert _rel(occ_p, occ_o) < 1e-4
 
 
+# The ray part of the refractory-period gradient is a sum over all rays of dL/dt_i that cancels to ~1 %
+# of sum |dL/dt_i| and then again against the direct terms.  The closed-form reverse mode of the ray
+# kernel and the reference's fp32 autograd through SLERP are BOTH within ~8e-6 of max |dL/dt_i| per ray of
+# the float64 evaluation (profiles/rays_grad_check2.py: reference 7.7e-6, kernel 5.6e-6), with different
+# rounding, which the cancellation amplifies to 5.7e-4 (reference) / 6.9e-4 (kernel) of the parameter
+# gradient against float64 and 1.26e-3 against each other.  So the kernel mode is held to the golden at
+# the standard bound plus this allowance on that one key, and the autograd mode (same kernels everywhere
+# else) to the standard bound on every key.
+TAU_KEY = "refractory_period.parametrizations._refractory_period.original"
+TAU_RAY_ROUNDING = 1e-3            # measured 1.3e-3 total on the pixel-bandwidth golden (bound 2e-3), 1.6e-4 / 1.2e-5 elsewhere
+
+
 def _run_training_step_golden(cuda, pb_on):
     golden = _scene.load_golden("training_step_pb_on" if pb_on else "training_step_pb_off")
     cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
-    model, poses = _scene.build_product_renderer(cfg, cuda, 8, pixel_bandwidth=pb_on)
-    names = ["nerf", "contrast_threshold", "refractory_period"] + (
-        ["pixel_bandwidth"] if pb_on else [])
-    for name in names:
-        _scene.load_golden_state(getattr(model, name), golden, name, cuda)
-    batch = {"event": _scene.golden_section(golden, "event", cuda),
-             "normalized": _scene.golden_section(golden, "normalized", cuda)}
-    jitters = [v for _, v in sorted(_scene.golden_section(golden, "jitter", cuda).items(),
-                                    key=lambda kv: int(kv[0]))]
-    model.train()
-    # the golden carries the occupancy grid AFTER the reference's step-0 update: skip ours
-    model.nerf.update_occ_grid = lambda *a, **k: None
-    loss = model.training_step(batch, 0, 0, jitters=jitters)
-    assert _rel(loss, golden["loss"]) < TOL
-    for key in ("log_intensity_diff", "log_intensity_tv"):
-        assert _rel(model.logged[f"train/{key}"], golden[f"logged/train/{key}"]) < TOL
-    assert abs(model.logged["train/mean_num_samples_per_ray"]
-               - float(golden["logged/train/mean_num_samples_per_ray"])) < 0.02
-    model.zero_grad()
-    loss.backward()
-    grads = _scene.flat_named_grads(model)
     ref = _scene.golden_section(golden, "grad")
-    assert set(ref) <= set(grads), set(ref) - set(grads)
-    worst = {}
-    for key in ref:
-        worst[key] = _rel(grads[key], ref[key])
-    print("golden pb_on" if pb_on else "golden pb_off", "worst relative gradient errors:",
-          {k.split(".")[-2] if k.endswith("original") else k.split("radiance_field.")[-1]: f"{v:.1e}"
-           for k, v in worst.items()})
-    bounds = _grad_bounds("pb_on" if pb_on else "pb_off", ref)
-    assert max(bounds.values()) < 4e-3, bounds            # synthetic shape: (almost) everything at 1e-3
-    bad = {k: (v, bounds[k]) for k, v in worst.items() if v > bounds[k]}
-    assert not bad, bad
+    modes = ("kernel", "autograd") if TAU_KEY in ref else ("kernel",)
+    for mode in modes:
+        model, poses = _scene.build_product_renderer(cfg, cuda, 8, pixel_bandwidth=pb_on)
+        model.rays_reverse_mode = mode
+        names = ["nerf", "contrast_threshold", "refractory_period"] + (
+            ["pixel_bandwidth"] if pb_on else [])
+        for name in names:
+            _scene.load_golden_state(getattr(model, name), golden, name, cuda)
+        batch = {"event": _scene.golden_section(golden, "event", cuda),
+                 "normalized": _scene.golden_section(golden, "normalized", cuda)}
+        jitters = [v for _, v in sorted(_scene.golden_section(golden, "jitter", cuda).items(),
+                                        key=lambda kv: int(kv[0]))]
+        model.train()
+        # the golden carries the occupancy grid AFTER the reference's step-0 update: skip ours
+        model.nerf.update_occ_grid = lambda *a, **k: None
+        loss = model.training_step(batch, 0, 0, jitters=jitters)
+        assert _rel(loss, golden["loss"]) < TOL
+        for key in ("log_intensity_diff", "log_intensity_tv"):
+            assert _rel(model.logged[f"train/{key}"], golden[f"logged/train/{key}"]) < TOL
+        assert abs(model.logged["train/mean_num_samples_per_ray"]
+                   - float(golden["logged/train/mean_num_samples_per_ray"])) < 0.02
+        model.zero_grad()
+        loss.backward()
+        grads = _scene.flat_named_grads(model)
+        assert set(ref) <= set(grads), set(ref) - set(grads)
+        worst = {}
+        for key in ref:
+            worst[key] = _rel(grads[key], ref[key])
+        print("golden pb_on" if pb_on else "golden pb_off", f"({mode} ray reverse mode)",
+              "worst relative gradient errors:",
+              {k.split(".")[-2] if k.endswith("original") else k.split("radiance_field.")[-1]: f"{v:.1e}"
+               for k, v in worst.items()})
+        bounds = _grad_bounds("pb_on" if pb_on else "pb_off", ref)
+        assert max(bounds.values()) < 4e-3, bounds            # synthetic shape: (almost) everything at 1e-3
+        if mode == "kernel" and TAU_KEY in bounds:
+            bounds[TAU_KEY] += TAU_RAY_ROUNDING
+        bad = {k: (v, bounds[k]) for k, v in worst.items() if v > bounds[k]}
+        assert not bad, (mode, bad)
 
 
 @pytest.mark.parametrize("pb_on", [False, True], ids=["pb_off", "pb_on"])
@@ -259,6 +277,55 @@ def test_fused_rays_match_the_torch_trajectory_path(den_lib, cuda):
     assert (o - o_ref).abs().max().item() < 2e-6 * o_ref.abs().max().item() + 1e-6
     assert (d - d_ref).abs().max().item() < 5e-6
     assert torch.allclose(d.norm(dim=-1), torch.ones_like(d[..., 0]), atol=1e-6)
+
+
+def test_fused_rays_reverse_mode_matches_the_torch_autograd_path(den_lib, cuda):
+    """dL/d(timestamp) of den_rays_from_trajectory_bwd (closed form per pose interval) vs torch autograd
+    through LinearTrajectory.forward + pixel_params_to_ray (the form the reference differentiates:
+    models/trajectories.py:30-90, utils/tensor_ops.py:118-184, models/nerf.py:206-228)."""
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    model, poses = _scene.build_product_renderer(cfg, cuda, 8, pixel_bandwidth=False)
+    tr = model.trajectory
+    g = torch.Generator().manual_seed(5)
+    n = 900
+    t0, t1 = float(tr.T_wc_timestamp[0]), float(tr.T_wc_timestamp[-1])
+    ts = (t0 + torch.rand(2, 4, n, generator=g, dtype=torch.float64) * (t1 - t0)).to(cuda)
+    pix = (torch.rand(n, 2, generator=g) * 300).to(cuda)
+    w_o = torch.randn(2, 4, n, 3, generator=g).to(cuda)
+    w_d = torch.randn(2, 4, n, 3, generator=g).to(cuda)
+
+    ts_ref = ts.clone().requires_grad_(True)
+    pos, rot = tr(ts_ref)
+    o_ref, d_ref = model.nerf.pixel_params_to_ray(model.train_intrinsics_inv, pix, pos, rot)
+    ((o_ref * w_o).sum() + (d_ref * w_d).sum()).backward()
+
+    ts_k = ts.clone().requires_grad_(True)
+    o, d = model.rays(ts_k, pix)
+    assert o.grad_fn is not None and type(o.grad_fn).__name__.startswith("_RaysFn")
+    ((o * w_o).sum() + (d * w_d).sum()).backward()
+    ref, got = ts_ref.grad, ts_k.grad
+    assert got.dtype == torch.float64 and got.shape == ts.shape
+    scale = ref.abs().max().item()
+    assert scale > 0
+    assert (got - ref).abs().max().item() < 2e-4 * scale, ((got - ref).abs().max().item(), scale)
+    # against the float64 evaluation of the same functions the closed form is at least as close as the
+    # reference's fp32 autograd (x 1.5 for noise)
+    from deblur_e_nerf_b200 import trajectories
+    tr64 = trajectories.LinearTrajectory((tr.T_wc_position.double(), tr.T_wc_orientation_quat.double(),
+                                          tr.T_wc_timestamp))
+    ts_64 = ts.clone().requires_grad_(True)
+    pos, rot = tr64(ts_64)
+    o64, d64 = model.nerf.pixel_params_to_ray(model.train_intrinsics_inv.double(), pix.double(), pos, rot)
+    ((o64 * w_o.double()).sum() + (d64 * w_d.double()).sum()).backward()
+    err_kernel = (got - ts_64.grad).abs().max().item()
+    err_autograd = (ref - ts_64.grad).abs().max().item()
+    assert err_kernel <= 1.5 * err_autograd + 1e-7 * scale, (err_kernel, err_autograd, scale)
+    # one output only (the other gradient is None inside autograd)
+    ts_o = ts.clone().requires_grad_(True)
+    (model.rays(ts_o, pix)[0] * w_o).sum().backward()
+    ts_o_ref = ts.clone().requires_grad_(True)
+    (tr(ts_o_ref)[0] * w_o).sum().backward()
+    assert (ts_o.grad - ts_o_ref.grad).abs().max().item() < 2e-4 * ts_o_ref.grad.abs().max().item()
 
 
 def test_training_step_pb_off_matches_reference_golden(den_lib, cuda):
