@@ -43,6 +43,7 @@ class GraphedStep:
         self.captures = 0
         self.replays = 0
         self.overflows = 0
+        self.eager_fallbacks = 0                # steps run eagerly because they did not fit the batched path
         self.launches_per_replay = 0            # den_b200 kernels recorded in the captured step
         self._side = None                       # every step of this object runs on one side stream
 
@@ -144,6 +145,15 @@ class GraphedStep:
         self._lagged_host_work()
         if self._graph is None or sig != self._sig:
             if model.nerf._capacity(1) is None:          # no estimate (e.g. after an overflow): learn it
+                return self._eager_no_update(batches, global_step)
+            if not all(model.step_fits_batched(b) for b in batches):
+                # the memory guard would split this step into sequential render calls with host
+                # read-backs (e.g. the enlarged estimate after an overflow on a 180 GB-filling batch):
+                # nothing a graph can record — run it eagerly, try to capture the next one
+                self._graph = None
+                self._static = None
+                self._loss = None
+                self.eager_fallbacks += 1
                 return self._eager_no_update(batches, global_step)
             self._capture(batches, global_step)         # records the step (nothing executes yet) ...
             self._sig = sig

@@ -350,6 +350,18 @@ class EventRenderer(torch.nn.Module):
         free = self._device_bytes - torch.cuda.memory_allocated()
         return rays * per_ray * self.batch_bytes_per_sample < 0.7 * free
 
+    def step_fits_batched(self, batch):
+        """Would `training_step` evaluate this batch's render calls as ONE launch sequence (the only form
+        without host read-backs, i.e. the only one a CUDA graph can record)?  The memory guard of
+        `_training_step`, from the batch alone: 2 render calls per supervised interval."""
+        weight = self.loss.loss_weight
+        n_segs = int(_get(weight, "log_intensity_diff") > 0) + int(_get(weight, "log_intensity_tv") > 0)
+        size = batch["event"]["start_ts"].numel()
+        gen = batch["normalized"].get("interval_gen")
+        if gen is not None and gen.dim() == 3 and gen.shape[0] == 1:
+            gen = gen.squeeze(0)
+        return self.batch_render_calls and n_segs > 0 and self._batch_fits(2 * n_segs * size, gen)
+
     def update_train_batch_size(self, mean_samples_per_call, batch_index):
         """models/deblur_e_nerf.py:1252-1308: N_next = int(budget / mean samples per ray)."""
         mean = sum(mean_samples_per_call) / len(mean_samples_per_call)
