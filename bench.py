@@ -113,13 +113,18 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
             return
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
+        # nvidia-smi's start-up (driver attach, a few hundred ms) must not overlap the warm-up / timed
+        # steps: an eagerly launched step (277 launches) stalls behind it.  Wait for the first line.
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < 3.0 and self.proc.poll() is None:
+            time.sleep(0.02)
 
     def _read(self):
         for line in self.proc.stdout:
