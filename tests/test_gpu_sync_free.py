@@ -135,3 +135,43 @@ def test_graph_replay_equals_eager_steps(den_lib, cuda, pb_on):
     assert set(sa.values()) == set(sb.values()) == {5}            # host-side Adam step numbers follow
     for name in pa:
         assert _rel(pb[name], pa[name]) < 2e-3, name             # 5 Adam steps of lr 1e-2 on fp32-atomic grads
+
+
+def test_graphed_step_falls_back_to_eager_when_the_step_does_not_fit(den_lib, cuda):
+    """The memory guard of `training_step` (`EventRenderer._batch_fits`) can refuse the batched render path
+    (e.g. with the enlarged sample estimate after a capacity overflow on a batch that fills the device);
+    the sequential path reads counts back, which no CUDA graph can record.  GraphedStep must then run
+    that step eagerly — with the same result as any other eager step — and capture a later one."""
+    from deblur_e_nerf_b200 import ddp, factory
+    from deblur_e_nerf_b200.graph_step import GraphedStep
+    finals = []
+    for refuse_once in (False, True):
+        model, batch, jitters = _setup(cuda, "synthetic", True)
+        reducer = ddp.GradReducer(model)
+        opt = factory.configure_optimizer(model)
+        reducer.bind(opt)
+        step = model.training_step
+        model.training_step = lambda b, m, gs: step(b, m, gs, jitters=[j.clone() for j in jitters])
+        stepper = GraphedStep(model, opt, reducer, 1)
+        fits = model._batch_fits
+        calls = {"n": 0}
+
+        def guarded(n_rays, gen, fits=fits, calls=calls, refuse_once=refuse_once):
+            calls["n"] += 1
+            # the third optimizer step (the first one GraphedStep would capture) is refused once
+            if refuse_once and stepper._eager_done >= stepper.warmup_steps and stepper.eager_fallbacks == 0:
+                return False
+            return fits(n_rays, gen)
+        model._batch_fits = guarded
+        losses = [stepper([batch], 1 + i).detach().clone() for i in range(5)]
+        torch.cuda.synchronize()
+        if refuse_once:
+            # step 3: the predicate said no -> eager (and, inside it, the sequential render calls)
+            assert stepper.eager_fallbacks >= 1 and stepper.captures == 1 and stepper.replays >= 1
+        else:
+            assert stepper.eager_fallbacks == 0 and stepper.captures == 1 and stepper.replays == 3
+        finals.append((torch.stack(losses), {n: p.detach().clone() for n, p in model.named_parameters()}))
+    (la, pa), (lb, pb) = finals
+    assert _rel(lb, la) < 1e-4, (la, lb)
+    for name in pa:
+        assert _rel(pb[name], pa[name]) < 2e-3, name
