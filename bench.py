@@ -539,10 +539,12 @@ def run_ours(args):
     if not use_graph:
         ops.enable_kernel_timing(rated_kernels)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     start.record()
     for i in range(args.steps):
         one_step(dev_batches[args.warmup + i], args.warmup + i)
         samples_seen += model.logged["train/mean_num_samples_per_ray"] * rays_per_step(n_events)
+        step_marks[i].record()                 # per-step boundaries (diagnostic: `step_ms`)
     end.record()
     graph_stats = {"enabled": use_graph, "captures": stepper.captures, "replays": stepper.replays,
                    "overflows": stepper.overflows, "setup_steps_before_warmup": setup_steps}
@@ -550,6 +552,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_wall1 = time.time()
     ms_total = start.elapsed_time(end)
+    step_ms = [round((start if i == 0 else step_marks[i - 1]).elapsed_time(step_marks[i]), 3)
+               for i in range(args.steps)]
     samples_seen = float(samples_seen)
     ms_step = ddp.max_over_ranks(ms_total / args.steps, dev)
     timings = ops.kernel_timings()
@@ -768,6 +772,7 @@ def run_ours(args):
         "events_per_s": world * n_events * acc / (ms_step * 1e-3),
         "mean_samples_per_ray": float(model.logged["train/mean_num_samples_per_ray"]),
         "cuda_graph": graph_stats,
+        "step_ms": step_ms,
         "hash_gather_gbs": HASH_GATHER_BYTES * global_samples / (ms_step * 1e-3) / 1e9,
         "e2e": e2e, "device_batches": producer_line, "weak_scaling": weak_line,
         "gpu_launches": launches, "cuda_mallocs_in_timed_region": mallocs,

@@ -223,8 +223,12 @@ __device__ __forceinline__ void event_epilogue(const LossArgs& a, const double (
 }
 
 // workspace layout (doubles): err (P*N) | ticket (1, as uint32)
-template <bool kBackward>
-__global__ void __launch_bounds__(32 * kMaxRequests)
+// kMaxK: the largest number of render requests (warps) a launch of this instance takes.  A training step
+// has K <= 4: with 128 threads per CTA the reverse pass is compiled for THREE CTAs per SM (168 registers,
+// ~0.5 KB of spills per thread) instead of the two its 250 registers allow — it is bound by the latency of
+// its fp64 chains at 8 resident warps per SM, not by the fp64 pipe.
+template <bool kBackward, int kMaxK>
+__global__ void __launch_bounds__(32 * kMaxK, (kBackward && kMaxK <= 4) ? 3 : 1)
 lpf_loss_kernel(const LossArgs a, double* __restrict__ err_buf, unsigned* __restrict__ ticket,
                 float* __restrict__ terms /* (P) */, int32_t* __restrict__ counts /* (P) */,
                 float* __restrict__ log_intensity /* (K, N) filter outputs after the reset, may be NULL */,
@@ -476,8 +480,12 @@ int den_lpf_loss_fwd(const den_lpf_loss_desc* d, const float* intensity, const f
     DEN_CHECK_ARG(terms && counts && workspace, "null pointer");
     double* err = reinterpret_cast<double*>(workspace);
     unsigned* ticket = reinterpret_cast<unsigned*>(err + (size_t)a.P * N);
-    lpf::lpf_loss_kernel<false><<<(unsigned)N, 32 * a.K, 0, as_stream(stream)>>>(
-        a, err, ticket, terms, counts, log_intensity, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (a.K <= 4)
+        lpf::lpf_loss_kernel<false, 4><<<(unsigned)N, 32 * a.K, 0, as_stream(stream)>>>(
+            a, err, ticket, terms, counts, log_intensity, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else
+        lpf::lpf_loss_kernel<false, lpf::kMaxRequests><<<(unsigned)N, 32 * a.K, 0, as_stream(stream)>>>(
+            a, err, ticket, terms, counts, log_intensity, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }
@@ -492,9 +500,14 @@ int den_lpf_loss_bwd(const den_lpf_loss_desc* d, const float* intensity, const f
     int rc = fill_args(a, d, intensity, sample_dt_ns, coef, reset_dt_ns, target, inv_k, valid, N);
     if (rc) return rc;
     DEN_CHECK_ARG(counts && d_terms && d_intensity, "null pointer");
-    lpf::lpf_loss_kernel<true><<<(unsigned)N, 32 * a.K, 0, as_stream(stream)>>>(
-        a, nullptr, nullptr, nullptr, const_cast<int32_t*>(counts), nullptr, d_terms, d_intensity, d_coef,
-        d_reset_dt_ns, d_target, d_inv_k);
+    if (a.K <= 4)
+        lpf::lpf_loss_kernel<true, 4><<<(unsigned)N, 32 * a.K, 0, as_stream(stream)>>>(
+            a, nullptr, nullptr, nullptr, const_cast<int32_t*>(counts), nullptr, d_terms, d_intensity, d_coef,
+            d_reset_dt_ns, d_target, d_inv_k);
+    else
+        lpf::lpf_loss_kernel<true, lpf::kMaxRequests><<<(unsigned)N, 32 * a.K, 0, as_stream(stream)>>>(
+            a, nullptr, nullptr, nullptr, const_cast<int32_t*>(counts), nullptr, d_terms, d_intensity, d_coef,
+            d_reset_dt_ns, d_target, d_inv_k);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }

@@ -9,7 +9,7 @@ import csv, io, json, subprocess, sys
 ENTRY = {"hashgrid_fwd_kernel": "den_hashgrid_fwd", "hashgrid_bwd_kernel": "den_hashgrid_bwd",
          "mlp_fwd_tc_kernel": "den_mlp_fwd", "mlp_bwd_tc_kernel": "den_mlp_bwd",
          "composite_fwd_kernel": "den_composite_fwd", "composite_bwd_sweep_kernel": "den_composite_bwd",
-         "lpf_loss_kernel<0>": "den_lpf_loss_fwd", "lpf_loss_kernel<1>": "den_lpf_loss_bwd",
+         "lpf_loss_kernel<0": "den_lpf_loss_fwd", "lpf_loss_kernel<1": "den_lpf_loss_bwd",
          "compact_kernel": "den_compact_samples_ex", "march_kernel<2>": "den_march_single"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
