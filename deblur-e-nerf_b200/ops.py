@@ -145,7 +145,10 @@ def grid_level_table(n_levels, base_resolution, per_level_scale, log2_hashmap_si
 
 
 def make_hashgrid_desc(n_levels, base_resolution, per_level_scale, log2_hashmap_size,
-                       n_features=2, agg_max_resolution=512):
+                       n_features=2, agg_max_resolution=800):
+    """`agg_max_resolution`: levels up to this resolution merge runs of consecutive samples in the same
+    cell before the scatter's atomics.  Measured on the synthetic.yaml shape (10.2 M samples,
+    profiles/time_hashgrid.py): 256 -> 3.22 ms, 512 -> 3.21, 800 -> 3.08, 1100 -> 3.09, 2100 -> 3.12."""
     if n_levels > _lib.DEN_MAX_LEVELS:
         raise ValueError("too many levels")
     scales, ress, sizes, offsets, total = grid_level_table(
