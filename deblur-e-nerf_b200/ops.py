@@ -148,7 +148,8 @@ def make_hashgrid_desc(n_levels, base_resolution, per_level_scale, log2_hashmap_
                        n_features=2, agg_max_resolution=800):
     """`agg_max_resolution`: levels up to this resolution merge runs of consecutive samples in the same
     cell before the scatter's atomics.  Measured on the synthetic.yaml shape (10.2 M samples,
-    profiles/time_hashgrid.py): 256 -> 3.22 ms, 512 -> 3.21, 800 -> 3.08, 1100 -> 3.09, 2100 -> 3.12."""
+    profiles/time_hashgrid.py): 256 -> 3.22 ms, 512 -> 3.21, 800 -> 3.08, 1100 -> 3.09, 2100 -> 3.12 alone;
+    inside the training step (41 M samples, survivors of the visibility filter) 512 and 800 both take 11.8 ms."""
     if n_levels > _lib.DEN_MAX_LEVELS:
         raise ValueError("too many levels")
     scales, ress, sizes, offsets, total = grid_level_table(
