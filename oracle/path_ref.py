@@ -355,6 +355,30 @@ class LinearTrajectory(torch.nn.Module):
         return pos, roma.unitquat_to_rotmat(quat)
 
 
+def trajectory_time_gradient(trajectory, ts, rays_d, d_rays_o, d_rays_d):
+    """dL/dt of rays_o, rays_d = pixel_params_to_ray(K^-1, pix, *trajectory(ts)) in CLOSED FORM per pose
+    interval — the reverse mode the CUDA kernel den_rays_from_trajectory_bwd evaluates, restated here so
+    that it can be pinned against torch autograd through the reference's own trajectory code
+    (models/trajectories.py:30-90, utils/tensor_ops.py:118-184, models/nerf.py:206-228;
+    tests/test_oracle_vs_reference.py).  With w = (t - t_left) / width:
+      position    lerp(p0, p1, w)            d o / d w = p1 - p0
+      orientation R(w) = R0 Exp(w r), r = full rotation vector of q0^-1 q1 (shortest path)
+                  d = R(w) c / |c|           d d / d w = (R0 r) x d
+    `rays_d`: the forward directions; returns dL/dt with the shape of `ts` (per ns)."""
+    T = trajectory.T_wc_timestamp
+    right = torch.searchsorted(T, ts.contiguous())
+    left = torch.where(ts == T[0], right, right - 1).clamp(0, len(T) - 2)
+    right = right.clamp(1, len(T) - 1)
+    p0, p1 = trajectory.T_wc_position[left], trajectory.T_wc_position[right]
+    q0, q1 = trajectory.T_wc_orientation_quat[left], trajectory.T_wc_orientation_quat[right]
+    q1 = torch.where(torch.sum(q0 * q1, dim=-1, keepdim=True) < 0, -q1, q1)
+    r = _full_rotvec(roma.quat_product(roma.quat_conjugation(q0), q1))
+    omega = (roma.unitquat_to_rotmat(q0) @ r[..., None])[..., 0]            # body -> world
+    g = torch.sum(d_rays_o * (p1 - p0), dim=-1) + torch.sum(
+        d_rays_d * torch.cross(omega, rays_d.to(omega.dtype), dim=-1), dim=-1)
+    return g.double() / trajectory.bin_width[left].double()
+
+
 # --------------------------------------------------------------------------- #
 # event-generation parameters
 # --------------------------------------------------------------------------- #

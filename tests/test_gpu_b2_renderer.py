@@ -320,6 +320,13 @@ def test_fused_rays_reverse_mode_matches_the_torch_autograd_path(den_lib, cuda):
     err_kernel = (got - ts_64.grad).abs().max().item()
     err_autograd = (ref - ts_64.grad).abs().max().item()
     assert err_kernel <= 1.5 * err_autograd + 1e-7 * scale, (err_kernel, err_autograd, scale)
+    # and against the ORACLE's closed form (pinned on CPU against autograd through the reference's own
+    # trajectory code: tests/test_oracle_vs_reference.py::test_trajectory_time_gradient_closed_form)
+    from oracle import path_ref
+    ora_tr = path_ref.LinearTrajectory(tr.T_wc_position.cpu(), tr.T_wc_orientation_quat.cpu(),
+                                       tr.T_wc_timestamp.cpu())
+    closed = path_ref.trajectory_time_gradient(ora_tr, ts.cpu(), d.detach().cpu(), w_o.cpu(), w_d.cpu())
+    assert (got.cpu() - closed).abs().max().item() < 2e-5 * scale, ((got.cpu() - closed).abs().max().item(), scale)
     # one output only (the other gradient is None inside autograd)
     ts_o = ts.clone().requires_grad_(True)
     (model.rays(ts_o, pix)[0] * w_o).sum().backward()

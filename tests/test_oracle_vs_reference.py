@@ -76,6 +76,23 @@ def test_trajectory_and_rays(pair):
     _close(d_o, d_r)
 
 
+def test_trajectory_time_gradient_closed_form(pair):
+    """The closed-form dL/dt per pose interval (what den_rays_from_trajectory_bwd evaluates, restated in
+    oracle/path_ref.py) against torch autograd through the REFERENCE'S trajectory + pinhole code."""
+    cfg, ref, ora, poses = pair
+    g = torch.Generator().manual_seed(7)
+    ts = (torch.rand(2, 300, generator=g, dtype=torch.float64) * float(poses[2][-1])).requires_grad_(True)
+    px = torch.rand(300, 2, generator=g) * 200
+    w_o, w_d = torch.randn(2, 300, 3, generator=g), torch.randn(2, 300, 3, generator=g)
+    pr, rr = ref.trajectory(ts)
+    o_r, d_r = ref.nerf.pixel_params_to_ray(ref.train_intrinsics_inv, px, pr, rr)
+    ((o_r * w_o).sum() + (d_r * w_d).sum()).backward()
+    closed = path_ref.trajectory_time_gradient(ora.trajectory, ts.detach(), d_r.detach(), w_o, w_d)
+    scale = ts.grad.abs().max()
+    assert scale > 0
+    assert (closed - ts.grad).abs().max() < 2e-5 * scale, ((closed - ts.grad).abs().max(), scale)
+
+
 @pytest.mark.parametrize("training", [False, True])
 def test_nerf_render(pair, training):
     cfg, ref, ora, poses = pair
