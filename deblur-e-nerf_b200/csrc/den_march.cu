@@ -422,16 +422,36 @@ compact_kernel(const uint8_t* __restrict__ mask, const int32_t* __restrict__ off
         if (off_out[r + 1] == dst) continue;
         for (int i0 = beg; i0 < end; i0 += 32) {
             const int i = i0 + lane;
-            const bool keep = i < end && mask[i] != 0;
+            const bool in = i < end;
+            // the row is loaded together with its mask byte (one memory latency per chunk instead of two:
+            // mask -> ballot -> loads); the rows of culled samples are read in vain, the usual case keeps most
+            const uint8_t m = in ? mask[i] : (uint8_t)0;
+            int32_t rv = 0;
+            float a = 0.f, b = 0.f, sg = 0.f, col[4] = {0.f, 0.f, 0.f, 0.f};
+            if (in) {
+                rv = ray_in[i];
+                a = t0_in[i];
+                b = t1_in[i];
+                if (sig_out) sg = sig_in[i];
+                if (rgb_out) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < channels) col[c] = rgb_in[i * (int64_t)channels + c];
+                }
+            }
+            const bool keep = m != 0;
             const unsigned ball = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int k = dst + __popc(ball & ((1u << lane) - 1u));
-                ray_out[k] = ray_in[i];
-                t0_out[k] = t0_in[i];
-                t1_out[k] = t1_in[i];
-                if (sig_out) sig_out[k] = sig_in[i];
-                if (rgb_out)
-                    for (int c = 0; c < channels; ++c) rgb_out[k * (int64_t)channels + c] = rgb_in[i * (int64_t)channels + c];
+                ray_out[k] = rv;
+                t0_out[k] = a;
+                t1_out[k] = b;
+                if (sig_out) sig_out[k] = sg;
+                if (rgb_out) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < channels) rgb_out[k * (int64_t)channels + c] = col[c];
+                }
                 if (src_rows) src_rows[k] = i;
             }
             dst += __popc(ball);
