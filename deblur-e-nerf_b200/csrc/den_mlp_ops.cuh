@@ -1,5 +1,6 @@
 // Operand tiles, descriptors and single-thread GEMM issue shared by the multi-slot tensor-core MLP
-// kernels (den_mlp_tc.cu forward: three tiles in flight, den_mlp_tc_bwd.cu backward: two).
+// kernels (den_mlp_tc.cu forward: three tiles in flight, den_mlp_tc_bwd.cu backward: two).  Every GEMM is
+// issued by one elected thread of the slot that owns the tile; there is no MMA warp.
 #pragma once
 #include "den_mlp_tc.cuh"
 
@@ -74,32 +75,6 @@ __device__ __forceinline__ void store16(uint8_t* tile, int r, int chunk0, const 
         const uint32_t o = T::off(r, chunk0 + c);
         *reinterpret_cast<uint4*>(tile + o) = hi;
         *reinterpret_cast<uint4*>(tile + T::half + o) = lo;
-    }
-}
-// the same store, also handing back the 16 packed words (hi chunk 0, lo chunk 0, hi chunk 1, lo chunk 1)
-template <class T>
-__device__ __forceinline__ void store16_keep(uint8_t* tile, int r, int chunk0, const float (&v)[16],
-                                             uint32_t (&words)[16]) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint4 hi, lo;
-        split8(&v[8 * c], hi, lo);
-        const uint32_t o = T::off(r, chunk0 + c);
-        *reinterpret_cast<uint4*>(tile + o) = hi;
-        *reinterpret_cast<uint4*>(tile + T::half + o) = lo;
-        words[8 * c + 0] = hi.x; words[8 * c + 1] = hi.y; words[8 * c + 2] = hi.z; words[8 * c + 3] = hi.w;
-        words[8 * c + 4] = lo.x; words[8 * c + 5] = lo.y; words[8 * c + 6] = lo.z; words[8 * c + 7] = lo.w;
-    }
-}
-template <class T>
-__device__ __forceinline__ void store16_words(uint8_t* tile, int r, int chunk0, const uint32_t (&words)[16]) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const uint32_t o = T::off(r, chunk0 + c);
-        *reinterpret_cast<uint4*>(tile + o) =
-            make_uint4(words[8 * c + 0], words[8 * c + 1], words[8 * c + 2], words[8 * c + 3]);
-        *reinterpret_cast<uint4*>(tile + T::half + o) =
-            make_uint4(words[8 * c + 4], words[8 * c + 5], words[8 * c + 6], words[8 * c + 7]);
     }
 }
 // registers <-> TMEM, 16 words per thread (warp-collective; thread i addresses lane base + i)
@@ -197,17 +172,6 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[N], int lane) {
 }
 
 
-// hand-off epilogue group -> MMA warp through a hardware named barrier: the producers arrive without
-// blocking and go on to their mbarrier wait, the MMA warp syncs (n_threads = group + 32)
-__device__ __forceinline__ void publish_to(int barrier_id, int n_threads) {
-    tc::fence_smem_to_async_proxy();
-    tc::tc_fence_before_sync();
-    asm volatile("bar.arrive %0, %1;" ::"r"(barrier_id), "r"(n_threads) : "memory");
-}
-__device__ __forceinline__ void handoff_from(int barrier_id, int n_threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(n_threads) : "memory");
-    tc::tc_fence_after_sync();
-}
 __device__ __forceinline__ void named_sync(int barrier_id, int n_threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(n_threads) : "memory");
 }
