@@ -36,6 +36,8 @@ class EventBatchProducer:
         n = events["position"].shape[0] if dataset_len is None else int(dataset_len)
         assert 0 < n <= events["position"].shape[0]
         self.events = {k: torch.as_tensor(events[k])[:n].to(device).contiguous() for k in EVENT_KEYS}
+        if "channel_idx" in events:         # Bayer sensors (data/datasets.py Event: the pixel's colour channel)
+            self.events["channel_idx"] = torch.as_tensor(events["channel_idx"])[:n].to(device).contiguous()
         assert self.events["position"].dtype == torch.float32
         for k in EVENT_KEYS[1:]:
             assert self.events[k].dtype == torch.int64 and self.events[k].shape == (n,)

@@ -7,7 +7,7 @@ LightningModule (models/deblur_e_nerf.py:396-586) and its render helpers
 (``{"event": {position, start_ts, end_ts, num_pos, num_neg}, "normalized": {ts_diff,
 diff_start_ts, ts_subdiff, subdiff_start_ts[, interval_gen]}}``, with or without the
 DataLoader's leading dim of 1) and returns the scalar loss; ``self.logged`` holds what the
-reference passes to ``self.log``.  Mono sensors only (``channel_idx is None``: every shipped
+reference passes to ``self.log``.  Mono sensors (``channel_idx is None``: every shipped
 config, SURVEY.md conventions table C = 1).
 """
 
@@ -91,6 +91,13 @@ class EventRenderer(torch.nn.Module):
         depth = depth * torch.sum(d * T_wc_orientation[..., 2], dim=-1)
         return intensity, opacity, depth, mean_samples, is_valid
 
+    @staticmethod
+    def bayering(intensity, channel_idx):
+        """models/deblur_e_nerf.py:1223-1234: a colour sensor behind a Bayer filter sees, at pixel n, only
+        channel `channel_idx[n]` of the rendered radiance.  `intensity` (..., N, 3) -> (..., N)."""
+        idx = channel_idx.reshape((1,) * (intensity.dim() - 2) + (-1, 1)).expand(*intensity.shape[:-1], 1)
+        return intensity.gather(-1, idx).squeeze(-1)
+
     def render_train_pixels(self, timestamp, pixel_position, pixel_channel_idx=None):
         """models/deblur_e_nerf.py:1162-1183 (training never uses the depth, so the camera-z
         correction of render_pixels is skipped and the rays come from the fused kernel)."""
@@ -98,6 +105,8 @@ class EventRenderer(torch.nn.Module):
         jitter = self._jitters.pop(0) if self._jitters else None
         intensity, opacity, _, mean_samples = self.nerf(o, d, jitter=jitter)
         intensity = intensity + self.min_modeled_intensity
+        if pixel_channel_idx is not None:
+            intensity = self.bayering(intensity, pixel_channel_idx)
         hit = opacity > 0
         is_valid = hit if self.render_bkgd is None else torch.ones_like(hit)
         occ_rate = torch.mean(hit, dtype=torch.get_default_dtype())
@@ -115,7 +124,8 @@ class EventRenderer(torch.nn.Module):
             timestamp, pixel_position, pixel_channel_idx)
         return intensity.log(), occ_rate, mean_samples, is_valid
 
-    def render_log_intensity_batched(self, requests, pixel_position, normalized_interval_gen):
+    def render_log_intensity_batched(self, requests, pixel_position, normalized_interval_gen,
+                                     pixel_channel_idx=None):
         """`render_log_intensity` for several (timestamp, reset_diff) requests of the same pixels
         at once.  Returns one (log_intensity, occ_rate, mean_samples, is_valid) tuple per request,
         in order (the pixel-bandwidth reset state is carried from request to request exactly as
@@ -137,6 +147,8 @@ class EventRenderer(torch.nn.Module):
             jitter = torch.cat([self._jitters.pop(0).reshape(-1) for _ in range(K)])
         intensity, opacity, _, means = self.nerf(o, d, jitter=jitter, groups=K)
         intensity = intensity + self.min_modeled_intensity
+        if pixel_channel_idx is not None:
+            intensity = self.bayering(intensity, pixel_channel_idx)
         hit = opacity > 0
         is_valid = hit if self.render_bkgd is None else torch.ones_like(hit)
         occ = hit.reshape(K, -1).to(torch.get_default_dtype()).mean(dim=1)
@@ -151,7 +163,8 @@ class EventRenderer(torch.nn.Module):
                 out.append((intensity[k].log(), occ[k], means[k], is_valid[k]))
         return out
 
-    def render_and_loss_fused(self, event, segs, pixel_position, normalized_interval_gen, mean_ct):
+    def render_and_loss_fused(self, event, segs, pixel_position, normalized_interval_gen, mean_ct,
+                              pixel_channel_idx=None):
         """All render requests of the step as one launch sequence, then the pixel-bandwidth filter of
         every request, the reset carried from the first one, the pair differences and the masked loss
         means in ONE kernel (`den_lpf_loss_fwd`; reverse mode `den_lpf_loss_bwd`).  `segs`: the
@@ -171,7 +184,9 @@ class EventRenderer(torch.nn.Module):
         if self._jitters:
             jitter = torch.cat([self._jitters.pop(0).reshape(-1) for _ in range(K)])
         intensity, opacity, _, means = self.nerf(o, d, jitter=jitter, groups=K)
-        intensity = intensity + self.min_modeled_intensity                    # (K, S, N)
+        intensity = intensity + self.min_modeled_intensity                    # (K, S, N [, 3])
+        if pixel_channel_idx is not None:
+            intensity = self.bayering(intensity, pixel_channel_idx).contiguous()
         hit = opacity > 0
         occ = hit.reshape(K, -1).to(torch.get_default_dtype()).mean(dim=1)
         P = K // 2
@@ -268,25 +283,30 @@ class EventRenderer(torch.nn.Module):
         batched = None
         fits = self.batch_render_calls and self.nerf.radiance_field.training and segs \
             and self._batch_fits(2 * len(segs) * size, gen)
+        # models/deblur_e_nerf.py:409-412: a Bayer sensor's events carry the colour channel of their pixel
+        channel_idx = event.get("channel_idx")
+        if channel_idx is not None:
+            channel_idx = channel_idx.reshape(-1).to(torch.int64)
         if fits and self.fuse_lpf_loss and self.pixel_bandwidth is not None \
                 and event["position"].is_cuda and gen.shape[0] + 1 <= 32 and segs[0][1]:
             terms, mean_samples, occ_rates = self.render_and_loss_fused(
-                event, segs, event["position"], gen, self.contrast_threshold.mean_contrast_threshold)
+                event, segs, event["position"], gen, self.contrast_threshold.mean_contrast_threshold,
+                channel_idx)
             return self._finish_step(terms, mean_samples, occ_rates, weight, size, batch_index)
         if fits:
             requests = []
             for seg, is_diff in segs:
                 requests += [(seg["start_ts"], is_diff), (seg["end_ts"], False)]
-            batched = self.render_log_intensity_batched(requests, event["position"], gen)
+            batched = self.render_log_intensity_batched(requests, event["position"], gen, channel_idx)
         for seg, is_diff in segs:
             if batched is not None:
                 (a, occ_a, ms_a, va), (b, occ_b, ms_b, vb) = batched[0], batched[1]
                 batched = batched[2:]
             else:
                 a, occ_a, ms_a, va = self.render_log_intensity(
-                    seg["start_ts"], event["position"], None, gen, reset_diff=is_diff)
+                    seg["start_ts"], event["position"], channel_idx, gen, reset_diff=is_diff)
                 b, occ_b, ms_b, vb = self.render_log_intensity(
-                    seg["end_ts"], event["position"], None, gen)
+                    seg["end_ts"], event["position"], channel_idx, gen)
             seg["log_intensity_diff"] = b - a
             seg["is_valid"] = va | vb
             mean_samples += [ms_a, ms_b]

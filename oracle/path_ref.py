@@ -650,19 +650,28 @@ class EventRenderer(torch.nn.Module):
             valid = torch.ones_like(opa, dtype=torch.bool)
         return rad, opa, mean_samples, valid
 
-    def render_train_pixels(self, ts, pixel_position):
+    @staticmethod
+    def bayering(intensity, channel_idx):
+        """models/deblur_e_nerf.py:1177-1178,1223-1234: the reference moves the colour axis first,
+        (3, [S,] N), and gathers channel `channel_idx[n]` for pixel n; here the axis stays last."""
+        idx = channel_idx.reshape((1,) * (intensity.dim() - 2) + (-1, 1)).expand(*intensity.shape[:-1], 1)
+        return intensity.gather(-1, idx).squeeze(-1)
+
+    def render_train_pixels(self, ts, pixel_position, channel_idx=None):
         pos, rot = self.trajectory(ts)
         px = pixel_position if ts.dim() == 1 else pixel_position.expand(ts.shape[0], -1, -1)
         rad, opa, mean_samples, valid = self.render_pixels(px, pos, rot)
+        if channel_idx is not None:
+            rad = self.bayering(rad, channel_idx)
         return rad, (opa > 0).float().mean(), mean_samples, valid
 
-    def render_log_intensity(self, ts, pixel_position, interval_gen, reset_diff=False):
+    def render_log_intensity(self, ts, pixel_position, interval_gen, reset_diff=False, channel_idx=None):
         if self.pixel_bandwidth is not None:
-            fn = lambda t: self.render_train_pixels(t, pixel_position)     # noqa: E731
+            fn = lambda t: self.render_train_pixels(t, pixel_position, channel_idx)     # noqa: E731
             log_it, aux = self.pixel_bandwidth(interval_gen, ts, fn, reset_diff)
             occ, mean_samples, valid = aux
             return log_it, occ, mean_samples, valid.any(dim=0)
-        rad, occ, mean_samples, valid = self.render_train_pixels(ts, pixel_position)
+        rad, occ, mean_samples, valid = self.render_train_pixels(ts, pixel_position, channel_idx)
         return rad.log(), occ, mean_samples, valid
 
     def training_step(self, event, normalized, jitters=None):
@@ -674,13 +683,18 @@ class EventRenderer(torch.nn.Module):
         use_tv = self.loss_weight["log_intensity_tv"] > 0
         diff, subdiff = supervision_timestamps(start_ts, end_ts, normalized, use_diff, use_tv)
         gen = normalized.get("interval_gen")
+        channel_idx = event.get("channel_idx")           # :409-412, Bayer sensors only
+        if channel_idx is not None:
+            channel_idx = channel_idx.to(torch.int64)
         samples = []
         for seg, first in ((diff, True), (subdiff, False)):
             if seg is None:
                 continue
             a, _, ms_a, va = self.render_log_intensity(seg["start_ts"], event["position"], gen,
-                                                       reset_diff=first and seg is diff)
-            b, _, ms_b, vb = self.render_log_intensity(seg["end_ts"], event["position"], gen)
+                                                       reset_diff=first and seg is diff,
+                                                       channel_idx=channel_idx)
+            b, _, ms_b, vb = self.render_log_intensity(seg["end_ts"], event["position"], gen,
+                                                       channel_idx=channel_idx)
             seg["log_intensity_diff"] = b - a
             seg["is_valid"] = va | vb
             samples += [ms_a, ms_b]

@@ -47,7 +47,8 @@ def build_oracle_nerf(cfg, seed=0):
     ctype = nerfacc_ref.ContractionType[CONTRACTIONS[cfg["contraction"]]]
     nerf = path_ref.NeRF(cfg["aabb"], ctype, cfg["occ_grid"], cfg["near_plane"], cfg["far_plane"],
                          cfg["step"], cfg["render_bkgd"], cfg["cone_angle"], cfg["early_stop_eps"],
-                         cfg["alpha_thre"], cfg["test_chunk_size"], cfg["arch"], radiance_dim=1)
+                         cfg["alpha_thre"], cfg["test_chunk_size"], cfg["arch"],
+                         radiance_dim=cfg.get("radiance_dim", 1))
     return randomize_field_(nerf, seed)
 
 
@@ -102,7 +103,8 @@ def build_reference_renderer(cfg, it_sample_size=8, pixel_bandwidth=True, seed=0
     nerf = nerf_mod.NeRF(cfg["aabb"], ctype, easydict.EasyDict(cfg["occ_grid"]),
                          cfg["near_plane"], cfg["far_plane"], cfg["step"], cfg["render_bkgd"],
                          cfg["cone_angle"], cfg["early_stop_eps"], cfg["alpha_thre"],
-                         cfg["test_chunk_size"], "ngp", easydict.EasyDict(cfg["arch"]), 3, 1)
+                         cfg["test_chunk_size"], "ngp", easydict.EasyDict(cfg["arch"]), 3,
+                         cfg.get("radiance_dim", 1))
     randomize_field_(nerf, seed)
     camera_poses = datasets.CameraPose(tmp, None)
     components = dict(
@@ -129,6 +131,7 @@ def build_reference_renderer(cfg, it_sample_size=8, pixel_bandwidth=True, seed=0
         nerf=dict(),
     )
     module = ref_shim.make_reference_module(hparams, components)
+    module.has_bayer_filter = cfg.get("radiance_dim", 1) == 3      # models/deblur_e_nerf.py:82-90
     module.trainer.accumulate_grad_batches = accumulate_grad_batches
     module.render_bkgd = cfg["render_bkgd"]
     module.register_buffer("train_intrinsics_inv",
@@ -206,7 +209,8 @@ def build_product_nerf(cfg, device, seed=0):
     model = nerf_mod.NeRF(cfg["aabb"], ContractionType[CONTRACTIONS[cfg["contraction"]]],
                           cfg["occ_grid"], cfg["near_plane"], cfg["far_plane"], cfg["step"],
                           cfg["render_bkgd"], cfg["cone_angle"], cfg["early_stop_eps"],
-                          cfg["alpha_thre"], cfg["test_chunk_size"], "ngp", cfg["arch"], 3, 1)
+                          cfg["alpha_thre"], cfg["test_chunk_size"], "ngp", cfg["arch"], 3,
+                          cfg.get("radiance_dim", 1))
     return model.to(device)
 
 

@@ -3,7 +3,8 @@ oracle/ref_shim, CPU fp32).  Build container only (needs /root/reference):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{training_step_pb_on,training_step_pb_off,training_step_eds,field_small}.npz.  Each
+Writes tests/golden/{training_step_pb_on,training_step_pb_off,training_step_eds,training_step_bayer,
+field_small}.npz (`python tests/golden/make_golden.py bayer` writes only the Bayer one).  Each
 file carries the parameters, the inputs (events, normalised samples, the stratified
 jitter the reference drew, the occupancy grid after its step-0 update) and the
 reference's outputs (loss, loss terms, mean samples per ray, every parameter gradient),
@@ -33,11 +34,17 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-def training_step_golden(pb_on, path):
+def training_step_golden(pb_on, path, bayer=False):
+    """`bayer`: a colour sensor behind a Bayer filter (models/deblur_e_nerf.py:82-90,175-178,287-290,
+    409-412,1177-1178,1223-1234): three radiance channels, every event carries the channel of its pixel."""
     cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    if bayer:
+        cfg["radiance_dim"] = 3
     ref, poses = _scene.build_reference_renderer(cfg, IT_SAMPLE_SIZE, pixel_bandwidth=pb_on)
     event, normalized = _scene.make_batch(cfg, poses, N_EVENTS, IT_SAMPLE_SIZE, seed=7,
                                           pixel_bandwidth=pb_on)
+    if bayer:
+        event["channel_idx"] = torch.randint(0, 3, (N_EVENTS,), generator=torch.Generator().manual_seed(5))
     ref.train()
     nerfacc_ref.JITTER_LOG = []
     torch.manual_seed(11)
@@ -195,6 +202,9 @@ def field_golden(path):
 
 if __name__ == "__main__":
     assert ref_shim.available(), "needs /root/reference"
+    training_step_golden(True, os.path.join(HERE, "training_step_bayer.npz"), bayer=True)
+    if sys.argv[1:] == ["bayer"]:
+        sys.exit(0)
     training_step_golden(True, os.path.join(HERE, "training_step_pb_on.npz"))
     training_step_golden(False, os.path.join(HERE, "training_step_pb_off.npz"))
     field_golden(os.path.join(HERE, "field_small.npz"))

@@ -180,9 +180,12 @@ TAU_KEY = "refractory_period.parametrizations._refractory_period.original"
 TAU_RAY_ROUNDING = 1e-3            # measured 1.3e-3 total on the pixel-bandwidth golden (bound 2e-3), 1.6e-4 / 1.2e-5 elsewhere
 
 
-def _run_training_step_golden(cuda, pb_on):
-    golden = _scene.load_golden("training_step_pb_on" if pb_on else "training_step_pb_off")
+def _run_training_step_golden(cuda, pb_on, bayer=False):
+    golden = _scene.load_golden("training_step_bayer" if bayer else
+                                "training_step_pb_on" if pb_on else "training_step_pb_off")
     cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    if bayer:
+        cfg["radiance_dim"] = 3
     ref = _scene.golden_section(golden, "grad")
     modes = ("kernel", "autograd") if TAU_KEY in ref else ("kernel",)
     for mode in modes:
@@ -222,6 +225,36 @@ def _run_training_step_golden(cuda, pb_on):
             bounds[TAU_KEY] += TAU_RAY_ROUNDING
         bad = {k: (v, bounds[k]) for k, v in worst.items() if v > bounds[k]}
         assert not bad, (mode, bad)
+
+
+def test_bayer_render_paths_agree(den_lib, cuda):
+    """The three host paths of a Bayer training step — fused filter + loss kernel, batched render calls with
+    the per-call filter, four sequential render calls — select the pixel's channel at the same place and
+    give the same loss and gradients."""
+    golden = _scene.load_golden("training_step_bayer")
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    cfg["radiance_dim"] = 3
+    results = []
+    for fused, batched in ((True, True), (False, True), (False, False)):
+        model, poses = _scene.build_product_renderer(cfg, cuda, 8, pixel_bandwidth=True)
+        for name in ["nerf", "contrast_threshold", "refractory_period", "pixel_bandwidth"]:
+            _scene.load_golden_state(getattr(model, name), golden, name, cuda)
+        batch = {"event": _scene.golden_section(golden, "event", cuda),
+                 "normalized": _scene.golden_section(golden, "normalized", cuda)}
+        jitters = [v for _, v in sorted(_scene.golden_section(golden, "jitter", cuda).items(),
+                                        key=lambda kv: int(kv[0]))]
+        model.train()
+        model.fuse_lpf_loss, model.batch_render_calls = fused, batched
+        model.nerf.update_occ_grid = lambda *a, **k: None
+        loss = model.training_step(batch, 0, 0, jitters=jitters)
+        loss.backward()
+        results.append((loss.detach(), _scene.flat_named_grads(model)))
+    cond = _scene.load_golden("gradient_conditioning")
+    for loss, grads in results[1:]:
+        assert _rel(loss, results[0][0]) < 1e-5
+        for key in grads:
+            bound = max(5e-4, 2 * float(cond.get(f"pb_on/{key}", 0.0)))     # fp32 filter vs fp64 fused kernel
+            assert _rel(grads[key], results[0][1][key]) < bound, (key, bound)
 
 
 @pytest.mark.parametrize("pb_on", [False, True], ids=["pb_off", "pb_on"])
@@ -337,6 +370,13 @@ def test_fused_rays_reverse_mode_matches_the_torch_autograd_path(den_lib, cuda):
 
 def test_training_step_pb_off_matches_reference_golden(den_lib, cuda):
     _run_training_step_golden(cuda, pb_on=False)
+
+
+def test_training_step_bayer_matches_reference_golden(den_lib, cuda):
+    """A colour sensor behind a Bayer filter (models/deblur_e_nerf.py:82-90,409-412,1177-1178,1223-1234):
+    three radiance channels through the field, compositing and their reverse passes, each event
+    supervised on the channel of its pixel.  Golden: the reference's own files, CPU fp32."""
+    _run_training_step_golden(cuda, pb_on=True, bayer=True)
 
 
 @pytest.mark.parametrize("S", [8, 30])

@@ -16,10 +16,16 @@ def _close(a, b, tol):
     assert err <= tol, err
 
 
-@pytest.mark.parametrize("pb_on", [True, False], ids=["pb_on", "pb_off"])
-def test_oracle_training_step_matches_reference_golden(pb_on):
-    golden = _scene.load_golden("training_step_pb_on" if pb_on else "training_step_pb_off")
+@pytest.mark.parametrize("pb_on,bayer", [(True, False), (False, False), (True, True)],
+                         ids=["pb_on", "pb_off", "bayer"])
+def test_oracle_training_step_matches_reference_golden(pb_on, bayer):
+    """`bayer`: three radiance channels, every event sees the channel of its pixel
+    (models/deblur_e_nerf.py:409-412,1177-1178,1223-1234)."""
+    golden = _scene.load_golden("training_step_bayer" if bayer else
+                                "training_step_pb_on" if pb_on else "training_step_pb_off")
     cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    if bayer:
+        cfg["radiance_dim"] = 3
     ora, poses = _scene.build_oracle_renderer(cfg, 8, pixel_bandwidth=pb_on)
     for name in ["nerf", "contrast_threshold", "refractory_period"] + (
             ["pixel_bandwidth"] if pb_on else []):
