@@ -8,9 +8,9 @@ terms of ``Metric.compute`` (loss_metric/metric.py:57-72).
 
 Each of them is a sum over pixels: one ``den_eval_*`` kernel pass with fp64 accumulation produces the
 moments, the 2x2 / 3x3 systems are solved on the device, and the images never leave HBM.  SSIM and
-LPIPS (torchmetrics / lpips, absent from this image) are not part of this module; the shared-scale
-Bayer variant (``per_channel_log_it_scale: false`` with a colour sensor, :756-766) is not built — mono
-sensors and per-channel scales are."""
+LPIPS (torchmetrics / lpips, absent from this image) are not part of this module.  Colour (Bayer) images
+are C = 3 channels; ``per_channel_log_it_scale: false`` (:753-766: one log-intensity scale shared by the
+channels, an offset per channel) is solved in closed form from the same per-channel moments."""
 
 import ctypes
 
@@ -33,13 +33,18 @@ def _moments(kind, pred, target, gain_vec, params, n_out):
     return out
 
 
-def affine_log_fit(pred, target, norm_gain):
-    """(C, 2) float64 (scale, offset) of the least squares  scale * log pred + offset ~ log target - log g."""
+def affine_log_fit(pred, target, norm_gain, per_channel_scale=True):
+    """(C, 2) float64 (scale, offset) of the least squares  scale * log pred + offset ~ log target - log g.
+    `per_channel_scale` False: the scale is shared by the channels (models/deblur_e_nerf.py:753-766); with
+    b_c = (Sy_c - a Sx_c) / n_c eliminated, a = sum_c (Sxy_c - Sx_c Sy_c / n_c) / sum_c (Sxx_c - Sx_c^2 / n_c)."""
     log_gain = norm_gain.log().double().contiguous()      # the reference takes this log in fp32 (:745)
     m = _moments("den_eval_affine_moments", pred, target, log_gain, None, 5)
     n, sx, sy, sxx, sxy = m.unbind(-1)
-    det = n * sxx - sx * sx
-    scale = (n * sxy - sx * sy) / det
+    if per_channel_scale or m.shape[0] == 1:
+        det = n * sxx - sx * sx
+        scale = (n * sxy - sx * sy) / det
+    else:
+        scale = ((sxy - sx * sy / n).sum() / (sxx - sx * sx / n).sum()).expand_as(n)
     offset = (sy - scale * sx) / n
     return torch.stack((scale, offset), dim=-1)
 
@@ -111,8 +116,9 @@ def lm_refine(pred, target, gain, affine, init, max_steps=10, radius=1e6):
 
 @torch.no_grad()
 def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_offset=True, init=None,
-             max_steps=10, radius=1e6):
-    """pred, target (B, C, H, W) or (B, H, W) fp32 CUDA tensors (C = 1: mono); exposure_time, gain (B,).
+             max_steps=10, radius=1e6, per_channel_scale=True):
+    """pred, target (B, C, H, W) or (B, H, W) fp32 CUDA tensors (C = 1: mono, 3: colour); exposure_time,
+    gain (B,); `per_channel_scale`: `correction.per_channel_log_it_scale` (only matters for C = 3).
     Returns dict(l1, psnr (device scalars), pred (corrected, fp32), affine (C, 2), correction (C, 3) |
     None, correction_errors)."""
     if not pred.is_cuda:
@@ -125,7 +131,7 @@ def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_of
     prod = gain.to(torch.float32) * exposure_time                           # :707
     norm = (prod / prod.mean()).to(pred.device)                             # :709-712
     gain64 = norm.double().contiguous()
-    affine = affine_log_fit(pred, target, norm)
+    affine = affine_log_fit(pred, target, norm, per_channel_scale)
     errors = None
     if black_level_offset:
         if init is None:

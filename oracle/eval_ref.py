@@ -22,18 +22,30 @@ def normalized_gain(gain, exposure_time):
     return prod / prod.mean()                                     # :709-712 (fp32 like the reference)
 
 
-def affine_log_correction(pred, target, norm_gain):
-    """:733-797, mono / per-channel scale.  pred, target (B,C,H,W) fp32; norm_gain (B,) fp32.
+def affine_log_correction(pred, target, norm_gain, per_channel_scale=True):
+    """:733-797.  pred, target (B,C,H,W) fp32; norm_gain (B,) fp32.  `per_channel_scale` False (a colour
+    sensor with `correction.per_channel_log_it_scale: false`, :753-766,781-788): ONE scale shared by the C
+    channels and an offset per channel — the reference's (C BHW, 1 + C) design matrix.
     Returns (scale_offset (C,2) f64, corrected log prediction (B,C,H,W) f64, log_gain (B,1,1,1) f32)."""
     B, C, H, W = target.shape
     log_gain = norm_gain.view(-1, 1, 1, 1).log()
     x = pred.log()
     y = target.log() - log_gain
-    A = torch.stack((x, torch.ones_like(x)), dim=-1).transpose(0, 1).flatten(1, 3).double()   # (C, BHW, 2)
     rhs = y.unsqueeze(-1).transpose(0, 1).flatten(1, 3).double()                               # (C, BHW, 1)
-    sol = torch.linalg.lstsq(A, rhs).solution                                                  # (C, 2, 1)
+    if per_channel_scale or C == 1:
+        A = torch.stack((x, torch.ones_like(x)), dim=-1).transpose(0, 1).flatten(1, 3).double()   # (C, BHW, 2)
+        sol = torch.linalg.lstsq(A, rhs).solution                                              # (C, 2, 1)
+        fitted = (A @ sol).view(C, B, H, W).transpose(0, 1)
+        return sol[:, :, 0], fitted, log_gain
+    A = torch.zeros((C, B * H * W, 1 + C), dtype=torch.float64)
+    A[:, :, 0] = x.transpose(0, 1).flatten(1, 3).double()
+    for c in range(C):
+        A[c, :, 1 + c] = 1
+    A = A.flatten(0, 1)                                                                        # (C BHW, 1 + C)
+    sol = torch.linalg.lstsq(A, rhs.flatten(0, 1)).solution                                    # (1 + C, 1)
     fitted = (A @ sol).view(C, B, H, W).transpose(0, 1)
-    return sol[:, :, 0], fitted, log_gain
+    scale_offset = torch.stack((sol[0, 0].expand(C), sol[1:, 0]), dim=-1)
+    return scale_offset, fitted, log_gain
 
 
 class _Correction:
@@ -128,11 +140,11 @@ def metrics(pred, target, min_val, max_val):
 
 
 def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_offset=True, init=None,
-             max_steps=10):
-    """pred, target (B,C,H,W) fp32 (C = 1: mono).  Returns dict(l1, psnr, pred (B,C,H,W) fp32, affine
-    (C,2), correction (C,3) | None)."""
+             max_steps=10, per_channel_scale=True):
+    """pred, target (B,C,H,W) fp32 (C = 1: mono, C = 3: a Bayer sensor's colour images).  Returns dict(l1,
+    psnr, pred (B,C,H,W) fp32, affine (C,2), correction (C,3) | None)."""
     norm = normalized_gain(gain, exposure_time)
-    sol, fitted, log_gain = affine_log_correction(pred, target, norm)
+    sol, fitted, log_gain = affine_log_correction(pred, target, norm, per_channel_scale)
     C = target.shape[1]
     if not black_level_offset:
         out = (fitted + log_gain).exp()                                                        # :822-829

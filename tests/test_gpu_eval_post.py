@@ -1,7 +1,7 @@
 """GPU parity of the evaluation post-processing (`eval_post.evaluate`, `den_eval_*` kernels, SURVEY.md
 §8(f) N4) against oracle/eval_ref.py — which is pinned against the reference's own
-`evaluation_epoch_end` for the affine path (tests/test_oracle_vs_reference.py) — on mono image batches
-with varying exposure / gain, with and without the black-level-offset refinement."""
+`evaluation_epoch_end` for the affine path (tests/test_oracle_vs_reference.py) — on mono and colour image
+batches with varying exposure / gain, with and without the black-level-offset refinement."""
 
 import pytest
 import torch
@@ -42,6 +42,37 @@ def test_eval_post_matches_oracle(den_lib, cuda, shape, black_level_offset):
     assert abs(float(got["l1"]) - want["l1"]) <= 1e-5 * want["l1"]
     assert abs(float(got["psnr"]) - want["psnr"]) <= 1e-5 * abs(want["psnr"])
     assert got["pred"].is_cuda and got["l1"].is_cuda          # nothing went through the host
+
+
+@pytest.mark.parametrize("per_channel", [True, False], ids=["per_channel_scale", "shared_scale"])
+@pytest.mark.parametrize("black_level_offset", [False, True])
+def test_eval_post_colour_images_match_oracle(den_lib, cuda, per_channel, black_level_offset):
+    """Colour images of a Bayer sensor (C = 3): a log-intensity scale per channel, or one shared by the
+    channels with an offset each (`correction.per_channel_log_it_scale`, models/deblur_e_nerf.py:753-766;
+    the oracle's version is pinned against the reference's evaluation_epoch_end for both)."""
+    from deblur_e_nerf_b200 import eval_post
+    B, H, W = 3, 41, 57
+    chans = [_images(20 + c, B, H, W, offset=0.03 if black_level_offset else 0.0) for c in range(3)]
+    exposure, gain = chans[0][2], chans[0][3]
+    norm = gain * exposure / (gain * exposure).mean()
+    target = torch.stack([ch[1] for ch in chans], dim=1)
+    # every channel an affinely (in log space) distorted view of ITS target under the shared exposure
+    scene = (target - (0.03 if black_level_offset else 0.0)) / norm.view(-1, 1, 1, 1)
+    g = torch.Generator().manual_seed(3)
+    pred = torch.stack([(0.5 + 0.2 * c) * scene[:, c].pow(1.0 + 0.1 * c) for c in range(3)], dim=1)
+    pred = (pred * torch.exp(0.02 * torch.randn(pred.shape, generator=g))).float()
+    want = eval_ref.evaluate(pred, target, exposure, gain, 0.0, 1.1, black_level_offset=black_level_offset,
+                             per_channel_scale=per_channel)
+    got = eval_post.evaluate(pred.to(cuda), target.to(cuda), exposure.to(cuda), gain.to(cuda), 0.0, 1.1,
+                             black_level_offset=black_level_offset, per_channel_scale=per_channel)
+    assert torch.allclose(got["affine"].cpu(), want["affine"], rtol=5e-6, atol=5e-7), (got["affine"], want["affine"])
+    if not per_channel:
+        assert float(got["affine"][:, 0].max() - got["affine"][:, 0].min()) == 0.0
+    if black_level_offset:
+        assert torch.allclose(got["correction"].cpu(), want["correction"], rtol=2e-4, atol=2e-6)
+    assert (got["pred"].cpu() - want["pred"]).abs().max().item() <= 1e-5 * want["pred"].abs().max().item()
+    assert abs(float(got["l1"]) - want["l1"]) <= 1e-5 * want["l1"]
+    assert abs(float(got["psnr"]) - want["psnr"]) <= 1e-5 * abs(want["psnr"])
 
 
 def test_eval_post_refuses_cpu_tensors(den_lib):

@@ -256,14 +256,23 @@ def _eval_images(seed, B=3, H=24, W=32):
     return pred.float(), target.float(), exposure, gain
 
 
-def test_eval_post_processing_matches_reference(pair):
+@pytest.mark.parametrize("colour,per_channel", [(False, False), (True, True), (True, False)],
+                         ids=["mono", "bayer_per_channel_scale", "bayer_shared_scale"])
+def test_eval_post_processing_matches_reference(pair, colour, per_channel):
     """oracle/eval_ref.py (gain-exposure normalisation, float64 log-space affine least squares, L1 /
     PSNR) against the reference's OWN evaluation_epoch_end (models/deblur_e_nerf.py:661-969) run under
-    the shim with `correction.black_level_offset: false` (the refinement needs pypose, absent here)."""
+    the shim with `correction.black_level_offset: false` (the refinement needs pypose, absent here):
+    mono images, and the colour images of a Bayer sensor with a log-intensity scale per channel or one
+    shared by the channels (`correction.per_channel_log_it_scale`, :753-766)."""
     import easydict
     from oracle import eval_ref
     _, ref, _, _ = pair
     pred, target, exposure, gain = _eval_images(0)
+    if colour:
+        # three channels with their own gamma / gain, so that the two scale variants differ
+        imgs = [_eval_images(10 + c) for c in range(3)]
+        target = torch.stack([im[1] for im in imgs], dim=1)
+        pred = torch.stack([(0.5 + 0.2 * c) * imgs[c][0].pow(1.0 + 0.1 * c) for c in range(3)], dim=1)
     recorded = {}
 
     class _Metric:
@@ -282,8 +291,8 @@ def test_eval_post_processing_matches_reference(pair):
         sanity_checking = False
 
     object.__setattr__(ref, "trainer", _Trainer())
-    ref.correction = easydict.EasyDict(per_channel_log_it_scale=False, black_level_offset=False)
-    ref.has_bayer_filter = False
+    ref.correction = easydict.EasyDict(per_channel_log_it_scale=per_channel, black_level_offset=False)
+    ref.has_bayer_filter = colour
     ref.metric = _Metric()
     ref.logger = None
     type(ref).current_epoch = 0
@@ -298,14 +307,21 @@ def test_eval_post_processing_matches_reference(pair):
     stage = easydict.EasyDict(name="val", min_normalized_pixel_value=0.0, max_normalized_pixel_value=1.0)
     ref.evaluation_epoch_end(outputs, stage)
 
-    res = eval_ref.evaluate(pred[:, None], target[:, None], exposure, gain, 0.0, 1.0,
-                            black_level_offset=False)
+    res = eval_ref.evaluate(pred if colour else pred[:, None], target if colour else target[:, None],
+                            exposure, gain, 0.0, 1.0, black_level_offset=False,
+                            per_channel_scale=per_channel or not colour)
     ref_pred = torch.stack(recorded["pred"])
+    if ref_pred.dim() == 3:
+        ref_pred = ref_pred[:, None]
     _close(res["pred"], ref_pred, 1e-6)
     assert abs(res["l1"] - float(logged["val/l1"])) <= 1e-6 * abs(float(logged["val/l1"]))
     assert abs(res["psnr"] - float(logged["val/psnr"])) <= 1e-5 * abs(float(logged["val/psnr"]))
-    # the fit recovers the construction: gamma 1 / 1.3 in log space
-    assert abs(float(res["affine"][0, 0]) - 1 / 1.3) < 0.02
+    if not colour:
+        # the fit recovers the construction: gamma 1 / 1.3 in log space
+        assert abs(float(res["affine"][0, 0]) - 1 / 1.3) < 0.02
+    elif not per_channel:
+        assert float(res["affine"][:, 0].max() - res["affine"][:, 0].min()) == 0.0      # one shared scale
+    ref.has_bayer_filter = False
 
 
 def test_eval_lm_refinement_reaches_the_least_squares_minimum():
