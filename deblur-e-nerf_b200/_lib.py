@@ -137,6 +137,7 @@ _SIGNATURES = {
     "den_eval_affine_moments": (_INT, [_P, _P, _P, _I32, _I32, _I64, _P, _P]),
     "den_eval_lm_moments": (_INT, [_P, _P, _P, _P, _I32, _I32, _I64, _P, _P]),
     "den_eval_apply": (_INT, [_P, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P]),
+    "den_eval_ssim": (_INT, [_P, _P, _I32, _I32, _I32, _I32, _I32, _D, _D, _D, _P, _P]),
     "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
 }

@@ -41,6 +41,41 @@ def world_size():
     return dist.get_world_size() if dist.is_initialized() else 1
 
 
+def rank():
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def gather_view_outputs(outputs):
+    """The `self.all_gather(outputs)` of evaluation_epoch_end (models/deblur_e_nerf.py:672): every rank
+    rendered views rank, rank + N, rank + 2N, ... of the evaluation set; returns the output dicts of ALL
+    views in their original order on every rank (images stay on the device: one all_gather per field over
+    stacks padded to the largest per-rank count)."""
+    n = world_size()
+    if n == 1:
+        return outputs
+    device = outputs[0]["pred_intensity_img"].device if outputs else None
+    if device is None:
+        raise ValueError("gather_view_outputs: every rank needs at least one view (fewer views than ranks)")
+    count = torch.tensor([len(outputs)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(count) for _ in range(n)]
+    dist.all_gather(counts, count)
+    counts = [int(c.item()) for c in counts]
+    most = max(counts)
+    gathered = {}
+    for key in ("pred_intensity_img", "target_intensity_img", "exposure_time", "gain"):
+        mine = torch.stack([torch.as_tensor(o[key]).to(device) for o in outputs])
+        if len(outputs) < most:
+            mine = torch.cat((mine, mine[-1:].expand(most - len(outputs), *mine.shape[1:])))
+        parts = [torch.empty_like(mine) for _ in range(n)]
+        dist.all_gather(parts, mine.contiguous())
+        gathered[key] = parts
+    merged = []
+    for i in range(sum(counts)):
+        r, j = i % n, i // n
+        merged.append({"sample_id": None, **{k: v[r][j] for k, v in gathered.items()}})
+    return merged
+
+
 def broadcast_parameters(module, src=0):
     """Replicate rank `src`'s parameters and buffers (DDP does this at construction)."""
     if world_size() == 1:

@@ -7,8 +7,9 @@ Marquardt refinement of the offset-gamma correction when ``correction.black_leve
 terms of ``Metric.compute`` (loss_metric/metric.py:57-72).
 
 Each of them is a sum over pixels: one ``den_eval_*`` kernel pass with fp64 accumulation produces the
-moments, the 2x2 / 3x3 systems are solved on the device, and the images never leave HBM.  SSIM and
-LPIPS (torchmetrics / lpips, absent from this image) are not part of this module.  Colour (Bayer) images
+moments, the 2x2 / 3x3 systems are solved on the device, and the images never leave HBM.  The SSIM term
+(loss_metric/metric.py:78-81, torchmetrics 0.6.2 `functional.ssim`) is one windowed pass (`den_eval_ssim`);
+LPIPS needs the pretrained lpips network (absent from this image) and is not part of this module.  Colour (Bayer) images
 are C = 3 channels; ``per_channel_log_it_scale: false`` (:753-766: one log-intensity scale shared by the
 channels, an offset per channel) is solved in closed form from the same per-channel moments."""
 
@@ -56,6 +57,25 @@ def _apply(pred, target, gain, params):
     ops._call("den_eval_apply", ops._ptr(pred), ops._ptr(target), ops._ptr(gain), ops._ptr(params), B, C,
               H * W, ops._ptr(out), ops._ptr(sums), ops._stream())
     return out, sums
+
+
+SSIM_DEFAULTS = dict(kernel_size=11, sigma=1.5, k1=0.01, k2=0.03)      # torchmetrics 0.6.2 functional.ssim
+
+
+def ssim(pred, target, data_range, kernel_size=11, sigma=1.5, k1=0.01, k2=0.03):
+    """Per-image SSIM (B,) f64 of (B, C, H, W) fp32 CUDA images: the Gaussian-windowed index averaged over
+    the channels and over the pixels whose window lies inside the image (what torchmetrics 0.6.2 keeps
+    after cropping its reflect-padded border).  `Metric.compute` passes data_range = max_target_val and
+    averages the per-image values (models/deblur_e_nerf.py:957-969)."""
+    if not pred.is_cuda:
+        raise NotImplementedError("eval_post: only CUDA tensors are supported (no CPU fallback)")
+    pred = ops._req(pred, torch.float32, "pred")
+    target = ops._req(target, torch.float32, "target")
+    B, C, H, W = target.shape
+    sums = torch.zeros((B,), dtype=torch.float64, device=pred.device)
+    ops._call("den_eval_ssim", ops._ptr(pred), ops._ptr(target), B, C, H, W, kernel_size, float(sigma),
+              float((k1 * data_range) ** 2), float((k2 * data_range) ** 2), ops._ptr(sums), ops._stream())
+    return sums / float(C * (H - kernel_size + 1) * (W - kernel_size + 1))
 
 
 def lm_refine(pred, target, gain, affine, init, max_steps=10, radius=1e6):
@@ -119,8 +139,8 @@ def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_of
              max_steps=10, radius=1e6, per_channel_scale=True):
     """pred, target (B, C, H, W) or (B, H, W) fp32 CUDA tensors (C = 1: mono, 3: colour); exposure_time,
     gain (B,); `per_channel_scale`: `correction.per_channel_log_it_scale` (only matters for C = 3).
-    Returns dict(l1, psnr (device scalars), pred (corrected, fp32), affine (C, 2), correction (C, 3) |
-    None, correction_errors)."""
+    Returns dict(l1, psnr, ssim (device scalars; ssim None for images smaller than its 11 x 11 window),
+    pred (corrected, fp32), affine (C, 2), correction (C, 3) | None, correction_errors)."""
     if not pred.is_cuda:
         raise NotImplementedError("eval_post: only CUDA tensors are supported (no CPU fallback)")
     if pred.dim() == 3:
@@ -144,5 +164,7 @@ def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_of
     n_img = float(C * H * W)
     l1 = (sums[:, 0] / n_img).mean()
     psnr = (10 * torch.log10((max_val - min_val) ** 2 / (sums[:, 1] / n_img))).mean()
-    return {"l1": l1, "psnr": psnr, "pred": out, "affine": affine,
+    fits = min(H, W) >= SSIM_DEFAULTS["kernel_size"]
+    ssim_mean = ssim(out, target, float(max_val), **SSIM_DEFAULTS).mean() if fits else None
+    return {"l1": l1, "psnr": psnr, "ssim": ssim_mean, "pred": out, "affine": affine,
             "correction": corr if black_level_offset else None, "correction_errors": errors}

@@ -83,6 +83,8 @@ class EventRenderer(torch.nn.Module):
                                              T_wc_orientation)
         jitter = self._jitters.pop(0) if self._jitters else None
         intensity, opacity, depth, mean_samples = self.nerf(o, d, jitter=jitter)
+        if intensity.dim() > opacity.dim():                       # colour: channels first (:1200-1201)
+            intensity = intensity.permute(-1, *range(opacity.dim()))
         intensity = intensity + self.min_modeled_intensity
         if self.render_bkgd is None:
             is_valid = opacity > 0
@@ -90,6 +92,64 @@ class EventRenderer(torch.nn.Module):
             is_valid = torch.ones_like(opacity, dtype=torch.bool)
         depth = depth * torch.sum(d * T_wc_orientation[..., 2], dim=-1)
         return intensity, opacity, depth, mean_samples, is_valid
+
+    # ----------------------------------------------------------------- evaluation ----
+    @staticmethod
+    def image_pixel_positions(height, width, device=None):
+        """(H, W, 2) pixel positions (x = column, y = row) of an image: the reference's
+        `val_img_pixel_pos` / `test_img_pixel_pos` buffers (models/deblur_e_nerf.py:120-127,153-160)."""
+        xs, ys = torch.meshgrid(torch.arange(width, device=device), torch.arange(height, device=device),
+                                indexing="xy")
+        return torch.stack((xs, ys), dim=2).to(torch.get_default_dtype())
+
+    @torch.no_grad()
+    def evaluation_step(self, batch, intrinsics_inv, img_pixel_pos):
+        """models/deblur_e_nerf.py:604-652 (validation_step / test_step): render the posed view
+        `batch` = {img ([3,] H, W), T_wc_position (3), T_wc_orientation (3, 3)[, sample_id, exposure_time,
+        gain]} at every pixel of `img_pixel_pos` (H, W, 2) and return the reference's output dict.  A
+        DataLoader's leading dim of 1 on every entry is removed like upstream (:609-613).  With the field
+        in eval mode the march is deterministic and runs `test_chunk_size` rays per chunk."""
+        batch = dict(batch)
+        if batch["T_wc_position"].dim() == 2:
+            assert len(batch["img"]) == 1
+            batch = {k: v.squeeze(0) if torch.is_tensor(v) else v for k, v in batch.items()}
+        target = batch["img"]
+        H, W = img_pixel_pos.shape[:2]
+        assert tuple(target.shape[-2:]) == (H, W), "the target image and the pixel grid differ in size"
+        device = img_pixel_pos.device
+        pos = batch["T_wc_position"].to(device).view(1, 1, 3).expand(H, W, -1)
+        rot = batch["T_wc_orientation"].to(device).view(1, 1, 3, 3).expand(H, W, -1, -1)
+        pred, _, _, _, _ = self.render_pixels(intrinsics_inv, img_pixel_pos, pos, rot)
+        one = torch.ones((), device=device)
+        return {
+            "sample_id": batch.get("sample_id"),
+            "pred_intensity_img": pred,
+            "target_intensity_img": target.to(device),
+            "exposure_time": batch.get("exposure_time", one.to(torch.int64)),      # :636-643: unity defaults
+            "gain": batch.get("gain", one.to(torch.get_default_dtype())),
+        }
+
+    @torch.no_grad()
+    def evaluation_epoch_end(self, outputs, min_normalized_pixel_value, max_normalized_pixel_value,
+                             black_level_offset=False, per_channel_log_it_scale=True, init_correction=None,
+                             max_steps=10, radius=1e6, stage="test"):
+        """models/deblur_e_nerf.py:674-969 on the device (`eval_post.evaluate`): stack the views, remove
+        the affine ambiguity of the predicted log intensity (with the optional black-level-offset
+        refinement) and average L1 / PSNR / SSIM over the views.  The images stay in HBM (the reference
+        moves them to the host, :714-718); LPIPS is not computed (no lpips network in this image).
+        Returns ({"<stage>/l1", "<stage>/psnr", "<stage>/ssim"}, corrected predictions (B, C, H, W))."""
+        from . import eval_post
+        pred = torch.stack([o["pred_intensity_img"] for o in outputs])
+        target = torch.stack([o["target_intensity_img"] for o in outputs]).to(pred.device, torch.float32)
+        exposure = torch.stack([torch.as_tensor(o["exposure_time"]).reshape(()) for o in outputs]).to(pred.device)
+        gain = torch.stack([torch.as_tensor(o["gain"]).reshape(()) for o in outputs]).to(pred.device)
+        res = eval_post.evaluate(pred.float(), target, exposure, gain, float(min_normalized_pixel_value),
+                                 float(max_normalized_pixel_value), black_level_offset=black_level_offset,
+                                 init=init_correction, max_steps=max_steps, radius=radius,
+                                 per_channel_scale=per_channel_log_it_scale)
+        metrics = {f"{stage}/{k}": res[k] for k in ("l1", "psnr", "ssim") if res[k] is not None}
+        self.logged.update(metrics)
+        return metrics, res["pred"]
 
     @staticmethod
     def bayering(intensity, channel_idx):

@@ -19,7 +19,11 @@ relies on, nothing else of Lightning:
   where they belong, plus the batch controller's state, which the reference keeps on the
   datamodule.
 
-Logging, validation loops, callbacks and the CLI stay out of scope."""
+``Trainer.test`` / ``Trainer.validate`` are the evaluation loop of `run.py test`: every
+posed view rendered in eval mode, then the post-processing and the metrics on the device
+(``EventRenderer.evaluation_step`` / ``evaluation_epoch_end``).
+
+Callbacks and the CLI stay out of scope."""
 
 import os
 import random
@@ -148,6 +152,44 @@ class Trainer:
                 self.save_checkpoint(os.path.join(self.checkpoint_dir, "last.ckpt"), model, optimizer,
                                      scheduler)
         return logged or self._log(model)
+
+    # ------------------------------------------------------------------- evaluation ----
+    def test(self, model, views, intrinsics_inv, min_normalized_pixel_value, max_normalized_pixel_value,
+             img_pixel_pos=None, stage="test", **correction):
+        """The evaluation loop Lightning runs for `run.py test` / `val` (test_step + test_epoch_end,
+        models/deblur_e_nerf.py:595-672): `views` yields posed-image batches ({img, T_wc_position,
+        T_wc_orientation[, exposure_time, gain, sample_id]}); `correction` = the keyword arguments of
+        `EventRenderer.evaluation_epoch_end` (black_level_offset, per_channel_log_it_scale, ...).  Under
+        torch.distributed every rank renders its share of the views (a DistributedSampler's round-robin
+        split) and the images are all-gathered (:672); the post-processing then runs on every rank (the
+        reference: rank 0 only) so that all of them return the same metrics.  Returns (metrics as floats, corrected predictions (B, C, H, W) on the device)."""
+        was_training = model.training
+        model.eval()
+        try:
+            outputs, pos = [], img_pixel_pos
+            rank, world = ddp.rank(), ddp.world_size()
+            for i, view in enumerate(views):
+                if i % world != rank:
+                    continue
+                if pos is None:
+                    h, w = view["img"].shape[-2:]
+                    pos = model.image_pixel_positions(h, w, device=intrinsics_inv.device)
+                outputs.append(model.evaluation_step(view, intrinsics_inv, pos))
+            outputs = ddp.gather_view_outputs(outputs)
+            metrics, pred = model.evaluation_epoch_end(
+                outputs, min_normalized_pixel_value, max_normalized_pixel_value, stage=stage, **correction)
+        finally:
+            model.train(was_training)
+        row = {k: float(v) for k, v in metrics.items()}
+        self.history.append((self.global_step, row))
+        if self.log_fn is not None:
+            self.log_fn(self.global_step, row)
+        return row, pred
+
+    def validate(self, model, views, intrinsics_inv, min_normalized_pixel_value, max_normalized_pixel_value,
+                 img_pixel_pos=None, **correction):
+        return self.test(model, views, intrinsics_inv, min_normalized_pixel_value,
+                         max_normalized_pixel_value, img_pixel_pos, stage="val", **correction)
 
     def _log(self, model):
         # the only host read of logged values: every log_every_n_steps optimizer steps

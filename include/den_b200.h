@@ -455,6 +455,14 @@ int den_eval_lm_moments(const float* pred, const float* target, const double* ga
                         int32_t B, int32_t C, int64_t HW, double* moments, void* stream);
 int den_eval_apply(const float* pred, const float* target, const double* gain, const double* params,
                    int32_t B, int32_t C, int64_t HW, float* out, double* image_sums, void* stream);
+/* SSIM term of Metric.compute (loss_metric/metric.py:74-81: torchmetrics 0.6.2 functional.ssim with
+ * data_range = max_target_val): images (B, C, H, W) fp32; Gaussian window kernel_size x kernel_size (odd,
+ * <= 15; upstream default 11) with `sigma` (1.5); c1 = (k1 data_range)^2, c2 = (k2 data_range)^2
+ * (k1 0.01, k2 0.03).  image_sums (B) fp64, pre-zeroed: the sum of the SSIM index over the channels and
+ * over the (H - k + 1) x (W - k + 1) pixels whose window lies inside the image (upstream crops the
+ * reflect-padded border before its mean); the mean divides by B C (H - k + 1)(W - k + 1). */
+int den_eval_ssim(const float* pred, const float* target, int32_t B, int32_t C, int32_t H, int32_t W,
+                  int32_t kernel_size, double sigma, double c1, double c2, double* image_sums, void* stream);
 
 #ifdef __cplusplus
 }

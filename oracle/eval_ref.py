@@ -128,15 +128,50 @@ def lm_refine(x, target, norm_gain, init, max_steps=10, radius=1e6):
     return model.p.clone(), errors
 
 
+def ssim(pred, target, data_range, kernel_size=11, sigma=1.5, k1=0.01, k2=0.03):
+    """torchmetrics 0.6.2 ``functional.ssim(preds, target, data_range=...)`` with its defaults (the call of
+    loss_metric/metric.py:78-81; environment.yml pins torchmetrics 0.6.2), restated from the published
+    ``functional/image/ssim.py::_ssim_compute``: Gaussian window ``exp(-(d / sigma)^2 / 2)`` over
+    ``d = arange((1 - k) / 2, (1 + k) / 2)``, normalised, 2-D window = outer product expanded per channel;
+    reflect padding by (k - 1) / 2; ONE grouped conv2d over cat(p, t, pp, tt, pt); the index
+    ((2 mu_pt + c1)(2 sigma_pt + c2)) / ((mu_p^2 + mu_t^2 + c1)(sigma_p^2 + sigma_t^2 + c2)); a CROP of
+    (k - 1) / 2 pixels per side (so the padded border never reaches the result); ``elementwise_mean``.
+    PARITY UNPINNED: torchmetrics is absent from this image; tests/test_oracle_kat.py checks this function
+    against closed forms (identical images, constant images) and an independent float64 numpy window sum.
+    pred, target (B, C, H, W) of one dtype; returns a 0-d tensor."""
+    assert pred.dtype == target.dtype and pred.dim() == 4 and pred.shape == target.shape
+    assert kernel_size % 2 == 1 and kernel_size > 0 and sigma > 0
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    B, C = pred.shape[:2]
+    dist = torch.arange((1 - kernel_size) / 2, (1 + kernel_size) / 2, 1, dtype=pred.dtype)
+    gauss = torch.exp(-torch.pow(dist / sigma, 2) / 2)
+    gauss = (gauss / gauss.sum()).unsqueeze(0)                                  # (1, k)
+    window = torch.matmul(gauss.t(), gauss).expand(C, 1, kernel_size, kernel_size)
+    pad = (kernel_size - 1) // 2
+    p = torch.nn.functional.pad(pred, (pad, pad, pad, pad), mode="reflect")
+    t = torch.nn.functional.pad(target, (pad, pad, pad, pad), mode="reflect")
+    out = torch.nn.functional.conv2d(torch.cat((p, t, p * p, t * t, p * t)), window, groups=C).split(B)
+    mu_pp, mu_tt, mu_pt = out[0].pow(2), out[1].pow(2), out[0] * out[1]
+    s_pp, s_tt, s_pt = out[2] - mu_pp, out[3] - mu_tt, out[4] - mu_pt
+    idx = ((2 * mu_pt + c1) * (2 * s_pt + c2)) / ((mu_pp + mu_tt + c1) * (s_pp + s_tt + c2))
+    return idx[..., pad:-pad, pad:-pad].mean()
+
+
 def metrics(pred, target, min_val, max_val):
-    """Mean over the images of Metric.compute's L1 and PSNR (loss_metric/metric.py:57-72)."""
+    """Mean over the images of Metric.compute's L1, PSNR and SSIM (loss_metric/metric.py:57-81; the SSIM
+    term only for images larger than its 11 x 11 window)."""
     pred = pred.to(target.dtype)
-    l1, psnr = [], []
+    l1, psnr, ss = [], [], []
     for p, t in zip(pred, target):
         l1.append(torch.nn.functional.l1_loss(p, t))
         mse = ((p - t) ** 2).mean()
         psnr.append(10 * torch.log10((max_val - min_val) ** 2 / mse))
-    return {"l1": float(sum(l1) / len(l1)), "psnr": float(sum(psnr) / len(psnr))}
+        if min(p.shape[-2:]) > 10:
+            ss.append(ssim(p[None], t[None], max_val))
+    res = {"l1": float(sum(l1) / len(l1)), "psnr": float(sum(psnr) / len(psnr))}
+    if ss:
+        res["ssim"] = float(sum(ss) / len(ss))
+    return res
 
 
 def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_offset=True, init=None,

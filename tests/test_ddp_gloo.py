@@ -165,6 +165,69 @@ def test_trainer_world_size_2_gloo(tmp_path):
     assert ckpt["global_step"] == 4 and torch.equal(ckpt["state_dict"]["w"], res[0]["w"])
 
 
+def _eval_worker(rank, world, port, out_dir):
+    """trainer.Trainer.test under world_size 2: five views over two ranks (3 + 2: the short rank is padded
+    for the all_gather), gathered back in view order, same metrics on both ranks."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from deblur_e_nerf_b200 import ddp, renderer, trainer
+    ddp.init_from_env(backend="gloo")
+
+    class Model(torch.nn.Module):
+        image_pixel_positions = staticmethod(renderer.EventRenderer.image_pixel_positions)
+
+        def __init__(self):
+            super().__init__()
+            self.rendered, self.modes = [], []
+
+        def evaluation_step(self, view, intrinsics_inv, pos):
+            self.rendered.append(int(view["sample_id"]))
+            self.modes.append(self.training)
+            img = view["img"]
+            return {"sample_id": view["sample_id"], "pred_intensity_img": img * 0.5 + pos[..., 0] * 0.01,
+                    "target_intensity_img": img, "exposure_time": view["exposure_time"],
+                    "gain": torch.ones(())}
+
+        def evaluation_epoch_end(self, outputs, lo, hi, stage="test", black_level_offset=False):
+            pred = torch.stack([o["pred_intensity_img"] for o in outputs])
+            target = torch.stack([o["target_intensity_img"] for o in outputs])
+            order = torch.stack([o["exposure_time"] for o in outputs])
+            return {f"{stage}/l1": (pred - target).abs().mean(), f"{stage}/first": target[0].mean(),
+                    f"{stage}/n": torch.tensor(float(len(outputs))), f"{stage}/flag": torch.tensor(float(black_level_offset)),
+                    f"{stage}/order": (order.double() * torch.arange(1, len(order) + 1)).sum()}, pred
+
+    g = torch.Generator().manual_seed(0)
+    views = [{"img": torch.rand(6, 9, generator=g) + i, "T_wc_position": torch.zeros(3),
+              "T_wc_orientation": torch.eye(3), "sample_id": torch.tensor(i),
+              "exposure_time": torch.tensor(i + 1)} for i in range(5)]
+    model = Model().train()
+    row, pred = trainer.Trainer().test(model, views, torch.eye(3), 0.0, 6.0, black_level_offset=True)
+    val_row, _ = trainer.Trainer().validate(model, views[:2], torch.eye(3), 0.0, 6.0)
+    torch.save({"row": row, "val_row": val_row, "pred": pred, "rendered": model.rendered, "modes": model.modes,
+                "training_after": model.training,
+                "want_l1": float(torch.stack([(v["img"] * 0.5 + model.image_pixel_positions(6, 9)[..., 0] * 0.01
+                                              - v["img"]).abs() for v in views]).mean())},
+               os.path.join(out_dir, f"eval_rank{rank}.pt"))
+    ddp.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_trainer_test_loop_world_size_2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_eval_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(tmp_path / f"eval_rank{r}.pt") for r in range(world)]
+    assert res[0]["rendered"] == [0, 2, 4, 0] and res[1]["rendered"] == [1, 3, 1]   # round-robin shares (+ validate)
+    assert not any(res[0]["modes"]) and res[0]["training_after"]                # eval mode inside, restored after
+    assert res[0]["row"] == res[1]["row"] and torch.equal(res[0]["pred"], res[1]["pred"])
+    row = res[0]["row"]
+    assert row["test/n"] == 5.0 and row["test/flag"] == 1.0
+    assert row["test/order"] == float(sum((i + 1) * (i + 1) for i in range(5)))   # views back in their order
+    assert abs(row["test/l1"] - res[0]["want_l1"]) < 1e-6
+    assert res[0]["val_row"]["val/n"] == 2.0 and "val/l1" in res[0]["val_row"]
+
+
 def test_single_process_is_a_noop():
     sys.path.insert(0, ROOT)
     from deblur_e_nerf_b200 import ddp

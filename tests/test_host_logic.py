@@ -200,3 +200,64 @@ def test_batch_controller_gating_follows_the_reference():
     stub.accumulate_grad_batches = 1
     stub.mean_samples_reduce_fn = lambda mean: (mean + 3 * mean) / 2        # two ranks: m and 3 m
     assert update(stub, [32.0], 0) == 64.0 and stub.next_train_batch_size == 2048
+
+
+@pytest.mark.parametrize("colour", [False, True], ids=["mono", "bayer"])
+def test_evaluation_loop_host_logic(monkeypatch, colour):
+    """`Trainer.test` -> `EventRenderer.evaluation_step` / `evaluation_epoch_end` (models/deblur_e_nerf.py:
+    604-969) on the CPU with the two device parts replaced: the field render by a closed-form stub, the
+    post-processing kernels by the oracle's `eval_ref.evaluate`.  Checks what the host code owns: the
+    squeeze of the DataLoader dim, pose expansion, channel-first colour images, unity exposure / gain
+    defaults, stacking, the metric names, eval mode inside and the mode restored after."""
+    from deblur_e_nerf_b200 import eval_post, trainer
+    from oracle import eval_ref
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    model, poses = _scene.build_product_renderer(cfg, "cpu", pixel_bandwidth=False, n_poses=20)
+    H, W, C = 19, 23, 3 if colour else 1
+    seen = []
+
+    def render(o, d, jitter=None):
+        assert o.shape == (H, W, 3) and d.shape == (H, W, 3) and not model.nerf.training
+        seen.append(o[0, 0].clone())
+        base = 0.3 + 0.2 * d[..., 0].abs() + 0.1 * d[..., 1].abs()
+        rad = torch.stack([base * (1 + 0.1 * c) for c in range(3)], dim=-1) if colour else base
+        return rad, torch.ones(H, W), torch.ones(H, W), 7.0
+
+    def evaluate(pred, target, exposure_time, gain, lo, hi, black_level_offset=True, init=None,
+                 max_steps=10, radius=1e6, per_channel_scale=True):
+        if pred.dim() == 3:
+            pred, target = pred[:, None], target[:, None]
+        res = eval_ref.evaluate(pred, target, exposure_time, gain, lo, hi,
+                                black_level_offset=black_level_offset, init=init, max_steps=max_steps,
+                                per_channel_scale=per_channel_scale)
+        return {k: (torch.tensor(v) if isinstance(v, float) else v) for k, v in res.items()}
+
+    monkeypatch.setattr(model.nerf, "forward", render)
+    monkeypatch.setattr(eval_post, "evaluate", evaluate)
+    traj = path_ref.LinearTrajectory(*poses)
+    pos, rot = traj(torch.tensor([2.0e6, 9.5e6, 17.25e6], dtype=torch.float64))
+    g = torch.Generator().manual_seed(0)
+    shape = (3, H, W) if colour else (H, W)
+    views = [{"img": (torch.rand(shape, generator=g) * 0.5 + 0.2)[None], "T_wc_position": pos[b][None],
+              "T_wc_orientation": rot[b][None], "gain": torch.tensor([1.0 + b])} for b in range(3)]
+    model.train()
+    row, pred = trainer.Trainer().test(model, views, model.train_intrinsics_inv, 0.0, 1.0,
+                                       black_level_offset=False, per_channel_log_it_scale=not colour)
+    assert model.training and set(row) == {"test/l1", "test/psnr", "test/ssim"}
+    assert pred.shape == (3, C, H, W)
+    assert all(torch.equal(s, pos[b]) for b, s in enumerate(seen))          # every view at its own pose
+    # the same numbers straight from the oracle on the stub's images
+    grid = model.image_pixel_positions(H, W)
+    preds = []
+    for b in range(3):
+        _, d = model.nerf.pixel_params_to_ray(model.train_intrinsics_inv, grid, pos[b].expand(H, W, -1),
+                                              rot[b].expand(H, W, -1, -1))
+        base = 0.3 + 0.2 * d[..., 0].abs() + 0.1 * d[..., 1].abs()
+        chans = [base * (1 + 0.1 * c) for c in range(3)] if colour else [base]
+        preds.append(torch.stack(chans) + model.min_modeled_intensity)
+    target = torch.stack([v["img"][0] for v in views]).view(3, C, H, W)
+    want = eval_ref.evaluate(torch.stack(preds), target, torch.ones(3, dtype=torch.int64),
+                             torch.tensor([1.0, 2.0, 3.0]), 0.0, 1.0, black_level_offset=False,
+                             per_channel_scale=not colour)
+    assert abs(row["test/l1"] - want["l1"]) < 1e-6 and abs(row["test/ssim"] - want["ssim"]) < 1e-6
+    assert torch.allclose(pred, want["pred"], rtol=1e-5, atol=1e-6)

@@ -150,3 +150,40 @@ def test_roma_restatement():
     qz = roma_ref.rotvec_to_unitquat(torch.tensor([[0.0, 0.0, math.pi / 2]]))
     assert torch.allclose(roma_ref.unitquat_to_rotmat(qz)[0] @ torch.tensor([1.0, 0, 0]),
                           torch.tensor([0.0, 1.0, 0.0]), atol=1e-6)
+
+
+def test_ssim_restatement_known_answers():
+    """oracle/eval_ref.ssim (torchmetrics 0.6.2 functional.ssim, restated: parity unpinned) against closed
+    forms and an independent float64 window sum written from the definition."""
+    from oracle import eval_ref
+    g = torch.Generator().manual_seed(5)
+    t = torch.rand(2, 3, 29, 40, generator=g, dtype=torch.float64) * 0.8 + 0.1
+    # identical images: every index is 1
+    assert abs(float(eval_ref.ssim(t, t, 1.0)) - 1.0) < 1e-12
+    # constant images a, b: variances and covariance vanish, the index is the luminance term alone
+    a, b, rng = 0.3, 0.5, 0.9
+    want = (2 * a * b + (0.01 * rng) ** 2) / (a * a + b * b + (0.01 * rng) ** 2)
+    got = eval_ref.ssim(torch.full((1, 1, 16, 20), a, dtype=torch.float64),
+                        torch.full((1, 1, 16, 20), b, dtype=torch.float64), rng)
+    assert abs(float(got) - want) < 1e-9
+    # an 11 x 11 image has exactly one pixel whose window fits
+    p = (t + 0.05 * torch.randn(t.shape, generator=g, dtype=torch.float64)).clamp(0.01, 1.0)
+    d = np.arange(-5, 6, dtype=np.float64)
+    w = np.exp(-(d / 1.5) ** 2 / 2)
+    w = np.outer(w / w.sum(), w / w.sum())
+
+    def index(pw, tw, rng):
+        c1, c2 = (0.01 * rng) ** 2, (0.03 * rng) ** 2
+        mp, mt = (w * pw).sum(), (w * tw).sum()
+        vp, vt, cov = (w * pw * pw).sum() - mp * mp, (w * tw * tw).sum() - mt * mt, (w * pw * tw).sum() - mp * mt
+        return (2 * mp * mt + c1) * (2 * cov + c2) / ((mp * mp + mt * mt + c1) * (vp + vt + c2))
+
+    one = eval_ref.ssim(p[:1, :1, :11, :11], t[:1, :1, :11, :11], 1.0)
+    assert abs(float(one) - index(p[0, 0, :11, :11].numpy(), t[0, 0, :11, :11].numpy(), 1.0)) < 1e-12
+    # the mean runs over the pixels whose window lies inside the image, over channels and images
+    pn, tn = p.numpy(), t.numpy()
+    vals = [index(pn[i, c, y:y + 11, x:x + 11], tn[i, c, y:y + 11, x:x + 11], 0.9)
+            for i in range(2) for c in range(3) for y in range(29 - 10) for x in range(40 - 10)]
+    assert abs(float(eval_ref.ssim(p, t, 0.9)) - float(np.mean(vals))) < 1e-12
+    # fp32 (what Metric.compute runs in) stays within 1e-5 of it
+    assert abs(float(eval_ref.ssim(p.float(), t.float(), 0.9)) - float(np.mean(vals))) < 1e-5
