@@ -78,40 +78,71 @@ def ssim(pred, target, data_range, kernel_size=11, sigma=1.5, k1=0.01, k2=0.03):
     return sums / float(C * (H - kernel_size + 1) * (W - kernel_size + 1))
 
 
+def _joint_layout(C, shared_gamma, device):
+    """Positions of (scale_c, gamma_c, offset_c) in the joint parameter vector [scale (C), gamma (C or 1),
+    offset (C)] — the order pypose flattens OffsetGammaCorrection's parameters in."""
+    n_gamma = 1 if shared_gamma else C
+    c = torch.arange(C, device=device)
+    return torch.stack((c, C + (torch.zeros_like(c) if shared_gamma else c), C + n_gamma + c), dim=-1), 2 * C + n_gamma
+
+
+def _joint_system(m, layout, P):
+    """J^T J (P, P) and J^T r (P) of the joint problem from the per-channel moments (C, 10): channel c's
+    rows of the Jacobian touch only (scale_c, gamma_c or the shared gamma, offset_c), so its 3 x 3 block is
+    ADDED at those positions (a shared gamma couples the channels through its row and column)."""
+    tri = torch.tensor([[0, 1, 2], [1, 3, 4], [2, 4, 5]], device=m.device)
+    blocks = m[:, :6][:, tri]                                            # (C, 3, 3)
+    A = torch.zeros((P, P), dtype=torch.float64, device=m.device)
+    g = torch.zeros((P,), dtype=torch.float64, device=m.device)
+    rows = layout.unsqueeze(-1).expand(-1, 3, 3).reshape(-1)
+    cols = layout.unsqueeze(1).expand(-1, 3, 3).reshape(-1)
+    A.index_put_((rows, cols), blocks.reshape(-1), accumulate=True)
+    g.index_put_((layout.reshape(-1),), m[:, 6:9].reshape(-1), accumulate=True)
+    return A, g
+
+
 def lm_refine(pred, target, gain, affine, init, max_steps=10, radius=1e6):
-    """Levenberg-Marquardt on (scale, gamma, offset) per channel, external/optimizer.py:60-111 step for
-    step; every J^T J / J^T r / loss evaluation is one den_eval_lm_moments pass.  Returns (C, 3) f64."""
+    """Levenberg-Marquardt on the offset-gamma correction, external/optimizer.py:60-111 step for step on
+    the JOINT parameter vector (scale per channel, gamma per channel or — `init` gamma of one element: a
+    colour sensor with `per_channel_log_it_scale: false`, models/deblur_e_nerf.py:185-197 — ONE gamma
+    shared by the channels, offset per channel); every J^T J / J^T r / loss evaluation is one
+    den_eval_lm_moments pass.  Returns ((C, 3) f64 (scale, gamma, offset) per channel, errors)."""
     C = pred.shape[1]
     cfg = LM_DEFAULTS
-    p = torch.cat((affine, torch.stack(init, dim=-1).double().to(pred.device)), dim=-1).contiguous()   # (C, 5)
+    dev = pred.device
+    scale0, gamma0, offset0 = (torch.as_tensor(v, dtype=torch.float64).reshape(-1).to(dev) for v in init)
+    shared_gamma = C > 1 and gamma0.numel() == 1
+    layout, P = _joint_layout(C, shared_gamma, dev)
+    theta = torch.cat((scale0, gamma0, offset0))                          # (P,)
+    assert theta.numel() == P, "init: scale and offset need C elements, gamma C or 1"
+
+    def params_of(theta):
+        return torch.cat((affine, theta[layout]), dim=-1).contiguous()    # (C, 5): a, b, s, gamma, o
+
+    def moments(theta):
+        return _moments("den_eval_lm_moments", pred, target, gain, params_of(theta), 10)
+
     damping, down = 1.0 / radius, cfg["down"]
     n = float(target.numel())
-
-    def moments(params):
-        return _moments("den_eval_lm_moments", pred, target, gain, params.contiguous(), 10)
-
-    m = moments(p)
+    m = moments(theta)
     loss = float(m[:, 9].sum())
     errors = [loss / n]
     for _ in range(max_steps):
-        prev = p[:, 2:].clone()
+        prev = theta.clone()
         last = loss
-        idx = torch.tensor([[0, 1, 2], [1, 3, 4], [2, 4, 5]], device=pred.device)
-        A = m[:, :6][:, idx].clone()                                   # (C, 3, 3)
-        g = m[:, 6:9].clone()                                          # J^T r
-        A.diagonal(dim1=1, dim2=2).clamp_(cfg["min"], cfg["max"])
+        A_und, g = _joint_system(m, layout, P)
+        A = A_und.clone()
+        A.diagonal().clamp_(cfg["min"], cfg["max"])
         rejects = 0
         while last <= loss:
-            d = A.diagonal(dim1=1, dim2=2)
+            d = A.diagonal()
             d.add_(d * damping)
-            D = torch.linalg.solve(A, -g.unsqueeze(-1))[:, :, 0]       # (C, 3)
-            trial = p.clone()
-            trial[:, 2:] += D
+            D = torch.linalg.solve(A, -g.unsqueeze(-1))[:, 0]             # (P,)
+            trial = theta + D
             m_trial = moments(trial)
             loss = float(m_trial[:, 9].sum())
             # predicted decrease -(J D)^T (2 R + J D) from the moments of the CURRENT point
-            Aund = m[:, :6][:, idx]
-            pred_dec = -float((D.unsqueeze(1) @ Aund @ D.unsqueeze(-1)).sum() + 2 * (D * m[:, 6:9]).sum())
+            pred_dec = -float(D @ A_und @ D + 2 * (D * g).sum())
             quality = (last - loss) / pred_dec if pred_dec != 0 else 0.0
             rad = 1.0 / damping
             if quality > cfg["high"]:
@@ -126,12 +157,12 @@ def lm_refine(pred, target, gain, affine, init, max_steps=10, radius=1e6):
             if last < loss and rejects < cfg["reject"]:
                 loss, rejects = last, rejects + 1                       # rejected: stay, more damping
             else:
-                p, m = trial, m_trial
+                theta, m = trial, m_trial
                 break
         errors.append(loss / n)
-        if abs(errors[-1] - errors[-2]) <= 1e-8 + 1e-5 * abs(errors[-2]) and torch.allclose(p[:, 2:], prev):
+        if abs(errors[-1] - errors[-2]) <= 1e-8 + 1e-5 * abs(errors[-2]) and torch.allclose(theta, prev):
             break
-    return p[:, 2:].clone(), errors
+    return theta[layout].clone(), errors
 
 
 @torch.no_grad()
@@ -155,7 +186,9 @@ def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_of
     errors = None
     if black_level_offset:
         if init is None:
-            init = (torch.ones(C), torch.ones(C), torch.zeros(C))
+            # models/deblur_e_nerf.py:174-197: unit scale / gamma, zero offset; ONE gamma when the
+            # log-intensity scale is shared by the channels of a colour sensor
+            init = (torch.ones(C), torch.ones(C if per_channel_scale or C == 1 else 1), torch.zeros(C))
         corr, errors = lm_refine(pred, target, gain64, affine, init, max_steps, radius)
     else:
         corr = torch.tensor([[1.0, 1.0, 0.0]], dtype=torch.float64, device=pred.device).repeat(C, 1)

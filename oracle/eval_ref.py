@@ -49,28 +49,53 @@ def affine_log_correction(pred, target, norm_gain, per_channel_scale=True):
 
 
 class _Correction:
-    """models/offset_gamma_correction.py: f(x) = const_scale (scale x^gamma - offset), parameters (C,)."""
+    """models/offset_gamma_correction.py: f(x) = const_scale (scale x^gamma - offset); scale and offset hold
+    C elements, gamma C or ONE shared by the channels (:60-65: `len(param) == 1 or len(param) == C`).  The
+    parameters live in one vector [scale, gamma, offset], the order pypose flattens them in."""
 
     def __init__(self, const_scale, scale, gamma, offset):
         self.g = const_scale.double().view(-1, 1, 1, 1)
-        self.p = torch.stack((scale.double(), gamma.double(), offset.double()), dim=-1)       # (C, 3)
+        self.C = scale.numel()
+        self.n_gamma = gamma.numel()
+        assert offset.numel() == self.C and self.n_gamma in (1, self.C)
+        self.theta = torch.cat((scale.double().reshape(-1), gamma.double().reshape(-1), offset.double().reshape(-1)))
+
+    def parts(self):
+        C, G = self.C, self.n_gamma
+        return (self.theta[:C].view(1, C, 1, 1), self.theta[C:C + G].view(1, G, 1, 1),
+                self.theta[C + G:].view(1, C, 1, 1))
+
+    @property
+    def p(self):
+        """(C, 3): scale, gamma (the shared one repeated), offset per channel."""
+        s, gm, o = self.parts()
+        return torch.stack((s.reshape(-1), gm.reshape(-1).expand(self.C), o.reshape(-1)), dim=-1)
 
     def forward(self, x):
-        s, gm, o = (self.p[:, k].view(1, -1, 1, 1) for k in range(3))
+        s, gm, o = self.parts()
         return self.g * (s * x.pow(gm) - o)
 
     def jacobian(self, x):
-        s, gm, _ = (self.p[:, k].view(1, -1, 1, 1) for k in range(3))
+        """:124-190: the (B C H W, P) Jacobian — every output element depends on its channel's scale and
+        offset and on its channel's (or the shared) gamma."""
+        s, gm, _ = self.parts()
+        B, C, H, W = x.shape
         js = self.g * x.pow(gm)
         jg = s * x.log() * js
         jo = (-self.g).expand_as(x)
-        return torch.stack((js, jg, jo), dim=-1)                                               # (B,C,H,W,3)
+        J = torch.zeros((B, C, H, W, self.theta.numel()), dtype=torch.float64)
+        for c in range(C):
+            J[:, c, :, :, c] = js[:, c]
+            J[:, c, :, :, C + (c if self.n_gamma == C else 0)] = jg[:, c]
+            J[:, c, :, :, C + self.n_gamma + c] = jo[:, c]
+        return J.reshape(-1, self.theta.numel())
 
 
 def lm_refine(x, target, norm_gain, init, max_steps=10, radius=1e6):
-    """:846-895 with external/optimizer.py:60-111.  x: affinely corrected prediction (B,C,H,W) f64;
-    target (B,C,H,W) fp32.  Returns (params (C,3), errors list)."""
-    C = x.shape[1]
+    """:846-895 with external/optimizer.py:60-111 (ONE joint problem over all parameters, like upstream:
+    the damping, the acceptance test and the loss are shared by the channels).  x: affinely corrected
+    prediction (B,C,H,W) f64; target (B,C,H,W) fp32; init = (scale (C), gamma (C or 1), offset (C)).
+    Returns (params (C,3), errors list)."""
     model = _Correction(norm_gain, *init)
     t = target.double()
     pg = dict(min=1e-6, max=1e32, radius=radius, high=0.5, low=1e-3, up=2.0, down=0.5, damping=1.0 / radius)
@@ -82,20 +107,20 @@ def lm_refine(x, target, norm_gain, init, max_steps=10, radius=1e6):
     state = {"loss": None}
 
     def step():
-        R = (model.forward(x) - t).transpose(0, 1).reshape(C, -1)                              # (C, N)
-        J = model.jacobian(x).transpose(0, 1).reshape(C, -1, 3)                                # (C, N, 3)
+        R = (model.forward(x) - t).reshape(-1, 1)                                              # (N, 1)
+        J = model.jacobian(x)                                                                  # (N, P)
         last = cur = state["loss"] if state["loss"] is not None else loss()
-        A = J.transpose(1, 2) @ J                                                              # (C, 3, 3)
-        g = J.transpose(1, 2) @ R.unsqueeze(-1)
-        A.diagonal(dim1=1, dim2=2).clamp_(pg["min"], pg["max"])
+        A = J.T @ J                                                                            # (P, P)
+        g = J.T @ R
+        A.diagonal().clamp_(pg["min"], pg["max"])
         rejects = 0
         while last <= cur:
-            d = A.diagonal(dim1=1, dim2=2)
+            d = A.diagonal()
             d.add_(d * pg["damping"])
-            D = torch.linalg.solve(A, -g)[:, :, 0]                                             # (C, 3)
-            model.p += D
+            D = torch.linalg.solve(A, -g)[:, 0]                                                # (P,)
+            model.theta = model.theta + D
             cur = loss()
-            JD = (J @ D.unsqueeze(-1))[:, :, 0]
+            JD = J @ D.unsqueeze(-1)
             quality = (last - cur) / -float((JD * (2 * R + JD)).sum())
             pg["radius"] = 1.0 / pg["damping"]
             if quality > pg["high"]:
@@ -111,7 +136,7 @@ def lm_refine(x, target, norm_gain, init, max_steps=10, radius=1e6):
             pg["radius"] = max(pg["min"], min(pg["radius"], pg["max"]))
             pg["damping"] = 1.0 / pg["radius"]
             if last < cur and rejects < reject:
-                model.p -= D
+                model.theta = model.theta - D
                 cur, rejects = last, rejects + 1
             else:
                 break
@@ -121,9 +146,9 @@ def lm_refine(x, target, norm_gain, init, max_steps=10, radius=1e6):
     n = t.numel()
     errors = [loss() / n]
     for _ in range(max_steps):
-        prev = model.p.clone()
+        prev = model.theta.clone()
         errors.append(step() / n)
-        if math.isclose(errors[-1], errors[-2], rel_tol=1e-5, abs_tol=1e-8) and torch.allclose(model.p, prev):
+        if math.isclose(errors[-1], errors[-2], rel_tol=1e-5, abs_tol=1e-8) and torch.allclose(model.theta, prev):
             break
     return model.p.clone(), errors
 
@@ -186,8 +211,8 @@ def evaluate(pred, target, exposure_time, gain, min_val, max_val, black_level_of
         params = None
     else:
         x = fitted.exp()
-        if init is None:
-            init = (torch.ones(C), torch.ones(C), torch.zeros(C))
+        if init is None:                                                                       # :174-197
+            init = (torch.ones(C), torch.ones(C if per_channel_scale or C == 1 else 1), torch.zeros(C))
         params, _ = lm_refine(x, target, norm, init, max_steps)
         out = _Correction(norm, params[:, 0], params[:, 1], params[:, 2]).forward(x)
     out = out.to(target.dtype)

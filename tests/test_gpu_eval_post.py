@@ -74,6 +74,8 @@ def test_eval_post_colour_images_match_oracle(den_lib, cuda, per_channel, black_
         assert float(got["affine"][:, 0].max() - got["affine"][:, 0].min()) == 0.0
     if black_level_offset:
         assert torch.allclose(got["correction"].cpu(), want["correction"], rtol=2e-4, atol=2e-6)
+        if not per_channel:       # a shared log-intensity scale comes with ONE gamma (models/deblur_e_nerf.py:185-197)
+            assert float(got["correction"][:, 1].max() - got["correction"][:, 1].min()) == 0.0
     assert (got["pred"].cpu() - want["pred"]).abs().max().item() <= 1e-5 * want["pred"].abs().max().item()
     assert abs(float(got["l1"]) - want["l1"]) <= 1e-5 * want["l1"]
     assert abs(float(got["psnr"]) - want["psnr"]) <= 1e-5 * abs(want["psnr"])

@@ -261,3 +261,44 @@ def test_evaluation_loop_host_logic(monkeypatch, colour):
                              per_channel_scale=not colour)
     assert abs(row["test/l1"] - want["l1"]) < 1e-6 and abs(row["test/ssim"] - want["ssim"]) < 1e-6
     assert torch.allclose(pred, want["pred"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shared_gamma", [False, True], ids=["gamma_per_channel", "gamma_shared"])
+def test_lm_refine_joint_system_host_logic(monkeypatch, shared_gamma):
+    """`eval_post.lm_refine` assembles the joint normal equations (scale / offset per channel, gamma per
+    channel or shared) from the per-channel moments of `den_eval_lm_moments`.  With the kernel replaced by
+    a float64 torch evaluation of the same ten moments, the host logic — joint layout, damping, trust
+    region, acceptance — must reproduce the oracle's refinement, which runs the reference's LM on the
+    explicit Jacobian."""
+    from deblur_e_nerf_b200 import eval_post
+    from oracle import eval_ref
+    g = torch.Generator().manual_seed(8)
+    B, C, H, W = 3, 3, 12, 15
+    target = torch.rand(B, C, H, W, generator=g) * 0.8 + 0.1
+    exposure, gain = torch.tensor([1, 2, 4]), torch.tensor([1.0, 1.5, 0.75])
+    norm = eval_ref.normalized_gain(gain, exposure)
+    scene = (target - 0.03) / norm.view(-1, 1, 1, 1)
+    pred = torch.stack([(0.5 + 0.2 * c) * scene[:, c].pow(1.2) for c in range(C)], dim=1)
+    pred = (pred * torch.exp(0.02 * torch.randn(pred.shape, generator=g))).float()
+    affine, fitted, _ = eval_ref.affine_log_correction(pred, target, norm, per_channel_scale=not shared_gamma)
+    init = (torch.ones(C), torch.ones(1 if shared_gamma else C), torch.zeros(C))
+    want, want_errors = eval_ref.lm_refine(fitted.exp(), target, norm, init)
+
+    def moments(kind, pred, target, gain_vec, params, n_out):
+        assert kind == "den_eval_lm_moments" and n_out == 10 and params.shape == (C, 5)
+        a, b, s, gm, o = (params[:, k].view(1, C, 1, 1) for k in range(5))
+        x = torch.exp(a * pred.log().double() + b)
+        gv = gain_vec.view(-1, 1, 1, 1)
+        xg = x.pow(gm)
+        js, jo = gv * xg, (-gv).expand_as(x)
+        jg = s * x.log() * js
+        r = gv * (s * xg - o) - target.double()
+        cols = [js * js, js * jg, js * jo, jg * jg, jg * jo, jo * jo, js * r, jg * r, jo * r, r * r]
+        return torch.stack([c.transpose(0, 1).reshape(C, -1).sum(-1) for c in cols], dim=-1)
+
+    monkeypatch.setattr(eval_post, "_moments", moments)
+    got, errors = eval_post.lm_refine(pred, target, norm.double(), affine, init)
+    assert torch.allclose(got, want, rtol=1e-7, atol=1e-9), (got, want)
+    assert len(errors) == len(want_errors) and abs(errors[-1] - want_errors[-1]) <= 1e-9 * want_errors[-1]
+    if shared_gamma:
+        assert float(got[:, 1].max() - got[:, 1].min()) == 0.0

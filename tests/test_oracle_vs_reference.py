@@ -344,3 +344,51 @@ def test_eval_lm_refinement_reaches_the_least_squares_minimum():
     no_refine = eval_ref.evaluate(pred[:, None], target[:, None], exposure, gain, 0.0, 1.1,
                                   black_level_offset=False)
     assert res["l1"] < no_refine["l1"]
+
+
+@pytest.mark.parametrize("shared_gamma", [False, True], ids=["gamma_per_channel", "gamma_shared"])
+def test_offset_gamma_correction_model_matches_reference(shared_gamma):
+    """oracle/eval_ref._Correction (forward and the joint Jacobian, parameter order [scale, gamma, offset])
+    against the reference's OWN models/offset_gamma_correction.py (pure torch, loaded by path) for colour
+    images with a gamma per channel and with ONE gamma shared by the channels (the shape
+    `per_channel_log_it_scale: false` gives it, models/deblur_e_nerf.py:185-197); then the refinement on a
+    shared-gamma problem: equal gammas, vanishing joint gradient."""
+    import importlib.util
+    from oracle import eval_ref
+    spec = importlib.util.spec_from_file_location(
+        "_ref_offset_gamma_correction", ref_shim.REFERENCE_ROOT + "/deblur_e_nerf/models/offset_gamma_correction.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(4)
+    B, C, H, W = 2, 3, 5, 7
+    x = torch.rand(B, C, H, W, generator=g, dtype=torch.float64) + 0.1
+    gain = torch.tensor([0.8, 1.2], dtype=torch.float64)
+    scale = torch.rand(C, generator=g, dtype=torch.float64) + 0.5
+    gamma = torch.rand(1 if shared_gamma else C, generator=g, dtype=torch.float64) + 0.7
+    offset = torch.rand(C, generator=g, dtype=torch.float64) * 0.1
+    ref = mod.OffsetGammaCorrection(gain.view(-1, 1, 1, 1, 1), scale.view(-1, 1, 1, 1),
+                                    gamma.view(-1, 1, 1, 1), offset.view(-1, 1, 1, 1))
+    ora = eval_ref._Correction(gain, scale, gamma, offset)
+    with torch.no_grad():
+        _close(ora.forward(x), ref(x.unsqueeze(-1)).squeeze(-1), 1e-14)
+        (jac,) = ref.jacobian(x.unsqueeze(-1))
+        assert jac.shape == (B * C * H * W, 2 * C + gamma.numel())
+        _close(ora.jacobian(x), jac, 1e-14)
+
+    if shared_gamma:
+        imgs = [_eval_images(30 + c) for c in range(3)]
+        exposure, gain32 = imgs[0][2], imgs[0][3]
+        target = torch.stack([im[1] for im in imgs], dim=1) + 0.03
+        pred = torch.stack([(0.5 + 0.2 * c) * imgs[c][0].pow(1.2) for c in range(3)], dim=1)
+        res = eval_ref.evaluate(pred, target, exposure, gain32, 0.0, 1.1, black_level_offset=True,
+                                per_channel_scale=False)
+        corr = res["correction"]
+        assert float(corr[:, 1].max() - corr[:, 1].min()) == 0.0            # one gamma
+        norm = eval_ref.normalized_gain(gain32, exposure)
+        _, fitted, _ = eval_ref.affine_log_correction(pred, target, norm, per_channel_scale=False)
+        theta = torch.cat((corr[:, 0], corr[:1, 1], corr[:, 2])).clone().requires_grad_(True)
+        gn = norm.double().view(-1, 1, 1, 1)
+        f = gn * (theta[:3].view(1, 3, 1, 1) * fitted.exp().pow(theta[3]) - theta[4:].view(1, 3, 1, 1))
+        loss = ((f - target.double()) ** 2).sum()
+        loss.backward()
+        assert float(theta.grad.abs().max()) < 1e-6 * float(loss) + 1e-9
