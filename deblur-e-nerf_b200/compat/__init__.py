@@ -2,7 +2,8 @@
 top of the den_b200 operators: a `pytorch_lightning` 1.4.9-shaped package with the
 part of the API `scripts/run.py:10,32,70-100` and the two Lightning classes of the reference use,
 `easydict`, the handful of `roma` functions of `utils/tensor_ops.py` / `models/trajectories.py`, and
-import-time stand-ins for the evaluation-only dependencies (`pypose`, `torchmetrics`, `lpips`).
+stand-ins for the evaluation-only dependencies (`torchmetrics.functional.psnr / ssim`: functional;
+`lpips`: NaN with a warning; `pypose`: import-time only).
 
 `install()` registers them in `sys.modules` under their upstream names — only where the real package
 is not importable — together with the B1 drop-ins (`nerfacc`, `tinycudann` → deblur_e_nerf_b200);

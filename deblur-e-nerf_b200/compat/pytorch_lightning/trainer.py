@@ -29,6 +29,15 @@ def _to_device(obj, device):
     return obj
 
 
+def _plain(obj):
+    """Nested mappings / sequences as plain dict / list (scalars, strings, tensors and None unchanged)."""
+    if isinstance(obj, dict):
+        return {k: _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_plain(v) for v in obj]
+    return obj
+
+
 class Trainer:
     def __init__(self, callbacks=None, logger=True, plugins=None, replace_sampler_ddp=True,
                  sync_batchnorm=False, terminate_on_nan=False, multiple_trainloader_mode="max_size_cycle",
@@ -160,9 +169,13 @@ class Trainer:
 
     # ----------------------------------------------------------------- checkpoints ----
     def save_checkpoint(self, path, weights_only=False):
+        """Lightning 1.4.9's top-level keys.  The hyper-parameters are stored as plain containers (EasyDict
+        -> dict, tuples -> lists): the file then loads with `torch.load`'s safe unpickler, which is the
+        default the reference's own `torch.load(checkpoint_filepath)` (models/deblur_e_nerf.py:332-334)
+        gets under torch >= 2.6."""
         ckpt = {"epoch": self.current_epoch + 1, "global_step": self.global_step,
                 "pytorch-lightning_version": "1.4.9", "state_dict": self.model.state_dict(),
-                "hyper_parameters": dict(getattr(self.model, "hparams", {}))}
+                "hyper_parameters": _plain(getattr(self.model, "hparams", {}))}
         if not weights_only:
             ckpt["optimizer_states"] = [o.state_dict() for o in self.optimizers]
             ckpt["lr_schedulers"] = [s["scheduler"].state_dict() for s in self.lr_schedulers]

@@ -131,7 +131,7 @@ def hashgrid_encode(x, params, scales, resolutions, sizes, offsets, n_features):
     out = torch.zeros(idx.shape[0], idx.shape[1], n_features, dtype=w.dtype)
     for corner in range(8):                                                 # corner order 0..7
         out = out + w[..., corner, None] * feats[..., corner, :]
-    return out.reshape(idx.shape[0], -1)
+    return out.reshape(idx.shape[0], idx.shape[1] * n_features)             # explicit width: M may be 0
 
 
 class Encoding(torch.nn.Module):

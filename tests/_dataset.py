@@ -13,7 +13,9 @@ import torch
 from deblur_e_nerf_b200 import synthetic
 
 
-def write(root, cfg, n_events=4096, n_views=2, size=(24, 32), seed=0):
+def write(root, cfg, n_events=4096, n_views=2, size=(24, 32), seed=0, channels=4):
+    """`channels` 4: BGRA renders (composited over white by `alpha_over_white_bg: true`); 3: BGR renders,
+    which a mono sensor's loader converts to grey (data/datasets.py:640-644)."""
     os.makedirs(root, exist_ok=True)
     poses = synthetic.camera_poses(cfg, n_poses=200)
     synthetic.write_dataset_dir(root, cfg, poses)
@@ -30,8 +32,9 @@ def write(root, cfg, n_events=4096, n_views=2, size=(24, 32), seed=0):
         os.makedirs(os.path.join(views, stage), exist_ok=True)
         frames = []
         for i in range(n_views):
-            img = rng.integers(20, 235, size=(h, w, 4), dtype=np.uint8)
-            img[..., 3] = 255
+            img = rng.integers(20, 235, size=(h, w, channels), dtype=np.uint8)
+            if channels == 4:
+                img[..., 3] = 255
             cv2.imwrite(os.path.join(views, stage, f"r_{i}.png"), img)
             ang = 0.3 * i
             pos = np.array([4.0 * math.cos(ang), 4.0 * math.sin(ang), 0.5])

@@ -131,12 +131,14 @@ def test_reference_run_py_trains_unchanged(tmp_path, monkeypatch):
     from deblur_e_nerf_b200 import run_reference, synthetic
     from oracle import nerfacc_ref, tcnn_ref
     data_dir = str(tmp_path / "data")
-    _dataset.write(data_dir, dict(synthetic.CONFIGS["synthetic"]))
+    # BGR views and no alpha compositing: the mono sensor's loader converts them to grey
+    # (data/datasets.py:640-644; BGRA views stay three-channel there and only suit a colour sensor)
+    _dataset.write(data_dir, dict(synthetic.CONFIGS["synthetic"]), channels=3)
     with open(os.path.join(REFERENCE, "configs", "train", "synthetic.yaml")) as fh:
         conf = yaml.full_load(fh)
     conf["seed"] = 3
     conf["data"].update(dataset_directory=data_dir, train_init_eff_batch_size=16,
-                        train_eff_ray_sample_batch_size=4096)
+                        train_eff_ray_sample_batch_size=4096, alpha_over_white_bg=False)
     conf["logger"]["save_dir"] = str(tmp_path / "logs")
     conf["trainer"].update(max_epochs=1, limit_train_batches=3, log_every_n_steps=1, limit_val_batches=0,
                            num_sanity_val_steps=0)
@@ -187,3 +189,34 @@ def test_reference_run_py_trains_unchanged(tmp_path, monkeypatch):
             "train/mean_num_samples_per_ray"} <= tags
     losses = [e.value for e in acc.Scalars("train/loss")]
     assert len(losses) == 3 and all(l == l and l > 0 for l in losses)
+
+    # ---- `run.py test` on the checkpoint just written: the reference's OWN test_step /
+    # evaluation_epoch_end (novel views rendered in eval mode, log-space affine correction, Metric.compute)
+    # under the façade's test loop, with the functional torchmetrics stand-in (PSNR, SSIM) and LPIPS
+    # reported as NaN (no pretrained weights offline).  The offset-gamma refinement needs pypose: off.
+    conf["model"]["checkpoint_filepath"] = str(log_dir / "checkpoints" / "epoch=0-step=2.ckpt")
+    conf["model"]["nerf"]["load_state_dict"] = True
+    conf["model"]["correction"]["black_level_offset"] = False
+    conf["model"]["eval_save_pred_intensity_img"] = True
+    conf["logger"]["name"] = "test_run"
+    with open(cfg_path, "w") as fh:
+        yaml.safe_dump(conf, fh)
+    for name in [m for m in sys.modules if m == "deblur_e_nerf" or m.startswith("deblur_e_nerf.")]:
+        sys.modules.pop(name, None)
+    before = set(sys.modules)
+    try:
+        with pytest.warns(UserWarning, match="LPIPS is reported as NaN"):
+            run_reference.main([str(ref / "scripts" / "run.py"), "test", cfg_path], operators=False)
+    finally:
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in ("deblur_e_nerf", "easydict", "roma", "pytorch_lightning", "pypose",
+                                      "torchmetrics", "lpips"):
+                sys.modules.pop(name, None)
+    test_dir = tmp_path / "logs" / "test_run" / "version_0"
+    with open(test_dir / "metrics.yaml") as fh:
+        metrics = yaml.full_load(fh)
+    assert isinstance(metrics, list) and len(metrics) == 1
+    row = metrics[0]
+    assert {"test/l1", "test/psnr", "test/ssim", "test/lpips"} <= set(row)
+    assert row["test/l1"] > 0 and row["test/psnr"] == row["test/psnr"] and -1.0 <= row["test/ssim"] <= 1.0
+    assert row["test/lpips"] != row["test/lpips"]                      # NaN: visibly missing
