@@ -382,9 +382,11 @@ def run_sweep(args):
     clock_info = clocks.stop() if rank == 0 else None
     # end to end: pixels from pinned host memory, the rendered view read back
     start.record()
+    rendered = []
     for i in range(args.steps):
         img, _ = render_view(args.warmup + i, pix_host.to(dev, non_blocking=True))
         img_host = img.to("cpu")
+        rendered.append(img)
     end.record()
     ddp.barrier()
     torch.cuda.synchronize()
@@ -392,6 +394,7 @@ def run_sweep(args):
     rays = ddp.sum_over_ranks(side * side, dev)
     if rank != 0:
         return
+    eval_post_info = _time_eval_post(model, rendered[:8], side, dev, cpu=not args.no_cpu_baseline)
     line = {
         "metric": "render rays/s (eval, fwd only)", "value": rays / (ms_step * 1e-3), "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -408,8 +411,51 @@ def run_sweep(args):
                 "h2d_bytes_per_step": pix_host.numel() * 4, "d2h_bytes_per_step": img_host.numel() * 4,
                 "ms_per_step": ms_e2e},
         "gpu_launches": launches, "clocks": clock_info, "roofline": None, "cpu_baseline": None,
+        "eval_post": eval_post_info,
     }
     print(json.dumps(line))
+
+
+def _time_eval_post(model, rendered, side, dev, cpu=True):
+    """SURVEY.md 8(f) N4 beside the sweep: the post-processing of `run.py test` (models/deblur_e_nerf.py:
+    674-969 — gain-exposure normalisation, float64 log-space affine fit, Levenberg-Marquardt offset-gamma
+    refinement, L1 / PSNR / SSIM) over the views just rendered, on the device (`evaluation_epoch_end`,
+    den_eval_* kernels), and — the reference does this part on the host — the oracle's restatement of it
+    on the host cores with the images copied there, as the reported CPU baseline."""
+    import torch
+    from deblur_e_nerf_b200 import ops
+    B = len(rendered)
+    g = torch.Generator(device=dev).manual_seed(5)
+    pred = torch.stack(rendered).view(B, side, side) + model.min_modeled_intensity
+    exposure = torch.arange(1, B + 1, device=dev) % 3 + 1
+    gain = 0.75 + 0.5 * torch.rand(B, generator=g, device=dev)
+    norm = gain * exposure / (gain * exposure).mean()
+    scene = torch.exp(0.8 * pred.log() + 0.3) * torch.exp(0.02 * torch.randn(pred.shape, generator=g, device=dev))
+    target = scene * norm.view(-1, 1, 1) + 0.02
+    lo, hi = 0.0, float(target.max()) * 1.05
+    outputs = [{"pred_intensity_img": pred[b], "target_intensity_img": target[b],
+                "exposure_time": exposure[b], "gain": gain[b]} for b in range(B)]
+    model.evaluation_epoch_end(outputs, lo, hi, black_level_offset=True)            # warm-up
+    torch.cuda.synchronize()
+    launches0 = ops.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    metrics, _ = model.evaluation_epoch_end(outputs, lo, hi, black_level_offset=True)
+    end.record()
+    torch.cuda.synchronize()
+    info = {"views": B, "view": f"{side}x{side}", "black_level_offset": True, "ms": start.elapsed_time(end),
+            "gpu_launches": ops.launch_count() - launches0,
+            "metrics": {k: float(v) for k, v in metrics.items()}}
+    if cpu:
+        from oracle import eval_ref                      # the cpu_baseline leg: the only use of oracle/ here
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        want = eval_ref.evaluate(pred.cpu()[:, None], target.cpu()[:, None], exposure.cpu(), gain.cpu(), lo, hi,
+                                 black_level_offset=True)
+        info["cpu_baseline"] = {"ms": (time.perf_counter() - t0) * 1e3, "kind": "port", "cores": os.cpu_count(),
+                                "sample": f"the same {B} views (device -> host copy included, as in the reference)",
+                                "metrics": {k: want[k] for k in ("l1", "psnr", "ssim")}}
+    return info
 
 
 # ------------------------------------------------------------------------- ours ------
