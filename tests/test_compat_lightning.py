@@ -220,3 +220,31 @@ def test_reference_run_py_trains_unchanged(tmp_path, monkeypatch):
     assert {"test/l1", "test/psnr", "test/ssim", "test/lpips"} <= set(row)
     assert row["test/l1"] > 0 and row["test/psnr"] == row["test/psnr"] and -1.0 <= row["test/ssim"] <= 1.0
     assert row["test/lpips"] != row["test/lpips"]                      # NaN: visibly missing
+
+
+def test_torchmetrics_and_lpips_stand_ins():
+    """The functional stand-ins the reference's `Metric.compute` (loss_metric/metric.py:57-93) calls under
+    the façade: PSNR by definition, SSIM equal to the oracle's restatement of torchmetrics 0.6.2 (mono and
+    colour, the data_range argument), argument checks like upstream's; LPIPS visibly missing (NaN + one
+    warning), never a number."""
+    from deblur_e_nerf_b200.compat import lpips, torchmetrics
+    from oracle import eval_ref
+    g = torch.Generator().manual_seed(2)
+    for shape in ((1, 1, 24, 32), (2, 3, 17, 40)):
+        t = torch.rand(shape, generator=g) * 0.8 + 0.1
+        p = (t + 0.05 * torch.randn(shape, generator=g)).clamp(0.01, 1.0)
+        got = torchmetrics.functional.ssim(preds=p, target=t, data_range=0.9, reduction="elementwise_mean")
+        assert abs(float(got) - float(eval_ref.ssim(p, t, 0.9))) < 1e-6
+        mse = ((p - t) ** 2).mean(dim=(1, 2, 3))
+        want_psnr = (10 * torch.log10(torch.tensor(0.9) ** 2 / mse)).mean()
+        got_psnr = torchmetrics.functional.psnr(preds=p, target=t, data_range=0.9, reduction="elementwise_mean",
+                                                dim=(1, 2, 3))
+        assert abs(float(got_psnr) - float(want_psnr)) < 1e-5
+    with pytest.raises(TypeError):
+        torchmetrics.functional.ssim(p, t.double(), data_range=1.0)
+    with pytest.raises(ValueError):
+        torchmetrics.functional.ssim(p[0], t[0], data_range=1.0)
+    net = lpips.LPIPS(net="alex")
+    with pytest.warns(UserWarning, match="LPIPS is reported as NaN"):
+        out = net(in0=p, in1=t)
+    assert out.shape == (2, 1, 1, 1) and torch.isnan(out).all()
