@@ -464,6 +464,35 @@ int den_eval_apply(const float* pred, const float* target, const double* gain, c
 int den_eval_ssim(const float* pred, const float* target, int32_t B, int32_t C, int32_t H, int32_t W,
                   int32_t kernel_size, double sigma, double c1, double c2, double* image_sums, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Raw event stream -> queued events (the data format in front of the hot path) — replaces the per-event
+ * Python loops of Event.queue_raw_events (data/datasets.py:186-276) and
+ * Event.extract_max_refractory_period (:131-183).  Both need, per raw event i, the PREVIOUS raw event at the
+ * same pixel: a stable sort of the stream indices by pixel id y * width + x puts it next to i.
+ *   den_radix_sort_pairs_u32: stable LSD radix sort of n (u32 key, u32 value) pairs on the low `key_bits`
+ *       bits (8 per pass); the result lands in (keys_out, vals_out), (keys_tmp, vals_tmp) is scratch of the
+ *       same size; the inputs are not modified.  workspace >= den_radix_sort_workspace_bytes(n).
+ *   den_queue_raw_events: position_xy (n, 2) int32 (x, y), timestamp (n) int64 in stream order ->
+ *       valid (n) u8: 1 iff an earlier event exists at the pixel and the latest one has a different timestamp
+ *           (the sliding-window test of :246-253);
+ *       start_ts (n) int64: that event's timestamp (0 where invalid); end_ts is `timestamp` itself, num_pos
+ *           / num_neg are polarity / 1 - polarity (:255-267) and are formed by the caller;
+ *       min_interval (1) int64, PRE-SET by the caller to INT64_MAX: atomically lowered to the smallest
+ *           non-zero timestamp[i] - timestamp[prev(i)] — the maximum refractory period of :131-183
+ *           (still INT64_MAX: no pixel saw two distinct timestamps; upstream keeps +inf);
+ *       out_of_range (1) int32, pre-zeroed: set to 1 if a position lies outside width x height (upstream
+ *           raises IndexError; the caller checks the flag).
+ *       workspace >= den_queue_events_workspace_bytes(n).  n < 2^31.
+ * ------------------------------------------------------------------------- */
+size_t den_radix_sort_workspace_bytes(int64_t n);
+int den_radix_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
+                             uint32_t* vals_out, uint32_t* keys_tmp, uint32_t* vals_tmp, int64_t n,
+                             int32_t key_bits, void* workspace, size_t workspace_bytes, void* stream);
+size_t den_queue_events_workspace_bytes(int64_t n);
+int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, int64_t n, int32_t width,
+                         int32_t height, void* workspace, size_t workspace_bytes, int64_t* start_ts,
+                         uint8_t* valid, int64_t* min_interval, int32_t* out_of_range, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -239,3 +239,16 @@ def build_product_renderer(cfg, device, it_sample_size=8, pixel_bandwidth=True, 
 
 def to_device(tree, device):
     return {k: v.to(device) for k, v in tree.items()}
+
+
+RAW_EVENT_CASES = ("ordered", "hot", "shuffled", "sparse")
+
+
+def raw_event_case(name):
+    """One case of tests/golden/raw_events.npz: (raw dict, height, width, bayer pattern, queued dict, max
+    refractory period) as the reference's own data/datasets.py produced them."""
+    gold = load_golden("raw_events")
+    raw = {k: gold[f"{name}/raw/{k}"] for k in ("position", "timestamp", "polarity")}
+    queued = {k[len(name) + 8:]: gold[k] for k in gold if k.startswith(f"{name}/queued/")}
+    return (raw, int(gold[f"{name}/height"]), int(gold[f"{name}/width"]), str(gold[f"{name}/bayer_pattern"]),
+            queued, np.asarray(gold[f"{name}/max_refractory_period"]))

@@ -4,7 +4,7 @@ oracle/ref_shim, CPU fp32).  Build container only (needs /root/reference):
     python tests/golden/make_golden.py
 
 Writes tests/golden/{training_step_pb_on,training_step_pb_off,training_step_eds,training_step_bayer,
-field_small}.npz (`python tests/golden/make_golden.py bayer` writes only the Bayer one).  Each
+field_small,raw_events}.npz (`python tests/golden/make_golden.py bayer` / `raw_events` write only that one).  Each
 file carries the parameters, the inputs (events, normalised samples, the stratified
 jitter the reference drew, the occupancy grid after its step-0 update) and the
 reference's outputs (loss, loss terms, mean samples per ray, every parameter gradient),
@@ -200,8 +200,57 @@ def field_golden(path):
     print(path, f"{os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def raw_event_stream(seed, n, height, width, hot_fraction=0.3, repeat_ts=0.2, sorted_ts=True):
+    """A raw event stream in the reference's `raw_events.npz` layout (data/datasets.py:19-21: position (N, 2)
+    uint16 (x, y), timestamp (N) int64, polarity (N) bool): part of the events crowd on a few hot pixels,
+    part of the timestamps repeat (the window tests of :163-168 and :246-253)."""
+    rng = np.random.default_rng(seed)
+    position = np.stack([rng.integers(0, width, n), rng.integers(0, height, n)], axis=1)
+    hot = rng.random(n) < hot_fraction
+    position[hot] = np.stack([rng.integers(0, min(width, 3), hot.sum()), rng.integers(0, min(height, 2), hot.sum())], axis=1)
+    step = rng.integers(1, 2000, n)
+    step[rng.random(n) < repeat_ts] = 0
+    timestamp = np.cumsum(step).astype(np.int64) + 1_000_000
+    if not sorted_ts:
+        timestamp = rng.permutation(timestamp)
+    return position.astype(np.uint16), timestamp, rng.random(n) < 0.5
+
+
+def raw_events_golden(path):
+    """Event.queue_raw_events / extract_max_refractory_period / colorize_events of the reference's OWN
+    data/datasets.py on small raw streams (time-ordered with repeats; shuffled in time; a Bayer sensor)."""
+    import tempfile
+    ds = ref_shim.load("data.datasets")
+    out = {}
+    cases = {"ordered": dict(seed=1, n=3000, height=9, width=13), "hot": dict(seed=2, n=2500, height=4, width=5, hot_fraction=0.8),
+             "shuffled": dict(seed=3, n=2000, height=7, width=6, sorted_ts=False),
+             "sparse": dict(seed=4, n=60, height=16, width=16, hot_fraction=0.0)}
+    for name, kw in cases.items():
+        position, timestamp, polarity = raw_event_stream(**kw)
+        calib = {"img_height": np.array(kw["height"], dtype=np.uint16), "img_width": np.array(kw["width"], dtype=np.uint16),
+                 "bayer_pattern": np.array("RGGB" if name == "hot" else "")}
+        with tempfile.TemporaryDirectory() as root:
+            np.savez(os.path.join(root, ds.Event.RAW_EVENTS_FILENAME), position=position, timestamp=timestamp,
+                     polarity=polarity)
+            queued = ds.Event.queue_raw_events(root, calib)
+            refractory = ds.Event.extract_max_refractory_period(
+                {"position": position, "timestamp": timestamp, "polarity": polarity}, calib)
+            queued = ds.Event.colorize_events(queued, calib)
+        out.update({f"{name}/raw/position": position, f"{name}/raw/timestamp": timestamp,
+                    f"{name}/raw/polarity": polarity, f"{name}/height": calib["img_height"],
+                    f"{name}/width": calib["img_width"], f"{name}/bayer_pattern": calib["bayer_pattern"],
+                    f"{name}/max_refractory_period": _np(refractory)})
+        out.update({f"{name}/queued/{k}": _np(v) for k, v in queued.items()})
+        print(name, len(position), "raw ->", len(queued["position"]), "queued; max refractory period", float(refractory))
+    np.savez_compressed(path, **out)
+    print(path, f"{os.path.getsize(path) / 1e6:.2f} MB")
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "needs /root/reference"
+    if sys.argv[1:] == ["raw_events"]:
+        raw_events_golden(os.path.join(HERE, "raw_events.npz"))
+        sys.exit(0)
     training_step_golden(True, os.path.join(HERE, "training_step_bayer.npz"), bayer=True)
     if sys.argv[1:] == ["bayer"]:
         sys.exit(0)
@@ -210,3 +259,4 @@ if __name__ == "__main__":
     field_golden(os.path.join(HERE, "field_small.npz"))
     training_step_eds_golden(os.path.join(HERE, "training_step_eds.npz"))
     conditioning_golden(os.path.join(HERE, "gradient_conditioning.npz"))
+    raw_events_golden(os.path.join(HERE, "raw_events.npz"))

@@ -62,3 +62,28 @@ def test_oracle_field_matches_reference_golden():
      + (sigma * torch.from_numpy(golden["w_sigma"])).sum()).backward()
     for key, p in field.named_parameters():
         _close(p.grad, golden["grad/" + key], 1e-5)
+
+
+RAW_EVENT_CASES, raw_event_case = _scene.RAW_EVENT_CASES, _scene.raw_event_case
+
+
+@pytest.mark.parametrize("name", RAW_EVENT_CASES)
+def test_oracle_raw_event_queueing_matches_reference_golden(name):
+    """oracle/events_ref.py (the literal loops AND the vectorised forms) against what the reference's OWN
+    Event.queue_raw_events / extract_max_refractory_period / colorize_events returned: bit for bit, dtypes
+    included."""
+    import numpy as np
+    from oracle import events_ref
+    raw, height, width, bayer, want, want_refractory = raw_event_case(name)
+    for fn in (events_ref.queue_raw_events_loop, events_ref.queue_raw_events):
+        got = fn(raw["position"], raw["timestamp"], raw["polarity"], height, width)
+        for key in ("position", "start_ts", "end_ts", "num_pos", "num_neg"):
+            assert got[key].dtype == want[key].dtype, (fn.__name__, key, got[key].dtype, want[key].dtype)
+            assert np.array_equal(got[key], want[key]), (fn.__name__, key)
+    for fn in (events_ref.max_refractory_period_loop, events_ref.max_refractory_period):
+        assert float(fn(raw["position"], raw["timestamp"], height, width)) == float(want_refractory), fn.__name__
+    channel = events_ref.colorize_events(want["position"], bayer)
+    if bayer:
+        assert channel.dtype == want["channel_idx"].dtype and np.array_equal(channel, want["channel_idx"])
+    else:
+        assert channel is None and "channel_idx" not in want

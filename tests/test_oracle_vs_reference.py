@@ -392,3 +392,33 @@ def test_offset_gamma_correction_model_matches_reference(shared_gamma):
         loss = ((f - target.double()) ** 2).sum()
         loss.backward()
         assert float(theta.grad.abs().max()) < 1e-6 * float(loss) + 1e-9
+
+
+def test_raw_event_queueing_matches_reference(tmp_path):
+    """oracle/events_ref.py against the reference's OWN Event.queue_raw_events /
+    extract_max_refractory_period / colorize_events (data/datasets.py:131-324) on a fresh seeded stream (the
+    committed golden holds four more): the literal loops and the vectorised forms, bit for bit."""
+    import numpy as np
+    from oracle import events_ref
+    sys_path = __import__("sys").path
+    sys_path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__file__), "golden"))
+    try:
+        from make_golden import raw_event_stream
+    finally:
+        sys_path.pop(0)
+    ds = ref_shim.load("data.datasets")
+    height, width = 11, 8
+    position, timestamp, polarity = raw_event_stream(seed=77, n=6000, height=height, width=width, hot_fraction=0.5)
+    calib = {"img_height": np.array(height, dtype=np.uint16), "img_width": np.array(width, dtype=np.uint16),
+             "bayer_pattern": np.array("BGGR")}
+    np.savez(tmp_path / ds.Event.RAW_EVENTS_FILENAME, position=position, timestamp=timestamp, polarity=polarity)
+    want = ds.Event.colorize_events(ds.Event.queue_raw_events(str(tmp_path), calib), calib)
+    want_refractory = ds.Event.extract_max_refractory_period(
+        {"position": position, "timestamp": timestamp, "polarity": polarity}, calib)
+    for fn in (events_ref.queue_raw_events_loop, events_ref.queue_raw_events):
+        got = fn(position, timestamp, polarity, height, width)
+        for key, value in got.items():
+            assert np.array_equal(value, want[key].numpy()) and value.dtype == want[key].numpy().dtype, (fn.__name__, key)
+    assert np.array_equal(events_ref.colorize_events(want["position"].numpy(), "BGGR"), want["channel_idx"].numpy())
+    for fn in (events_ref.max_refractory_period_loop, events_ref.max_refractory_period):
+        assert float(fn(position, timestamp, height, width)) == float(want_refractory)
