@@ -489,8 +489,8 @@ def run_raw_events(args):
     position, timestamp, polarity = events._raw_to_device(raw, dev)
 
     def step_device():
-        valid, start_ts, min_interval = events._stream_pass(position, timestamp, height, width)
-        return events._queued(position, timestamp, polarity, valid, start_ts), min_interval
+        valid, start_ts, offsets, min_interval, flag = events._stream_pass(position, timestamp, height, width)
+        return events._queued(position, timestamp, polarity, valid, start_ts, offsets, flag), min_interval
 
     for _ in range(args.warmup):
         step_device()
@@ -500,7 +500,7 @@ def run_raw_events(args):
     if rank == 0:
         clocks.start()
     launches0 = ops.launch_count()
-    ops.enable_kernel_timing(["den_queue_raw_events"], pool_size=2 * args.steps + 8)
+    ops.enable_kernel_timing(["den_queue_raw_events", "den_compact_queued_events"], pool_size=4 * args.steps + 8)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(args.steps):
@@ -508,7 +508,9 @@ def run_raw_events(args):
     end.record()
     ddp.barrier()
     torch.cuda.synchronize()
-    n_timed, total_kernel_ms = ops.kernel_timings()["den_queue_raw_events"]
+    timings = ops.kernel_timings()
+    n_timed, total_kernel_ms = timings["den_queue_raw_events"]
+    compact_ms = timings["den_compact_queued_events"][1] / max(timings["den_compact_queued_events"][0], 1)
     ops.disable_kernel_timing()
     ms_step = ddp.max_over_ranks(start.elapsed_time(end) / args.steps, dev)
     launches = ops.launch_count() - launches0
@@ -516,14 +518,18 @@ def run_raw_events(args):
     # end to end: the raw arrays from pinned host memory, the queued events back on the host
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.astype(np.int32) if k == "position" else v)).pin_memory()
               for k, v in raw.items()}
+    # pinned landing buffers for the queued events (capacity = the raw count), allocated once
+    landing = {k: torch.empty((n, 2) if k == "position" else (n,), dtype=torch.int64).pin_memory()
+               for k in ("position", "start_ts", "end_ts", "num_pos", "num_neg")}
     start.record()
     for _ in range(args.steps):
         pos_d = pinned["position"].to(dev, non_blocking=True)
         ts_d = pinned["timestamp"].to(dev, non_blocking=True)
         pol_d = pinned["polarity"].to(dev, non_blocking=True)
-        valid, start_ts, min_interval = events._stream_pass(pos_d, ts_d, height, width)
-        host = {k: v.cpu() for k, v in events._queued(pos_d, ts_d, pol_d, valid, start_ts).items()}
-        refractory = events._refractory_tensor(min_interval)
+        valid, start_ts, offsets, min_interval, flag = events._stream_pass(pos_d, ts_d, height, width)
+        kept = events._queued(pos_d, ts_d, pol_d, valid, start_ts, offsets, flag)
+        host = {k: landing[k][:len(v)].copy_(v, non_blocking=True) for k, v in kept.items()}
+        refractory = events._refractory_tensor(min_interval)          # .item(): also drains the copies
     end.record()
     ddp.barrier()
     torch.cuda.synchronize()
@@ -552,12 +558,13 @@ def run_raw_events(args):
         "gpu_launches": launches, "clocks": clock_info,
         "roofline": {"kernel": "den_queue_raw_events", "bound": "hbm", "achieved": algorithmic / (avg_kernel_ms * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": algorithmic / (avg_kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                     "traffic": None, "avg_launch_ms": avg_kernel_ms,
+                     "traffic": None, "avg_launch_ms": avg_kernel_ms, "compaction_ms": compact_ms,
                      "peak_source": ("measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)") + " HBM copy",
                      "note": "algorithmic bytes = 25 B per raw event (position + timestamp read, start_ts + valid "
                              "written); the entry point runs the key kernel, three radix passes (histogram, scan, "
-                             "stable scatter: ~24 B moved per event and pass) and the neighbour pass (two dependent "
-                             "timestamp gathers) — implementation traffic ~5x the algorithmic bytes"},
+                             "stable scatter: ~24 B moved per event and pass), the neighbour pass (two dependent "
+                             "timestamp gathers) and the prefix sum of the keep flags — implementation traffic ~5x "
+                             "the algorithmic bytes; den_compact_queued_events (compaction_ms) follows"},
         "cpu_baseline": None,
     }
     if not args.no_cpu_baseline:

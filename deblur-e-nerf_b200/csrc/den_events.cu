@@ -18,7 +18,9 @@
 //                              per-tile digit histograms -> one exclusive scan over [digit][tile] ->
 //                              stable scatter (rows of 256 consecutive elements in order; inside a row
 //                              __match_any_sync ranks the lanes of a warp, per-warp digit counts rank the warps)
-//   den_queue_raw_events       pixel keys -> sort -> neighbour pass (valid, start_ts, min interval)
+//   den_queue_raw_events       pixel keys -> sort -> neighbour pass (valid, start_ts, min interval) -> exclusive
+//                              scan of the flags (where each kept event goes)
+//   den_compact_queued_events  the kept events in stream order, in the reference's layout
 // Integer work, bit-exact against the reference's loops (oracle/events_ref.py, tests/golden/raw_events.npz).
 #include <limits.h>
 
@@ -120,7 +122,8 @@ __global__ void event_keys_kernel(const int32_t* __restrict__ position_xy, int64
 __global__ void __launch_bounds__(256)
 queue_events_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order,
                     const int64_t* __restrict__ timestamp, int64_t n, int64_t* __restrict__ start_ts,
-                    uint8_t* __restrict__ valid, long long* __restrict__ min_interval) {
+                    uint8_t* __restrict__ valid, int32_t* __restrict__ valid32,
+                    long long* __restrict__ min_interval) {
     long long local_min = LLONG_MAX;
     for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t i = order[s];
@@ -133,11 +136,33 @@ queue_events_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restric
             if (ok) local_min = min(local_min, ts - prev_ts);
         }
         valid[i] = ok ? 1 : 0;
+        valid32[i] = ok ? 1 : 0;
         start_ts[i] = ok ? prev_ts : 0;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, d));
     if ((threadIdx.x & 31) == 0 && local_min != LLONG_MAX) atomicMin(min_interval, local_min);
+}
+
+// kept events, in stream order, in the reference's layout (position int64 (M, 2), the rest int64 (M))
+__global__ void __launch_bounds__(256)
+compact_queued_kernel(const int32_t* __restrict__ position_xy, const int64_t* __restrict__ timestamp,
+                      const uint8_t* __restrict__ polarity, const int64_t* __restrict__ start_ts,
+                      const uint8_t* __restrict__ valid, const int32_t* __restrict__ kept_offsets, int64_t n,
+                      int64_t* __restrict__ out_position, int64_t* __restrict__ out_start_ts,
+                      int64_t* __restrict__ out_end_ts, int64_t* __restrict__ out_num_pos,
+                      int64_t* __restrict__ out_num_neg) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!valid[i]) continue;
+        const int64_t m = kept_offsets[i];
+        const int2 xy = __ldg(reinterpret_cast<const int2*>(position_xy) + i);
+        reinterpret_cast<longlong2*>(out_position)[m] = make_longlong2(xy.x, xy.y);
+        out_start_ts[m] = start_ts[i];
+        out_end_ts[m] = timestamp[i];
+        const int64_t pos = polarity[i] ? 1 : 0;
+        out_num_pos[m] = pos;
+        out_num_neg[m] = 1 - pos;
+    }
 }
 
 static int sort_tiles(int64_t n) { return (int)((n + kSortTile - 1) / kSortTile); }
@@ -212,16 +237,22 @@ int den_radix_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, u
 
 size_t den_queue_events_workspace_bytes(int64_t n) {
     const size_t arr = den::align256((size_t)(n < 1 ? 1 : n) * sizeof(uint32_t));
-    return 6 * arr + den::sort_workspace_bytes(n);
+    return 7 * arr + den::sort_workspace_bytes(n) + den::align256(den_scan_workspace_bytes(n < 1 ? 1 : n));
 }
 
 int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, int64_t n, int32_t width,
                          int32_t height, void* workspace, size_t workspace_bytes, int64_t* start_ts,
-                         uint8_t* valid, int64_t* min_interval, int32_t* out_of_range, void* stream) {
+                         uint8_t* valid, int32_t* kept_offsets, int64_t* min_interval, int32_t* out_of_range,
+                         void* stream) {
     using namespace den;
     DEN_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31), "event count out of range");
     DEN_CHECK_ARG(width >= 1 && height >= 1 && (int64_t)width * height <= ((int64_t)1 << 32), "bad sensor size");
-    if (n == 0) return DEN_OK;
+    DEN_CHECK_ARG(kept_offsets != nullptr, "null pointer");
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(kept_offsets, 0, sizeof(int32_t), as_stream(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "den_queue_raw_events");
+        return DEN_OK;
+    }
     DEN_CHECK_ARG(position_xy && timestamp && workspace && start_ts && valid && min_interval && out_of_range,
                   "null pointer");
     DEN_CHECK_ARG(workspace_bytes >= den_queue_events_workspace_bytes(n), "workspace too small");
@@ -233,14 +264,33 @@ int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, i
     uint32_t* v1 = reinterpret_cast<uint32_t*>(w + 3 * arr);
     uint32_t* k2 = reinterpret_cast<uint32_t*>(w + 4 * arr);
     uint32_t* v2 = reinterpret_cast<uint32_t*>(w + 5 * arr);
+    int32_t* valid32 = reinterpret_cast<int32_t*>(w + 6 * arr);
+    const size_t sort_ws = sort_workspace_bytes(n);
     cudaStream_t s = as_stream(stream);
     event_keys_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(position_xy, n, width, height, k0, v0, out_of_range);
     DEN_CHECK_LAUNCH();
-    int rc = radix_sort_pairs(k0, v0, k1, v1, k2, v2, n, bits_for((int64_t)width * height), w + 6 * arr,
-                              workspace_bytes - 6 * arr, s);
+    int rc = radix_sort_pairs(k0, v0, k1, v1, k2, v2, n, bits_for((int64_t)width * height), w + 7 * arr, sort_ws, s);
     if (rc) return rc;
-    queue_events_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(k1, v1, timestamp, n, start_ts, valid,
+    queue_events_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(k1, v1, timestamp, n, start_ts, valid, valid32,
                                                            reinterpret_cast<long long*>(min_interval));
+    DEN_CHECK_LAUNCH();
+    // kept_offsets[i] = number of kept events before i, kept_offsets[n] = M
+    return den_exclusive_scan_i32(valid32, kept_offsets, n, w + 7 * arr + sort_ws,
+                                  workspace_bytes - 7 * arr - sort_ws, s);
+}
+
+int den_compact_queued_events(const int32_t* position_xy, const int64_t* timestamp, const uint8_t* polarity,
+                              const int64_t* start_ts, const uint8_t* valid, const int32_t* kept_offsets,
+                              int64_t n, int64_t* out_position, int64_t* out_start_ts, int64_t* out_end_ts,
+                              int64_t* out_num_pos, int64_t* out_num_neg, void* stream) {
+    using namespace den;
+    DEN_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31), "event count out of range");
+    if (n == 0) return DEN_OK;
+    DEN_CHECK_ARG(position_xy && timestamp && polarity && start_ts && valid && kept_offsets, "null pointer");
+    DEN_CHECK_ARG(out_position && out_start_ts && out_end_ts && out_num_pos && out_num_neg, "null output");
+    compact_queued_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
+        position_xy, timestamp, polarity, start_ts, valid, kept_offsets, n, out_position, out_start_ts,
+        out_end_ts, out_num_pos, out_num_neg);
     DEN_CHECK_LAUNCH();
     return DEN_OK;
 }

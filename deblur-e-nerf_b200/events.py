@@ -8,7 +8,8 @@ its interval; the first event of a pixel, and an event that repeats the previous
 ``extract_max_refractory_period`` (:131-183: the smallest interval between distinct consecutive timestamps of
 a pixel).  Here both are ONE pass: a stable radix sort of the stream indices by pixel id puts the previous
 event of the pixel next to each event (``den_queue_raw_events``: key kernel, ``den_radix_sort_pairs_u32``,
-neighbour kernel); the valid events are then kept in stream order.  ``colorize_events`` (:278-324, the
+neighbour kernel, prefix sum of the keep flags); ``den_compact_queued_events`` then writes the kept events in
+stream order.  ``colorize_events`` (:278-324, the
 Bayer channel of a pixel) is elementwise; ``undistort_events`` (:326-365) calls OpenCV like upstream when
 the calibration carries distortion parameters.
 
@@ -43,25 +44,25 @@ def _raw_to_device(raw_events, device):
 
 
 def _stream_pass(position, timestamp, img_height, img_width):
-    """den_queue_raw_events over device tensors -> (valid (N) bool, start_ts (N) int64, min interval (1) int64)."""
+    """den_queue_raw_events over device tensors -> (valid (N) u8, start_ts (N) int64, kept_offsets (N + 1) int32,
+    min interval (1) int64)."""
     if not position.is_cuda:
         raise NotImplementedError("events: only CUDA tensors are supported (no CPU fallback)")
     n = position.shape[0]
     dev = position.device
-    valid = torch.zeros(n, dtype=torch.uint8, device=dev)
-    start_ts = torch.zeros(n, dtype=torch.int64, device=dev)
+    valid = torch.empty(n, dtype=torch.uint8, device=dev)
+    start_ts = torch.empty(n, dtype=torch.int64, device=dev)
+    offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
     min_interval = torch.full((1,), INT64_MAX, dtype=torch.int64, device=dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    if n:
-        nbytes = int(_lib.lib().cdll.den_queue_events_workspace_bytes(n))
-        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        ops._call("den_queue_raw_events", ops._ptr(position), ops._ptr(timestamp), n, int(img_width),
-                  int(img_height), ops._ptr(workspace), ctypes.c_size_t(nbytes), ops._ptr(start_ts),
-                  ops._ptr(valid), ops._ptr(min_interval), ops._ptr(flag), ops._stream(),
-                  launches=2 + 5 * max(1, (max(int(img_width) * int(img_height) - 1, 1).bit_length() + 7) // 8))
-        if int(flag.item()):
-            raise IndexError("raw events: a position lies outside the img_width x img_height sensor")
-    return valid.bool(), start_ts, min_interval
+    nbytes = int(_lib.lib().cdll.den_queue_events_workspace_bytes(n))
+    workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    passes = max(1, (max(int(img_width) * int(img_height) - 1, 1).bit_length() + 7) // 8)
+    ops._call("den_queue_raw_events", ops._ptr(position), ops._ptr(timestamp), n, int(img_width),
+              int(img_height), ops._ptr(workspace), ctypes.c_size_t(nbytes), ops._ptr(start_ts),
+              ops._ptr(valid), ops._ptr(offsets), ops._ptr(min_interval), ops._ptr(flag), ops._stream(),
+              launches=(5 + 5 * passes) if n else 0)
+    return valid, start_ts, offsets, min_interval, flag
 
 
 def _refractory_tensor(min_interval):
@@ -70,27 +71,42 @@ def _refractory_tensor(min_interval):
     return torch.tensor(float("inf"), dtype=torch.float64) if value == INT64_MAX else torch.tensor(value)
 
 
-def _queued(position, timestamp, polarity, valid, start_ts):
-    pol = polarity.to(torch.int64)
-    return {"position": position.to(torch.int64)[valid], "start_ts": start_ts[valid], "end_ts": timestamp[valid],
-            "num_pos": pol[valid], "num_neg": (1 - pol)[valid]}
+def _queued(position, timestamp, polarity, valid, start_ts, offsets, flag):
+    """den_compact_queued_events: the kept events in stream order.  Reads the kept count and the range flag
+    back (the one host synchronisation of the pass)."""
+    n = position.shape[0]
+    head = torch.stack((offsets[n], flag[0])).tolist()
+    if head[1]:
+        raise IndexError("raw events: a position lies outside the img_width x img_height sensor")
+    m = int(head[0])
+    dev = position.device
+    out = {"position": torch.empty((m, 2), dtype=torch.int64, device=dev)}
+    out.update({k: torch.empty(m, dtype=torch.int64, device=dev) for k in ("start_ts", "end_ts", "num_pos", "num_neg")})
+    pol = polarity if polarity.dtype in (torch.bool, torch.uint8) else (polarity != 0)
+    ops._call("den_compact_queued_events", ops._ptr(position), ops._ptr(timestamp), ops._ptr(pol.contiguous()),
+              ops._ptr(start_ts), ops._ptr(valid), ops._ptr(offsets), n, ops._ptr(out["position"]),
+              ops._ptr(out["start_ts"]), ops._ptr(out["end_ts"]), ops._ptr(out["num_pos"]), ops._ptr(out["num_neg"]),
+              ops._stream(), launches=1 if n else 0)
+    return out
 
 
 def queue_raw_events(raw_events, camera_calibration, device="cuda"):
     """``Event.queue_raw_events`` (:186-276) for an in-memory raw stream: dict(position (M, 2) int64, start_ts,
     end_ts, num_pos, num_neg (M) int64) on `device`, the kept events in stream order."""
     position, timestamp, polarity = _raw_to_device(raw_events, torch.device(device))
-    valid, start_ts, _ = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
-                                      int(camera_calibration["img_width"]))
-    return _queued(position, timestamp, polarity, valid, start_ts)
+    valid, start_ts, offsets, _, flag = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
+                                                     int(camera_calibration["img_width"]))
+    return _queued(position, timestamp, polarity, valid, start_ts, offsets, flag)
 
 
 def extract_max_refractory_period(raw_events, camera_calibration, device="cuda"):
     """``Event.extract_max_refractory_period`` (:131-183): 0-d tensor, the minimum event interval over the
     per-pixel substreams (events repeating the previous timestamp of their pixel are skipped)."""
     position, timestamp, _ = _raw_to_device(raw_events, torch.device(device))
-    _, _, min_interval = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
-                                      int(camera_calibration["img_width"]))
+    _, _, _, min_interval, flag = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
+                                               int(camera_calibration["img_width"]))
+    if int(flag.item()):
+        raise IndexError("raw events: a position lies outside the img_width x img_height sensor")
     return _refractory_tensor(min_interval)
 
 
@@ -139,9 +155,9 @@ def transform_raw_events(raw_events, camera_calibration, device="cuda"):
     """The raw branch of ``Event.__init__`` (:44-54) — queue, colourise, undistort — and the maximum refractory
     period of the same stream, from ONE sort of the raw events.  Returns (events dict on `device`, 0-d tensor)."""
     position, timestamp, polarity = _raw_to_device(raw_events, torch.device(device))
-    valid, start_ts, min_interval = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
-                                                 int(camera_calibration["img_width"]))
-    events = _queued(position, timestamp, polarity, valid, start_ts)
+    valid, start_ts, offsets, min_interval, flag = _stream_pass(
+        position, timestamp, int(camera_calibration["img_height"]), int(camera_calibration["img_width"]))
+    events = _queued(position, timestamp, polarity, valid, start_ts, offsets, flag)
     events = undistort_events(colorize_events(events, camera_calibration), camera_calibration)
     return events, _refractory_tensor(min_interval)
 

@@ -480,9 +480,14 @@ int den_eval_ssim(const float* pred, const float* target, int32_t B, int32_t C, 
  *       min_interval (1) int64, PRE-SET by the caller to INT64_MAX: atomically lowered to the smallest
  *           non-zero timestamp[i] - timestamp[prev(i)] — the maximum refractory period of :131-183
  *           (still INT64_MAX: no pixel saw two distinct timestamps; upstream keeps +inf);
+ *       kept_offsets (n + 1) int32: exclusive prefix sum of `valid` — the row of event i among the kept
+ *           events; kept_offsets[n] = their number M;
  *       out_of_range (1) int32, pre-zeroed: set to 1 if a position lies outside width x height (upstream
  *           raises IndexError; the caller checks the flag).
  *       workspace >= den_queue_events_workspace_bytes(n).  n < 2^31.
+ *   den_compact_queued_events: the kept events in stream order in upstream's layout (:232-238,270-274):
+ *       out_position (M, 2) int64, out_start_ts / out_end_ts / out_num_pos / out_num_neg (M) int64;
+ *       polarity (n) u8 (0 / 1).
  * ------------------------------------------------------------------------- */
 size_t den_radix_sort_workspace_bytes(int64_t n);
 int den_radix_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
@@ -491,7 +496,12 @@ int den_radix_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, u
 size_t den_queue_events_workspace_bytes(int64_t n);
 int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, int64_t n, int32_t width,
                          int32_t height, void* workspace, size_t workspace_bytes, int64_t* start_ts,
-                         uint8_t* valid, int64_t* min_interval, int32_t* out_of_range, void* stream);
+                         uint8_t* valid, int32_t* kept_offsets, int64_t* min_interval, int32_t* out_of_range,
+                         void* stream);
+int den_compact_queued_events(const int32_t* position_xy, const int64_t* timestamp, const uint8_t* polarity,
+                              const int64_t* start_ts, const uint8_t* valid, const int32_t* kept_offsets,
+                              int64_t n, int64_t* out_position, int64_t* out_start_ts, int64_t* out_end_ts,
+                              int64_t* out_num_pos, int64_t* out_num_neg, void* stream);
 
 #ifdef __cplusplus
 }
