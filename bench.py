@@ -488,9 +488,11 @@ def run_raw_events(args):
     calib = {"img_height": height, "img_width": width, "bayer_pattern": "", "distortion_params": np.zeros(0)}
     position, timestamp, polarity = events._raw_to_device(raw, dev)
 
+    scratch = {}                # buffers of one stream size, reused by every pass (no allocator traffic)
+
     def step_device():
-        valid, start_ts, offsets, min_interval, flag = events._stream_pass(position, timestamp, height, width)
-        return events._queued(position, timestamp, polarity, valid, start_ts, offsets, flag), min_interval
+        valid, start_ts, offsets, min_interval, flag = events._stream_pass(position, timestamp, height, width, scratch)
+        return events._queued(position, timestamp, polarity, valid, start_ts, offsets, flag, scratch), min_interval
 
     for _ in range(args.warmup):
         step_device()
@@ -526,8 +528,8 @@ def run_raw_events(args):
         pos_d = pinned["position"].to(dev, non_blocking=True)
         ts_d = pinned["timestamp"].to(dev, non_blocking=True)
         pol_d = pinned["polarity"].to(dev, non_blocking=True)
-        valid, start_ts, offsets, min_interval, flag = events._stream_pass(pos_d, ts_d, height, width)
-        kept = events._queued(pos_d, ts_d, pol_d, valid, start_ts, offsets, flag)
+        valid, start_ts, offsets, min_interval, flag = events._stream_pass(pos_d, ts_d, height, width, scratch)
+        kept = events._queued(pos_d, ts_d, pol_d, valid, start_ts, offsets, flag, scratch)
         host = {k: landing[k][:len(v)].copy_(v, non_blocking=True) for k, v in kept.items()}
         refractory = events._refractory_tensor(min_interval)          # .item(): also drains the copies
     end.record()

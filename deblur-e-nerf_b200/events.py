@@ -43,20 +43,31 @@ def _raw_to_device(raw_events, device):
     return position, timestamp.contiguous(), polarity
 
 
-def _stream_pass(position, timestamp, img_height, img_width):
+def _buffer(scratch, name, shape, dtype, device):
+    """A tensor from `scratch` (a dict reused across passes over streams of one size: no allocator traffic in
+    a repeated pass) or a fresh one."""
+    if scratch is None:
+        return torch.empty(shape, dtype=dtype, device=device)
+    t = scratch.get(name)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != device:
+        t = scratch[name] = torch.empty(shape, dtype=dtype, device=device)
+    return t
+
+
+def _stream_pass(position, timestamp, img_height, img_width, scratch=None):
     """den_queue_raw_events over device tensors -> (valid (N) u8, start_ts (N) int64, kept_offsets (N + 1) int32,
-    min interval (1) int64)."""
+    min interval (1) int64, out-of-range flag (1) int32)."""
     if not position.is_cuda:
         raise NotImplementedError("events: only CUDA tensors are supported (no CPU fallback)")
     n = position.shape[0]
     dev = position.device
-    valid = torch.empty(n, dtype=torch.uint8, device=dev)
-    start_ts = torch.empty(n, dtype=torch.int64, device=dev)
-    offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    valid = _buffer(scratch, "valid", (n,), torch.uint8, dev)
+    start_ts = _buffer(scratch, "start_ts", (n,), torch.int64, dev)
+    offsets = _buffer(scratch, "offsets", (n + 1,), torch.int32, dev)
     min_interval = torch.full((1,), INT64_MAX, dtype=torch.int64, device=dev)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     nbytes = int(_lib.lib().cdll.den_queue_events_workspace_bytes(n))
-    workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    workspace = _buffer(scratch, "workspace", (nbytes,), torch.uint8, dev)
     passes = max(1, (max(int(img_width) * int(img_height) - 1, 1).bit_length() + 7) // 8)
     ops._call("den_queue_raw_events", ops._ptr(position), ops._ptr(timestamp), n, int(img_width),
               int(img_height), ops._ptr(workspace), ctypes.c_size_t(nbytes), ops._ptr(start_ts),
@@ -71,22 +82,26 @@ def _refractory_tensor(min_interval):
     return torch.tensor(float("inf"), dtype=torch.float64) if value == INT64_MAX else torch.tensor(value)
 
 
-def _queued(position, timestamp, polarity, valid, start_ts, offsets, flag):
+def _queued(position, timestamp, polarity, valid, start_ts, offsets, flag, scratch=None):
     """den_compact_queued_events: the kept events in stream order.  Reads the kept count and the range flag
-    back (the one host synchronisation of the pass)."""
+    back (the one host synchronisation of the pass).  With `scratch` the results are views of buffers sized
+    for the whole stream (valid until the next pass over the same scratch)."""
     n = position.shape[0]
     head = torch.stack((offsets[n], flag[0])).tolist()
     if head[1]:
         raise IndexError("raw events: a position lies outside the img_width x img_height sensor")
     m = int(head[0])
     dev = position.device
-    out = {"position": torch.empty((m, 2), dtype=torch.int64, device=dev)}
-    out.update({k: torch.empty(m, dtype=torch.int64, device=dev) for k in ("start_ts", "end_ts", "num_pos", "num_neg")})
-    pol = polarity if polarity.dtype in (torch.bool, torch.uint8) else (polarity != 0)
-    ops._call("den_compact_queued_events", ops._ptr(position), ops._ptr(timestamp), ops._ptr(pol.contiguous()),
-              ops._ptr(start_ts), ops._ptr(valid), ops._ptr(offsets), n, ops._ptr(out["position"]),
-              ops._ptr(out["start_ts"]), ops._ptr(out["end_ts"]), ops._ptr(out["num_pos"]), ops._ptr(out["num_neg"]),
-              ops._stream(), launches=1 if n else 0)
+    rows = m if scratch is None else n
+    out = {"position": _buffer(scratch, "out_position", (rows, 2), torch.int64, dev)[:m]}
+    out.update({k: _buffer(scratch, "out_" + k, (rows,), torch.int64, dev)[:m]
+                for k in ("start_ts", "end_ts", "num_pos", "num_neg")})
+    if m:
+        pol = polarity if polarity.dtype in (torch.bool, torch.uint8) else (polarity != 0)
+        ops._call("den_compact_queued_events", ops._ptr(position), ops._ptr(timestamp), ops._ptr(pol.contiguous()),
+                  ops._ptr(start_ts), ops._ptr(valid), ops._ptr(offsets), n, ops._ptr(out["position"]),
+                  ops._ptr(out["start_ts"]), ops._ptr(out["end_ts"]), ops._ptr(out["num_pos"]),
+                  ops._ptr(out["num_neg"]), ops._stream())
     return out
 
 
