@@ -491,8 +491,8 @@ def run_raw_events(args):
     scratch = {}                # buffers of one stream size, reused by every pass (no allocator traffic)
 
     def step_device():
-        valid, start_ts, offsets, min_interval, flag = events._stream_pass(position, timestamp, height, width, scratch)
-        return events._queued(position, timestamp, polarity, valid, start_ts, offsets, flag, scratch), min_interval
+        start_ts, offsets, min_interval, flag = events._stream_pass(position, timestamp, height, width, scratch)
+        return events._queued(position, timestamp, polarity, start_ts, offsets, flag, scratch), min_interval
 
     for _ in range(args.warmup):
         step_device()
@@ -528,8 +528,8 @@ def run_raw_events(args):
         pos_d = pinned["position"].to(dev, non_blocking=True)
         ts_d = pinned["timestamp"].to(dev, non_blocking=True)
         pol_d = pinned["polarity"].to(dev, non_blocking=True)
-        valid, start_ts, offsets, min_interval, flag = events._stream_pass(pos_d, ts_d, height, width, scratch)
-        kept = events._queued(pos_d, ts_d, pol_d, valid, start_ts, offsets, flag, scratch)
+        start_ts, offsets, min_interval, flag = events._stream_pass(pos_d, ts_d, height, width, scratch)
+        kept = events._queued(pos_d, ts_d, pol_d, start_ts, offsets, flag, scratch)
         host = {k: landing[k][:len(v)].copy_(v, non_blocking=True) for k, v in kept.items()}
         refractory = events._refractory_tensor(min_interval)          # .item(): also drains the copies
     end.record()
@@ -545,7 +545,7 @@ def run_raw_events(args):
             peaks = json.load(fh)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     avg_kernel_ms = total_kernel_ms / max(n_timed, 1)
-    algorithmic = 25.0 * n                 # 8 B position + 8 B timestamp read, 8 B start_ts + 1 B valid written
+    algorithmic = 28.0 * n                 # 8 B position + 8 B timestamp read, 8 B start_ts + 4 B keep flag written
     line = {
         "metric": "raw events/s (queue + max refractory period)", "value": total / (ms_step * 1e-3),
         "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -562,7 +562,7 @@ def run_raw_events(args):
                      "peak": hbm_peak, "unit": "GB/s", "frac": algorithmic / (avg_kernel_ms * 1e-3) / 1e9 / hbm_peak,
                      "traffic": None, "avg_launch_ms": avg_kernel_ms, "compaction_ms": compact_ms,
                      "peak_source": ("measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)") + " HBM copy",
-                     "note": "algorithmic bytes = 25 B per raw event (position + timestamp read, start_ts + valid "
+                     "note": "algorithmic bytes = 28 B per raw event (position + timestamp read, start_ts + keep flag "
                              "written); the entry point runs the key kernel, three radix passes (histogram, scan, "
                              "stable scatter: ~24 B moved per event and pass), the neighbour pass (two dependent "
                              "timestamp gathers) and the prefix sum of the keep flags — implementation traffic ~5x "

@@ -141,8 +141,8 @@ _SIGNATURES = {
     "den_radix_sort_workspace_bytes": (_SZ, [_I64]),
     "den_radix_sort_pairs_u32": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P, _SZ, _P]),
     "den_queue_events_workspace_bytes": (_SZ, [_I64]),
-    "den_queue_raw_events": (_INT, [_P, _P, _I64, _I32, _I32, _P, _SZ, _P, _P, _P, _P, _P, _P]),
-    "den_compact_queued_events": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "den_queue_raw_events": (_INT, [_P, _P, _I64, _I32, _I32, _P, _SZ, _P, _P, _P, _P, _P]),
+    "den_compact_queued_events": (_INT, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "den_composite_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
 }

@@ -18,8 +18,8 @@
 //                              per-tile digit histograms -> one exclusive scan over [digit][tile] ->
 //                              stable scatter (rows of 256 consecutive elements in order; inside a row
 //                              __match_any_sync ranks the lanes of a warp, per-warp digit counts rank the warps)
-//   den_queue_raw_events       pixel keys -> sort -> neighbour pass (valid, start_ts, min interval) -> exclusive
-//                              scan of the flags (where each kept event goes)
+//   den_queue_raw_events       pixel keys -> sort -> neighbour pass (keep flag, start_ts, min interval) ->
+//                              exclusive scan of the flags (where each kept event goes)
 //   den_compact_queued_events  the kept events in stream order, in the reference's layout
 // Integer work, bit-exact against the reference's loops (oracle/events_ref.py, tests/golden/raw_events.npz).
 #include <limits.h>
@@ -118,43 +118,64 @@ __global__ void event_keys_kernel(const int32_t* __restrict__ position_xy, int64
     }
 }
 
-// sorted (key, index) pairs -> per event (stream order): valid, start_ts; global min of the non-zero intervals
+// sorted (key, index) pairs -> per event (stream order): keep flag, start_ts; global min of the non-zero
+// intervals.  Each thread fetches the timestamp of ITS event (one random 8-byte read); the left neighbour's
+// comes over a shuffle (lane 0 fetches it).  One atomicMin per CTA.
 __global__ void __launch_bounds__(256)
 queue_events_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ order,
                     const int64_t* __restrict__ timestamp, int64_t n, int64_t* __restrict__ start_ts,
-                    uint8_t* __restrict__ valid, int32_t* __restrict__ valid32,
-                    long long* __restrict__ min_interval) {
+                    int32_t* __restrict__ keep, long long* __restrict__ min_interval) {
+    __shared__ long long s_min[8];
+    const int lane = threadIdx.x & 31;
     long long local_min = LLONG_MAX;
-    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t i = order[s];
-        bool ok = false;
-        long long prev_ts = 0;
-        if (s > 0 && keys[s - 1] == keys[s]) {
-            prev_ts = timestamp[order[s - 1]];
-            const long long ts = timestamp[i];
-            ok = prev_ts != ts;
-            if (ok) local_min = min(local_min, ts - prev_ts);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (n + stride - 1) / stride;               // every lane runs every round (shuffles)
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int64_t s = r * stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const bool in = s < n;
+        uint32_t i = 0, key = 0;
+        long long ts = 0;
+        if (in) {
+            i = order[s];
+            key = keys[s];
+            ts = timestamp[i];
         }
-        valid[i] = ok ? 1 : 0;
-        valid32[i] = ok ? 1 : 0;
-        start_ts[i] = ok ? prev_ts : 0;
+        uint32_t key_left = __shfl_up_sync(0xffffffffu, key, 1);
+        long long ts_left = __shfl_up_sync(0xffffffffu, ts, 1);
+        if (lane == 0 && in && s > 0) {
+            key_left = keys[s - 1];
+            ts_left = timestamp[order[s - 1]];
+        }
+        if (in) {
+            const bool ok = s > 0 && key_left == key && ts_left != ts;
+            if (ok) local_min = min(local_min, ts - ts_left);
+            keep[i] = ok ? 1 : 0;
+            start_ts[i] = ok ? ts_left : 0;
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, d));
-    if ((threadIdx.x & 31) == 0 && local_min != LLONG_MAX) atomicMin(min_interval, local_min);
+    if (lane == 0) s_min[threadIdx.x >> 5] = local_min;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long m = s_min[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = min(m, s_min[w]);
+        if (m != LLONG_MAX) atomicMin(min_interval, m);
+    }
 }
 
 // kept events, in stream order, in the reference's layout (position int64 (M, 2), the rest int64 (M))
 __global__ void __launch_bounds__(256)
 compact_queued_kernel(const int32_t* __restrict__ position_xy, const int64_t* __restrict__ timestamp,
                       const uint8_t* __restrict__ polarity, const int64_t* __restrict__ start_ts,
-                      const uint8_t* __restrict__ valid, const int32_t* __restrict__ kept_offsets, int64_t n,
+                      const int32_t* __restrict__ kept_offsets, int64_t n,
                       int64_t* __restrict__ out_position, int64_t* __restrict__ out_start_ts,
                       int64_t* __restrict__ out_end_ts, int64_t* __restrict__ out_num_pos,
                       int64_t* __restrict__ out_num_neg) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        if (!valid[i]) continue;
         const int64_t m = kept_offsets[i];
+        if (kept_offsets[i + 1] == m) continue;                    // not kept: the prefix sum did not move
         const int2 xy = __ldg(reinterpret_cast<const int2*>(position_xy) + i);
         reinterpret_cast<longlong2*>(out_position)[m] = make_longlong2(xy.x, xy.y);
         out_start_ts[m] = start_ts[i];
@@ -242,8 +263,7 @@ size_t den_queue_events_workspace_bytes(int64_t n) {
 
 int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, int64_t n, int32_t width,
                          int32_t height, void* workspace, size_t workspace_bytes, int64_t* start_ts,
-                         uint8_t* valid, int32_t* kept_offsets, int64_t* min_interval, int32_t* out_of_range,
-                         void* stream) {
+                         int32_t* kept_offsets, int64_t* min_interval, int32_t* out_of_range, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31), "event count out of range");
     DEN_CHECK_ARG(width >= 1 && height >= 1 && (int64_t)width * height <= ((int64_t)1 << 32), "bad sensor size");
@@ -253,8 +273,7 @@ int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, i
         if (e != cudaSuccess) return cuda_fail(e, "den_queue_raw_events");
         return DEN_OK;
     }
-    DEN_CHECK_ARG(position_xy && timestamp && workspace && start_ts && valid && min_interval && out_of_range,
-                  "null pointer");
+    DEN_CHECK_ARG(position_xy && timestamp && workspace && start_ts && min_interval && out_of_range, "null pointer");
     DEN_CHECK_ARG(workspace_bytes >= den_queue_events_workspace_bytes(n), "workspace too small");
     const size_t arr = align256((size_t)n * sizeof(uint32_t));
     uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
@@ -271,7 +290,7 @@ int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, i
     DEN_CHECK_LAUNCH();
     int rc = radix_sort_pairs(k0, v0, k1, v1, k2, v2, n, bits_for((int64_t)width * height), w + 7 * arr, sort_ws, s);
     if (rc) return rc;
-    queue_events_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(k1, v1, timestamp, n, start_ts, valid, valid32,
+    queue_events_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(k1, v1, timestamp, n, start_ts, valid32,
                                                            reinterpret_cast<long long*>(min_interval));
     DEN_CHECK_LAUNCH();
     // kept_offsets[i] = number of kept events before i, kept_offsets[n] = M
@@ -280,16 +299,16 @@ int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, i
 }
 
 int den_compact_queued_events(const int32_t* position_xy, const int64_t* timestamp, const uint8_t* polarity,
-                              const int64_t* start_ts, const uint8_t* valid, const int32_t* kept_offsets,
-                              int64_t n, int64_t* out_position, int64_t* out_start_ts, int64_t* out_end_ts,
+                              const int64_t* start_ts, const int32_t* kept_offsets, int64_t n,
+                              int64_t* out_position, int64_t* out_start_ts, int64_t* out_end_ts,
                               int64_t* out_num_pos, int64_t* out_num_neg, void* stream) {
     using namespace den;
     DEN_CHECK_ARG(n >= 0 && n < ((int64_t)1 << 31), "event count out of range");
     if (n == 0) return DEN_OK;
-    DEN_CHECK_ARG(position_xy && timestamp && polarity && start_ts && valid && kept_offsets, "null pointer");
+    DEN_CHECK_ARG(position_xy && timestamp && polarity && start_ts && kept_offsets, "null pointer");
     DEN_CHECK_ARG(out_position && out_start_ts && out_end_ts && out_num_pos && out_num_neg, "null output");
     compact_queued_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(
-        position_xy, timestamp, polarity, start_ts, valid, kept_offsets, n, out_position, out_start_ts,
+        position_xy, timestamp, polarity, start_ts, kept_offsets, n, out_position, out_start_ts,
         out_end_ts, out_num_pos, out_num_neg);
     DEN_CHECK_LAUNCH();
     return DEN_OK;

@@ -55,13 +55,12 @@ def _buffer(scratch, name, shape, dtype, device):
 
 
 def _stream_pass(position, timestamp, img_height, img_width, scratch=None):
-    """den_queue_raw_events over device tensors -> (valid (N) u8, start_ts (N) int64, kept_offsets (N + 1) int32,
-    min interval (1) int64, out-of-range flag (1) int32)."""
+    """den_queue_raw_events over device tensors -> (start_ts (N) int64, kept_offsets (N + 1) int32, min interval
+    (1) int64, out-of-range flag (1) int32)."""
     if not position.is_cuda:
         raise NotImplementedError("events: only CUDA tensors are supported (no CPU fallback)")
     n = position.shape[0]
     dev = position.device
-    valid = _buffer(scratch, "valid", (n,), torch.uint8, dev)
     start_ts = _buffer(scratch, "start_ts", (n,), torch.int64, dev)
     offsets = _buffer(scratch, "offsets", (n + 1,), torch.int32, dev)
     min_interval = torch.full((1,), INT64_MAX, dtype=torch.int64, device=dev)
@@ -71,9 +70,9 @@ def _stream_pass(position, timestamp, img_height, img_width, scratch=None):
     passes = max(1, (max(int(img_width) * int(img_height) - 1, 1).bit_length() + 7) // 8)
     ops._call("den_queue_raw_events", ops._ptr(position), ops._ptr(timestamp), n, int(img_width),
               int(img_height), ops._ptr(workspace), ctypes.c_size_t(nbytes), ops._ptr(start_ts),
-              ops._ptr(valid), ops._ptr(offsets), ops._ptr(min_interval), ops._ptr(flag), ops._stream(),
+              ops._ptr(offsets), ops._ptr(min_interval), ops._ptr(flag), ops._stream(),
               launches=(5 + 5 * passes) if n else 0)
-    return valid, start_ts, offsets, min_interval, flag
+    return start_ts, offsets, min_interval, flag
 
 
 def _refractory_tensor(min_interval):
@@ -82,7 +81,7 @@ def _refractory_tensor(min_interval):
     return torch.tensor(float("inf"), dtype=torch.float64) if value == INT64_MAX else torch.tensor(value)
 
 
-def _queued(position, timestamp, polarity, valid, start_ts, offsets, flag, scratch=None):
+def _queued(position, timestamp, polarity, start_ts, offsets, flag, scratch=None):
     """den_compact_queued_events: the kept events in stream order.  Reads the kept count and the range flag
     back (the one host synchronisation of the pass).  With `scratch` the results are views of buffers sized
     for the whole stream (valid until the next pass over the same scratch)."""
@@ -99,7 +98,7 @@ def _queued(position, timestamp, polarity, valid, start_ts, offsets, flag, scrat
     if m:
         pol = polarity if polarity.dtype in (torch.bool, torch.uint8) else (polarity != 0)
         ops._call("den_compact_queued_events", ops._ptr(position), ops._ptr(timestamp), ops._ptr(pol.contiguous()),
-                  ops._ptr(start_ts), ops._ptr(valid), ops._ptr(offsets), n, ops._ptr(out["position"]),
+                  ops._ptr(start_ts), ops._ptr(offsets), n, ops._ptr(out["position"]),
                   ops._ptr(out["start_ts"]), ops._ptr(out["end_ts"]), ops._ptr(out["num_pos"]),
                   ops._ptr(out["num_neg"]), ops._stream())
     return out
@@ -109,16 +108,16 @@ def queue_raw_events(raw_events, camera_calibration, device="cuda"):
     """``Event.queue_raw_events`` (:186-276) for an in-memory raw stream: dict(position (M, 2) int64, start_ts,
     end_ts, num_pos, num_neg (M) int64) on `device`, the kept events in stream order."""
     position, timestamp, polarity = _raw_to_device(raw_events, torch.device(device))
-    valid, start_ts, offsets, _, flag = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
-                                                     int(camera_calibration["img_width"]))
-    return _queued(position, timestamp, polarity, valid, start_ts, offsets, flag)
+    start_ts, offsets, _, flag = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
+                                              int(camera_calibration["img_width"]))
+    return _queued(position, timestamp, polarity, start_ts, offsets, flag)
 
 
 def extract_max_refractory_period(raw_events, camera_calibration, device="cuda"):
     """``Event.extract_max_refractory_period`` (:131-183): 0-d tensor, the minimum event interval over the
     per-pixel substreams (events repeating the previous timestamp of their pixel are skipped)."""
     position, timestamp, _ = _raw_to_device(raw_events, torch.device(device))
-    _, _, _, min_interval, flag = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
+    _, _, min_interval, flag = _stream_pass(position, timestamp, int(camera_calibration["img_height"]),
                                                int(camera_calibration["img_width"]))
     if int(flag.item()):
         raise IndexError("raw events: a position lies outside the img_width x img_height sensor")
@@ -170,9 +169,9 @@ def transform_raw_events(raw_events, camera_calibration, device="cuda"):
     """The raw branch of ``Event.__init__`` (:44-54) — queue, colourise, undistort — and the maximum refractory
     period of the same stream, from ONE sort of the raw events.  Returns (events dict on `device`, 0-d tensor)."""
     position, timestamp, polarity = _raw_to_device(raw_events, torch.device(device))
-    valid, start_ts, offsets, min_interval, flag = _stream_pass(
+    start_ts, offsets, min_interval, flag = _stream_pass(
         position, timestamp, int(camera_calibration["img_height"]), int(camera_calibration["img_width"]))
-    events = _queued(position, timestamp, polarity, valid, start_ts, offsets, flag)
+    events = _queued(position, timestamp, polarity, start_ts, offsets, flag)
     events = undistort_events(colorize_events(events, camera_calibration), camera_calibration)
     return events, _refractory_tensor(min_interval)
 

@@ -473,15 +473,16 @@ int den_eval_ssim(const float* pred, const float* target, int32_t B, int32_t C, 
  *       bits (8 per pass); the result lands in (keys_out, vals_out), (keys_tmp, vals_tmp) is scratch of the
  *       same size; the inputs are not modified.  workspace >= den_radix_sort_workspace_bytes(n).
  *   den_queue_raw_events: position_xy (n, 2) int32 (x, y), timestamp (n) int64 in stream order ->
- *       valid (n) u8: 1 iff an earlier event exists at the pixel and the latest one has a different timestamp
- *           (the sliding-window test of :246-253);
- *       start_ts (n) int64: that event's timestamp (0 where invalid); end_ts is `timestamp` itself, num_pos
- *           / num_neg are polarity / 1 - polarity (:255-267) and are formed by the caller;
+ *       an event is KEPT iff an earlier event exists at its pixel and the latest one has a different
+ *           timestamp (the sliding-window test of :246-253);
+ *       start_ts (n) int64: that earlier event's timestamp (0 where not kept); end_ts is `timestamp` itself,
+ *           num_pos / num_neg are polarity / 1 - polarity (:255-267);
  *       min_interval (1) int64, PRE-SET by the caller to INT64_MAX: atomically lowered to the smallest
  *           non-zero timestamp[i] - timestamp[prev(i)] — the maximum refractory period of :131-183
  *           (still INT64_MAX: no pixel saw two distinct timestamps; upstream keeps +inf);
- *       kept_offsets (n + 1) int32: exclusive prefix sum of `valid` — the row of event i among the kept
- *           events; kept_offsets[n] = their number M;
+ *       kept_offsets (n + 1) int32: exclusive prefix sum of the keep flags — the row of event i among the
+ *           kept events (event i is kept iff kept_offsets[i + 1] > kept_offsets[i]); kept_offsets[n] = their
+ *           number M;
  *       out_of_range (1) int32, pre-zeroed: set to 1 if a position lies outside width x height (upstream
  *           raises IndexError; the caller checks the flag).
  *       workspace >= den_queue_events_workspace_bytes(n).  n < 2^31.
@@ -496,11 +497,10 @@ int den_radix_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, u
 size_t den_queue_events_workspace_bytes(int64_t n);
 int den_queue_raw_events(const int32_t* position_xy, const int64_t* timestamp, int64_t n, int32_t width,
                          int32_t height, void* workspace, size_t workspace_bytes, int64_t* start_ts,
-                         uint8_t* valid, int32_t* kept_offsets, int64_t* min_interval, int32_t* out_of_range,
-                         void* stream);
+                         int32_t* kept_offsets, int64_t* min_interval, int32_t* out_of_range, void* stream);
 int den_compact_queued_events(const int32_t* position_xy, const int64_t* timestamp, const uint8_t* polarity,
-                              const int64_t* start_ts, const uint8_t* valid, const int32_t* kept_offsets,
-                              int64_t n, int64_t* out_position, int64_t* out_start_ts, int64_t* out_end_ts,
+                              const int64_t* start_ts, const int32_t* kept_offsets, int64_t n,
+                              int64_t* out_position, int64_t* out_start_ts, int64_t* out_end_ts,
                               int64_t* out_num_pos, int64_t* out_num_neg, void* stream);
 
 #ifdef __cplusplus
