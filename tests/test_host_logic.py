@@ -302,3 +302,42 @@ def test_lm_refine_joint_system_host_logic(monkeypatch, shared_gamma):
     assert len(errors) == len(want_errors) and abs(errors[-1] - want_errors[-1]) <= 1e-9 * want_errors[-1]
     if shared_gamma:
         assert float(got[:, 1].max() - got[:, 1].min()) == 0.0
+
+
+def test_posed_views_feed_the_evaluation_loop(tmp_path, monkeypatch):
+    """Dataset directory -> `views.PosedViews` -> `Trainer.test`: the views iterate as the per-view dicts the
+    loop takes, `test_arguments()` supplies the inverse intrinsics and the pixel range, quantised 8-bit images
+    land in [0.5 / 256, 1 - 0.5 / 256], poses are in the common camera frame (rotation matrices)."""
+    import _dataset
+    from deblur_e_nerf_b200 import eval_post, trainer, views
+    from oracle import eval_ref
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    _dataset.write(str(tmp_path), dict(synthetic.CONFIGS["synthetic"]), n_events=8, n_views=3, size=(19, 23), channels=3)
+    posed = views.PosedViews(str(tmp_path), "test")
+    assert len(posed) == 3 and posed.img.shape == (3, 19, 23) and posed.img.dtype == torch.float32
+    assert posed.min_normalized_pixel_value == 0.5 / 256 and posed.max_normalized_pixel_value == 1 - 0.5 / 256
+    assert float(posed.img.min()) >= posed.min_normalized_pixel_value and float(posed.img.max()) <= posed.max_normalized_pixel_value
+    R = posed.T_wc_orientation
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(3, 3, 3), atol=1e-5)
+    assert torch.allclose(torch.linalg.det(R), torch.ones(3), atol=1e-5)
+    assert "".join(chr(c) for c in posed.sample_id[1]).strip() == "r_1"
+    shuffled = views.PosedViews(str(tmp_path), "test", permutation_seed=4)
+    perm = torch.randperm(3, generator=torch.Generator().manual_seed(4))
+    assert torch.equal(shuffled.img, posed.img[perm]) and torch.equal(shuffled.sample_id, posed.sample_id[perm])
+
+    model, _ = _scene.build_product_renderer(cfg, "cpu", pixel_bandwidth=False, n_poses=20)
+
+    def render(o, d, jitter=None):
+        return 0.3 + 0.2 * d[..., 0].abs(), torch.ones(19, 23), torch.ones(19, 23), 7.0
+
+    def evaluate(pred, target, exposure_time, gain, lo, hi, black_level_offset=True, init=None,
+                 max_steps=10, radius=1e6, per_channel_scale=True):
+        res = eval_ref.evaluate(pred[:, None], target[:, None], exposure_time, gain, lo, hi,
+                                black_level_offset=black_level_offset)
+        return {k: (torch.tensor(v) if isinstance(v, float) else v) for k, v in res.items()}
+
+    monkeypatch.setattr(model.nerf, "forward", render)
+    monkeypatch.setattr(eval_post, "evaluate", evaluate)
+    row, pred = trainer.Trainer().test(model, posed, black_level_offset=False, **posed.test_arguments())
+    assert set(row) == {"test/l1", "test/psnr", "test/ssim"} and pred.shape == (3, 1, 19, 23)
+    assert 0 < row["test/l1"] < 1 and row["test/psnr"] > 0

@@ -422,3 +422,50 @@ def test_raw_event_queueing_matches_reference(tmp_path):
     assert np.array_equal(events_ref.colorize_events(want["position"].numpy(), "BGGR"), want["channel_idx"].numpy())
     for fn in (events_ref.max_refractory_period_loop, events_ref.max_refractory_period):
         assert float(fn(position, timestamp, height, width)) == float(want_refractory)
+
+
+@pytest.mark.parametrize("channels,alpha,bayer,seed", [(3, False, "", None), (4, True, "", 5), (4, False, "RGGB", None),
+                                                      (3, False, "GBRG", 2), (4, True, "BGGR", None)])
+def test_posed_views_match_reference_posed_image(tmp_path, channels, alpha, bayer, seed):
+    """`views.PosedViews` (the input side of Trainer.test) against the reference's OWN `PosedImage`
+    (data/datasets.py:377-713) on a tiny on-disk dataset: BGR / BGRA renders, with and without compositing over
+    white, mono and Bayer sensors, with a permutation seed — every tensor, the intrinsics and the pixel range."""
+    import numpy as np
+    import _dataset
+    from deblur_e_nerf_b200 import synthetic, views
+    ds = ref_shim.load("data.datasets")
+    root = str(tmp_path)
+    _dataset.write(root, dict(synthetic.CONFIGS["synthetic"]), n_events=8, n_views=3, size=(10, 14), channels=channels)
+    calib = dict(np.load(tmp_path / "camera_calibration.npz"))
+    calib["bayer_pattern"] = np.array(bayer)
+    np.savez(tmp_path / "camera_calibration.npz", **calib)
+    if seed == 2:               # real captures carry an exposure time and a gain per frame, and explicit intrinsics
+        import json
+        path = tmp_path / "views" / "transforms_test.json"
+        meta = json.loads(path.read_text())
+        meta.pop("camera_angle_x")
+        meta["intrinsics"] = [[20.5, 0, 7.0], [0, 20.25, 5.0], [0, 0, 1]]
+        meta["bit_depth"] = 8
+        for k, frame in enumerate(meta["frames"]):
+            frame["exposure_time"], frame["gain"] = 1000 * (k + 1), 1.0 + 0.5 * k
+        path.write_text(json.dumps(meta))
+    for stage in ("val", "test"):
+        want = ds.PosedImage(root, stage, seed, alpha_over_white_bg=alpha)
+        got = views.PosedViews(root, stage, seed, alpha_over_white_bg=alpha)
+        assert len(got) == len(want) == 3
+        assert got.img.shape == want.posed_imgs.img.shape and got.img.dtype == want.posed_imgs.img.dtype
+        _close(got.img, want.posed_imgs.img, 1e-6)
+        keys = ["sample_id", "T_wc_position", "T_wc_orientation", "intrinsics"]
+        if seed == 2 and stage == "test":
+            keys += ["exposure_time", "gain"]
+        else:
+            assert got.exposure_time is None and got.gain is None and "gain" not in want.posed_imgs
+        for key in keys:
+            ref_value = want.posed_imgs[key]
+            assert getattr(got, key).dtype == ref_value.dtype and torch.equal(getattr(got, key), ref_value), key
+        assert got.min_normalized_pixel_value == want.min_normalized_pixel_value
+        assert got.max_normalized_pixel_value == want.max_normalized_pixel_value
+        item, ref_item = got[1], want[1]
+        assert set(item) == set(ref_item) and all(torch.allclose(item[k].double(), ref_item[k].double(), atol=1e-6) for k in item)
+        args = got.test_arguments()
+        assert torch.allclose(args["intrinsics_inv"] @ got.intrinsics, torch.eye(3), atol=1e-5)
