@@ -73,3 +73,29 @@ def test_evaluation_loop_matches_oracle(den_lib, cuda, black_level_offset):
     small = [{k: (v[..., :13, :17] if k == "img" else v) for k, v in view.items()} for view in views[:2]]
     val_row, val_pred = tr.validate(prod, [_scene.to_device(v, cuda) for v in small], kinv, lo, hi)
     assert set(val_row) == {"val/l1", "val/psnr", "val/ssim"} and val_pred.shape == (2, 1, 13, 17)
+
+
+def test_evaluation_from_a_dataset_directory(den_lib, cuda, tmp_path):
+    """`run.py test` end to end on the device: dataset directory -> `views.PosedViews` -> `Trainer.test`
+    (every view rendered by the CUDA path in eval mode, post-processing and metrics by `eval_post`) against the
+    same views pushed through `evaluation_step` / `evaluation_epoch_end` one by one."""
+    import _dataset
+    from deblur_e_nerf_b200 import synthetic, trainer, views
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    _dataset.write(str(tmp_path), dict(synthetic.CONFIGS["synthetic"]), n_events=8, n_views=3, size=(24, 32), channels=3)
+    posed = views.PosedViews(str(tmp_path), "test", device=cuda)
+    assert posed.img.is_cuda and posed.img.shape == (3, 24, 32)
+    prod, _ = _scene.build_product_renderer(cfg, cuda, pixel_bandwidth=False, n_poses=50)
+    prod.nerf.occupancy_grid._binary = synthetic.solid_sphere_occupancy(32).to(cuda)
+    args = posed.test_arguments()
+    row, pred = trainer.Trainer().test(prod, posed, black_level_offset=False, **args)
+    assert set(row) == {"test/l1", "test/psnr", "test/ssim"} and pred.shape == (3, 1, 24, 32) and pred.is_cuda
+    assert all(v == v for v in row.values()) and row["test/l1"] > 0 and -1.0 <= row["test/ssim"] <= 1.0
+    prod.eval()
+    grid = prod.image_pixel_positions(24, 32, device=cuda)
+    outs = [prod.evaluation_step(view, args["intrinsics_inv"], grid) for view in posed]
+    want, want_pred = prod.evaluation_epoch_end(outs, args["min_normalized_pixel_value"],
+                                                args["max_normalized_pixel_value"], black_level_offset=False)
+    assert torch.equal(pred, want_pred) and all(abs(row[k] - float(want[k])) <= 1e-12 for k in row)
+    # the random views share nothing with the renders: the affine fit flattens the prediction, errors stay finite
+    assert float(pred.min()) > 0
