@@ -65,6 +65,8 @@ def calibration():
         "neg_contrast_threshold": np.array(0.25, dtype=np.float32),
         "refractory_period": np.array(int(round(tau_s * 1e9))),
         "bayer_pattern": np.array(""),
+        "distortion_model": np.array("plumb_bob"),          # data/datasets.py:24-25: an ideal pinhole camera
+        "distortion_params": np.zeros(0),
         "input_time_const_eff_it_prod": np.array(4.375e-4, dtype=np.float32),
         "miller_time_const_eff_it_prod": np.array(7.5e-6, dtype=np.float32),
         "amplifier_gain": np.array(140.0, dtype=np.float32),

@@ -248,3 +248,95 @@ def test_torchmetrics_and_lpips_stand_ins():
     with pytest.warns(UserWarning, match="LPIPS is reported as NaN"):
         out = net(in0=p, in1=t)
     assert out.shape == (2, 1, 1, 1) and torch.isnan(out).all()
+
+
+@pytest.mark.reference
+@pytest.mark.timeout(600)
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "deblur_e_nerf")), reason="needs /root/reference")
+@pytest.mark.parametrize("variant", ["synthetic", "unfrozen_auto"])
+def test_config_builds_what_the_reference_builds(tmp_path, monkeypatch, variant):
+    """`config.build_model` / `build_optimizer` against the reference's OWN `DeblurENeRF.__init__` /
+    `configure_optimizers` (models/deblur_e_nerf.py:31-392, 1055-1112) from the same YAML and dataset directory:
+    the same parameter names, shapes, calibration-derived values, frozen / trainable split (per-parameter
+    overrides included), `auto` bounding box and step size, per-rank sample budget, optimizer groups (order,
+    learning rates, weight decay, members) and scheduler."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _dataset
+    from deblur_e_nerf_b200 import compat, config, synthetic
+    from oracle import nerfacc_ref, tcnn_ref
+    data_dir = str(tmp_path / "data")
+    _dataset.write(data_dir, dict(synthetic.CONFIGS["synthetic"]), channels=3)
+    conf = config.load(os.path.join(REFERENCE, "configs", "train", "synthetic.yaml"))
+    conf["seed"] = 3
+    conf["data"].update(dataset_directory=data_dir, train_init_eff_batch_size=16,
+                        train_eff_ray_sample_batch_size=4096, alpha_over_white_bg=False)
+    conf["model"]["nerf"]["occ_grid"]["resolution"] = 16
+    conf["model"]["nerf"]["ngp"]["pos_encoding"].update(n_levels=4, log2_hashmap_size=12)
+    conf["model"]["pixel_bandwidth"]["it_sample_size"] = 4
+    if variant == "unfrozen_auto":          # 08_peanuts_running.yaml's switches on the same tiny dataset
+        conf["model"]["nerf"].update(aabb="auto", render_step_size="auto", contraction_type="sphere", cone_angle=0.004)
+        conf["model"]["refractory_period"]["freeze"] = False
+        conf["model"]["contrast_threshold"]["freeze"].update(default=False, mean_contrast_threshold=True)
+        conf["model"]["pixel_bandwidth"]["freeze"].update(default=True, tau_out=False, A_amp_inv=False)
+        conf["optimizer"]["lr"]["pixel_bandwidth"]["tau_out"] = 0.003
+        conf["lr_scheduler"]["multi_step_lr"].update(milestones=[2, 5], gamma=0.5)
+
+    for name in [m for m in sys.modules if m == "deblur_e_nerf" or m.startswith("deblur_e_nerf.")]:
+        monkeypatch.delitem(sys.modules, name)
+    for name in ("easydict", "roma", "pytorch_lightning", "pypose", "torchmetrics", "lpips"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    monkeypatch.setitem(sys.modules, "nerfacc", nerfacc_ref)
+    monkeypatch.setitem(sys.modules, "tinycudann", tcnn_ref)
+    monkeypatch.setattr(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())
+    monkeypatch.syspath_prepend(REFERENCE)
+    before = set(sys.modules)
+    try:
+        compat.install(operators=False)
+        import easydict
+        import deblur_e_nerf as den
+        c = easydict.EasyDict(conf)
+        torch.manual_seed(3)
+        ref = den.models.deblur_e_nerf.DeblurENeRF(
+            "0" * 40, c.eval_target, c.trainer.num_nodes, c.trainer.gpus, c.model.min_modeled_intensity,
+            c.model.eval_save_pred_intensity_img, c.model.checkpoint_filepath, c.model.contrast_threshold,
+            c.model.refractory_period, c.model.pixel_bandwidth, c.model.nerf, c.model.correction, c.loss, c.metric,
+            c.optimizer, c.lr_scheduler, c.data.dataset_directory, c.data.alpha_over_white_bg,
+            c.data.train_eff_ray_sample_batch_size)
+        ref_opt = ref.configure_optimizers()
+        ref_names = {id(p): n for n, p in ref.named_parameters()}
+        ref_groups = [dict(names=sorted(ref_names[id(p)] for p in g["params"]), lr=g["lr"],
+                           weight_decay=g["weight_decay"]) for g in ref_opt["optimizer"].param_groups]
+        ref_params = {n: (tuple(p.shape), p.dtype, p.requires_grad, p.detach().clone())
+                      for n, p in ref.named_parameters() if not n.startswith("metric.")}
+        ref_sched = ref_opt["lr_scheduler"]["scheduler"]
+        ref_facts = dict(step=ref.nerf.render_step_size, aabb=ref.nerf.aabb.tolist() if hasattr(ref.nerf, "aabb") else None,
+                         budget=ref.train_ray_sample_batch_size, milestones=dict(ref_sched.milestones),
+                         gamma=ref_sched.gamma, interval=ref_opt["lr_scheduler"]["interval"])
+    finally:
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in ("deblur_e_nerf", "easydict", "roma", "pytorch_lightning", "pypose",
+                                      "torchmetrics", "lpips"):
+                sys.modules.pop(name, None)
+
+    model = config.build_model(conf, device="cpu", world_size=1)
+    optimizer, scheduler = config.build_optimizer(conf, model, fused=False)
+    ours = {n: p for n, p in model.named_parameters()}
+    assert set(ours) == set(ref_params)
+    for name, (shape, dtype, trainable, value) in ref_params.items():
+        p = ours[name]
+        assert tuple(p.shape) == shape and p.dtype == dtype and p.requires_grad == trainable, name
+        if not name.startswith("nerf.radiance_field"):            # calibration-derived: no RNG involved
+            assert torch.allclose(p.detach(), value, rtol=1e-6, atol=0), name
+    assert model.nerf.render_step_size == pytest.approx(ref_facts["step"], rel=1e-7)
+    if ref_facts["aabb"] is not None and hasattr(model.nerf, "aabb"):
+        assert torch.allclose(torch.as_tensor(model.nerf.aabb).flatten(), torch.tensor(ref_facts["aabb"]).flatten())
+    assert model.train_ray_sample_batch_size == ref_facts["budget"]
+    names = {id(p): n for n, p in model.named_parameters()}
+    groups = [dict(names=sorted(names[id(p)] for p in g["params"]), lr=g["lr"], weight_decay=g["weight_decay"])
+              for g in optimizer.param_groups]
+    assert len(groups) == len(ref_groups)
+    for mine, theirs in zip(groups, ref_groups):
+        assert mine["names"] == theirs["names"]
+        assert mine["lr"] == pytest.approx(theirs["lr"]) and mine["weight_decay"] == theirs["weight_decay"]
+    assert dict(scheduler.milestones) == ref_facts["milestones"] and scheduler.gamma == ref_facts["gamma"]
+    assert conf["lr_scheduler"]["interval"] == ref_facts["interval"]
