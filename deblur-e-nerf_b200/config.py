@@ -201,3 +201,32 @@ def test(cfg, device="cuda", stage="test", model=None, log_fn=None):
     return run(model, posed_views, black_level_offset=c["black_level_offset"],
                per_channel_log_it_scale=c["per_channel_log_it_scale"], max_steps=c["optimizer"]["max_steps"],
                radius=c["optimizer"]["lm"]["radius"], **posed.test_arguments(device))
+
+
+def main(argv=None):
+    """`python -m deblur_e_nerf_b200.config {train,val,test} cfg.yaml` — scripts/run.py's three stages (under
+    torchrun: one process per GPU)."""
+    import argparse
+    import json
+    ap = argparse.ArgumentParser(description="Deblur e-NeRF on den_b200, from a config of the reference")
+    ap.add_argument("stage", choices=("train", "val", "test"))
+    ap.add_argument("config")
+    ap.add_argument("--checkpoint-dir", default=None)
+    ap.add_argument("--trust-checkpoint", action="store_true", help="unpickle model.checkpoint_filepath fully")
+    args = ap.parse_args(argv)
+    rank, local_rank, _ = ddp.init_from_env()
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    cfg = load(args.config)
+    log = (lambda step, row: print(json.dumps({"step": step, **row}), flush=True)) if rank == 0 else None
+    if args.stage == "train":
+        train(cfg, device, checkpoint_dir=args.checkpoint_dir if rank == 0 else None, log_fn=log)
+    else:
+        model = build_model(cfg, device, trust_checkpoint=args.trust_checkpoint)
+        ddp.broadcast_parameters(model)
+        test(cfg, device, stage=args.stage, model=model, log_fn=log)
+    ddp.barrier()
+
+
+if __name__ == "__main__":
+    main()
