@@ -99,3 +99,49 @@ def test_evaluation_from_a_dataset_directory(den_lib, cuda, tmp_path):
     assert torch.equal(pred, want_pred) and all(abs(row[k] - float(want[k])) <= 1e-12 for k in row)
     # the random views share nothing with the renders: the affine fit flattens the prediction, errors stay finite
     assert float(pred.min()) > 0
+
+
+@pytest.mark.parametrize("per_channel", [True, False], ids=["per_channel_scale", "shared_scale"])
+def test_evaluation_loop_colour_sensor_matches_oracle(den_lib, cuda, per_channel):
+    """A sensor behind a Bayer filter: three radiance channels rendered per view (channels first, models/
+    deblur_e_nerf.py:1200-1201), the log-intensity scale per channel or shared (then ONE gamma in the offset-
+    gamma refinement, :185-197), against the oracle's renderer + eval_ref."""
+    from deblur_e_nerf_b200 import trainer
+    cfg = _scene.scene_config("synthetic", occ_resolution=32, small=True)
+    cfg["radiance_dim"] = 3
+    ora, poses = _scene.build_oracle_renderer(cfg, pixel_bandwidth=False, n_poses=50)
+    prod, _ = _scene.build_product_renderer(cfg, cuda, pixel_bandwidth=False, n_poses=50)
+    _scene.copy_params(ora.nerf, prod.nerf)
+    ora.nerf.train()
+    torch.manual_seed(3)
+    ora.nerf.update_occ_grid(0, poses[0])
+    prod.nerf.occupancy_grid._binary = ora.nerf.occupancy_grid.binary.to(cuda)
+    prod.nerf.occupancy_grid.occs.copy_(ora.nerf.occupancy_grid.occs)
+    ora.nerf.eval()
+    H, W, B = 20, 28, 3
+    grid = prod.image_pixel_positions(H, W) * torch.tensor([cfg["width"] / W, cfg["height"] / H])
+    traj = _scene.path_ref.LinearTrajectory(*poses)
+    pos, rot = traj(torch.tensor([5.0e6, 20.5e6, 41.25e6], dtype=torch.float64))
+    with torch.no_grad():
+        pred_o = torch.stack([ora.render_pixels(grid.view(-1, 2), pos[b].expand(H * W, -1),
+                                                rot[b].expand(H * W, -1, -1))[0].view(H, W, 3).permute(2, 0, 1)
+                              for b in range(B)])
+    g = torch.Generator().manual_seed(13)
+    exposure, gain = torch.tensor([2, 1, 3]), torch.tensor([1.0, 1.25, 0.8])
+    norm = gain * exposure / (gain * exposure).mean()
+    gammas = torch.tensor([0.8, 0.9, 0.85]).view(1, 3, 1, 1)
+    scene = torch.exp(gammas * pred_o.log() + torch.tensor([0.3, 0.1, 0.2]).view(1, 3, 1, 1))
+    target = (scene * torch.exp(0.02 * torch.randn(scene.shape, generator=g)) * norm.view(-1, 1, 1, 1) + 0.02).float()
+    lo, hi = 0.0, float(target.max()) * 1.05
+    views = [{"img": target[b], "T_wc_position": pos[b].float(), "T_wc_orientation": rot[b].float(),
+              "exposure_time": exposure[b], "gain": gain[b]} for b in range(B)]
+    want = eval_ref.evaluate(pred_o, target, exposure, gain, lo, hi, black_level_offset=True,
+                             per_channel_scale=per_channel)
+    row, pred = trainer.Trainer().test(prod, [_scene.to_device(v, cuda) for v in views], prod.train_intrinsics_inv,
+                                       lo, hi, img_pixel_pos=grid.to(cuda), black_level_offset=True,
+                                       per_channel_log_it_scale=per_channel)
+    assert pred.shape == (B, 3, H, W)
+    assert (pred.cpu() - want["pred"]).abs().max().item() <= 3e-3 * want["pred"].abs().max().item()
+    assert abs(row["test/l1"] - want["l1"]) <= 3e-3 * want["l1"] + 1e-6
+    assert abs(row["test/psnr"] - want["psnr"]) <= 3e-2
+    assert abs(row["test/ssim"] - want["ssim"]) <= 1e-3
