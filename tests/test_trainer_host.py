@@ -2,6 +2,7 @@
 the hot path relies on — step / epoch counting, gradient accumulation,
 the two-batch lag of the batch controller, scheduler interval, checkpoint round trip."""
 
+import pytest
 import torch
 
 from deblur_e_nerf_b200 import trainer as trainer_mod
@@ -134,3 +135,50 @@ def test_seed_everything_reseeds_torch():
     a = torch.rand(3)
     trainer_mod.seed_everything(7)
     assert torch.equal(a, torch.rand(3))
+
+
+def test_config_round_trips_a_checkpoint(tmp_path):
+    """`config.build_model` with `model.checkpoint_filepath` + per-component `load_state_dict` (models/
+    deblur_e_nerf.py:321-343): a checkpoint written by `trainer.Trainer.save_checkpoint` (Lightning's keys) is
+    read with the safe unpickler, only the selected components are restored, a frozen loaded field stays frozen;
+    `build_producer`'s dataset ratio follows data/datamodule.py:127-142."""
+    import copy
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _dataset
+    from deblur_e_nerf_b200 import config, synthetic, trainer
+    root = str(tmp_path / "data")
+    _dataset.write(root, dict(synthetic.CONFIGS["synthetic"]), channels=3)
+    cfg = _dataset.reference_style_config(root)
+    torch.manual_seed(0)
+    first = config.build_model(cfg, device="cpu", world_size=2)
+    assert first.train_ray_sample_batch_size == cfg["data"]["train_eff_ray_sample_batch_size"] // 2
+    optimizer, scheduler = config.build_optimizer(cfg, first, fused=False)
+    with torch.no_grad():
+        for p in first.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    path = str(tmp_path / "last.ckpt")
+    trainer.Trainer().save_checkpoint(path, first, optimizer, scheduler)
+
+    cfg2 = copy.deepcopy(cfg)
+    cfg2["model"]["checkpoint_filepath"] = path
+    cfg2["model"]["nerf"].update(load_state_dict=True, freeze=True)
+    cfg2["model"]["contrast_threshold"]["load_state_dict"] = True
+    torch.manual_seed(1)
+    second = config.build_model(cfg2, device="cpu", world_size=1)
+    a, b = dict(first.named_parameters()), dict(second.named_parameters())
+    for name in a:
+        same = torch.equal(a[name], b[name])
+        if name.startswith(("nerf.", "contrast_threshold.")):
+            assert same, name                                           # restored
+        elif name.startswith("pixel_bandwidth."):
+            assert not same, name                                       # not selected: calibration values
+    assert not any(p.requires_grad for p in second.nerf.parameters())
+    cfg3 = copy.deepcopy(cfg)
+    cfg3["model"]["nerf"]["freeze"] = True                              # frozen but random: refused (:66-69)
+    with pytest.raises(AssertionError):
+        config.build_model(cfg3, device="cpu")
+    assert config._subset_length(0.5, 64, 1001) == 500 and config._subset_length(3, 64, 1001) == 192
+    with pytest.raises(AssertionError):
+        config._subset_length(100, 64, 1001)
