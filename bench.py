@@ -545,6 +545,12 @@ def run_raw_events(args):
             peaks = json.load(fh)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     avg_kernel_ms = total_kernel_ms / max(n_timed, 1)
+    traffic, traffic_src = None, None           # dram bytes of one den_queue_raw_events call, from the ncu capture
+    traffic_path = os.path.join(ROOT, "profiles", "r02_ncu_raw_events_traffic.json")
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as fh:
+            traffic = json.load(fh)["den_queue_raw_events"]["dram_bytes_per_event"] * n
+        traffic_src = "profiles/r02_ncu_raw_events_traffic.json"
     algorithmic = 28.0 * n                 # 8 B position + 8 B timestamp read, 8 B start_ts + 4 B keep flag written
     line = {
         "metric": "raw events/s (queue + max refractory period)", "value": total / (ms_step * 1e-3),
@@ -560,13 +566,15 @@ def run_raw_events(args):
         "gpu_launches": launches, "clocks": clock_info,
         "roofline": {"kernel": "den_queue_raw_events", "bound": "hbm", "achieved": algorithmic / (avg_kernel_ms * 1e-3) / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": algorithmic / (avg_kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                     "traffic": None, "avg_launch_ms": avg_kernel_ms, "compaction_ms": compact_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "avg_launch_ms": avg_kernel_ms,
+                     "compaction_ms": compact_ms,
                      "peak_source": ("measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)") + " HBM copy",
                      "note": "algorithmic bytes = 28 B per raw event (position + timestamp read, start_ts + keep flag "
                              "written); the entry point runs the key kernel, three radix passes (histogram, scan, "
-                             "stable scatter: ~24 B moved per event and pass), the neighbour pass (two dependent "
-                             "timestamp gathers) and the prefix sum of the keep flags — implementation traffic ~5x "
-                             "the algorithmic bytes; den_compact_queued_events (compaction_ms) follows"},
+                             "stable scatter: ~24 B moved per event and pass), the neighbour pass (one random timestamp "
+                             "gather, two random scatters: 226 B of DRAM traffic per event at sector / atom "
+                             "granularity) and the prefix sum of the keep flags — measured traffic 328 B per event, "
+                             "12x the algorithmic bytes; den_compact_queued_events (compaction_ms) follows"},
         "cpu_baseline": None,
     }
     if not args.no_cpu_baseline:
