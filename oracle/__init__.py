@@ -27,6 +27,17 @@ Contents
     ``models/deblur_e_nerf.py``) so the oracle travels to the GPU box, where
     ``/root/reference`` does not exist.
 
+``eval_ref``
+    the evaluation post-processing (``evaluation_epoch_end``: gain-exposure normalisation,
+    log-space affine fit, offset-gamma Levenberg-Marquardt refinement, L1 / PSNR / SSIM);
+    pinned against the reference's own method and its ``OffsetGammaCorrection``; the
+    trust-region constants (pypose) and SSIM (torchmetrics 0.6.2) are restated from the
+    published sources, parity unpinned.
+``events_ref``
+    the raw-event preprocessing (``Event.queue_raw_events``, ``extract_max_refractory_period``,
+    ``colorize_events``): the literal loops and a vectorised form, pinned bit for bit against
+    the reference's own classmethods (live and ``tests/golden/raw_events.npz``).
+
 Parity status: the reference ships no tests, golden vectors or fixtures and the
 two kernel packages are absent, so the THIRD-PARTY restatements are "parity
 unpinned" against upstream binaries (closed-form known-answer tests only);
