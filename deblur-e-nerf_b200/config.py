@@ -160,9 +160,11 @@ def build_producer(cfg, model, device="cuda", rank=None, world_size=None):
                                    seed=cfg["seed"] or 0, rank=rank, dataset_len=length)
 
 
-def train(cfg, device="cuda", checkpoint_dir=None, log_fn=None, max_steps=None):
-    """`run.py train`: seed, model, optimizer, scheduler, event producer, the optimizer-step loop.  Under
-    torchrun every rank calls this (``ddp.init_from_env()`` first).  Returns (model, trainer)."""
+def train(cfg, device="cuda", checkpoint_dir=None, log_fn=None, max_steps=None, validate=None):
+    """`run.py train`: seed, model, optimizer, scheduler, event producer, the optimizer-step loop, and — like
+    Lightning between epochs — the validation views scored every `trainer.check_val_every_n_epoch` epochs
+    (`validate`: default on unless `trainer.limit_val_batches` is 0).  Under torchrun every rank calls this
+    (``ddp.init_from_env()`` first).  Returns (model, trainer)."""
     t = cfg["trainer"]
     cfg["seed"] = trainer.seed_everything(cfg["seed"] if cfg.get("seed") is not None else 0)
     model = build_model(cfg, device)
@@ -175,7 +177,11 @@ def train(cfg, device="cuda", checkpoint_dir=None, log_fn=None, max_steps=None):
                            lr_scheduler_interval=cfg["lr_scheduler"]["interval"], checkpoint_dir=checkpoint_dir,
                            checkpoint_every_n_epochs=cfg.get("checkpoint", {}).get("every_n_epochs", 1),
                            log_every_n_steps=t.get("log_every_n_steps", 100), log_fn=log_fn, max_steps=max_steps)
-    loop.fit(model, producer, optimizer, scheduler)
+    if validate is None:
+        validate = t.get("limit_val_batches", 1.0) != 0
+    validate_fn = (lambda m: test(cfg, device, stage="val", model=m, log_fn=log_fn)) if validate else None
+    loop.fit(model, producer, optimizer, scheduler, validate_fn=validate_fn,
+             check_val_every_n_epoch=t.get("check_val_every_n_epoch", 1))
     return model, loop
 
 

@@ -101,9 +101,12 @@ class Trainer:
         return ckpt
 
     # ------------------------------------------------------------------------ loop ----
-    def fit(self, model, producer, optimizer, scheduler=None, reducer=None):
+    def fit(self, model, producer, optimizer, scheduler=None, reducer=None, validate_fn=None,
+            check_val_every_n_epoch=1):
         """Run up to `max_epochs` epochs (or `max_steps` optimizer steps) from the trainer's current
-        epoch / global step; returns the last logged dict."""
+        epoch / global step; returns the last logged dict.  `validate_fn(model)`, if given, runs after
+        every `check_val_every_n_epoch`-th epoch (Lightning's validation loop between training epochs,
+        configs/train/*.yaml `trainer.check_val_every_n_epoch`); the model is back in training mode after."""
         acc = self.accumulate_grad_batches
         model.accumulate_grad_batches = acc
         model.train()
@@ -145,6 +148,9 @@ class Trainer:
                     break
             if done:
                 break
+            if validate_fn is not None and (self.current_epoch + 1) % check_val_every_n_epoch == 0:
+                validate_fn(model)
+                model.train()
             self.current_epoch += 1
             if scheduler is not None and self.lr_scheduler_interval == "epoch":
                 scheduler.step()

@@ -92,7 +92,8 @@ def reference_style_config(data_dir, it_sample_size=4):
         "lr_scheduler": {"algo": "multi_step_lr", "interval": "epoch",
                          "multi_step_lr": {"milestones": [20, 30, 36], "gamma": 0.33}},
         "checkpoint": {"every_n_epochs": 1},
-        "trainer": {"max_epochs": 1, "log_every_n_steps": 1, "limit_train_batches": 4},
+        "trainer": {"max_epochs": 1, "log_every_n_steps": 1, "limit_train_batches": 4, "limit_val_batches": 0,
+                    "check_val_every_n_epoch": 1},
     }
 
 

@@ -182,3 +182,19 @@ def test_config_round_trips_a_checkpoint(tmp_path):
     assert config._subset_length(0.5, 64, 1001) == 500 and config._subset_length(3, 64, 1001) == 192
     with pytest.raises(AssertionError):
         config._subset_length(100, 64, 1001)
+
+
+def test_validation_runs_between_epochs():
+    """`fit(validate_fn=...)`: Lightning's validation loop between training epochs — after every
+    `check_val_every_n_epoch`-th epoch, with the model handed back in training mode."""
+    model, producer = _Model(), _Producer(8)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    calls = []
+
+    def validate(m):
+        m.eval()
+        calls.append((tr.current_epoch, tr.global_step, m.training))
+
+    tr = trainer_mod.Trainer(max_epochs=4, limit_train_batches=3)
+    tr.fit(model, producer, opt, validate_fn=validate, check_val_every_n_epoch=2)
+    assert calls == [(1, 6, False), (3, 12, False)] and model.training
