@@ -341,3 +341,50 @@ def test_posed_views_feed_the_evaluation_loop(tmp_path, monkeypatch):
     row, pred = trainer.Trainer().test(model, posed, black_level_offset=False, **posed.test_arguments())
     assert set(row) == {"test/l1", "test/psnr", "test/ssim"} and pred.shape == (3, 1, 19, 23)
     assert 0 < row["test/l1"] < 1 and row["test/psnr"] > 0
+
+
+def test_config_train_wires_the_loop_and_the_validation(tmp_path, monkeypatch):
+    """`config.train` end to end on the CPU with the three device parts replaced (training step, field render,
+    post-processing kernels): seed, model, optimizer groups, scheduler interval, event producer from the cached
+    events.pt (per-rank batch, dataset ratio), the optimizer-step loop, and the validation views scored between
+    epochs when `limit_val_batches` is not 0."""
+    import _dataset
+    from deblur_e_nerf_b200 import config, eval_post
+    from oracle import eval_ref
+    root = str(tmp_path)
+    _dataset.write(root, dict(synthetic.CONFIGS["synthetic"]), channels=3)
+    cfg = _dataset.reference_style_config(root)
+    cfg["trainer"].update(max_epochs=2, limit_train_batches=3, limit_val_batches=1.0, check_val_every_n_epoch=1)
+    cfg["data"]["train_dataset_ratio"] = 0.5
+    cfg["model"]["correction"]["black_level_offset"] = False
+    seen = {"batches": [], "renders": 0}
+
+    def training_step(self, batch, batch_index=0, global_step=0, jitters=None):
+        seen["batches"].append((batch["event"]["position"].shape[0], batch["normalized"]["interval_gen"].shape))
+        loss = sum((p ** 2).sum() for p in self.nerf.radiance_field.mlp_head.parameters()) * 1e-3
+        self.logged = {"train/loss": loss.detach()}
+        return loss
+
+    def forward(self, o, d, jitter=None, groups=1):
+        seen["renders"] += 1
+        return 0.3 + 0.2 * d[..., 0].abs(), torch.ones(o.shape[:-1]), torch.ones(o.shape[:-1]), 7.0
+
+    def evaluate(pred, target, exposure_time, gain, lo, hi, black_level_offset=True, init=None,
+                 max_steps=10, radius=1e6, per_channel_scale=True):
+        res = eval_ref.evaluate(pred[:, None], target[:, None], exposure_time, gain, lo, hi,
+                                black_level_offset=black_level_offset)
+        return {k: (torch.tensor(v) if isinstance(v, float) else v) for k, v in res.items()}
+
+    monkeypatch.setattr(renderer.EventRenderer, "training_step", training_step)
+    from deblur_e_nerf_b200 import nerf as nerf_mod
+    monkeypatch.setattr(nerf_mod.NeRF, "forward", forward)
+    monkeypatch.setattr(eval_post, "evaluate", evaluate)
+    rows = []
+    model, loop = config.train(cfg, device="cpu", log_fn=lambda step, row: rows.append((step, row)))
+    assert loop.global_step == 6 and loop.current_epoch == 2
+    assert seen["batches"] == [(64, (3, 64))] * 6                      # train_init_eff_batch_size, S - 1 = 3
+    assert seen["renders"] == 2 * 2                                    # two validation views after each epoch
+    val_rows = [row for _, row in rows if "val/l1" in row]
+    assert len(val_rows) == 2 and set(val_rows[0]) == {"val/l1", "val/psnr", "val/ssim"}
+    assert len([row for _, row in rows if "train/loss" in row]) == 6 and model.training
+    assert cfg["seed"] == 3
