@@ -160,14 +160,17 @@ def build_producer(cfg, model, device="cuda", rank=None, world_size=None):
                                    seed=cfg["seed"] or 0, rank=rank, dataset_len=length)
 
 
-def train(cfg, device="cuda", checkpoint_dir=None, log_fn=None, max_steps=None, validate=None):
+def train(cfg, device="cuda", checkpoint_dir=None, log_fn=None, max_steps=None, validate=None,
+          trust_checkpoint=False):
     """`run.py train`: seed, model, optimizer, scheduler, event producer, the optimizer-step loop, and — like
     Lightning between epochs — the validation views scored every `trainer.check_val_every_n_epoch` epochs
     (`validate`: default on unless `trainer.limit_val_batches` is 0).  Under torchrun every rank calls this
-    (``ddp.init_from_env()`` first).  Returns (model, trainer)."""
+    (``ddp.init_from_env()`` first).  `trainer.resume_from_checkpoint` restores the model, the optimizer, the
+    scheduler, the counters and the controller's batch size from a checkpoint of this loop.  Returns (model,
+    trainer)."""
     t = cfg["trainer"]
     cfg["seed"] = trainer.seed_everything(cfg["seed"] if cfg.get("seed") is not None else 0)
-    model = build_model(cfg, device)
+    model = build_model(cfg, device, trust_checkpoint=trust_checkpoint)
     ddp.broadcast_parameters(model)
     ddp.attach(model)
     optimizer, scheduler = build_optimizer(cfg, model)
@@ -177,6 +180,11 @@ def train(cfg, device="cuda", checkpoint_dir=None, log_fn=None, max_steps=None, 
                            lr_scheduler_interval=cfg["lr_scheduler"]["interval"], checkpoint_dir=checkpoint_dir,
                            checkpoint_every_n_epochs=cfg.get("checkpoint", {}).get("every_n_epochs", 1),
                            log_every_n_steps=t.get("log_every_n_steps", 100), log_fn=log_fn, max_steps=max_steps)
+    if t.get("resume_from_checkpoint"):                 # Lightning's key: model, optimizer, scheduler, counters
+        loop.load_checkpoint(t["resume_from_checkpoint"], model, optimizer, scheduler,
+                             trust_pickle=trust_checkpoint)
+        if model.next_train_batch_size:
+            producer.set_batch_size(model.next_train_batch_size)
     if validate is None:
         validate = t.get("limit_val_batches", 1.0) != 0
     validate_fn = (lambda m: test(cfg, device, stage="val", model=m, log_fn=log_fn)) if validate else None
@@ -219,6 +227,7 @@ def main(argv=None):
     ap.add_argument("config")
     ap.add_argument("--checkpoint-dir", default=None)
     ap.add_argument("--trust-checkpoint", action="store_true", help="unpickle model.checkpoint_filepath fully")
+    ap.add_argument("--metrics-out", default=None, help="val / test: write the metrics as YAML (run.py's metrics.yaml)")
     args = ap.parse_args(argv)
     rank, local_rank, _ = ddp.init_from_env()
     device = torch.device("cuda", local_rank)
@@ -226,11 +235,15 @@ def main(argv=None):
     cfg = load(args.config)
     log = (lambda step, row: print(json.dumps({"step": step, **row}), flush=True)) if rank == 0 else None
     if args.stage == "train":
-        train(cfg, device, checkpoint_dir=args.checkpoint_dir if rank == 0 else None, log_fn=log)
+        train(cfg, device, checkpoint_dir=args.checkpoint_dir if rank == 0 else None, log_fn=log,
+              trust_checkpoint=args.trust_checkpoint)
     else:
         model = build_model(cfg, device, trust_checkpoint=args.trust_checkpoint)
         ddp.broadcast_parameters(model)
-        test(cfg, device, stage=args.stage, model=model, log_fn=log)
+        metrics, _ = test(cfg, device, stage=args.stage, model=model, log_fn=log)
+        if args.metrics_out and rank == 0:                      # scripts/run.py:122-133
+            with open(args.metrics_out, "w") as fh:
+                yaml.dump([metrics], fh)
     ddp.barrier()
 
 

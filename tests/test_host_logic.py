@@ -8,7 +8,7 @@ import torch
 from deblur_e_nerf_b200 import event_generation_params as egp
 from deblur_e_nerf_b200 import loss as loss_mod
 from deblur_e_nerf_b200 import pixel_bandwidth as pb_mod
-from deblur_e_nerf_b200 import renderer, synthetic, trajectories
+from deblur_e_nerf_b200 import factory, renderer, synthetic, trajectories
 from oracle import path_ref
 
 import _scene
@@ -388,3 +388,10 @@ def test_config_train_wires_the_loop_and_the_validation(tmp_path, monkeypatch):
     assert len(val_rows) == 2 and set(val_rows[0]) == {"val/l1", "val/psnr", "val/ssim"}
     assert len([row for _, row in rows if "train/loss" in row]) == 6 and model.training
     assert cfg["seed"] == 3
+    # resume: `trainer.resume_from_checkpoint` restores the counters, so two more epochs end at step 12
+    ckpt = str(tmp_path / "ckpt" / "last.ckpt")
+    loop.save_checkpoint(ckpt, model, torch.optim.Adam(factory.optimizer_param_groups(model), lr=0.01))
+    cfg["trainer"].update(resume_from_checkpoint=ckpt, max_epochs=4, limit_val_batches=0)
+    model2, loop2 = config.train(cfg, device="cpu")
+    assert loop2.global_step == 12 and loop2.current_epoch == 4
+    assert len(seen["batches"]) == 12
