@@ -227,6 +227,7 @@ def main(argv=None):
     ap.add_argument("config")
     ap.add_argument("--checkpoint-dir", default=None)
     ap.add_argument("--trust-checkpoint", action="store_true", help="unpickle model.checkpoint_filepath fully")
+    ap.add_argument("--log-dir", default=None, help="write the logged scalars as TensorBoard event files there")
     ap.add_argument("--metrics-out", default=None, help="val / test: write the metrics as YAML (run.py's metrics.yaml)")
     args = ap.parse_args(argv)
     rank, local_rank, _ = ddp.init_from_env()
@@ -234,6 +235,8 @@ def main(argv=None):
     torch.cuda.set_device(device)
     cfg = load(args.config)
     log = (lambda step, row: print(json.dumps({"step": step, **row}), flush=True)) if rank == 0 else None
+    if args.log_dir and rank == 0:
+        log = trainer.tensorboard_log_fn(args.log_dir, also=log)
     if args.stage == "train":
         train(cfg, device, checkpoint_dir=args.checkpoint_dir if rank == 0 else None, log_fn=log,
               trust_checkpoint=args.trust_checkpoint)

@@ -43,6 +43,24 @@ def seed_everything(seed):
     return seed
 
 
+def tensorboard_log_fn(log_dir, also=None):
+    """A `log_fn` that writes every logged scalar to TensorBoard event files in `log_dir` (what Lightning's
+    TensorBoardLogger does with `self.log`, scripts/run.py:76-81); `also(step, row)` is called after it."""
+    from torch.utils.tensorboard import SummaryWriter
+    writer = SummaryWriter(log_dir=log_dir)
+
+    def log(step, row):
+        for name, value in row.items():
+            if isinstance(value, (int, float)):
+                writer.add_scalar(name, value, global_step=step)
+        writer.flush()
+        if also is not None:
+            also(step, row)
+
+    log.writer = writer
+    return log
+
+
 class Trainer:
     def __init__(self, max_epochs=40, limit_train_batches=1000, accumulate_grad_batches=1,
                  lr_scheduler_interval="epoch", checkpoint_dir=None, checkpoint_every_n_epochs=1,

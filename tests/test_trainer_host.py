@@ -198,3 +198,17 @@ def test_validation_runs_between_epochs():
     tr = trainer_mod.Trainer(max_epochs=4, limit_train_batches=3)
     tr.fit(model, producer, opt, validate_fn=validate, check_val_every_n_epoch=2)
     assert calls == [(1, 6, False), (3, 12, False)] and model.training
+
+
+def test_tensorboard_log_fn(tmp_path):
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    seen = []
+    log = trainer_mod.tensorboard_log_fn(str(tmp_path), also=lambda step, row: seen.append(step))
+    model, prod = _Model(), _Producer(8)
+    tr = trainer_mod.Trainer(max_epochs=1, limit_train_batches=4, log_every_n_steps=2, log_fn=log)
+    tr.fit(model, prod, torch.optim.SGD(model.parameters(), lr=0.05))
+    log.writer.close()
+    acc = EventAccumulator(str(tmp_path))
+    acc.Reload()
+    assert seen == [2, 4] and [e.step for e in acc.Scalars("train/loss")] == [2, 4]
+    assert "train/batch_size" in acc.Tags()["scalars"]
