@@ -45,21 +45,26 @@ def rank():
     return dist.get_rank() if dist.is_initialized() else 0
 
 
-def gather_view_outputs(outputs):
+def gather_view_outputs(outputs, device=None):
     """The `self.all_gather(outputs)` of evaluation_epoch_end (models/deblur_e_nerf.py:672): every rank
     rendered views rank, rank + N, rank + 2N, ... of the evaluation set; returns the output dicts of ALL
     views in their original order on every rank (images stay on the device: one all_gather per field over
-    stacks padded to the largest per-rank count)."""
+    stacks padded to the largest per-rank count).  Fewer views than ranks is refused on EVERY rank (the counts
+    are exchanged first, so no rank is left waiting in a collective); `device`: where to exchange them when
+    this rank rendered nothing."""
     n = world_size()
     if n == 1:
         return outputs
-    device = outputs[0]["pred_intensity_img"].device if outputs else None
+    if device is None and outputs:
+        device = outputs[0]["pred_intensity_img"].device
     if device is None:
-        raise ValueError("gather_view_outputs: every rank needs at least one view (fewer views than ranks)")
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     count = torch.tensor([len(outputs)], dtype=torch.int64, device=device)
     counts = [torch.zeros_like(count) for _ in range(n)]
     dist.all_gather(counts, count)
     counts = [int(c.item()) for c in counts]
+    if min(counts) == 0:
+        raise ValueError(f"gather_view_outputs: {sum(counts)} view(s) for {n} ranks — every rank needs at least one")
     most = max(counts)
     gathered = {}
     for key in ("pred_intensity_img", "target_intensity_img", "exposure_time", "gain"):

@@ -199,7 +199,7 @@ class Trainer:
                     h, w = view["img"].shape[-2:]
                     pos = model.image_pixel_positions(h, w, device=intrinsics_inv.device)
                 outputs.append(model.evaluation_step(view, intrinsics_inv, pos))
-            outputs = ddp.gather_view_outputs(outputs)
+            outputs = ddp.gather_view_outputs(outputs, device=intrinsics_inv.device)
             metrics, pred = model.evaluation_epoch_end(
                 outputs, min_normalized_pixel_value, max_normalized_pixel_value, stage=stage, **correction)
         finally:

@@ -204,7 +204,13 @@ def _eval_worker(rank, world, port, out_dir):
     model = Model().train()
     row, pred = trainer.Trainer().test(model, views, torch.eye(3), 0.0, 6.0, black_level_offset=True)
     val_row, _ = trainer.Trainer().validate(model, views[:2], torch.eye(3), 0.0, 6.0)
+    try:                                    # fewer views than ranks: refused on BOTH ranks, nobody hangs
+        trainer.Trainer().test(model, views[:1], torch.eye(3), 0.0, 6.0)
+        refused = False
+    except ValueError:
+        refused = True
     torch.save({"row": row, "val_row": val_row, "pred": pred, "rendered": model.rendered, "modes": model.modes,
+                "refused": refused,
                 "training_after": model.training,
                 "want_l1": float(torch.stack([(v["img"] * 0.5 + model.image_pixel_positions(6, 9)[..., 0] * 0.01
                                               - v["img"]).abs() for v in views]).mean())},
@@ -218,7 +224,8 @@ def test_trainer_test_loop_world_size_2_gloo(tmp_path):
     world = 2
     mp.spawn(_eval_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     res = [torch.load(tmp_path / f"eval_rank{r}.pt") for r in range(world)]
-    assert res[0]["rendered"] == [0, 2, 4, 0] and res[1]["rendered"] == [1, 3, 1]   # round-robin shares (+ validate)
+    assert res[0]["rendered"] == [0, 2, 4, 0, 0] and res[1]["rendered"] == [1, 3, 1]   # round-robin shares (+ validate, + the refused one)
+    assert res[0]["refused"] and res[1]["refused"]
     assert not any(res[0]["modes"]) and res[0]["training_after"]                # eval mode inside, restored after
     assert res[0]["row"] == res[1]["row"] and torch.equal(res[0]["pred"], res[1]["pred"])
     row = res[0]["row"]
