@@ -187,11 +187,19 @@ def load_events(root_directory, device="cuda", cache=True):
     calib = np.load(os.path.join(root_directory, CAMERA_CALIBRATION_FILENAME))
     events, refractory = transform_raw_events(raw, calib, device)
     if cache:
-        torch.save({k: v.cpu() for k, v in events.items()}, path)
+        # several ranks may get here at once (one process per GPU): each writes its own temporary file and
+        # renames it into place — the rename is atomic, the contents are identical
+        _save_atomically({k: v.cpu() for k, v in events.items()}, path)
         refractory_path = os.path.join(root_directory, MAX_REFRACTORY_PERIOD_FILENAME)
         if not os.path.isfile(refractory_path):
-            torch.save(refractory, refractory_path)
+            _save_atomically(refractory, refractory_path)
     return events
+
+
+def _save_atomically(obj, path):
+    tmp = f"{path}.{os.getpid()}.tmp"
+    torch.save(obj, tmp)
+    os.replace(tmp, path)
 
 
 def sort_pairs(keys, values, key_bits=32):
