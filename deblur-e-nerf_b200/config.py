@@ -77,6 +77,10 @@ def build_model(cfg, device="cuda", world_size=None, trust_checkpoint=False):
     calib = egp.load_calibration(root)
     has_bayer_filter = str(calib["bayer_pattern"]) != ""
     poses = camera_poses(root)
+    refractory_path = os.path.join(root, events.MAX_REFRACTORY_PERIOD_FILENAME)
+    if not os.path.isfile(refractory_path):             # models/event_generation_params.py:135-149: extract & cache
+        raw = np.load(os.path.join(root, events.RAW_EVENTS_FILENAME))
+        events._save_atomically(events.extract_max_refractory_period(raw, calib, device), refractory_path)
 
     n = m["nerf"]
     aabb = n["aabb"]
