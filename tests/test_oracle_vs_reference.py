@@ -469,3 +469,36 @@ def test_posed_views_match_reference_posed_image(tmp_path, channels, alpha, baye
         assert set(item) == set(ref_item) and all(torch.allclose(item[k].double(), ref_item[k].double(), atol=1e-6) for k in item)
         args = got.test_arguments()
         assert torch.allclose(args["intrinsics_inv"] @ got.intrinsics, torch.eye(3), atol=1e-5)
+
+
+@pytest.mark.parametrize("model,params", [("plumb_bob", []), ("plumb_bob", [-0.31, 0.12, 0.0007, -0.0004]),
+                                          ("equidistant", [-0.02, 0.006, -0.004, 0.0009])])
+def test_colorize_and_undistort_events_match_reference(model, params):
+    """The two elementwise / OpenCV steps of the event preprocessing that run without a kernel —
+    `events.colorize_events`, `events.undistort_events` — against the reference's OWN classmethods
+    (data/datasets.py:278-365): Bayer channel indices bit for bit, undistorted positions (plumb_bob and
+    equidistant models, and the distortion-free cast) to float32 rounding."""
+    import numpy as np
+    from deblur_e_nerf_b200 import events
+    ds = ref_shim.load("data.datasets")
+    import easydict                                        # registered by the shim
+    g = torch.Generator().manual_seed(6)
+    n, height, width = 500, 260, 346
+    position = torch.stack([torch.randint(0, width, (n,), generator=g), torch.randint(0, height, (n,), generator=g)], dim=1)
+    calib = {"bayer_pattern": np.array("GRBG"), "distortion_model": np.array(model),
+             "distortion_params": np.array(params, dtype=np.float64),
+             "intrinsics": np.array([[300.0, 0, 173.0], [0, 300.0, 130.0], [0, 0, 1]])}
+    base = {"position": position, "start_ts": torch.arange(n), "end_ts": torch.arange(n) + 1,
+            "num_pos": torch.ones(n, dtype=torch.int64), "num_neg": torch.zeros(n, dtype=torch.int64)}
+    want = ds.Event.undistort_events(ds.Event.colorize_events(easydict.EasyDict({k: v.clone() for k, v in base.items()}),
+                                                              calib), calib)
+    got = events.undistort_events(events.colorize_events({k: v.clone() for k, v in base.items()}, calib), calib)
+    assert set(got) == set(want)
+    assert got["channel_idx"].dtype == want["channel_idx"].dtype and torch.equal(got["channel_idx"], want["channel_idx"])
+    assert got["position"].dtype == want["position"].dtype == torch.float32
+    assert torch.allclose(got["position"], want["position"], rtol=0, atol=1e-4)
+    if not params:
+        assert torch.equal(got["position"], position.float())
+    with pytest.raises(NotImplementedError):
+        events.undistort_events({"position": position.clone()}, {**calib, "distortion_model": np.array("fov"),
+                                                                 "distortion_params": np.ones(4)})
