@@ -340,3 +340,64 @@ def test_config_builds_what_the_reference_builds(tmp_path, monkeypatch, variant)
         assert mine["lr"] == pytest.approx(theirs["lr"]) and mine["weight_decay"] == theirs["weight_decay"]
     assert dict(scheduler.milestones) == ref_facts["milestones"] and scheduler.gamma == ref_facts["gamma"]
     assert conf["lr_scheduler"]["interval"] == ref_facts["interval"]
+
+
+@pytest.mark.reference
+@pytest.mark.timeout(600)
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "deblur_e_nerf")), reason="needs /root/reference")
+@pytest.mark.parametrize("ratio,perm_seed", [(1.0, None), (0.25, 7), (3, None)])
+def test_config_producer_draws_what_the_reference_datamodule_draws(tmp_path, monkeypatch, ratio, perm_seed):
+    """`config.build_producer` against the reference's OWN `DataModule` (data/datamodule.py) built from the same
+    config and dataset directory: the same training batches, bit for bit, in the order Lightning fetches them
+    (events, then the normalised samplers, one shared generator seeded with the run's seed) — dataset
+    permutation, dataset ratio (fraction or number of effective batches) and batch size included."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import types
+    import _dataset
+    from deblur_e_nerf_b200 import compat, config, synthetic
+    data_dir = str(tmp_path / "data")
+    _dataset.write(data_dir, dict(synthetic.CONFIGS["synthetic"]), channels=3, n_events=600)
+    conf = config.load(os.path.join(REFERENCE, "configs", "train", "synthetic.yaml"))
+    conf["seed"] = 11
+    conf["data"].update(dataset_directory=data_dir, train_init_eff_batch_size=16, train_dataset_ratio=ratio,
+                        train_dataset_perm_seed=perm_seed, alpha_over_white_bg=False)
+    conf["trainer"]["gpus"] = None
+    conf["model"]["pixel_bandwidth"]["it_sample_size"] = 5
+    for name in [m for m in sys.modules if m == "deblur_e_nerf" or m.startswith("deblur_e_nerf.")]:
+        monkeypatch.delitem(sys.modules, name)
+    for name in ("easydict", "roma", "pytorch_lightning", "pypose", "torchmetrics", "lpips"):
+        monkeypatch.delitem(sys.modules, name, raising=False)
+    from oracle import nerfacc_ref, tcnn_ref
+    monkeypatch.setitem(sys.modules, "nerfacc", nerfacc_ref)
+    monkeypatch.setitem(sys.modules, "tinycudann", tcnn_ref)
+    monkeypatch.syspath_prepend(REFERENCE)
+    before = set(sys.modules)
+    try:
+        compat.install(operators=False)
+        import easydict
+        import deblur_e_nerf as den
+        c = easydict.EasyDict(conf)
+        torch.manual_seed(conf["seed"])                       # pl.seed_everything (scripts/run.py:32)
+        dm = den.data.datamodule.DataModule(c.seed, c.eval_target, c.trainer.num_nodes, c.trainer.gpus,
+                                            c.model.pixel_bandwidth, **c.data)
+        dm.setup("fit")
+        loaders = dm.train_dataloader()
+        it_event, it_norm = iter(loaders["event"]), iter(loaders["normalized"])
+        want = []
+        for _ in range(3):
+            event = next(it_event)
+            want.append(({k: v.squeeze(0).clone() for k, v in event.items()},
+                         {k: v.squeeze(0).clone() for k, v in next(it_norm).items()}))
+    finally:
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in ("deblur_e_nerf", "easydict", "roma", "pytorch_lightning", "pypose",
+                                      "torchmetrics", "lpips"):
+                sys.modules.pop(name, None)
+    producer = config.build_producer(conf, types.SimpleNamespace(it_sample_size=5), device="cpu", rank=0, world_size=1)
+    for event, normalized in want:
+        got = producer.next_batch()
+        assert set(got["event"]) == set(event) and set(got["normalized"]) == set(normalized)
+        for k, v in event.items():
+            assert torch.equal(got["event"][k], v), k
+        for k, v in normalized.items():
+            assert got["normalized"][k].dtype == v.dtype and torch.equal(got["normalized"][k], v), k
