@@ -197,10 +197,12 @@ def train(cfg, device="cuda", checkpoint_dir=None, log_fn=None, max_steps=None, 
     return model, loop
 
 
-def test(cfg, device="cuda", stage="test", model=None, log_fn=None):
+def test(cfg, device="cuda", stage="test", model=None, log_fn=None, predictions_dir=None):
     """`run.py test` / `val`: the posed images of the stage (`eval_target: [novel_view]` -> `test` / `val`
     views, `[event_view]` -> the train views, data/datamodule.py:107-118; `<stage>_dataset_ratio` trims them) rendered in eval mode and scored on the
-    device with the `model.correction` options.  Returns (metrics, corrected predictions)."""
+    device with the `model.correction` options; with `model.eval_save_pred_intensity_img` and a
+    `predictions_dir` the corrected predictions are written there as 8-bit PNGs.  Returns (metrics, corrected
+    predictions)."""
     d, c = cfg["data"], cfg["model"]["correction"]
     if model is None:
         model = build_model(cfg, device)
@@ -216,9 +218,14 @@ def test(cfg, device="cuda", stage="test", model=None, log_fn=None):
         raise NotImplementedError("correction.optimizer.algo: only the Levenberg-Marquardt refinement is built")
     loop = trainer.Trainer(log_fn=log_fn)
     run = loop.test if stage == "test" else loop.validate
-    return run(model, posed_views, black_level_offset=c["black_level_offset"],
-               per_channel_log_it_scale=c["per_channel_log_it_scale"], max_steps=c["optimizer"]["max_steps"],
-               radius=c["optimizer"]["lm"]["radius"], **posed.test_arguments(device))
+    metrics, pred = run(model, posed_views, black_level_offset=c["black_level_offset"],
+                        per_channel_log_it_scale=c["per_channel_log_it_scale"],
+                        max_steps=c["optimizer"]["max_steps"], radius=c["optimizer"]["lm"]["radius"],
+                        **posed.test_arguments(device))
+    if predictions_dir and cfg["model"].get("eval_save_pred_intensity_img") and ddp.rank() == 0:    # :1008-1054
+        views.save_predictions(pred, torch.stack([v["sample_id"] for v in posed_views]), predictions_dir,
+                               posed.min_normalized_pixel_value, posed.max_normalized_pixel_value)
+    return metrics, pred
 
 
 def main(argv=None):
@@ -232,6 +239,8 @@ def main(argv=None):
     ap.add_argument("--checkpoint-dir", default=None)
     ap.add_argument("--trust-checkpoint", action="store_true", help="unpickle model.checkpoint_filepath fully")
     ap.add_argument("--log-dir", default=None, help="write the logged scalars as TensorBoard event files there")
+    ap.add_argument("--predictions-dir", default=None,
+                    help="val / test: where model.eval_save_pred_intensity_img writes the predicted images")
     ap.add_argument("--metrics-out", default=None, help="val / test: write the metrics as YAML (run.py's metrics.yaml)")
     args = ap.parse_args(argv)
     rank, local_rank, _ = ddp.init_from_env()
@@ -247,7 +256,8 @@ def main(argv=None):
     else:
         model = build_model(cfg, device, trust_checkpoint=args.trust_checkpoint)
         ddp.broadcast_parameters(model)
-        metrics, _ = test(cfg, device, stage=args.stage, model=model, log_fn=log)
+        metrics, _ = test(cfg, device, stage=args.stage, model=model, log_fn=log,
+                          predictions_dir=args.predictions_dir)
         if args.metrics_out and rank == 0:                      # scripts/run.py:122-133
             with open(args.metrics_out, "w") as fh:
                 yaml.dump([metrics], fh)

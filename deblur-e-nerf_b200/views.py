@@ -154,3 +154,34 @@ class PosedViews:
         return {"intrinsics_inv": torch.linalg.inv(self.intrinsics).to(device),
                 "min_normalized_pixel_value": self.min_normalized_pixel_value,
                 "max_normalized_pixel_value": self.max_normalized_pixel_value}
+
+
+def sample_id_strings(sample_id):
+    """(B, 16) unicode code points -> file names without the padding (models/deblur_e_nerf.py:1311-1319)."""
+    return ["".join(map(chr, row.tolist())).rstrip() for row in sample_id]
+
+
+def save_predictions(pred, sample_id, folder, min_normalized_pixel_value, max_normalized_pixel_value,
+                     bit_depth=8):
+    """`eval_save_pred_intensity_img` (models/deblur_e_nerf.py:1008-1054): the corrected predictions (B, C, H, W)
+    — C = 1 grey, C = 3 RGB of a sensor behind a Bayer filter — normalised to the stage's pixel range, clipped,
+    quantised to `bit_depth` bits on the device and written as `<folder>/<sample id>.png` (OpenCV: BGR order).
+    Returns the file paths."""
+    import cv2
+    if bit_depth not in (8, 16):
+        raise NotImplementedError("prediction bit depth must be 8 or 16")
+    names = sample_id_strings(sample_id) if torch.is_tensor(sample_id) else list(sample_id)
+    if len(names) != len(pred):
+        raise ValueError("one sample id per predicted image")
+    levels = 2 ** bit_depth - 1
+    span = max_normalized_pixel_value - min_normalized_pixel_value
+    q = (levels * ((pred - min_normalized_pixel_value) / span).clamp(min=0, max=1)).round()
+    q = q.permute(0, 2, 3, 1).cpu().numpy().astype(np.uint8 if bit_depth == 8 else np.uint16)
+    if q.shape[-1] == 3:
+        q = q[..., ::-1]                                                                            # RGB -> BGR
+    os.makedirs(folder, exist_ok=True)
+    paths = []
+    for name, img in zip(names, q):
+        paths.append(os.path.join(folder, name + ".png"))
+        cv2.imwrite(paths[-1], np.ascontiguousarray(img))
+    return paths

@@ -2,6 +2,8 @@
 trajectory / SLERP, event-generation parameters, supervision timestamps, loss, the
 pixel-bandwidth sample schedule and the affine linearisation coefficients."""
 
+import os
+
 import pytest
 import torch
 
@@ -395,3 +397,28 @@ def test_config_train_wires_the_loop_and_the_validation(tmp_path, monkeypatch):
     model2, loop2 = config.train(cfg, device="cpu")
     assert loop2.global_step == 12 and loop2.current_epoch == 4
     assert len(seen["batches"]) == 12
+
+
+def test_save_predictions_follows_the_reference_quantisation(tmp_path):
+    """`views.save_predictions` (`eval_save_pred_intensity_img`, models/deblur_e_nerf.py:1008-1054): range
+    normalisation, clipping, rounding to 8 bits, grey or RGB -> BGR on disk, files named by the sample ids."""
+    import cv2
+    import numpy as np
+    from deblur_e_nerf_b200 import views
+    g = torch.Generator().manual_seed(0)
+    lo, hi = 0.5 / 256, 1 - 0.5 / 256
+    ids = torch.tensor([[ord(ch) for ch in name.ljust(16)] for name in ("r_0", "view_12")])
+    assert views.sample_id_strings(ids) == ["r_0", "view_12"]
+    for channels in (1, 3):
+        pred = torch.rand(2, channels, 9, 11, generator=g) * 1.2 - 0.1            # some values outside the range
+        paths = views.save_predictions(pred, ids, str(tmp_path / f"c{channels}"), lo, hi)
+        assert [os.path.basename(p) for p in paths] == ["r_0.png", "view_12.png"]
+        want = (255 * ((pred - lo) / (hi - lo)).clamp(0, 1)).round().numpy().astype(np.uint8)
+        for b, path in enumerate(paths):
+            img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+            if channels == 1:
+                assert img.shape == (9, 11) and np.array_equal(img, want[b, 0])
+            else:
+                assert img.shape == (9, 11, 3) and np.array_equal(img[..., ::-1], want[b].transpose(1, 2, 0))
+    with pytest.raises(ValueError):
+        views.save_predictions(torch.rand(3, 1, 4, 4), ids, str(tmp_path / "bad"), lo, hi)
